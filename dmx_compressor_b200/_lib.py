@@ -1,0 +1,123 @@
+"""ctypes binding of libdmxq.so (include/dmxq.h) -- the thin torch shim.
+
+torch is used for what it is good at here: device memory (``torch.empty``), the current CUDA
+stream and the device guard.  No torch types cross the C ABI: tensors become ``dmxq_tensor``
+views (data pointer, dtype, shape, element strides).
+
+There is NO CPU fallback: if the shared library is missing, importing this module raises;
+if a CPU tensor reaches a cast, the op raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libdmxq.so")
+MAX_DIMS = 8
+MAX_STAGES = 4
+ABI_VERSION = 1
+
+# enums of include/dmxq.h
+F32, BF16, F16 = 0, 1, 2
+ROUND = {"nearest": 0, "stochastic": 1, "up": 2, "down": 3}
+TIE_AWAY, TIE_EVEN = 0, 1
+ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED = 0, 1, 2, 3, 4, 5
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+
+class Tensor(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("dtype", C.c_int32), ("ndim", C.c_int32),
+                ("shape", C.c_int64 * MAX_DIMS), ("stride", C.c_int64 * MAX_DIMS)]
+
+
+class Stage(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "kind", "block", "precision", "fraction", "man", "exp", "bias", "flush", "is_unsigned", "fp16_flush",
+        "symmetric", "clamp", "rounding", "tie", "n_keep", "sc_man", "sc_exp", "sc_bias", "sc_flush", "sc_unsigned",
+        "sc_fp16_flush", "sc_rounding")] + [("scale", C.c_float), ("zero_point", C.c_float)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m dmx_compressor_b200.build` "
+            "(nvcc, sm_100a). dmx_compressor_b200 has no CPU / PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    TP, SP, VP, I, I64 = C.POINTER(Tensor), C.POINTER(Stage), C.c_void_p, C.c_int, C.c_int64
+    sigs = {
+        "dmxq_abi_version": ([], I),
+        "dmxq_last_error": ([], C.c_char_p),
+        "dmxq_status_string": ([I], C.c_char_p),
+        "dmxq_launch_count": ([], I64),
+        "dmxq_cast_chain": ([TP, TP, I, SP, I, TP, TP, VP, VP], I),
+        "dmxq_bfp_qdq": ([TP, TP, I, I, I, I, I, VP, VP], I),
+        "dmxq_sbfp_qdq": ([TP, TP] + [I] * 13 + [VP], I),
+        "dmxq_float_qdq": ([TP, TP] + [I] * 7 + [VP, VP], I),
+        "dmxq_fixed_qdq": ([TP, TP] + [I] * 6 + [VP, VP, I64, I, I64, VP, VP], I),
+        "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, VP], I),
+        "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
+        "dmxq_minmax": ([TP, I, VP, VP, VP], I),
+        "dmxq_cast_chain_host": ([VP, VP, I, I, I64, I64, SP, I, I], I),
+        "dmxq_host_alloc": ([I64], VP),
+        "dmxq_host_free": ([VP], None),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(lib, name)  # AttributeError here == header / library mismatch
+        fn.argtypes = args
+        fn.restype = res
+    if lib.dmxq_abi_version() != ABI_VERSION:
+        raise ImportError(f"libdmxq ABI {lib.dmxq_abi_version()} != binding ABI {ABI_VERSION}")
+    return lib, list(sigs)
+
+
+lib, EXPORTS = _load()
+
+
+def check(rc: int, what: str = "dmxq") -> None:
+    """Non-zero status -> RuntimeError, the reference's TORCH_CHECK convention
+    (Q/quant_cuda/quant_cuda.cpp:7-11)."""
+    if rc != 0:
+        msg = lib.dmxq_last_error().decode(errors="replace")
+        if rc == -1 and ("not a multiple of block size" in msg):
+            raise AssertionError(msg)  # S/sparse.py:166-168 asserts
+        raise RuntimeError(f"{what}: {lib.dmxq_status_string(rc).decode()} ({rc}): {msg}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DTYPES[dt]
+    except KeyError:
+        raise RuntimeError(f"dmxq: unsupported dtype {dt} (float32, bfloat16, float16 only)") from None
+
+
+def require_cuda(t: torch.Tensor, name: str = "x") -> None:
+    if not isinstance(t, torch.Tensor):
+        raise AssertionError(f"{name} is not a torch.Tensor")
+    if not t.is_cuda:
+        # same message as the reference's CHECK_CUDA (Q/quant_cuda/quant_cuda.cpp:7)
+        raise RuntimeError(f"{name} must be a CUDA tensor (dmx_compressor_b200 is CUDA-only: no CPU fallback)")
+
+
+def view(t: torch.Tensor) -> Tensor:
+    if t.dim() > MAX_DIMS:
+        raise RuntimeError(f"dmxq: tensors of more than {MAX_DIMS} dims are not supported")
+    v = Tensor()
+    v.data = t.data_ptr()
+    v.dtype = dtype_code(t.dtype)
+    v.ndim = t.dim()
+    for i, (n, s) in enumerate(zip(t.shape, t.stride())):
+        v.shape[i] = n
+        v.stride[i] = s
+    return v
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib.dmxq_launch_count())

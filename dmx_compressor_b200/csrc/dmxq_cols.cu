@@ -1,0 +1,203 @@
+// dmxq_cols.cu -- chain_cols_kernel: the blocked dim is strided, another dim is contiguous
+// (the PV multiplier v:[.., S, 64] blocked along S, conv inputs/weights blocked along channels).
+//
+// One warp per tile of B rows (along the blocked dim) x LI*4 contiguous inner elements.
+// lane = lk * LI + li; lane (lk, li) owns rows [lk*RPT, (lk+1)*RPT) of the tile and the 4
+// columns at li*4.  Every column is its own block, so a thread carries 4 running maxima and
+// reduces them over the LK lanes that share li with xor-shuffles.  All RPT row loads of a
+// thread are issued back to back (RPT x 16 B in flight per thread); rows are LI*16 B (fp32)
+// contiguous segments, i.e. whole 128-byte lines for LI = 8.  Nothing is transposed in HBM.
+#include "dmxq_stages.cuh"
+
+namespace dmxq {
+
+// 4-element accesses (16 B for fp32, 8 B for 16-bit types)
+template <typename T> __device__ __forceinline__ void load4(const T *p, float (&v)[4])
+{
+    if constexpr (sizeof(T) == 4) {
+        VecIO<float>::load(reinterpret_cast<const float *>(p), v);
+    } else {
+        uint2 w = *reinterpret_cast<const uint2 *>(p);
+        T h[4];
+        *reinterpret_cast<uint2 *>(h) = w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = Cvt<T>::to_f32(h[j]);
+    }
+}
+template <typename T> __device__ __forceinline__ void store4(T *p, const float (&v)[4])
+{
+    if constexpr (sizeof(T) == 4) {
+        VecIO<float>::store<4>(reinterpret_cast<float *>(p), v);
+    } else {
+        T h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = Cvt<T>::from_f32(v[j]);
+        *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<uint2 *>(h);
+    }
+}
+
+template <typename Tin, typename Tout, int RPT, int LK>
+__global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_constant__ ColsParams p)
+{
+    constexpr int V = 4;
+    constexpr int LI = 32 / LK;
+    constexpr int B = RPT * LK;
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= p.n_tiles) return;  // whole warp leaves together
+    const int li = lane % LI, lk = lane / LI;
+
+    int64_t t = tile;
+    const int64_t chunk = t % p.nchunk; t /= p.nchunk;
+    const int64_t blk = t % p.nblk;
+    int64_t o = t / p.nblk;
+    int64_t xo = 0, yo = 0, ro = 0;
+    for (int d = p.nouter - 1; d >= 0; --d) {
+        int64_t i = (d == 0) ? o : o % p.odim[d];
+        if (d != 0) o /= p.odim[d];
+        xo += i * p.xs[d]; yo += i * p.ys[d]; ro += i * p.rs[d];
+    }
+    const int64_t i0 = (chunk * LI + li) * V;
+    const bool col_ok = i0 < p.inner;
+    const int64_t kb = blk * B + (int64_t)lk * RPT;
+
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x) + xo + i0;
+    Tout *__restrict__ y = static_cast<Tout *>(p.y) + yo + i0;
+
+    float v[RPT][V];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        int64_t k = kb + r;
+        if (col_ok && k < p.K) {
+            load4<Tin>(x + k * p.xks, v[r]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[r][j] = 0.0f;
+        }
+    }
+
+#pragma unroll 1
+    for (int s = 0; s < p.chain.n; ++s) {
+        const StageDev &st = p.chain.st[s];
+        if (st.kind == ST_BFP || st.kind == ST_SBFP) {
+            uint32_t m[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                m[j] = 0;
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) m[j] = max(m[j], f2u(v[r][j]) & 0x7FFFFFFFu);
+#pragma unroll
+                for (int off = LI; off < 32; off <<= 1) m[j] = max(m[j], __shfl_xor_sync(0xFFFFFFFFu, m[j], off));
+            }
+            if (st.kind == ST_BFP && st.mode == R_NEAREST) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    BfpBlock b = bfp_block(m[j], st.wl);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        float q = bfp_elem<R_NEAREST>(v[r][j], b, st.sh, st.mask, 0u);
+                        if (st.asym) q = bfp_asym_fix(q, v[r][j], b);
+                        v[r][j] = q;
+                    }
+                }
+            } else if (st.kind == ST_BFP) {
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        uint32_t rnd = 0;
+                        if (st.mode == R_STOCHASTIC && p.rnd != nullptr && col_ok && kb + r < p.K)
+                            rnd = __ldg(static_cast<const uint32_t *>(p.rnd) + ro + (kb + r) * p.rks + (i0 + j) * p.ris);
+                        v[r][j] = bfp_elem_slow(v[r][j], m[j], st.wl, st.sh, st.mask, st.mode, st.asym, rnd);
+                    }
+            } else {
+                const bool fast = sbfp_fast(st.sb);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    SbfpBlock b = sbfp_block_ol(m[j], st.sb);
+                    if (fast) {
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) v[r][j] = sbfp_elem_fast(v[r][j], b, st.sb);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) v[r][j] = sbfp_elem_slow(v[r][j], b.cmax, b.fs, &st.sb.xp);
+                    }
+                }
+            }
+        } else if (st.kind == ST_FLOAT) {
+            if (st.ff.mode == R_NEAREST) {
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[r][j] = float_elem<R_NEAREST>(v[r][j], st.ff, 0u);
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[r][j] = float_elem_slow(v[r][j], &st.ff, 0u);
+            }
+        } else if (st.kind == ST_FIXED) {
+#pragma unroll
+            for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[r][j] = fixed_elem_slow(v[r][j], &st.xf, st.affine, st.sc, st.zp, 0.5f);
+        }
+        if (st.requant) {
+#pragma unroll
+            for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[r][j] = requant1<Tout>(v[r][j]);
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        int64_t k = kb + r;
+        if (col_ok && k < p.K) store4<Tout>(y + k * p.yks, v[r]);
+    }
+}
+
+struct ColsCfg { int B, RPT, LK; };
+static const ColsCfg kColsCfgs[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 16, 4}, {128, 16, 8}};
+
+bool cols_supported(int, int B)
+{
+    for (auto &c : kColsCfgs) if (c.B == B) return true;
+    return false;
+}
+int cols_tile_inner(int, int B)
+{
+    for (auto &c : kColsCfgs) if (c.B == B) return (32 / c.LK) * 4;
+    return 0;
+}
+
+template <typename Tin, typename Tout> static cudaError_t launch_cols_t(int B, const ColsParams &p, cudaStream_t s)
+{
+    constexpr int wpc = kThreads / 32;
+    int64_t grid = (p.n_tiles + wpc - 1) / wpc;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    dim3 g((unsigned)grid), b(kThreads);
+    switch (B) {
+    case 8: chain_cols_kernel<Tin, Tout, 2, 4><<<g, b, 0, s>>>(p); break;
+    case 16: chain_cols_kernel<Tin, Tout, 4, 4><<<g, b, 0, s>>>(p); break;
+    case 32: chain_cols_kernel<Tin, Tout, 8, 4><<<g, b, 0, s>>>(p); break;
+    case 64: chain_cols_kernel<Tin, Tout, 16, 4><<<g, b, 0, s>>>(p); break;
+    case 128: chain_cols_kernel<Tin, Tout, 16, 8><<<g, b, 0, s>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cols(int in_dt, int out_dt, int B, const ColsParams &p, cudaStream_t s)
+{
+    if (in_dt == 0 && out_dt == 0) return launch_cols_t<float, float>(B, p, s);
+    if (in_dt == 1 && out_dt == 1) return launch_cols_t<__nv_bfloat16, __nv_bfloat16>(B, p, s);
+    if (in_dt == 2 && out_dt == 2) return launch_cols_t<__half, __half>(B, p, s);
+    if (in_dt == 1 && out_dt == 0) return launch_cols_t<__nv_bfloat16, float>(B, p, s);
+    if (in_dt == 2 && out_dt == 0) return launch_cols_t<__half, float>(B, p, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dmxq

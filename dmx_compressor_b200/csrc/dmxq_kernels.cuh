@@ -1,0 +1,135 @@
+// dmxq_kernels.cuh -- device-side parameter blocks shared by the kernels (dmxq_kernels.cu)
+// and the dispatcher (dmxq_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "dmxq_numerics.cuh"
+
+namespace dmxq {
+
+constexpr int kMaxStages = 4;
+constexpr int kMaxOuter = 3;   // outer dims the tiled kernels decompose (after collapsing)
+constexpr int kMaxDims = 8;
+
+// One stage of a cast chain, fully decoded for the device.
+struct StageDev {
+    int kind;        // ST_*
+    int block;       // block size (BFP/SBFP) or M (NM)
+    int requant;     // 1: round the stage result to the output dtype before the next stage
+                     //    (what consecutive CastTo.forward calls do, S/numerical/cast.py:306)
+    // BFP
+    int wl, sh, mode, asym;
+    uint32_t mask;
+    // NM
+    int n_prune;
+    // FLOAT
+    FloatFmt ff;
+    // FIXED (+ per-tensor affine)
+    FixedFmt xf;
+    int affine;
+    float sc, zp;
+    // SBFP
+    SbfpFmt sb;
+};
+
+struct ChainDev {
+    int n;
+    StageDev st[kMaxStages];
+};
+
+// Row-tiled kernel: the blocked dim is contiguous (stride 1).  A "row" is one index tuple of
+// the remaining (outer) dims.
+struct RowsParams {
+    const void *x;
+    void *y;
+    const float *score;  // nullable, NM stage
+    float *mask;         // nullable, NM stage
+    const void *rnd;     // nullable, stochastic stage (int32 or fp32)
+    int64_t n_vec;       // total (padded) vectors = rows * vpr
+    int64_t rows;
+    int64_t K;
+    uint32_t vpr;        // vectors per padded row (multiple of lanes per tile)
+    uint32_t kvec;       // valid vectors per row = K / V
+    int nouter;          // 1..kMaxOuter
+    int64_t odim[kMaxOuter];
+    int64_t xs[kMaxOuter], ys[kMaxOuter], ss[kMaxOuter], ms[kMaxOuter], rs[kMaxOuter];
+    int64_t rks;         // rand stride along K
+    ChainDev chain;
+};
+
+// Column-tiled kernel: the blocked dim is strided, another dim ("inner") is contiguous.
+struct ColsParams {
+    const void *x;
+    void *y;
+    const void *rnd;
+    int64_t n_tiles;     // outer * nblk * nchunk
+    int64_t K, inner;
+    int64_t nblk;        // ceil(K / B)
+    int64_t nchunk;      // ceil(inner / (LI * V))
+    int64_t xks, yks, rks;  // strides along K
+    int64_t ris;            // rand stride along inner
+    int nouter;
+    int64_t odim[kMaxOuter];
+    int64_t xs[kMaxOuter], ys[kMaxOuter], rs[kMaxOuter];
+    ChainDev chain;
+    int blocked;  // index of the (single) blocked stage in chain, or -1
+};
+
+// Generic kernel: arbitrary strides, one thread per (block, everything-else) pair.
+struct GenericParams {
+    const void *x;
+    void *y;
+    const float *score;
+    float *mask;
+    const void *rnd;
+    int64_t n_items;  // prod(other dims) * nblk
+    int64_t K, nblk;
+    int64_t xks, yks, sks, mks, rks;
+    int nd;  // number of non-block dims
+    int64_t dim[kMaxDims];
+    int64_t xs[kMaxDims], ys[kMaxDims], ss[kMaxDims], ms[kMaxDims], rs[kMaxDims];
+    StageDev st;
+};
+
+// Per-channel / group affine fixed point on a contiguous (outer, C, inner) tensor.
+struct FixedChanParams {
+    const void *x;
+    void *y;
+    const float *scale, *zp, *rnd;
+    int64_t n, C, inner, group, nq;
+    FixedFmt xf;
+};
+
+// L1 block_quantize apply: per-"channel" max bits given in `maxbits`.
+struct BlockQParams {
+    const float *x;
+    float *y;
+    const int32_t *rnd;
+    const uint32_t *maxbits;
+    int64_t n, C, inner;  // channel of element i = (i / inner) % C  (C == 1: whole tensor)
+    int wl, sh, mode, symmetric;
+    uint32_t mask;
+};
+
+struct MinMaxParams {
+    const void *x;
+    int dtype;
+    int64_t outer, C, inner;
+    int64_t xo, xc, xi;  // strides
+    int *omin, *omax;    // ordered-int accumulators, aliased onto the float outputs
+};
+
+// launchers (dmxq_kernels.cu)
+cudaError_t launch_rows(int in_dt, int out_dt, bool flat, int special, const RowsParams &p, cudaStream_t s);
+cudaError_t launch_cols(int in_dt, int out_dt, int B, const ColsParams &p, cudaStream_t s);
+bool cols_supported(int in_dt, int B);
+int cols_tile_inner(int in_dt, int B);  // LI * V of the instantiation used for block size B
+cudaError_t launch_generic(int in_dt, int out_dt, const GenericParams &p, cudaStream_t s);
+cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, cudaStream_t s);
+cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s);
+cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s);
+cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s);
+int64_t launch_count();
+
+}  // namespace dmxq

@@ -1,0 +1,271 @@
+// dmxq_misc.cu -- the correctness-net and support kernels:
+//   chain_generic_kernel  any strides / odd sizes (scalar, two-pass)
+//   fixed_chan_kernel     FixedPoint with per-channel / group affine parameters
+//   blockq_kernel         L1 block_quantize(x, wl, dim) apply step
+//   minmax_kernel         calibration amin/amax (exact, order independent)
+#include <algorithm>
+#include <atomic>
+
+#include "dmxq_stages.cuh"
+
+namespace dmxq {
+
+static std::atomic<int64_t> g_launches{0};
+int64_t launch_count() { return g_launches.load(); }
+void count_launch(int n) { g_launches += n; }
+
+// ------------------------------------------------------------------------------------------------
+// generic kernel: any strides, any block size; one thread per (other-dims index, block).
+// Two passes over the block (statistic, then apply); the second pass re-reads through L1/L2.
+// In-place safe: a thread finishes reading its block statistic before it writes any element,
+// and blocks are disjoint.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads) chain_generic_kernel(const __grid_constant__ GenericParams p)
+{
+    const int64_t item = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (item >= p.n_items) return;
+    const StageDev &st = p.st;
+    // fastest: last non-block dim, then the block index, then the remaining dims
+    int64_t t = item;
+    int64_t xo = 0, yo = 0, so = 0, mo = 0, ro = 0;
+    if (p.nd > 0) {
+        int d = p.nd - 1;
+        int64_t i = t % p.dim[d]; t /= p.dim[d];
+        xo += i * p.xs[d]; yo += i * p.ys[d]; so += i * p.ss[d]; mo += i * p.ms[d]; ro += i * p.rs[d];
+    }
+    const int64_t blk = t % p.nblk; t /= p.nblk;
+    for (int d = p.nd - 2; d >= 0; --d) {
+        int64_t i = t % p.dim[d]; t /= p.dim[d];
+        xo += i * p.xs[d]; yo += i * p.ys[d]; so += i * p.ss[d]; mo += i * p.ms[d]; ro += i * p.rs[d];
+    }
+    const int64_t B = (st.kind == ST_FLOAT || st.kind == ST_FIXED) ? 1 : st.block;
+    const int64_t k0 = blk * B;
+    const int64_t k1 = min(k0 + B, p.K);
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x) + xo;
+    Tout *y = static_cast<Tout *>(p.y) + yo;
+    const uint32_t *rnd = p.rnd ? static_cast<const uint32_t *>(p.rnd) + ro : nullptr;
+
+    if (st.kind == ST_BFP || st.kind == ST_SBFP) {
+        uint32_t m = 0;
+        for (int64_t k = k0; k < k1; ++k) m = max(m, f2u(Cvt<Tin>::to_f32(x[k * p.xks])) & 0x7FFFFFFFu);
+        if (st.kind == ST_BFP) {
+            for (int64_t k = k0; k < k1; ++k) {
+                float xv = Cvt<Tin>::to_f32(x[k * p.xks]);
+                uint32_t r = (rnd && st.mode == R_STOCHASTIC) ? rnd[k * p.rks] : 0u;
+                y[k * p.yks] = Cvt<Tout>::from_f32(bfp_elem_slow(xv, m, st.wl, st.sh, st.mask, st.mode, st.asym, r));
+            }
+        } else {
+            SbfpBlock b = sbfp_block_ol(m, st.sb);
+            for (int64_t k = k0; k < k1; ++k)
+                y[k * p.yks] = Cvt<Tout>::from_f32(sbfp_elem_slow(Cvt<Tin>::to_f32(x[k * p.xks]), b.cmax, b.fs, &st.sb.xp));
+        }
+    } else if (st.kind == ST_NM) {
+        // rank each element of the group against the others (keys recomputed on the fly);
+        // all ranks are computed from the pristine input before the first write (in-place safe
+        // because masks are buffered in a bit set: M <= 64).
+        unsigned long long keepbits = 0ull;
+        for (int64_t a = k0; a < k1; ++a) {
+            float xa = Cvt<Tin>::to_f32(x[a * p.xks]);
+            uint32_t ka = p.score ? score_key(p.score[so + a * p.sks]) : absx_key(xa);
+            int rank = 0;
+            for (int64_t bb = k0; bb < k1; ++bb) {
+                if (bb == a) continue;
+                float xb = Cvt<Tin>::to_f32(x[bb * p.xks]);
+                uint32_t kb = p.score ? score_key(p.score[so + bb * p.sks]) : absx_key(xb);
+                rank += (kb < ka || (kb == ka && bb < a)) ? 1 : 0;
+            }
+            if (rank >= st.n_prune) keepbits |= 1ull << (a - k0);
+        }
+        for (int64_t a = k0; a < k1; ++a) {
+            bool keep = (keepbits >> (a - k0)) & 1ull;
+            float xa = Cvt<Tin>::to_f32(x[a * p.xks]);
+            y[a * p.yks] = Cvt<Tout>::from_f32(nm_apply(xa, keep));
+            if (p.mask) p.mask[mo + a * p.mks] = keep ? 1.0f : 0.0f;
+        }
+    } else if (st.kind == ST_FLOAT) {
+        float xv = Cvt<Tin>::to_f32(x[k0 * p.xks]);
+        uint32_t r = (rnd && st.ff.mode == R_STOCHASTIC) ? rnd[k0 * p.rks] : 0u;
+        y[k0 * p.yks] = Cvt<Tout>::from_f32(float_elem_slow(xv, &st.ff, r));
+    } else if (st.kind == ST_FIXED) {
+        float xv = Cvt<Tin>::to_f32(x[k0 * p.xks]);
+        float r = (rnd && st.xf.mode == R_STOCHASTIC) ? u2f(rnd[k0 * p.rks]) : 0.5f;
+        float q = fixed_elem_slow(xv, &st.xf, st.affine, st.sc, st.zp, r);
+        y[k0 * p.yks] = Cvt<Tout>::from_f32(q);
+    } else {
+        y[k0 * p.yks] = Cvt<Tout>::from_f32(Cvt<Tin>::to_f32(x[k0 * p.xks]));
+    }
+}
+
+template <typename Tin, typename Tout> static cudaError_t launch_generic_t(const GenericParams &p, cudaStream_t s)
+{
+    int64_t grid = (p.n_items + kThreads - 1) / kThreads;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    chain_generic_kernel<Tin, Tout><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generic(int in_dt, int out_dt, const GenericParams &p, cudaStream_t s)
+{
+    if (in_dt == 0 && out_dt == 0) return launch_generic_t<float, float>(p, s);
+    if (in_dt == 1 && out_dt == 1) return launch_generic_t<__nv_bfloat16, __nv_bfloat16>(p, s);
+    if (in_dt == 2 && out_dt == 2) return launch_generic_t<__half, __half>(p, s);
+    if (in_dt == 1 && out_dt == 0) return launch_generic_t<__nv_bfloat16, float>(p, s);
+    if (in_dt == 2 && out_dt == 0) return launch_generic_t<__half, float>(p, s);
+    return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FixedPoint with per-channel / group affine parameters (S/numerical/cast.py:228-237, 279-296)
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_constant__ FixedChanParams p)
+{
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
+    Tout *__restrict__ y = static_cast<Tout *>(p.y);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * kThreads) {
+        int64_t c = (i / p.inner) % p.C;
+        int64_t q = p.nq == 1 ? 0 : min(c / p.group, p.nq - 1);
+        float r = p.rnd ? p.rnd[i] : 0.5f;
+        y[i] = Cvt<Tout>::from_f32(fixed_elem_affine(Cvt<Tin>::to_f32(x[i]), p.xf, __ldg(p.scale + q), __ldg(p.zp + q), r));
+    }
+}
+
+cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, cudaStream_t s)
+{
+    if (p.n <= 0) return cudaSuccess;
+    int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
+    if (in_dt == 0 && out_dt == 0) fixed_chan_kernel<float, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else if (in_dt == 1 && out_dt == 1) fixed_chan_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else if (in_dt == 2 && out_dt == 2) fixed_chan_kernel<__half, __half><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else if (in_dt == 1 && out_dt == 0) fixed_chan_kernel<__nv_bfloat16, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else if (in_dt == 2 && out_dt == 0) fixed_chan_kernel<__half, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else return cudaErrorInvalidValue;
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// L1 block_quantize apply (Q/quant_cuda/block_kernel.cu:7-139) given per-slice max|x| bits,
+// including the reference's `!symmetric` exponent bump for x == -max with an all-ones top
+// mantissa byte (block_kernel.cu:51-57).
+__global__ void __launch_bounds__(kThreads) blockq_kernel(const __grid_constant__ BlockQParams p)
+{
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * kThreads) {
+        int64_t c = p.C == 1 ? 0 : (i / p.inner) % p.C;
+        uint32_t mb = __ldg(p.maxbits + c);
+        float xv = p.x[i];
+        if (!p.symmetric) {
+            float mf = u2f(mb);
+            if (xv == -mf && ((mb >> 16) << 25) == 0xFE000000u) mb = ((mb >> 23) + 1u) << 23;
+        }
+        BfpBlock b = bfp_block(mb, p.wl);
+        uint32_t r = p.rnd ? (uint32_t)p.rnd[i] : 0u;
+        float q;
+        switch (p.mode) {
+        case R_NEAREST: q = bfp_elem<R_NEAREST>(xv, b, p.sh, p.mask, r); break;
+        case R_STOCHASTIC: q = bfp_elem<R_STOCHASTIC>(xv, b, p.sh, p.mask, r); break;
+        case R_UP: q = bfp_elem<R_UP>(xv, b, p.sh, p.mask, r); break;
+        default: q = bfp_elem<R_DOWN>(xv, b, p.sh, p.mask, r); break;
+        }
+        p.y[i] = q;
+    }
+}
+
+cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s)
+{
+    if (p.n <= 0) return cudaSuccess;
+    int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
+    blockq_kernel<<<(unsigned)grid, kThreads, 0, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// amin / amax: ordered-int atomics (exact, order independent).  NaN -> INT_MAX on the max side,
+// INT_MIN on the min side; the finalize kernel turns those sentinels back into NaN.
+__device__ __forceinline__ int ord(float f) { int k = (int)f2u(f); return k < 0 ? k ^ 0x7FFFFFFF : k; }
+__device__ __forceinline__ float unord(int k) { return u2f((uint32_t)(k < 0 ? k ^ 0x7FFFFFFF : k)); }
+
+__global__ void minmax_init_kernel(int *omin, int *omax, int64_t C)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) { omin[i] = 0x7F800000; omax[i] = ord(u2f(0xFF800000u)); }
+}
+
+template <typename T> __global__ void __launch_bounds__(kThreads) minmax_kernel(const __grid_constant__ MinMaxParams p)
+{
+    // grid: (chunks, C); each CTA reduces a slice of channel c over (outer, inner)
+    const T *__restrict__ x = static_cast<const T *>(p.x);
+    const int64_t c = blockIdx.y;
+    const int64_t per = p.outer * p.inner;
+    int lo = 0x7F800000, hi = ord(u2f(0xFF800000u));
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < per; i += (int64_t)gridDim.x * kThreads) {
+        int64_t o = i / p.inner, in = i - o * p.inner;
+        float v = Cvt<T>::to_f32(x[o * p.xo + c * p.xc + in * p.xi]);
+        if (v != v) { lo = (int)0x80000000; hi = 0x7FFFFFFF; }
+        else { int k = ord(v); lo = min(lo, k); hi = max(hi, k); }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+    }
+    __shared__ int slo[kThreads / 32], shi[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        atomicMin(p.omin + c, lo);
+        atomicMax(p.omax + c, hi);
+    }
+}
+
+__global__ void minmax_final_kernel(int *omin, int *omax, int64_t C)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) {
+        int lo = omin[i], hi = omax[i];
+        float fl = lo == (int)0x80000000 ? u2f(0x7FC00000u) : unord(lo);
+        float fh = hi == 0x7FFFFFFF ? u2f(0x7FC00000u) : unord(hi);
+        reinterpret_cast<float *>(omin)[i] = fl;
+        reinterpret_cast<float *>(omax)[i] = fh;
+    }
+}
+
+cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
+{
+    int64_t C = p.C;
+    if (C <= 0) return cudaSuccess;
+    if (C > 65535) return cudaErrorInvalidConfiguration;
+    unsigned ib = (unsigned)((C + 255) / 256);
+    minmax_init_kernel<<<ib, 256, 0, s>>>(p.omin, p.omax, C);
+    int64_t per = p.outer * p.inner;
+    if (per > 0) {
+        int64_t chunks = (per + (int64_t)kThreads * 8 - 1) / ((int64_t)kThreads * 8);
+        int64_t cap = std::max<int64_t>(1, (148 * 8) / C);
+        chunks = std::max<int64_t>(1, std::min(chunks, cap));
+        dim3 g((unsigned)chunks, (unsigned)C);
+        if (p.dtype == 0) minmax_kernel<float><<<g, kThreads, 0, s>>>(p);
+        else if (p.dtype == 1) minmax_kernel<__nv_bfloat16><<<g, kThreads, 0, s>>>(p);
+        else minmax_kernel<__half><<<g, kThreads, 0, s>>>(p);
+    }
+    minmax_final_kernel<<<ib, 256, 0, s>>>(p.omin, p.omax, C);
+    count_launch(3);
+    return cudaGetLastError();
+}
+
+__global__ void fold_absmax_kernel(const float *mn, const float *mx, uint32_t *out, int64_t C)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) out[i] = max(f2u(mn[i]) & 0x7FFFFFFFu, f2u(mx[i]) & 0x7FFFFFFFu);
+}
+
+cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s)
+{
+    if (C <= 0) return cudaSuccess;
+    fold_absmax_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(mn, mx, out, C);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace dmxq

@@ -1,0 +1,266 @@
+// dmxq_numerics.cuh -- bit-exact element codecs of the CastTo / Sparsify path (device side).
+//
+// Each function states the reference arithmetic it reproduces ("Q/" = reference
+// src/dmx/compressor/quant/, "S/" = src/dmx/compressor/).  The algebra is re-derived for the
+// GPU (fused masks, 3-input adds, branch-free selects); the *results* are bit-identical to the
+// reference's CUDA kernels, which is what tests/test_parity_gpu.py checks against the oracle.
+//
+// Rules that keep it exact (hard part 1):
+//   * every fp32 add/sub/mul/div that the reference performs as a separate rounded op is an
+//     explicit __f*_rn intrinsic here (never contracted into an FMA, never reassociated);
+//   * no fast-math, no flush-to-zero (denormals survive), true IEEE division;
+//   * block maxima are taken on |x| bit patterns as unsigned integers: NaN > Inf > finite,
+//     which reproduces torch.max's NaN propagation for everything downstream consumes.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace dmxq {
+
+enum : int { R_NEAREST = 0, R_STOCHASTIC = 1, R_UP = 2, R_DOWN = 3 };
+enum : int { TIE_AWAY = 0, TIE_EVEN = 1 };
+enum : int { ST_NONE = 0, ST_NM = 1, ST_BFP = 2, ST_SBFP = 3, ST_FLOAT = 4, ST_FIXED = 5 };
+
+__device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
+__device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
+
+// Keep `23 - sh` mantissa bits of the fp32 pattern `t`.
+// Reference: round_bitwise_{nearest,stochastic,up,down}, Q/quant_cuda/bit_helper.cu:10-46.
+// Nearest (RNE on the magnitude pattern): the reference adds `half` unless the discarded
+// field is exactly `half` and the kept LSB is even; that equals adding (half - 1) + keptLSB
+// and truncating, which is one IADD3 + one LOP3.  sh == 0 (man_bits >= 23, undefined in the
+// reference, identity on its CUDA build) must be passed with mode R_DOWN by the host.
+template <int MODE>
+__device__ __forceinline__ uint32_t round_bits(uint32_t t, int sh, uint32_t mask, uint32_t rnd)
+{
+    if (MODE == R_NEAREST) {
+        uint32_t lsb = (t >> sh) & 1u;
+        return (t + (mask >> 1) + lsb) & ~mask;
+    } else if (MODE == R_STOCHASTIC) {
+        return (t + (rnd & mask)) & ~mask;
+    } else if (MODE == R_UP) {
+        return (t + mask + 1u) & ~mask;
+    } else {
+        return t & ~mask;
+    }
+}
+
+__device__ __forceinline__ uint32_t round_bits_rt(uint32_t t, int sh, uint32_t mask, int mode, uint32_t rnd)
+{
+    switch (mode) {
+    case R_NEAREST: return round_bits<R_NEAREST>(t, sh, mask, rnd);
+    case R_STOCHASTIC: return round_bits<R_STOCHASTIC>(t, sh, mask, rnd);
+    case R_UP: return round_bits<R_UP>(t, sh, mask, rnd);
+    default: return round_bits<R_DOWN>(t, sh, mask, rnd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block floating point.  Per block (uniform): E = exponent field of max|x| (in place, bits
+// 23..30), base = 6 * 2^e, maxnum = E | top (wl-2) mantissa bits.
+// Reference: block_kernel_*, Q/quant_cuda/block_kernel.cu:43-74 + clip_max_exponent,
+// bit_helper.cu:68-79.
+struct BfpBlock {
+    uint32_t E;       // exponent field of the block max
+    uint32_t maxnum;  // E | max mantissa: largest representable magnitude of the block
+    float base;       // 6 * 2^e  (Inf when e >= 126, exactly as the reference's fp32 product)
+    float quantum;    // 2^(e + 2 - wl), only used by the asymmetric post-pass
+};
+
+__device__ __forceinline__ BfpBlock bfp_block(uint32_t maxabs_bits, int wl)
+{
+    BfpBlock b;
+    b.E = maxabs_bits & 0x7F800000u;
+    b.base = __fmul_rn(u2f(b.E), 6.0f);
+    int m = wl - 2;
+    b.maxnum = b.E | ((0x007FFFFFu >> (23 - m)) << (23 - m));
+    b.quantum = __fmul_rn(u2f(b.E), u2f((uint32_t)(127 + 2 - wl) << 23));
+    return b;
+}
+
+template <int MODE>
+__device__ __forceinline__ float bfp_elem(float x, const BfpBlock &b, int sh, uint32_t mask, uint32_t rnd)
+{
+    float t = __fadd_rn(x, b.base);
+    uint32_t tb = round_bits<MODE>(f2u(t), sh, mask, rnd);
+    float q = __fsub_rn(u2f(tb), b.base);
+    uint32_t qb = f2u(q);
+    if ((qb & 0x7F800000u) > b.E) qb = (qb & 0x80000000u) | b.maxnum;
+    return u2f(qb);
+}
+
+// BlockFloatingPoint.make_mantissa_asymmetric, S/numerical/format.py:349-372: an element whose
+// integer mantissa is exactly -(2^(wl-1)-1) moves one quantum down to -2^(wl-1) when that does
+// not increase |error| (ties go to the even mantissa).  old/candidate errors are separately
+// rounded fp32 subtractions, as the torch ops are.
+__device__ __forceinline__ float bfp_asym_fix(float q, float x, const BfpBlock &b)
+{
+    if (f2u(q) == (0x80000000u | b.maxnum) && b.E != 0u) {
+        float old_err = __fsub_rn(q, x);
+        float cand_err = __fsub_rn(old_err, b.quantum);
+        if (fabsf(cand_err) <= fabsf(old_err)) q = -u2f(b.E + 0x00800000u);
+    }
+    return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Low-bit floating point.  Reference: float_kernel_*, Q/quant_cuda/float_kernel.cu:131-168 +
+// clip_exponent, bit_helper.cu:48-65; python wrapper extras S/numerical/format.py:223-233.
+struct FloatFmt {
+    int sh;              // 23 - man_bits (0 => identity rounding)
+    uint32_t mask;       // (1 << sh) - 1
+    int min_exp;         // -(bias - 1)
+    uint32_t shift_exp;  // (127 + min_exp) << 23: the subnormal-rounding shift magnitude
+    uint32_t max_store;  // (1 << (exp_bits-1)) + 127: saturation exponent (nothing reserved for Inf/NaN)
+    uint32_t max_num;    // (max_store << 23) | max mantissa
+    int flush;           // flush_subnormal
+    int is_unsigned;     // abs() afterwards
+    int fp16_flush;      // extra |q| < 2^-14 -> +0
+    int mode;
+};
+
+template <int MODE>
+__device__ __forceinline__ float float_elem(float x, const FloatFmt &f, uint32_t rnd)
+{
+    uint32_t target = f2u(x);
+    int texp = (int)((target & 0x7FFFFFFFu) >> 23) - 127;
+    float q;
+    if (texp < f.min_exp) {
+        if (f.flush) {
+            q = 0.0f;
+        } else {
+            float shift = u2f(f.shift_exp | (target & 0x80000000u));
+            float val = __fadd_rn(x, shift);
+            uint32_t qb = round_bits<MODE>(f2u(val), f.sh, f.mask, rnd);
+            q = __fsub_rn(u2f(qb), shift);
+        }
+    } else {
+        uint32_t qb = round_bits<MODE>(target, f.sh, f.mask, rnd);
+        if (((qb & 0x7FFFFFFFu) >> 23) > f.max_store) qb = (target & 0x80000000u) | f.max_num;
+        q = u2f(qb);
+    }
+    if (f.fp16_flush && fabsf(q) < 6.103515625e-05f) q = 0.0f;
+    if (f.is_unsigned) q = fabsf(q);
+    return q;
+}
+
+__device__ __forceinline__ float float_elem_rt(float x, const FloatFmt &f, uint32_t rnd)
+{
+    switch (f.mode) {
+    case R_NEAREST: return float_elem<R_NEAREST>(x, f, rnd);
+    case R_STOCHASTIC: return float_elem<R_STOCHASTIC>(x, f, rnd);
+    case R_UP: return float_elem<R_UP>(x, f, rnd);
+    default: return float_elem<R_DOWN>(x, f, rnd);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed point.  Reference: fixed_point_quantize_kernel_*, Q/quant_cuda/fixed_point_kernel.cu:34-101
+// + sim_helper.cu:4-51 (CUDA) / Q/quant_cpu/sim_helper.cpp:14-38 (CPU tie quirk).
+// ldexp(a, +-fl) is an exact power-of-two scaling: a single correctly rounded multiply by
+// 2^fl is bit-identical (|fl| <= 126 is enforced by the host).
+struct FixedFmt {
+    float up, down;      // 2^fl, 2^-fl
+    float t_min, t_max;  // fixed_min_max, quant.cu:230-237
+    int clamp;
+    int mode;
+    int tie;
+};
+
+__device__ __forceinline__ float fixed_elem(float a, const FixedFmt &f, float r)
+{
+    a = __fmul_rn(a, f.up);
+    switch (f.mode) {
+    case R_NEAREST:
+        if (f.tie == TIE_AWAY) a = roundf(a);
+        else a = (float)rint(__dadd_rn((double)__fadd_rn(a, 0.5f), -0.5));
+        break;
+    case R_STOCHASTIC: a = (float)rint(__dadd_rn((double)__fadd_rn(a, r), -0.5)); break;
+    case R_UP: a = ceilf(a); break;
+    default: a = floorf(a); break;
+    }
+    a = __fmul_rn(a, f.down);
+    if (f.clamp) {
+        if (a > f.t_max) a = f.t_max;
+        else if (a < f.t_min) a = f.t_min;
+    }
+    return a;
+}
+
+// CastTo.forward's affine wrap, S/numerical/cast.py:293,296: four separately rounded ops.
+__device__ __forceinline__ float fixed_elem_affine(float x, const FixedFmt &f, float sc, float zp, float r)
+{
+    float v = __fadd_rn(__fdiv_rn(x, sc), zp);
+    v = fixed_elem(v, f, r);
+    return __fmul_rn(__fsub_rn(v, zp), sc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scaled BFP.  Reference: ScaledBlockFloatingPoint.cast, S/numerical/format.py:453-479.
+struct SbfpFmt {
+    FixedFmt xp;        // XP[p,0] block format (fl = 0: up = down = 1)
+    FloatFmt sc;        // scaler FloatingPoint format
+    float man_scaling;  // 2^(p-1) - 1
+};
+
+struct SbfpBlock {
+    float cmax;  // max|x| / man_scaling   (NaN when the block holds a NaN)
+    float fs;    // FP_cast(cmax)
+    bool on;     // cmax > 0 (false => pass the block through, format.py:467-472)
+};
+
+__device__ __forceinline__ SbfpBlock sbfp_block(uint32_t maxabs_bits, const SbfpFmt &f)
+{
+    SbfpBlock b;
+    b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
+    b.fs = float_elem_rt(b.cmax, f.sc, 0u);
+    b.on = b.cmax > 0.0f;
+    return b;
+}
+
+__device__ __forceinline__ float sbfp_elem(float x, const SbfpBlock &b, const SbfpFmt &f)
+{
+    if (!b.on) return x;
+    float v = __fdiv_rn(x, b.cmax);
+    v = fixed_elem(v, f.xp, 0.5f);
+    return __fmul_rn(v, b.fs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// N:M prune.  Reference: BlockTopK.forward, S/sparse.py:163-180 (ascending argsort of the
+// score, the M-K lowest get mask 0) and Sparsify.forward :287-301 (y = x * mask, an fp32
+// multiply: masked negatives become -0.0, masked Inf/NaN become NaN).  Order: ascending,
+// ties -> lower index first (stable), NaN largest, -0 == +0.
+__device__ __forceinline__ uint32_t score_key(float s)
+{
+    uint32_t b = f2u(s);
+    if ((b & 0x7FFFFFFFu) > 0x7F800000u) return 0xFFFFFFFFu;  // NaN: largest
+    if (b == 0x80000000u) b = 0u;                              // -0 == +0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t absx_key(float x)  // score = |x|
+{
+    uint32_t b = f2u(x) & 0x7FFFFFFFu;
+    return b > 0x7F800000u ? 0xFFFFFFFFu : b;
+}
+__device__ __forceinline__ float nm_apply(float x, bool keep) { return keep ? x : __fmul_rn(x, 0.0f); }
+
+// ---------------------------------------------------------------------------------------------
+// dtype conversion exactly as torch does it around every cast (S/numerical/cast.py:262,306):
+// widening is exact, narrowing is round-to-nearest-even.
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+    static __device__ __forceinline__ float to_f32(float v) { return v; }
+    static __device__ __forceinline__ float from_f32(float v) { return v; }
+};
+template <> struct Cvt<__nv_bfloat16> {
+    static __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f32(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Cvt<__half> {
+    static __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f32(float v) { return __float2half_rn(v); }
+};
+
+}  // namespace dmxq

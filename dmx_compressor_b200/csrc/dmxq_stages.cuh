@@ -1,0 +1,300 @@
+// dmxq_stages.cuh -- vector I/O and per-stage register-vector code shared by the tiled kernels.
+//
+// Code-size discipline: the formats the BASIC rule set and the BASELINE configs use
+// (nearest rounding, symmetric BFP, half-away XP) are inlined straight-line code; every other
+// mode goes through one __noinline__ scalar function per format, so a kernel carries a single
+// copy of the rarely used paths instead of one per unrolled element.
+#pragma once
+#include "dmxq_kernels.cuh"
+
+namespace dmxq {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// ------------------------------------------------------------------------------------------------
+// 128-bit streaming loads / stores (read-once / write-once data: do not allocate in L1)
+__device__ __forceinline__ uint4 ldg_stream(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(void *p, uint4 v)
+{
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+template <typename T> struct VecIO;  // V = 16 bytes of T on the input side
+
+template <> struct VecIO<float> {
+    static constexpr int V = 4;
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4])
+    {
+        uint4 r = ldg_stream(p);
+        v[0] = u2f(r.x); v[1] = u2f(r.y); v[2] = u2f(r.z); v[3] = u2f(r.w);
+    }
+    template <int N> static __device__ __forceinline__ void store(float *p, const float (&v)[N])
+    {
+#pragma unroll
+        for (int i = 0; i < N; i += 4) stg_stream(p + i, make_uint4(f2u(v[i]), f2u(v[i + 1]), f2u(v[i + 2]), f2u(v[i + 3])));
+    }
+};
+template <> struct VecIO<__nv_bfloat16> {
+    static constexpr int V = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8])
+    {
+        uint4 r = ldg_stream(p);
+        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = u2f(w[i] << 16); v[2 * i + 1] = u2f(w[i] & 0xFFFF0000u); }
+    }
+    template <int N> static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[N])
+    {
+        static_assert(N == 8, "bf16 stores are 8 wide");
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        stg_stream(p, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+};
+template <> struct VecIO<__half> {
+    static constexpr int V = 8;
+    static __device__ __forceinline__ void load(const __half *p, float (&v)[8])
+    {
+        uint4 r = ldg_stream(p);
+        uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __half22float2(*reinterpret_cast<__half2 *>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    template <int N> static __device__ __forceinline__ void store(__half *p, const float (&v)[N])
+    {
+        static_assert(N == 8, "fp16 stores are 8 wide");
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+        stg_stream(p, make_uint4(w[0], w[1], w[2], w[3]));
+    }
+};
+
+template <typename Tout> __device__ __forceinline__ float requant1(float v)
+{
+    if constexpr (sizeof(Tout) == 4) return v;
+    else return Cvt<Tout>::to_f32(Cvt<Tout>::from_f32(v));
+}
+
+// ------------------------------------------------------------------------------------------------
+// out-of-line scalar paths (one copy per kernel)
+static __device__ __noinline__ float bfp_elem_slow(float x, uint32_t maxabs_bits, int wl, int sh, uint32_t mask, int mode, int asym, uint32_t rnd)
+{
+    BfpBlock b = bfp_block(maxabs_bits, wl);
+    float t = __fadd_rn(x, b.base);
+    uint32_t tb = round_bits_rt(f2u(t), sh, mask, mode, rnd);
+    float q = __fsub_rn(u2f(tb), b.base);
+    uint32_t qb = f2u(q);
+    if ((qb & 0x7F800000u) > b.E) qb = (qb & 0x80000000u) | b.maxnum;
+    q = u2f(qb);
+    if (asym) q = bfp_asym_fix(q, x, b);
+    return q;
+}
+static __device__ __noinline__ float float_elem_slow(float x, const FloatFmt *f, uint32_t rnd) { return float_elem_rt(x, *f, rnd); }
+static __device__ __noinline__ float fixed_elem_slow(float x, const FixedFmt *f, int affine, float sc, float zp, float r)
+{
+    return affine ? fixed_elem_affine(x, *f, sc, zp, r) : fixed_elem(x, *f, r);
+}
+
+// SBFP block header (once per block per lane) and element
+__device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const SbfpFmt &f)
+{
+    SbfpBlock b;
+    b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
+    b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
+    b.on = b.cmax > 0.0f;
+    return b;
+}
+__device__ __forceinline__ bool sbfp_fast(const SbfpFmt &f) { return f.xp.mode == R_NEAREST && f.xp.tie == TIE_AWAY; }
+__device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, const SbfpFmt &f)
+{
+    // XP[p,0] nearest, half away (the reference's CUDA behaviour): fl = 0 => no scaling multiplies
+    float v = roundf(__fdiv_rn(x, b.cmax));
+    if (f.xp.clamp) v = v > f.xp.t_max ? f.xp.t_max : (v < f.xp.t_min ? f.xp.t_min : v);
+    return b.on ? __fmul_rn(v, b.fs) : x;
+}
+static __device__ __noinline__ float sbfp_elem_slow(float x, float cmax, float fs, const FixedFmt *xp)
+{
+    if (!(cmax > 0.0f)) return x;
+    float v = fixed_elem(__fdiv_rn(x, cmax), *xp, 0.5f);
+    return __fmul_rn(v, fs);
+}
+
+// ------------------------------------------------------------------------------------------------
+// stages on one register vector (V consecutive elements along the blocked dim)
+template <int V> __device__ __forceinline__ uint32_t vec_absmax(const float (&v)[V])
+{
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) m = max(m, f2u(v[j]) & 0x7FFFFFFFu);
+    return m;
+}
+__device__ __forceinline__ uint32_t lanes_max(uint32_t m, int lanes)
+{
+    for (int off = 1; off < lanes; off <<= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    return m;
+}
+
+template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const StageDev &st, int lanes, const uint32_t (&r)[V])
+{
+    uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
+    if (st.mode == R_NEAREST) {
+        BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float q = bfp_elem<R_NEAREST>(v[j], b, st.sh, st.mask, 0u);
+            if (st.asym) q = bfp_asym_fix(q, v[j], b);
+            v[j] = q;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem_slow(v[j], m, st.wl, st.sh, st.mask, st.mode, st.asym, r[j]);
+    }
+}
+
+template <int V> __device__ __forceinline__ void sbfp_stage(float (&v)[V], const StageDev &st, int lanes)
+{
+    uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
+    SbfpBlock b = sbfp_block_ol(m, st.sb);
+    if (sbfp_fast(st.sb)) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = sbfp_elem_fast(v[j], b, st.sb);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = sbfp_elem_slow(v[j], b.cmax, b.fs, &st.sb.xp);
+    }
+}
+
+template <int V> __device__ __forceinline__ void float_stage(float (&v)[V], const StageDev &st, const uint32_t (&r)[V])
+{
+    if (st.ff.mode == R_NEAREST) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = float_elem<R_NEAREST>(v[j], st.ff, 0u);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = float_elem_slow(v[j], &st.ff, r[j]);
+    }
+}
+
+template <int V> __device__ __forceinline__ void fixed_stage(float (&v)[V], const StageDev &st, const uint32_t (&r)[V])
+{
+    if (st.xf.mode == R_NEAREST && st.xf.tie == TIE_AWAY && !st.affine) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float a = __fmul_rn(roundf(__fmul_rn(v[j], st.xf.up)), st.xf.down);
+            if (st.xf.clamp) a = a > st.xf.t_max ? st.xf.t_max : (a < st.xf.t_min ? st.xf.t_min : a);
+            v[j] = a;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &st.xf, st.affine, st.sc, st.zp, u2f(r[j]));
+    }
+}
+
+// N:M inside one thread (M <= V): ranks by pairwise compares, ties -> lower index first.
+template <int V, int M> __device__ __forceinline__ void nm_local(const uint32_t (&key)[V], int n_prune, bool (&keep)[V])
+{
+#pragma unroll
+    for (int g0 = 0; g0 < V; g0 += M)
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            int rank = 0;
+#pragma unroll
+            for (int b = 0; b < M; ++b) {
+                if (b == a) continue;
+                bool less = key[g0 + b] < key[g0 + a] || (key[g0 + b] == key[g0 + a] && b < a);
+                rank += less ? 1 : 0;
+            }
+            keep[g0 + a] = rank >= n_prune;
+        }
+}
+
+// N:M across `lanes` = M / V neighbouring lanes (M > V): partner keys arrive by shuffle.
+template <int V> __device__ __forceinline__ void nm_lanes(const uint32_t (&key)[V], int n_prune, int lanes, int lane, bool (&keep)[V])
+{
+    int rank[V];
+    int me = lane & (lanes - 1);
+#pragma unroll
+    for (int a = 0; a < V; ++a) {
+        rank[a] = 0;
+#pragma unroll
+        for (int b = 0; b < V; ++b)
+            if (b != a) rank[a] += (key[b] < key[a] || (key[b] == key[a] && b < a)) ? 1 : 0;
+    }
+    for (int d = 1; d < lanes; ++d) {
+        bool partner_first = (me ^ d) < me;  // partner's elements have lower indices than mine
+#pragma unroll
+        for (int b = 0; b < V; ++b) {
+            uint32_t pk = __shfl_xor_sync(0xFFFFFFFFu, key[b], d);
+#pragma unroll
+            for (int a = 0; a < V; ++a) rank[a] += (pk < key[a] || (pk == key[a] && partner_first)) ? 1 : 0;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < V; ++a) keep[a] = rank[a] >= n_prune;
+}
+
+template <int V>
+__device__ __forceinline__ void nm_stage(float (&v)[V], const StageDev &st, int lane, const float *score_vec, float *mask_vec, bool valid)
+{
+    uint32_t key[V];
+    if (score_vec != nullptr) {
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < V; j += 4) {
+                uint4 r = ldg_stream(score_vec + j);
+                key[j] = score_key(u2f(r.x)); key[j + 1] = score_key(u2f(r.y));
+                key[j + 2] = score_key(u2f(r.z)); key[j + 3] = score_key(u2f(r.w));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) key[j] = 0u;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) key[j] = absx_key(v[j]);
+    }
+    bool keep[V];
+    const int M = st.block;
+    if (M > V) {
+        nm_lanes<V>(key, st.n_prune, M / V, lane, keep);
+    } else if (M == 2) {
+        nm_local<V, 2>(key, st.n_prune, keep);
+    } else if (M == 4) {
+        nm_local<V, 4>(key, st.n_prune, keep);
+    } else {
+        nm_local<V, (V >= 8 ? 8 : V)>(key, st.n_prune, keep);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = nm_apply(v[j], keep[j]);
+    if (mask_vec != nullptr && valid) {
+        float mk[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) mk[j] = keep[j] ? 1.0f : 0.0f;
+        VecIO<float>::store<V>(mask_vec, mk);
+    }
+}
+
+void count_launch(int n = 1);
+
+}  // namespace dmxq

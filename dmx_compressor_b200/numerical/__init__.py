@@ -1,0 +1,12 @@
+from .format import (  # noqa: F401
+    Format,
+    Same,
+    FixedPoint,
+    FloatingPoint,
+    BlockFloatingPoint,
+    ScaledBlockFloatingPoint,
+    MXINT,
+    ROUNDING_MODE,
+)
+from .observer import DMXObserverBase, DummyObserver, MinMaxObserver  # noqa: F401
+from .cast import CastTo, CastToDict, CastToFormat  # noqa: F401

@@ -1,0 +1,230 @@
+"""Functional front-end of the CUDA cast path: torch tensors in, torch tensors out, every
+call one trip through the C ABI (dmx_compressor_b200/_lib.py -> libdmxq.so).
+
+Output allocation policy (the reference returns a fresh tensor, Q/quant_cuda/quant.cu:60):
+``torch.empty_like(x)`` with preserved strides when x is dense, so strided views (e.g.
+``key.transpose(-2, -1)``) are cast in place of their layout with no ``.contiguous()`` copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _out_like(x: torch.Tensor, dtype: Optional[torch.dtype]) -> torch.Tensor:
+    dtype = dtype or x.dtype
+    if x.is_contiguous() or x.numel() == 0:
+        return torch.empty(x.shape, dtype=dtype, device=x.device)
+    return torch.empty_like(x, dtype=dtype)  # preserve_format: keeps dense permuted layouts
+
+
+def make_stage(**kw) -> L.Stage:
+    s = L.Stage()
+    s.scale = 1.0
+    s.zero_point = 0.0
+    for k, v in kw.items():
+        setattr(s, k, v)
+    return s
+
+
+def bfp_stage(block_size: int, precision: int, symmetric: bool = True, rounding: str = "nearest") -> L.Stage:
+    return make_stage(kind=L.ST_BFP, block=block_size, precision=precision, symmetric=int(symmetric),
+                      rounding=L.ROUND[rounding])
+
+
+def float_stage(mantissa: int, exponent: int, bias: int, flush_subnormal: bool = True, unsigned: bool = False,
+                fp16_flush: bool = False, rounding: str = "nearest") -> L.Stage:
+    return make_stage(kind=L.ST_FLOAT, man=mantissa, exp=exponent, bias=bias, flush=int(flush_subnormal),
+                      is_unsigned=int(unsigned), fp16_flush=int(fp16_flush), rounding=L.ROUND[rounding])
+
+
+def fixed_stage(precision: int, fraction: int, clamp: bool = True, symmetric: bool = True, rounding: str = "nearest",
+                tie: int = L.TIE_AWAY, scale: float = 1.0, zero_point: float = 0.0) -> L.Stage:
+    return make_stage(kind=L.ST_FIXED, precision=precision, fraction=fraction, clamp=int(clamp), symmetric=int(symmetric),
+                      rounding=L.ROUND[rounding], tie=tie, scale=scale, zero_point=zero_point)
+
+
+def sbfp_stage(block_size: int, xp_precision: int, xp_clamp: bool, xp_rounding: str, tie: int, sc_mantissa: int,
+               sc_exponent: int, sc_bias: int, sc_flush: bool, sc_unsigned: bool, sc_fp16_flush: bool = False,
+               sc_rounding: str = "nearest") -> L.Stage:
+    return make_stage(kind=L.ST_SBFP, block=block_size, precision=xp_precision, clamp=int(xp_clamp),
+                      rounding=L.ROUND[xp_rounding], tie=tie, sc_man=sc_mantissa, sc_exp=sc_exponent, sc_bias=sc_bias,
+                      sc_flush=int(sc_flush), sc_unsigned=int(sc_unsigned), sc_fp16_flush=int(sc_fp16_flush),
+                      sc_rounding=L.ROUND[sc_rounding])
+
+
+def nm_stage(n_keep: int, m: int) -> L.Stage:
+    return make_stage(kind=L.ST_NM, block=m, n_keep=n_keep)
+
+
+def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, out: Optional[torch.Tensor] = None,
+               out_dtype: Optional[torch.dtype] = None, score: Optional[torch.Tensor] = None,
+               mask: Optional[torch.Tensor] = None, rand: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = stages[-1](... stages[0](x)) in one pass over HBM (dmxq_cast_chain)."""
+    L.require_cuda(x)
+    n = len(stages)
+    if not 1 <= n <= L.MAX_STAGES:
+        raise RuntimeError(f"dmxq: a chain holds 1..{L.MAX_STAGES} stages, got {n}")
+    y = out if out is not None else _out_like(x, out_dtype)
+    arr = (L.Stage * n)(*stages)
+    vx, vy = L.view(x), L.view(y)
+    vs = vm = None
+    if score is not None:
+        L.require_cuda(score, "score")
+        score = score if score.dtype == torch.float32 else score.float()
+        vs = C.byref(L.view(score))
+    if mask is not None:
+        vm = C.byref(L.view(mask))
+    rp = None
+    if rand is not None:
+        L.require_cuda(rand, "rand")
+        if not rand.is_contiguous() or rand.shape != x.shape or rand.element_size() != 4:
+            raise RuntimeError("dmxq: rand must be a contiguous 4-byte tensor with the shape of x")
+        rp = rand.data_ptr()
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_cast_chain(C.byref(vx), C.byref(vy), block_dim, arr, n, vs, vm, rp, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_cast_chain")
+    return y
+
+
+def bfp_qdq(x, block_dim=-1, block_size=64, precision=8, symmetric=True, rounding="nearest", rand=None, out=None,
+            out_dtype=None):
+    """BlockFloatingPoint.cast (reference S/numerical/format.py:304-372) via dmxq_bfp_qdq."""
+    L.require_cuda(x)
+    if rounding == "stochastic" and rand is None:
+        rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:40
+    y = out if out is not None else _out_like(x, out_dtype)
+    vx, vy = L.view(x), L.view(y)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), block_dim, block_size, precision, int(symmetric),
+                                L.ROUND[rounding], rand.data_ptr() if rand is not None else None, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_bfp_qdq")
+    return y
+
+
+def sbfp_qdq(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_rounding="nearest", tie=L.TIE_AWAY,
+             sc_mantissa=4, sc_exponent=4, sc_bias=7, sc_flush=True, sc_unsigned=True, sc_fp16_flush=False,
+             sc_rounding="nearest", out=None, out_dtype=None):
+    """ScaledBlockFloatingPoint.cast (reference S/numerical/format.py:453-479) via dmxq_sbfp_qdq."""
+    L.require_cuda(x)
+    y = out if out is not None else _out_like(x, out_dtype)
+    vx, vy = L.view(x), L.view(y)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_sbfp_qdq(C.byref(vx), C.byref(vy), block_dim, block_size, xp_precision, int(xp_clamp),
+                                 L.ROUND[xp_rounding], tie, sc_mantissa, sc_exponent, sc_bias, int(sc_flush),
+                                 int(sc_unsigned), int(sc_fp16_flush), L.ROUND[sc_rounding], L.stream_ptr(x.device))
+    L.check(rc, "dmxq_sbfp_qdq")
+    return y
+
+
+def float_qdq(x, mantissa, exponent, bias, flush_subnormal=True, unsigned=False, fp16_flush=False, rounding="nearest",
+              rand=None, out=None, out_dtype=None):
+    """FloatingPoint.cast (reference S/numerical/format.py:208-233) via dmxq_float_qdq."""
+    L.require_cuda(x)
+    if rounding == "stochastic" and rand is None:
+        rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:160
+    y = out if out is not None else _out_like(x, out_dtype)
+    vx, vy = L.view(x), L.view(y)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_float_qdq(C.byref(vx), C.byref(vy), mantissa, exponent, bias, int(flush_subnormal), int(unsigned),
+                                  int(fp16_flush), L.ROUND[rounding], rand.data_ptr() if rand is not None else None,
+                                  L.stream_ptr(x.device))
+    L.check(rc, "dmxq_float_qdq")
+    return y
+
+
+def fixed_qdq(x, precision, fraction, clamp=True, symmetric=True, rounding="nearest", tie=L.TIE_AWAY, scale=None,
+              zero_point=None, ch_axis=-1, group_size=None, rand=None, out=None, out_dtype=None):
+    """FixedPoint.cast incl. CastTo's affine wrap (reference S/numerical/format.py:134-142,
+    S/numerical/cast.py:279-296) via dmxq_fixed_qdq.  scale / zero_point: fp32 CUDA tensors."""
+    L.require_cuda(x)
+    if rounding == "stochastic" and rand is None:
+        rand = torch.rand_like(x, dtype=torch.float32)  # Q/quant_cuda/quant.cu:244
+    sp = zp = None
+    nq = 0
+    if scale is not None:
+        scale = scale.to(device=x.device, dtype=torch.float32).contiguous().view(-1)
+        zero_point = zero_point.to(device=x.device, dtype=torch.float32).contiguous().view(-1)
+        nq = scale.numel()
+        sp, zp = scale.data_ptr(), zero_point.data_ptr()
+        if not x.is_contiguous():
+            x = x.contiguous()
+    y = out if out is not None else _out_like(x, out_dtype)
+    vx, vy = L.view(x), L.view(y)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_fixed_qdq(C.byref(vx), C.byref(vy), precision, fraction, int(clamp), int(symmetric), L.ROUND[rounding],
+                                  tie, sp, zp, nq, ch_axis, group_size or 1, rand.data_ptr() if rand is not None else None,
+                                  L.stream_ptr(x.device))
+    L.check(rc, "dmxq_fixed_qdq")
+    return y
+
+
+def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None, out_dtype=None):
+    """Sparsify.forward with BlockTopK (reference S/sparse.py:163-180, 287-301) via dmxq_nm_prune."""
+    L.require_cuda(x)
+    y = out if out is not None else _out_like(x, out_dtype)
+    mask = torch.empty(x.shape, dtype=torch.float32, device=x.device) if return_mask else None
+    vx, vy = L.view(x), L.view(y)
+    vs = vm = None
+    if score is not None:
+        L.require_cuda(score, "score")
+        score = score if score.dtype == torch.float32 else score.float()
+        vs = C.byref(L.view(score))
+    if mask is not None:
+        vm = C.byref(L.view(mask))
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_nm_prune(C.byref(vx), vs, C.byref(vy), vm, block_dim, n_keep, m, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_nm_prune")
+    return (y, mask) if return_mask else y
+
+
+def minmax(x, ch_axis: Optional[int] = None):
+    """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    c = 1 if ch_axis is None else x.shape[ch_axis]
+    mn = torch.empty(c, dtype=torch.float32, device=x.device)
+    mx = torch.empty(c, dtype=torch.float32, device=x.device)
+    vx = L.view(x)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_minmax(C.byref(vx), -1 if ch_axis is None else ch_axis % x.dim(), mn.data_ptr(), mx.data_ptr(),
+                               L.stream_ptr(x.device))
+    L.check(rc, "dmxq_minmax")
+    return mn, mx
+
+
+def block_quantize_l1(x, wl, dim=-1, symmetric=True, rounding="stochastic", rand=None):
+    """quant_cuda.block_quantize_<rounding>(x, wl, dim, symmetric) (reference Q/quant_cuda/quant.cu:36-112)."""
+    L.require_cuda(x)
+    if x.dtype != torch.float32:
+        raise RuntimeError("x is not a single precision Floating Point Tensor")
+    if not x.is_contiguous():
+        raise RuntimeError("a must be contiguous")
+    if rounding == "stochastic" and rand is None:
+        rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)
+    y = torch.empty_like(x)
+    c = 1 if dim == -1 else x.shape[dim]
+    ws = torch.empty(3 * max(c, 1), dtype=torch.int32, device=x.device)
+    vx, vy = L.view(x), L.view(y)
+    with torch.cuda.device(x.device):
+        rc = L.lib.dmxq_block_quantize(C.byref(vx), C.byref(vy), wl, dim, int(symmetric), L.ROUND[rounding],
+                                       rand.data_ptr() if rand is not None else None, ws.data_ptr(), L.stream_ptr(x.device))
+    L.check(rc, "dmxq_block_quantize")
+    return y
+
+
+def cast_chain_host(x_host: torch.Tensor, y_host: torch.Tensor, stages: Sequence[L.Stage], device: int = 0) -> torch.Tensor:
+    """The e2e entry: host [rows, K] in, host out (dmxq_cast_chain_host); pinned tensors run at PCIe speed."""
+    if x_host.is_cuda or y_host.is_cuda or not x_host.is_contiguous() or not y_host.is_contiguous():
+        raise RuntimeError("cast_chain_host needs contiguous host tensors")
+    rows = x_host.numel() // x_host.shape[-1] if x_host.numel() else 0
+    n = len(stages)
+    arr = (L.Stage * n)(*stages)
+    rc = L.lib.dmxq_cast_chain_host(x_host.data_ptr(), y_host.data_ptr(), L.dtype_code(x_host.dtype),
+                                    L.dtype_code(y_host.dtype), rows, x_host.shape[-1], arr, n, device)
+    L.check(rc, "dmxq_cast_chain_host")
+    return y_host

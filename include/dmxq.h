@@ -1,0 +1,186 @@
+/*
+ * dmxq.h -- C ABI of libdmxq, the B200-native (sm_100a) CastTo / Sparsify numerics path.
+ *
+ * This header is the drop-in boundary: every entry point replaces a native entry of the
+ * reference (d-matrix-ai/dmx-compressor v0.1.11) or the python loop that sits directly on
+ * top of it.  "S/" = src/dmx/compressor/, "Q/" = src/dmx/compressor/quant/ of the reference.
+ *
+ *   entry point            replaces (reference file:line)
+ *   ---------------------  ------------------------------------------------------------------
+ *   dmxq_bfp_qdq           BlockFloatingPoint.cast           S/numerical/format.py:304-372
+ *                          -> block_quantize                 Q/quant_function.py:87-117
+ *                          -> block_quantize_*_cuda          Q/quant_cuda/quant.cu:14-112
+ *                          -> block_kernel_*                 Q/quant_cuda/block_kernel.cu:7-139
+ *   dmxq_sbfp_qdq          ScaledBlockFloatingPoint.cast     S/numerical/format.py:453-479
+ *   dmxq_float_qdq         FloatingPoint.cast                S/numerical/format.py:208-233
+ *                          -> float_quantize_*_cuda          Q/quant_cuda/quant.cu:155-228
+ *                          -> float_kernel_*                 Q/quant_cuda/float_kernel.cu:6-168
+ *   dmxq_fixed_qdq         FixedPoint.cast + affine wrap     S/numerical/format.py:134-142,
+ *                                                            S/numerical/cast.py:279-296
+ *                          -> fixed_point_quantize_*_cuda    Q/quant_cuda/quant.cu:230-327
+ *   dmxq_nm_prune          BlockTopK.forward + x*mask        S/sparse.py:163-180, 287-301
+ *   dmxq_cast_chain        DmxModule.weight_hypernet chain   S/modeling/nn/core.py:178-198
+ *                          (sparsify -> storage cast -> weight cast in ONE pass), and any
+ *                          back-to-back CastTo pair (output cast -> next input cast)
+ *   dmxq_block_quantize    L1 block_quantize(x, wl, dim,...) Q/quant_cuda/quant.cu:14-112
+ *   dmxq_minmax            MinMaxObserver.forward statistics S/numerical/observer.py:173-193
+ *   dmxq_cast_chain_host   same as dmxq_cast_chain on HOST buffers (pipelined H2D/compute/D2H)
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, enums; no torch types.  All tensors are described by a
+ *     dmxq_tensor view (device pointer + dtype + shape + element strides), because real call
+ *     sites pass views (e.g. key.transpose(-2,-1), per-head slices) and the reference's
+ *     .contiguous()/transpose/reshape copies are exactly the HBM traffic this path removes.
+ *   - the input is never modified; the output is caller-allocated (no memset needed) and may
+ *     have its own strides; x and y must have the same shape.  In-place (y == x, same
+ *     strides) is allowed.
+ *   - kernels are enqueued on the caller's stream (a cudaStream_t passed as void*); the
+ *     calls never synchronise and never allocate, except the *_host entry points.
+ *   - return value: DMXQ_OK (0) or a negative dmxq_status; dmxq_last_error() holds a
+ *     thread-local message.  Language bindings turn non-zero into their exception type
+ *     (the reference raises RuntimeError from TORCH_CHECK, Q/quant_cuda/quant_cuda.cpp:7-11).
+ *   - numerics are bit-exact with the reference's CUDA kernels for deterministic rounding
+ *     and "same random tensor in => same bits out" for stochastic rounding.
+ */
+#ifndef DMXQ_H_
+#define DMXQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMXQ_ABI_VERSION 1
+#define DMXQ_MAX_DIMS 8
+#define DMXQ_MAX_STAGES 4
+
+typedef enum dmxq_status {
+    DMXQ_OK = 0,
+    DMXQ_ERR_BAD_ARG = -1,      /* malformed argument (the reference would assert / TORCH_CHECK) */
+    DMXQ_ERR_UNSUPPORTED = -2,  /* well-formed but outside what the kernels implement */
+    DMXQ_ERR_CUDA = -3,         /* a CUDA runtime call failed; message holds cudaGetErrorString */
+    DMXQ_ERR_NO_DEVICE = -4
+} dmxq_status;
+
+typedef enum dmxq_dtype { DMXQ_F32 = 0, DMXQ_BF16 = 1, DMXQ_F16 = 2 } dmxq_dtype;
+
+/* ROUNDING_MODE of S/numerical/format.py:23-30 ("N","S","U","D") */
+typedef enum dmxq_rounding {
+    DMXQ_ROUND_NEAREST = 0,
+    DMXQ_ROUND_STOCHASTIC = 1,
+    DMXQ_ROUND_UP = 2,
+    DMXQ_ROUND_DOWN = 3
+} dmxq_rounding;
+
+/* FixedPoint "nearest" differs between the reference's own two back ends:
+ *   CUDA  (Q/quant_cuda/sim_helper.cu:18-27)  roundf            -> half away from zero
+ *   CPU   (Q/quant_cpu/sim_helper.cpp:14-21)  nearbyint(a+.5f-.5) -> ties to even (+ float add)
+ * DMXQ_TIE_AWAY is what a user of the reference gets on CUDA tensors (the default of the
+ * python binding); DMXQ_TIE_EVEN reproduces the CPU extension bit for bit. */
+typedef enum dmxq_tie { DMXQ_TIE_AWAY = 0, DMXQ_TIE_EVEN = 1 } dmxq_tie;
+
+typedef struct dmxq_tensor {
+    void *data;                    /* device pointer (host pointer for *_host entry points) */
+    int32_t dtype;                 /* dmxq_dtype */
+    int32_t ndim;                  /* 0..DMXQ_MAX_DIMS */
+    int64_t shape[DMXQ_MAX_DIMS];
+    int64_t stride[DMXQ_MAX_DIMS]; /* in elements, like torch.Tensor.stride() */
+} dmxq_tensor;
+
+/* One stage of a fused cast chain.  Unused fields are ignored. */
+typedef enum dmxq_stage_kind {
+    DMXQ_STAGE_NONE = 0,
+    DMXQ_STAGE_NM = 1,    /* N:M prune        : block = M, n_keep                                    */
+    DMXQ_STAGE_BFP = 2,   /* block floating pt: block, precision, symmetric, rounding                */
+    DMXQ_STAGE_SBFP = 3,  /* scaled BFP       : block, precision(XP wl), clamp, rounding(XP), tie,   */
+                          /*                    sc_* = scaler FloatingPoint format                   */
+    DMXQ_STAGE_FLOAT = 4, /* low-bit float    : man, exp, bias, flush, is_unsigned, fp16_flush, rounding */
+    DMXQ_STAGE_FIXED = 5  /* fixed point      : precision(wl), fraction(fl), clamp, symmetric,       */
+                          /*                    rounding, tie, scale, zero_point (per-tensor affine) */
+} dmxq_stage_kind;
+
+typedef struct dmxq_stage {
+    int32_t kind;       /* dmxq_stage_kind */
+    int32_t block;      /* block size along block_dim (BFP/SBFP) or M (NM) */
+    int32_t precision;  /* BFP precision / XP word length */
+    int32_t fraction;   /* XP fraction bits */
+    int32_t man, exp, bias; /* FLOAT (and unused otherwise) */
+    int32_t flush;      /* FLOAT flush_subnormal */
+    int32_t is_unsigned;/* FLOAT: abs() after the cast (format.py:233) */
+    int32_t fp16_flush; /* FLOAT: extra |x| < 2^-14 -> +0 pass of "FP[1|5|10,15](FN)" (format.py:223-232) */
+    int32_t symmetric;  /* BFP: 0 => make_mantissa_asymmetric post-pass (format.py:349-372); XP: symmetric range */
+    int32_t clamp;      /* XP clamp */
+    int32_t rounding;   /* dmxq_rounding */
+    int32_t tie;        /* dmxq_tie (XP nearest) */
+    int32_t n_keep;     /* NM: K of K:M */
+    int32_t sc_man, sc_exp, sc_bias, sc_flush, sc_unsigned, sc_fp16_flush, sc_rounding; /* SBFP scaler format */
+    float scale, zero_point; /* FIXED per-tensor affine (cast.py:293,296); scale = 1, zp = 0 for none */
+} dmxq_stage;
+
+int dmxq_abi_version(void);
+const char *dmxq_last_error(void);
+const char *dmxq_status_string(int status);
+/* number of kernels this library has launched in the calling process (bench "gpu_launches") */
+int64_t dmxq_launch_count(void);
+
+/* ---- fused chain: y = stage[n-1](... stage[0](x)) along block_dim, one pass over HBM ------
+ * `score`  (nullable) drives an NM stage (S/sparse.py:289-293); NULL => score = |x|.
+ * `mask`   (nullable) receives the fp32 0/1 mask of the NM stage (Sparsify.mask).
+ * `rand`   (nullable) contiguous random tensor in logical element order for the (single)
+ *          stochastic stage: int32 for BFP/FLOAT (quant.cu:40,160), fp32 in [0,1) for FIXED
+ *          (quant.cu:244).                                                                   */
+int dmxq_cast_chain(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim,
+                    const dmxq_stage *stages, int n_stages,
+                    const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand,
+                    void *stream);
+
+/* ---- single-format conveniences (thin wrappers over dmxq_cast_chain) ---------------------- */
+int dmxq_bfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size,
+                 int precision, int symmetric, int rounding, const int32_t *rand, void *stream);
+int dmxq_sbfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size,
+                  int xp_precision, int xp_clamp, int xp_rounding, int xp_tie,
+                  int sc_man, int sc_exp, int sc_bias, int sc_flush, int sc_unsigned,
+                  int sc_fp16_flush, int sc_rounding, void *stream);
+int dmxq_float_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int man, int exp, int bias,
+                   int flush_subnormal, int is_unsigned, int fp16_flush, int rounding,
+                   const int32_t *rand, void *stream);
+/* scale / zero_point: device arrays of n_qparams floats (NULL => no affine wrap).
+ * n_qparams == 1: per tensor.  Otherwise the qparam of index c along ch_axis is
+ * scale[c / group_size] (group_size == 1: per channel, cast.py:228-237; > 1: group
+ * quantisation, cast.py:281-292). */
+int dmxq_fixed_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int fl, int clamp,
+                   int symmetric, int rounding, int tie, const float *scale,
+                   const float *zero_point, int64_t n_qparams, int ch_axis, int64_t group_size,
+                   const float *rand, void *stream);
+int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_tensor *y,
+                  const dmxq_tensor *mask, int block_dim, int n_keep, int m, void *stream);
+
+/* ---- L1 mirror: block_quantize(x, wl, dim, symmetric, rounding) of quant_cuda --------------
+ * dim == -1: one exponent for the whole tensor; dim == 0: per row of view(size0,-1);
+ * dim == d: per index of dimension d (quant.cu:14-34).  x, y contiguous fp32 (as the
+ * reference requires).  `workspace`: device scratch of 3 * C 4-byte words, C = shape[dim]
+ * (C = 1 for dim == -1). */
+int dmxq_block_quantize(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int dim, int symmetric,
+                        int rounding, const int32_t *rand, void *workspace, void *stream);
+
+/* ---- calibration statistics: amin / amax per tensor (ch_axis < 0) or per channel -----------
+ * out_min/out_max: device arrays of 1 or shape[ch_axis] floats.  NaN propagates.  Exact and
+ * order independent, so a sharded reduction followed by an all-reduce(MIN/MAX) is
+ * bit-identical to the single-device result. */
+int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream);
+
+/* ---- host-buffer entry (the e2e path): x_host / y_host are HOST pointers to contiguous
+ * [rows, K] matrices blocked along K (pinned memory gives full PCIe speed).  The call
+ * pipelines H2D copy, the chain kernel and D2H copy over internal streams in row chunks and
+ * returns when y_host is complete. */
+int dmxq_cast_chain_host(const void *x_host, void *y_host, int in_dtype, int out_dtype,
+                         int64_t rows, int64_t K, const dmxq_stage *stages, int n_stages,
+                         int device);
+void *dmxq_host_alloc(int64_t bytes); /* pinned host memory; NULL on failure */
+void dmxq_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMXQ_H_ */

@@ -1,0 +1,133 @@
+"""CPU-side checks of the drop-in boundary: libdmxq.so loads, exports every symbol that
+include/dmxq.h declares, validates arguments like the reference does, and the host-side mirror
+of the reference interface parses / prints the same shorthands.  No compute calls (no GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from util import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dmxq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(dmxq_[a-z0-9_]+)\s*\(", hdr))
+    assert {"dmxq_cast_chain", "dmxq_bfp_qdq", "dmxq_sbfp_qdq", "dmxq_float_qdq", "dmxq_fixed_qdq", "dmxq_nm_prune",
+            "dmxq_block_quantize", "dmxq_minmax", "dmxq_cast_chain_host", "dmxq_last_error", "dmxq_abi_version"} <= declared
+    lib = C.CDLL(os.path.join(ROOT, "dmx_compressor_b200", "lib", "libdmxq.so"))
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libdmxq.so does not export {name}"
+    assert lib.dmxq_abi_version() == 1
+    from dmx_compressor_b200 import _lib
+
+    assert set(_lib.EXPORTS) == declared, "python binding and header disagree"
+
+
+def test_struct_layout_matches_header():
+    from dmx_compressor_b200 import _lib as L
+
+    assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 8 * 8 * 2
+    assert C.sizeof(L.Stage) == 22 * 4 + 2 * 4
+
+
+def test_argument_validation_without_a_device():
+    """bad arguments are rejected before any CUDA call, with the reference's wording"""
+    from dmx_compressor_b200 import _lib as L
+
+    x = torch.zeros(4, 64)
+    vx, vy = L.view(x), L.view(torch.zeros(4, 64))
+    rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), -1, 64, 1, 1, 0, None, None)
+    assert rc == -1 and b"highest integer precision" in L.lib.dmxq_last_error()
+    rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), -1, 0, 8, 1, 0, None, None)
+    assert rc == -1 and b"block size has to be positive" in L.lib.dmxq_last_error()
+    rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), 5, 64, 8, 1, 0, None, None)
+    assert rc == -1 and b"block_dim" in L.lib.dmxq_last_error()
+    rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), -1, 64, 8, 1, 1, None, None)
+    assert rc == -1 and b"random tensor" in L.lib.dmxq_last_error()
+    rc = L.lib.dmxq_nm_prune(C.byref(vx), None, C.byref(vy), None, -1, 2, 5, None)
+    assert rc == -1 and b"not a multiple of block size" in L.lib.dmxq_last_error()
+    with pytest.raises(AssertionError):
+        L.check(rc)
+    rc = L.lib.dmxq_float_qdq(C.byref(vx), C.byref(vy), 24, 8, 127, 0, 0, 0, 0, None, None)
+    assert rc == -1
+    vz = L.view(torch.zeros(4, 32))
+    rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vz), -1, 64, 8, 1, 0, None, None)
+    assert rc == -1 and b"same shape" in L.lib.dmxq_last_error()
+    # empty tensors are a no-op
+    ve = L.view(torch.zeros(0, 64))
+    assert L.lib.dmxq_bfp_qdq(C.byref(ve), C.byref(ve), -1, 64, 8, 1, 0, None, None) == 0
+
+
+def test_no_cpu_fallback():
+    from dmx_compressor_b200.numerical import CastTo, Format
+    from dmx_compressor_b200.sparse import Sparsify
+    from dmx_compressor_b200 import quant
+
+    x = torch.randn(4, 64)
+    for call in (lambda: Format.from_shorthand("BFP[8|8]{64}(SN)").cast(x, -1), lambda: CastTo("FP[1|5|10,15](FN)")(x),
+                 lambda: CastTo("XP[8,0](CSN)")(x), lambda: Sparsify(x.shape, "BTOPK{2:4,-1}(U)")(x),
+                 lambda: quant.float_quantize(x, 5, 10, rounding="nearest"), lambda: quant.block_quantize(x, 8, rounding="nearest"),
+                 lambda: quant.fixed_point_quantize(x, 8, 0, rounding="nearest")):
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            call()
+
+
+SHORTHANDS = ["SAME", "XP[8,0](CSN)", "XP[4,0](CSN)", "XP[8,+4](C_U)", "XP[8,-2](_SD)", "FP[1|5|10,15](FN)", "FP[1|8|7,127](FN)",
+              "FP[1|4|3,7](_N)", "FP[0|4|4,7](FN)", "BFP[8|8]{64}(SN)", "BFP[4|8]{128}(_N)", "BFP[24|8]{1}(SN)", "BFP[8|8]{64}(SS)",
+              "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "MXINT8{32}"]
+
+
+@pytest.mark.parametrize("sh", SHORTHANDS)
+def test_format_shorthand_round_trip(sh):  # reference grammar, SURVEY.md appendix A
+    from dmx_compressor_b200.numerical import Format
+
+    assert repr(Format.from_shorthand(sh)) == sh
+
+
+def test_format_errors_match_reference():
+    from dmx_compressor_b200.numerical import BlockFloatingPoint, FixedPoint, FloatingPoint, Format
+    from dmx_compressor_b200.sparse import BlockTopK, Sparseness
+
+    with pytest.raises(ValueError, match="unrecognized format shorthand"):
+        Format.from_shorthand("INT8")
+    with pytest.raises(ValueError, match="unrecognized sparseness shorthand"):
+        Sparseness.from_shorthand("NM{2:4}")
+    with pytest.raises(AssertionError):
+        BlockFloatingPoint(precision=1)
+    with pytest.raises(AssertionError):
+        BlockFloatingPoint(block_size=0)
+    with pytest.raises(AssertionError):
+        FixedPoint(25, 0)
+    with pytest.raises(AssertionError):
+        FloatingPoint(mantissa=24)
+    with pytest.raises(AssertionError):
+        FloatingPoint(mantissa=3, exponent=4, bias=-200)
+    with pytest.raises(AssertionError):
+        BlockTopK(K=5, block_size=4)
+    for sh in ["DENSE", "TOPK{0.5}(U)", "BTOPK{2:4,-1}(U)", "BTOPK{4:8,1}(M)", "BERN"]:
+        assert repr(Sparseness.from_shorthand(sh)) == sh
+
+
+def test_castto_state_and_config_surface():
+    from dmx_compressor_b200.numerical import CastTo, CastToDict, Same
+
+    c = CastTo("XP[8,0](CSN)", qscheme=torch.per_channel_affine, ch_axis=1)
+    assert set(c.state_dict()) >= {"scale", "zero_point", "fake_quant_enabled", "observer_enabled"}
+    assert c._fq_on and not c._obs_on
+    c.disable_fake_quant()
+    sd = c.state_dict()
+    d = CastTo("XP[8,0](CSN)", qscheme=torch.per_channel_affine, ch_axis=1)
+    d.load_state_dict(sd)
+    assert not d._fq_on
+    assert torch.equal(d(torch.ones(2, 3)), torch.ones(2, 3))  # fake-quant off: identity, no kernel
+    c.set_format("BFP[8|8]{64}(SN)")
+    assert repr(c.format) == "BFP[8|8]{64}(SN)" and c.activation_post_process.dtype is c.format
+    dd = CastToDict({"input_cast": CastTo(), "multiplier_cast": CastTo()})
+    dd.set_format(["BFP[8|8]{64}(SN)", None])
+    assert repr(dd["input_cast"].format) == "BFP[8|8]{64}(SN)" and isinstance(dd["multiplier_cast"].format, Same)
+    x = torch.randn(3)
+    y = CastTo("SAME")(x)
+    assert torch.equal(x, y) and y.data_ptr() != x.data_ptr()  # SAME clones (reference format.py:89-90)

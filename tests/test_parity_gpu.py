@@ -1,0 +1,457 @@
+"""GPU parity tests: the CUDA path (through the C ABI, libdmxq.so) against
+  (a) the committed golden vectors produced by the reference's own python,
+  (b) the CPU oracle (oracle/dmxq_oracle.c) on fresh seeded inputs over many layouts,
+  (c) the reference's own CUDA kernels (oracle/_ref/ref_quant_cuda.so) when that binary travelled,
+  (d) size-independent properties at BASELINE sizes (idempotence, block-scale equivariance).
+Bit-exact everywhere (NaNs compare by class).  Run with:  pytest -m gpu
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from util import ROOT, assert_bits_equal, bits, case, f32, golden_cases
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import dmx_compressor_b200 as dmx
+    from dmx_compressor_b200 import _lib as L
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format, FixedPoint, ScaledBlockFloatingPoint
+
+DEV = "cuda:0"
+TIE = {"even": 1, "away": 0}
+
+
+def fmt_from(sh, tie="away"):
+    f = Format.from_shorthand(sh)
+    if isinstance(f, FixedPoint):
+        f.tie = TIE[tie]
+    if isinstance(f, ScaledBlockFloatingPoint):
+        f.block_format.tie = TIE[tie]
+    return f
+
+
+def gpu_cast(x, sh, block_dim=-1, tie="away"):
+    """x: torch CUDA tensor (any dtype/strides) -> fp32 result of Format.cast, as numpy bits."""
+    y = fmt_from(sh, tie).cast(x, block_dim)
+    torch.cuda.synchronize()
+    return y
+
+
+def huge_block_mask(x, block_dim, bs):
+    """elements whose block max has exponent field >= 253: the reference computes inf - inf
+    there and clips the NaN with *its sign*, which is hardware specific (x86 default NaN is
+    negative, the GPU's is positive).  Only the magnitude is comparable across CPU and GPU."""
+    a = np.abs(np.moveaxis(x, block_dim, -1)).astype(np.float32)
+    K = a.shape[-1]
+    m = np.zeros_like(a, dtype=bool)
+    for k0 in range(0, K, bs):
+        blk = a[..., k0:k0 + bs]
+        with np.errstate(invalid="ignore"):
+            big = (np.nan_to_num(blk, nan=0.0, posinf=0.0).max(-1, keepdims=True) >= 2.0**126)
+        m[..., k0:k0 + bs] = big
+    return np.moveaxis(m, -1, block_dim % x.ndim)
+
+
+def check(got_t, want_bits, what, x=None, fmt=None, block_dim=-1, dtype="float32"):
+    got = got_t.detach().contiguous().cpu()
+    if dtype == "float32":
+        g = got.numpy().view(np.uint32)
+    else:
+        g = got.view(torch.int16).numpy().view(np.uint16)
+    w = np.asarray(want_bits).reshape(g.shape)
+    if x is not None and fmt is not None and fmt.startswith("BFP") and "{1}" not in fmt:
+        bs = int(fmt.split("{")[1].split("}")[0])
+        hm = huge_block_mask(x, block_dim, bs)
+        if hm.any():
+            g = np.where(hm, g & 0x7FFFFFFF, g)
+            w = np.where(hm, w & 0x7FFFFFFF, w)
+    assert_bits_equal(g, w, what, dtype=dtype)
+
+
+# =============================================================================== (a) golden vectors
+@pytest.mark.parametrize("name", golden_cases(kind="cast"))
+def test_golden_cast(name):
+    m, d = case(name)
+    x = f32(d["x"]).reshape(m["shape"])
+    y = gpu_cast(torch.from_numpy(x).to(DEV), m["fmt"], m["block_dim"], m.get("tie", "even"))
+    check(y, d["y"], f"{name} {m['fmt']}", x=x, fmt=m["fmt"], block_dim=m["block_dim"])
+
+
+@pytest.mark.parametrize("name", golden_cases(kind="xp_affine"))
+def test_golden_xp_affine(name):
+    m, d = case(name)
+    x = torch.from_numpy(f32(d["x"]).reshape(m["shape"])).to(DEV)
+    f = fmt_from(m["fmt"], "even")
+    sc = torch.tensor(m["scale"], dtype=torch.float32, device=DEV)
+    zp = torch.tensor(m["zero_point"], dtype=torch.float32, device=DEV)
+    y = ops.fixed_qdq(x, f.precision, f.fraction, f.clamp, f.symmetric, f.rounding, f.tie, sc, zp,
+                      ch_axis=m["ch_axis"] if m["ch_axis"] is not None else -1, group_size=m["group_size"])
+    check(y, d["y"], name)
+
+
+@pytest.mark.parametrize("name", golden_cases(kind="nm"))
+def test_golden_nm(name):
+    m, d = case(name)
+    x = torch.from_numpy(f32(d["x"]).reshape(m["shape"])).to(DEV)
+    score = torch.from_numpy(f32(d["score"]).reshape(m["shape"])).to(DEV)
+    k, rest = m["sparseness"][len("BTOPK{"):].split(":")
+    mm, dim = rest.split("}")[0].split(",")
+    y, mask = ops.nm_prune(x, int(k), int(mm), int(dim), score=score, return_mask=True)
+    check(mask, d["mask"], name + " mask")
+    check(y, d["y"], name)
+    if m["variant"] != "param":
+        check(ops.nm_prune(x, int(k), int(mm), int(dim)), d["y"], name + " implicit |x| score")
+
+
+@pytest.mark.parametrize("name", golden_cases(kind="cast_dtype"))
+def test_golden_cast_dtype(name):
+    """CastTo.forward on bf16 / fp16 tensors: x.float() -> cast -> .to(dtype), fused in-kernel."""
+    m, d = case(name)
+    dt = getattr(torch, m["dtype"])
+    x = torch.from_numpy(d["x"].view(np.int16).reshape(m["shape"])).view(dt).to(DEV)
+    st = fmt_from(m["fmt"], "even").stage()
+    y = ops.cast_chain(x, [st], m["block_dim"])
+    assert y.dtype == dt
+    check(y, d["y"], name, dtype=m["dtype"])
+
+
+@pytest.mark.parametrize("name", golden_cases(kind="hyper"))
+def test_golden_hypernet(name):
+    """sparsify -> storage cast -> weight cast (DmxModule.weight_hypernet) as ONE fused kernel."""
+    m, d = case(name)
+    x = torch.from_numpy(f32(d["x"]).reshape(m["shape"])).to(DEV)
+    k, rest = m["sparseness"][len("BTOPK{"):].split(":")
+    mm, dim = rest.split("}")[0].split(",")
+    stages = [ops.nm_stage(int(k), int(mm))]
+    for sh in (m["storage"], m["fmt"]):
+        st = fmt_from(sh, m.get("tie", "even")).stage()
+        if st is not None:
+            stages.append(st)
+    y = ops.cast_chain(x, stages, -1)
+    check(y, d["y"], name)
+
+
+# =============================================================================== (b) oracle, many layouts
+def _rand(shape, seed, spread=8, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(shape, generator=g)
+    e = torch.randint(-spread, spread + 1, shape[:-1] + (1,), generator=g).float()
+    x = x * torch.pow(2.0, e)
+    flat = x.view(-1)
+    flat[::37] = 0.0
+    flat[5::101] = torch.round(flat[5::101] * 32) / 32
+    return x.to(dtype)
+
+
+LAYOUTS = [
+    # (shape, block_dim, description)
+    ((64, 4096), -1, "flat rows"),
+    ((8, 33, 256), -1, "3-d contiguous"),
+    ((16, 100), -1, "ragged K, vectorisable"),
+    ((16, 70), -1, "ragged K, K%4!=0 -> generic"),
+    ((5, 6), -1, "tiny"),
+    ((12, 128, 64), -2, "cols: block along strided dim, inner 64"),
+    ((3, 200, 32), 1, "cols ragged K"),
+    ((4, 6, 5, 5), 1, "conv weight: cols generic (inner 25)"),
+    ((2, 4, 96, 64), -1, "4-d"),
+    ((1, 1, 64), -1, "leading ones"),
+    ((257, 64), -1, "odd rows"),
+    ((3, 1), -1, "K == 1"),
+]
+FORMATS = ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)", "BFP[8|8]{16}(SN)", "BFP[6|8]{32}(SN)", "BFP[8|8]{128}(SN)",
+           "BFP[8|8]{64}(_N)", "BFP[8|8]{64}(SU)", "BFP[8|8]{64}(SD)", "BFP[16|8]{64}(SN)", "BFP[8|8]{256}(SN)",
+           "BFP[8|8]{24}(SN)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,7](FN)>{64}"]
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+@pytest.mark.parametrize("shape,bd,desc", LAYOUTS)
+def test_oracle_blocked_layouts(fmt, shape, bd, desc):
+    x = _rand(shape, hash((fmt, shape)) % 10000)
+    want = O.cast(x.numpy(), fmt, bd, tie=O.TIE_AWAY)
+    y = gpu_cast(x.to(DEV), fmt, bd, "away")
+    check(y, bits(want), f"{fmt} {desc}")
+
+
+@pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(_N)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"])
+def test_oracle_strided_views(fmt):
+    """Views must be consumed in place: transposes, slices, attention-head views."""
+    dev = DEV
+    # k.transpose(-2,-1) blocked along -2: physically contiguous blocks (rows path, no copy)
+    k = _rand((6, 128, 64), 1).to(dev)
+    kt = k.transpose(-2, -1)
+    want = np.swapaxes(O.cast(k.cpu().numpy(), fmt, -1, tie=O.TIE_AWAY), -2, -1)
+    check(gpu_cast(kt, fmt, -2), bits(np.ascontiguousarray(want)), "k^T view")
+    # HF attention layout: [B,S,H*D] viewed as [B,H,S,D]
+    B, S, H, D = 2, 96, 4, 64
+    base = _rand((B, S, H * D), 2).to(dev)
+    q = base.view(B, S, H, D).transpose(1, 2)
+    assert not q.is_contiguous()
+    want = O.cast(q.cpu().contiguous().numpy(), fmt, -1, tie=O.TIE_AWAY)
+    check(gpu_cast(q, fmt, -1), bits(want), "[B,H,S,D] view, blocks along D")
+    want = O.cast(q.cpu().contiguous().numpy(), fmt, -2, tie=O.TIE_AWAY)
+    check(gpu_cast(q, fmt, -2), bits(want), "[B,H,S,D] view, blocks along S (cols)")
+    # row-sliced matrix (row stride != K)
+    w = _rand((32, 512), 3).to(dev)[:, 128:384]
+    want = O.cast(w.cpu().contiguous().numpy(), fmt, -1, tie=O.TIE_AWAY)
+    check(gpu_cast(w, fmt, -1), bits(want), "column slice")
+    # misaligned slice -> generic
+    w = _rand((32, 515), 4).to(dev)[:, 3:]
+    want = O.cast(w.cpu().contiguous().numpy(), fmt, -1, tie=O.TIE_AWAY)
+    check(gpu_cast(w, fmt, -1), bits(want), "misaligned slice")
+
+
+ELEMENTWISE = ["FP[1|5|10,15](FN)", "FP[1|5|10,15](_N)", "FP[1|8|7,127](FN)", "FP[1|4|3,7](_N)", "FP[1|5|2,15](_N)",
+               "FP[0|4|4,7](FN)", "BFP[24|8]{1}(SN)", "BFP[8|8]{1}(SN)", "XP[8,0](CSN)", "XP[4,0](CSN)", "XP[8,+4](CSN)",
+               "XP[8,0](C_N)", "XP[8,0](_SN)", "XP[8,0](CSU)", "XP[8,0](CSD)", "XP[16,+8](CSN)"]
+
+
+@pytest.mark.parametrize("fmt", ELEMENTWISE)
+@pytest.mark.parametrize("tie", ["away", "even"])
+def test_oracle_elementwise(fmt, tie):
+    if not fmt.startswith("XP") and tie == "even":
+        pytest.skip("tie mode only affects XP")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 1000, 8, generator=g) * torch.pow(2.0, torch.randint(-24, 18, (3, 1000, 1), generator=g).float())
+    x.view(-1)[::7] = torch.round(x.view(-1)[::7]) + 0.5
+    for xt, desc in ((x, "contiguous"), (x.transpose(0, 2), "permuted dense"), (x[:, ::2], "strided"), (x.view(-1)[:4093], "odd length")):
+        want = O.cast(xt.contiguous().numpy(), fmt, -1, tie=O.TIE_AWAY if tie == "away" else O.TIE_EVEN)
+        y = gpu_cast(xt.to(DEV) if xt.is_contiguous() else _same_layout(xt), fmt, -1, tie)
+        check(y, bits(want), f"{fmt} {desc} tie={tie}")
+
+
+def _same_layout(xt):
+    """move a strided CPU view to the GPU keeping its strides"""
+    base = xt._base if xt._base is not None else xt
+    gb = base.to(DEV)
+    return gb.as_strided(xt.shape, xt.stride(), xt.storage_offset())
+
+
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("fmt,bd", [("BFP[8|8]{64}(SN)", -1), ("BFP[4|8]{64}(SN)", -1), ("BFP[8|8]{64}(SN)", -2),
+                                    ("FP[1|5|10,15](FN)", -1), ("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", -1),
+                                    ("BFP[8|8]{16}(_N)", -1)])
+def test_oracle_16bit_io(dt, fmt, bd):
+    tdt = getattr(torch, dt)
+    x = _rand((24, 128, 64), 5, spread=5, dtype=tdt)
+    xf = x.float().numpy()
+    want32 = O.cast(xf, fmt, bd, tie=O.TIE_AWAY)
+    # Format.cast semantics: 16-bit in -> fp32 out
+    check(gpu_cast(x.to(DEV), fmt, bd), bits(want32), f"{fmt} {dt}->f32")
+    # CastTo.forward semantics: back to the input dtype
+    y = ops.cast_chain(x.to(DEV), [fmt_from(fmt).stage()], bd)
+    want16 = torch.from_numpy(want32).to(tdt).view(torch.int16).numpy().view(np.uint16)
+    check(y, want16, f"{fmt} {dt}->{dt}", dtype=dt)
+
+
+@pytest.mark.parametrize("shape,bd", [((32, 256), -1), ((4, 128, 16), 1), ((16, 70), -1)])
+@pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SS)", "BFP[4|8]{16}(SS)", "FP[1|4|3,7](_S)", "XP[8,0](CSS)"])
+def test_oracle_stochastic_same_random_tensor(shape, bd, fmt):
+    """'identical given the same random tensor': the random tensor is an explicit input."""
+    x = _rand(shape, 21, spread=3)
+    g = torch.Generator().manual_seed(3)
+    f = fmt_from(fmt)
+    if fmt.startswith("XP"):
+        r = torch.rand(shape, generator=g)
+        want = O.cast(x.numpy(), fmt, bd, tie=O.TIE_AWAY, rand=r.numpy())
+        y = ops.fixed_qdq(x.to(DEV), f.precision, f.fraction, f.clamp, f.symmetric, "stochastic", rand=r.to(DEV))
+    else:
+        r = torch.randint(0, 2**31 - 1, shape, generator=g, dtype=torch.int32)
+        want = O.cast(x.numpy(), fmt, bd, rand=r.numpy())
+        y = ops.cast_chain(x.to(DEV), [f.stage()], bd, rand=r.to(DEV))
+    check(y, bits(want), f"{fmt} {shape}")
+
+
+@pytest.mark.parametrize("k,m", [(2, 4), (4, 8), (2, 8), (1, 2), (8, 16), (1, 4), (3, 4), (5, 6), (2, 32)])
+@pytest.mark.parametrize("shape,bd", [((32, 96), -1), ((6, 96, 8), 1), ((96, 5), 0)])
+def test_oracle_nm(k, m, shape, bd):
+    if shape[bd] % m:
+        pytest.skip("not divisible")
+    x = _rand(shape, 31)
+    x = torch.round(x * 4) / 4  # plenty of ties
+    want, wmask = O.nm_prune(x.numpy(), k, m, bd, return_mask=True)
+    y, mask = ops.nm_prune(x.to(DEV), k, m, bd, return_mask=True)
+    check(mask, bits(wmask), f"{k}:{m} mask")
+    check(y, bits(want), f"{k}:{m}")
+    g = torch.Generator().manual_seed(1)
+    score = torch.rand(shape, generator=g)
+    want = O.nm_prune(x.numpy(), k, m, bd, score=score.numpy())
+    check(ops.nm_prune(x.to(DEV), k, m, bd, score=score.to(DEV)), bits(want), f"{k}:{m} explicit score")
+    xb = x.to(torch.bfloat16)
+    want = O.nm_prune(xb.float().numpy(), k, m, bd)
+    check(ops.nm_prune(xb.to(DEV), k, m, bd, out_dtype=torch.float32), bits(want), f"{k}:{m} bf16 in")
+
+
+def test_nm_not_divisible_raises():
+    with pytest.raises(AssertionError):
+        ops.nm_prune(torch.randn(4, 10, device=DEV), 2, 4)
+
+
+def test_fused_chain_matches_sequential():
+    x = _rand((64, 512), 41, spread=2) * 0.05
+    stages = [ops.nm_stage(2, 4), fmt_from("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}").stage(), fmt_from("BFP[8|8]{64}(SN)").stage()]
+    want = O.cast(O.cast(O.nm_prune(x.numpy(), 2, 4), "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", tie=O.TIE_AWAY), "BFP[8|8]{64}(SN)")
+    check(ops.cast_chain(x.to(DEV), stages, -1), bits(want), "prune->sbfp->bfp fused")
+    # FLOAT16 output cast followed by BFP16 input cast (the BASIC-mode pair) in one pass
+    stages = [fmt_from("FP[1|5|10,15](FN)").stage(), fmt_from("BFP[8|8]{64}(SN)").stage()]
+    want = O.cast(O.cast(x.numpy(), "FP[1|5|10,15](FN)"), "BFP[8|8]{64}(SN)")
+    check(ops.cast_chain(x.to(DEV), stages, -1), bits(want), "float16->bfp16 fused")
+    # bf16 tensor: intermediates are rounded to bf16 like consecutive CastTo.forward calls
+    xb = x.to(torch.bfloat16)
+    t = torch.from_numpy(O.cast(xb.float().numpy(), "FP[1|5|10,15](FN)")).to(torch.bfloat16)
+    t = torch.from_numpy(O.cast(t.float().numpy(), "BFP[8|8]{64}(SN)")).to(torch.bfloat16)
+    y = ops.cast_chain(xb.to(DEV), stages, -1)
+    check(y, t.view(torch.int16).numpy().view(np.uint16), "bf16 chain", dtype="bfloat16")
+
+
+def test_minmax_exact():
+    x = _rand((7, 33, 50), 51)
+    mn, mx = ops.minmax(x.to(DEV))
+    assert mn.item() == x.min().item() and mx.item() == x.max().item()
+    mn, mx = ops.minmax(x.to(DEV), ch_axis=1)
+    assert torch.equal(mn.cpu(), x.amin((0, 2))) and torch.equal(mx.cpu(), x.amax((0, 2)))
+    xb = x.to(torch.bfloat16)
+    mn, mx = ops.minmax(xb.to(DEV), ch_axis=0)
+    assert torch.equal(mn.cpu(), xb.float().amin((1, 2))) and torch.equal(mx.cpu(), xb.float().amax((1, 2)))
+    x[2, 3, 4] = float("nan")
+    mn, mx = ops.minmax(x.to(DEV))
+    assert torch.isnan(mn).all() and torch.isnan(mx).all()
+
+
+@pytest.mark.parametrize("dim", [-1, 0, 1])
+@pytest.mark.parametrize("mode", ["nearest", "up", "down", "stochastic"])
+@pytest.mark.parametrize("symmetric", [True, False])
+def test_l1_block_quantize(dim, mode, symmetric):
+    """L1 mirror of quant_cuda.block_quantize_* (dim semantics of Q/quant_cuda/quant.cu:14-34)."""
+    x = _rand((12, 20, 16), 61, spread=2)
+    x[3, 4, 5] = -x[3].abs().max() * 1.0  # exercise the !symmetric branch candidates
+    g = torch.Generator().manual_seed(2)
+    r = torch.randint(0, 2**31 - 1, x.shape, generator=g, dtype=torch.int32)
+    xn = x.numpy()
+    if dim == -1:
+        rows = xn.reshape(1, -1)
+        rr = r.numpy().reshape(1, -1)
+        want = O.block_quantize_rows(rows, 8, symmetric, mode, rand=rr).reshape(xn.shape)
+    elif dim == 0:
+        want = O.block_quantize_rows(xn.reshape(12, -1), 8, symmetric, mode, rand=r.numpy().reshape(12, -1)).reshape(xn.shape)
+    else:
+        xt = np.ascontiguousarray(np.swapaxes(xn, 0, 1)).reshape(20, -1)
+        rt = np.ascontiguousarray(np.swapaxes(r.numpy(), 0, 1)).reshape(20, -1)
+        want = np.swapaxes(O.block_quantize_rows(xt, 8, symmetric, mode, rand=rt).reshape(20, 12, 16), 0, 1)
+    y = ops.block_quantize_l1(x.to(DEV), 8, dim, symmetric, mode, rand=r.to(DEV))
+    check(y, bits(np.ascontiguousarray(want)), f"block_quantize dim={dim} {mode} sym={symmetric}")
+
+
+# =============================================================================== (c) reference CUDA kernels
+@pytest.fixture(scope="module")
+def ref_cuda():
+    import build_ref
+
+    try:
+        mod = build_ref.load("ref_quant_cuda")
+    except Exception as e:  # pragma: no cover
+        pytest.skip(f"ref_quant_cuda.so not loadable: {e}")
+    if mod is None:
+        pytest.skip("oracle/_ref/ref_quant_cuda.so did not travel")
+    return mod
+
+
+def test_vs_reference_cuda_float_fixed_block(ref_cuda):
+    x = _rand((256, 64), 71, spread=12).to(DEV)
+    x.view(-1)[::5] = torch.round(x.view(-1)[::5]) + 0.5  # exact .5 ties: pins half-away
+    for man, exp, bias, flush in [(10, 5, 15, True), (3, 4, 7, False), (2, 5, 15, False), (7, 8, 127, True)]:
+        want = ref_cuda.float_quantize_nearest(x, man, exp, bias, flush)
+        got = ops.float_qdq(x, man, exp, bias, flush)
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"float m{man}e{exp}"
+    for wl, fl, clamp, sym in [(8, 0, True, True), (4, 0, True, True), (8, 4, True, False), (8, 0, False, True)]:
+        for mode in ("nearest", "up", "down"):
+            want = getattr(ref_cuda, f"fixed_point_quantize_{mode}")(x, wl, fl, clamp, sym)
+            got = ops.fixed_qdq(x, wl, fl, clamp, sym, mode, tie=L.TIE_AWAY)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"fixed {wl},{fl} {mode}"
+    for wl in (4, 8, 16):
+        for mode in ("nearest", "up", "down"):
+            want = getattr(ref_cuda, f"block_quantize_{mode}")(x, wl, 0, True)
+            got = ops.bfp_qdq(x, -1, 64, wl, True, mode)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"block wl={wl} {mode}"
+            got = ops.block_quantize_l1(x, wl, 0, True, mode)
+            assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"L1 block wl={wl} {mode}"
+
+
+def test_vs_reference_cuda_stochastic_stream(ref_cuda):
+    """The reference draws randint_like(a, INT_MAX) / rand_like(a) internally (quant.cu:40,160,244):
+    re-seeding torch and drawing the same tensor ourselves must reproduce its output bit for bit."""
+    x = _rand((128, 64), 81, spread=4).to(DEV)
+    torch.manual_seed(123)
+    want = ref_cuda.block_quantize_stochastic(x, 8, 0, True)
+    torch.manual_seed(123)
+    zeros = torch.zeros_like(x)  # the reference allocates its output before drawing
+    r = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)
+    got = ops.bfp_qdq(x, -1, 64, 8, True, "stochastic", rand=r)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+    torch.manual_seed(7)
+    want = ref_cuda.fixed_point_quantize_stochastic(x, 8, 0, True, True)
+    torch.manual_seed(7)
+    r = torch.rand_like(x)
+    got = ops.fixed_qdq(x, 8, 0, True, True, "stochastic", rand=r)
+    assert torch.equal(got.view(torch.int32), want.view(torch.int32))
+
+
+def test_vs_torch_cuda_argsort_tie_order():
+    """BlockTopK on CUDA uses torch.argsort (S/sparse.py:172): on ties our 'lowest index pruned
+    first' rule must equal what torch's CUDA sort does for these row lengths."""
+    for m, k in ((4, 2), (8, 4), (8, 2)):
+        x = torch.round(torch.randn(4096, m, device=DEV) * 2) / 2
+        score = x.abs()
+        idx = torch.argsort(score, dim=1)[:, : m - k]
+        mask = torch.ones_like(score).scatter_(dim=1, index=idx, value=0)
+        want = x * mask
+        got = ops.nm_prune(x, k, m, -1)
+        assert torch.equal(got.view(torch.int32), want.view(torch.int32)), f"{k}:{m}"
+
+
+# =============================================================================== (d) properties at full size
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)"])
+def test_full_size_properties(dt, fmt):
+    n = 2**28
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(n // 4096, 4096, device=DEV, generator=g)
+    x *= torch.pow(2.0, torch.randint(-8, 9, (n // 4096, 1), device=DEV, generator=g).float())
+    x = x.to(dt)
+    st = [fmt_from(fmt).stage()]
+    y = ops.cast_chain(x, st, -1)
+    # idempotence: cast(cast(x)) == cast(x)
+    y2 = ops.cast_chain(y, st, -1)
+    assert torch.equal(y.view(torch.int16 if dt == torch.bfloat16 else torch.int32), y2.view(torch.int16 if dt == torch.bfloat16 else torch.int32))
+    # block-scale equivariance: cast(x * 2^k) == cast(x) * 2^k (exact, no overflow at these scales)
+    y3 = ops.cast_chain(x * 8.0, st, -1)
+    assert torch.equal(y3, y * 8.0)
+    # error bound: |y - x| <= half a quantum of the block (+ bf16 re-rounding is exact for BFP16/12)
+    wl = int(fmt[4:].split("|")[0])
+    xf, yf = x.float().view(-1, 64), y.float().view(-1, 64)
+    e = torch.floor(torch.log2(xf.abs().amax(-1, keepdim=True).clamp_min(1e-30)))
+    assert ((yf - xf).abs() <= torch.pow(2.0, e + 2 - wl) * 0.5 + 1e-30).all()
+    # a sampled slab equals the oracle bit for bit
+    rows = slice(1000, 1016)
+    want = O.cast(x[rows].float().cpu().numpy(), fmt, -1)
+    if dt == torch.float32:
+        check(y[rows], bits(want), "sampled slab")
+    else:
+        check(y[rows], torch.from_numpy(want).to(dt).view(torch.int16).numpy().view(np.uint16), "sampled slab", dtype="bfloat16")
+
+
+def test_host_entry_matches_device():
+    x = _rand((3000, 4096), 91)
+    st = [fmt_from("BFP[8|8]{64}(SN)").stage()]
+    xh = x.pin_memory()
+    yh = torch.empty_like(xh).pin_memory()
+    ops.cast_chain_host(xh, yh, st, 0)
+    want = ops.cast_chain(x.to(DEV), st, -1).cpu()
+    assert torch.equal(yh.view(torch.int32), want.view(torch.int32))
