@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- BFP cast throughput on B200 (BASELINE.json metric: "BFP cast GB/s & % of HBM peak").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): the standalone
+block-size-64 cast sweep point  n = 2^28 elements as [65536, 4096]:
+    BFP16 = BFP[8|8]{64}(SN) and BFP12 = BFP[4|8]{64}(SN), on fp32 and on bf16 tensors.
+One "step" = those four casts over the batch.  Algorithmic bytes per cast = read the input once
++ write the output once = 2 * sizeof(dtype) * n: 6 GiB per step.  Each
+cast touches 1-2 GiB, far above the 126 MB L2, so every step streams from HBM (no L2 flush
+needed; stated in config.l2).
+
+value     whole-job GB/s with inputs resident in HBM (device timed with CUDA events around the
+          K steps, barrier + synchronize on both sides, max over ranks).
+e2e       the same metric through the C ABI host entry (dmxq_cast_chain_host): pinned HOST
+          buffers in, host buffers out, H2D + kernel + D2H inside the timed region.
+roofline  the dominant kernel (chain_rows_kernel<float,float,flat,bfp>; the two fp32 casts are
+          2/3 of the step's bytes): algorithmic bytes per launch / its mean duration measured
+          with CUDA events around every launch of it inside the timed region.
+cpu_baseline  the reference's own CPU path on a bounded sample, on the host cores of this box.
+--impl reference  times that CPU path alone (rank 0 only), same metric / unit / config.
+
+N > 1 (torchrun): every rank runs the same workload on its own GPU (independent tensors, no
+data-path collective) -> weak scaling; value = bytes of all ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ELEMS = 1 << 28
+COLS = 4096
+FORMATS = [("BFP16_64", "BFP[8|8]{64}(SN)", 8), ("BFP12_64", "BFP[4|8]{64}(SN)", 4)]
+CPU_SAMPLE_ELEMS = 1 << 22
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(n_gpus):
+    return {
+        "workload": "configs[1]: standalone BFP16_64 + BFP12_64 cast of fp32 and bf16 [65536,4096] (2^28 elements), block 64 along the last dim",
+        "formats": [f[1] for f in FORMATS], "dtypes": ["fp32", "bf16"], "elements_per_cast": N_ELEMS,
+        "bytes_per_step": bytes_per_step(), "l2": "inputs (1-2 GiB per cast) exceed the 126 MB L2; no flush needed",
+        "parallelism": f"independent replicas x{n_gpus} (no collective on the data path)",
+    }
+
+
+def bytes_per_step():
+    return sum(2 * es * N_ELEMS for es in (4, 2)) * len(FORMATS)
+
+
+# ------------------------------------------------------------------------------------------ CPU path
+def _make_rows(n, seed=0):
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n // COLS, COLS, generator=g)
+    return x * torch.pow(2.0, torch.randint(-8, 9, (n // COLS, 1), generator=g).float())
+
+
+def _reference_cpu_cast():
+    """-> (callable(x_fp32_or_bf16_tensor, precision) -> tensor, kind, cores).
+
+    kind "reference": the reference's compiled quant_cpu kernels (oracle/_ref/ref_quant_cpu.so, built
+    from /root/reference by oracle/build_ref.py) driven by the restated python loop of
+    BlockFloatingPoint.cast (S/numerical/format.py:322-341) + CastTo.forward's dtype round trip
+    (S/numerical/cast.py:262,306) -- i.e. exactly what the reference executes for a CPU tensor.
+    kind "port": oracle/dmxq_oracle.c when the reference binary is not available."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    try:
+        import build_ref
+
+        ref = build_ref.load("ref_quant_cpu")
+    except Exception:
+        ref = None
+    if ref is not None:
+        def cast(x, precision):
+            dt = x.dtype
+            _x = x.float().transpose(-1, -1)
+            shp = _x.shape
+            chunks = torch.split(_x.reshape(-1, shp[-1]), 64, dim=-1)
+            out = [ref.block_quantize_nearest(c.contiguous(), precision, 0, True) for c in chunks]
+            return torch.cat(out, dim=-1).reshape(shp).to(dt)
+
+        return cast, "reference", cores
+    import oracle as O
+
+    def cast(x, precision):
+        dt = x.dtype
+        y = O.bfp_cast(x.float().numpy(), -1, 64, precision)
+        return torch.from_numpy(y).to(dt)
+
+    return cast, "port", 1
+
+
+def cpu_pass(cast, xs):
+    """one bounded-sample pass of the workload; returns (seconds, algorithmic bytes)"""
+    t0 = time.perf_counter()
+    nbytes = 0
+    for x in xs:
+        for _, _, prec in FORMATS:
+            cast(x, prec)
+            nbytes += 2 * x.element_size() * x.numel()
+    return time.perf_counter() - t0, nbytes
+
+
+def run_reference_arm(args):
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cast, kind, cores = _reference_cpu_cast()
+    x32 = _make_rows(CPU_SAMPLE_ELEMS)
+    xs = [x32, x32.to(torch.bfloat16)]
+    for _ in range(args.warmup):
+        cpu_pass(cast, xs)
+    t = 0.0
+    nbytes = 0
+    for _ in range(args.steps):
+        dt, nb = cpu_pass(cast, xs)
+        t += dt
+        nbytes += nb
+    gbs = nbytes / t / 1e9
+    sample = f"each step = the 4 casts on a bounded sample of n=2^{CPU_SAMPLE_ELEMS.bit_length() - 1} elements per tensor ([{CPU_SAMPLE_ELEMS // COLS},{COLS}])"
+    line = {
+        "impl": "reference", "metric": "BFP cast GB/s", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus),
+        "cpu_baseline": {"value": round(gbs, 4), "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for t, ln in self.rows:
+            if not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            f = [s.strip() for s in ln.split(",")]
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    import dmx_compressor_b200 as dmx  # raises if libdmxq.so is missing: no fallback
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format
+
+    stages = {name: [Format.from_shorthand(sh).stage()] for name, sh, _ in FORMATS}
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x32 = torch.randn(N_ELEMS // COLS, COLS, device=dev, generator=g)
+    x32 *= torch.pow(2.0, torch.randint(-8, 9, (N_ELEMS // COLS, 1), device=dev, generator=g).float())
+    x16 = x32.to(torch.bfloat16)
+    y32, y16 = torch.empty_like(x32), torch.empty_like(x16)
+    casts = [(x32, y32, n) for n in stages] + [(x16, y16, n) for n in stages]
+
+    def step(events=None):
+        for x, y, name in casts:
+            if events is not None and x.dtype == torch.float32:
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.cast_chain(x, stages[name], -1, out=y)
+                b.record()
+                events.append((a, b))
+            else:
+                ops.cast_chain(x, stages[name], -1, out=y)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = dmx._lib.launch_count()
+    kern_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step(kern_events)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+    launches = dmx._lib.launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    value = bytes_per_step() * args.steps * world / (ms * 1e-3) / 1e9
+    kms = sorted(a.elapsed_time(b) for a, b in kern_events)
+    k_mean = sum(kms) / len(kms)
+
+    # ---------------- e2e: host buffers through the C ABI host entry (H2D + kernel + D2H timed)
+    e2e = None
+    if args.e2e_steps > 0:
+        xh32 = torch.empty(x32.shape, dtype=torch.float32, pin_memory=True)
+        xh32.copy_(x32)
+        xh16 = torch.empty(x16.shape, dtype=torch.bfloat16, pin_memory=True)
+        xh16.copy_(x16)
+        yh32 = torch.empty(x32.shape, dtype=torch.float32, pin_memory=True)
+        yh16 = torch.empty(x16.shape, dtype=torch.bfloat16, pin_memory=True)
+        hcasts = [(xh32, yh32, n) for n in stages] + [(xh16, yh16, n) for n in stages]
+
+        def hstep():
+            for xh, yh, name in hcasts:
+                ops.cast_chain_host(xh, yh, stages[name], local)
+
+        hstep()
+        barrier()
+        th0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            hstep()
+        torch.cuda.synchronize()
+        th = time.perf_counter() - th0
+        if dist is not None:
+            t = torch.tensor([th], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            th = float(t.item())
+        # check the host path against the device path on the last cast
+        ok = torch.equal(yh16.view(torch.int16)[:64], y16[:64].cpu().view(torch.int16))
+        half = bytes_per_step() // 2
+        e2e = {"value": round(bytes_per_step() * args.e2e_steps * world / th / 1e9, 3), "unit": "GB/s",
+               "h2d_bytes_per_step": half, "d2h_bytes_per_step": half, "steps": args.e2e_steps,
+               "api": "dmxq_cast_chain_host (pinned host in/out, 3-stream chunked pipeline)", "matches_device_path": bool(ok)}
+        del xh32, xh16, yh32, yh16
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    k_bytes = 8 * N_ELEMS
+    achieved = k_bytes / (k_mean * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("chain_rows_kernel_f32_flat_bfp", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "chain_rows_kernel<float,float,FLAT,SPECIAL=2> (BFP16/BFP12 fp32 casts)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "frac_of_8TBps_nominal": round(achieved / 8000.0, 4), "peak_source": peak_src, "traffic": traffic,
+                "algorithmic_bytes_per_launch": k_bytes, "launch_ms_mean": round(k_mean, 4), "launch_ms_median": round(kms[len(kms) // 2], 4),
+                "launches_timed": len(kms)}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cast, kind, cores = _reference_cpu_cast()
+        c32 = _make_rows(CPU_SAMPLE_ELEMS)
+        xs = [c32, c32.to(torch.bfloat16)]
+        cpu_pass(cast, xs)
+        best = None
+        tot = 0.0
+        while tot < 10.0:
+            dt, nb = cpu_pass(cast, xs)
+            tot += dt
+            best = dt if best is None else min(best, dt)
+        cpu_baseline = {"value": round(nb / best / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": kind,
+                        "sample": f"the step's 4 casts on n=2^{CPU_SAMPLE_ELEMS.bit_length() - 1} elements per tensor, best pass of ~10 s of CPU work"}
+
+    line = {
+        "metric": "BFP cast GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": config_dict(world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "frac_of_hbm_peak": round(value / world / peak, 4),
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -70,7 +70,8 @@ int decode_float(int man, int exp, int bias, int flush, int is_unsigned, int fp1
     if (rounding < 0 || rounding > 3) return fail(DMXQ_ERR_BAD_ARG, "invalid rounding mode %d", rounding);
     f.sh = 23 - man;
     f.mode = rounding;
-    if (man >= 23) { f.sh = 0; f.mode = R_DOWN; }  // reference UB; identity on its CUDA build
+    f.exact = 0;
+    if (man >= 23) { f.sh = 0; f.mode = rounding == R_NEAREST ? R_NEAREST : R_DOWN; f.exact = 1; }  // reference UB; identity on its CUDA build
     f.mask = (1u << f.sh) - 1u;
     f.min_exp = -(bias - 1);
     f.shift_exp = (uint32_t)(127 + f.min_exp) << 23;
@@ -79,6 +80,9 @@ int decode_float(int man, int exp, int bias, int flush, int is_unsigned, int fp1
     f.flush = flush != 0;
     f.is_unsigned = is_unsigned != 0;
     f.fp16_flush = fp16_flush != 0;
+    // the extra fp16 pass (|q| < 2^-14 -> +0, format.py:223-232) is implied by flush_subnormal
+    // whenever the format's own smallest normal is >= 2^-14 and rounding is to nearest
+    if (f.flush && f.min_exp >= -14 && f.mode == R_NEAREST) f.fp16_flush = 0;
     return DMXQ_OK;
 }
 
@@ -123,6 +127,7 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         d.mask = (1u << d.sh) - 1u;
         d.mode = s.rounding;
         d.asym = s.symmetric ? 0 : 1;
+        d.fast = s.precision <= 20;
         return DMXQ_OK;
     case DMXQ_STAGE_SBFP: {
         if (s.block < 1) return fail(DMXQ_ERR_BAD_ARG, "block size has to be positive, got %d", s.block);
@@ -264,6 +269,11 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     for (int s = 0; s < n_stages; ++s) {
         int rc = decode_stage(stages[s], chain.st[s]);
         if (rc) return rc;
+        if (s == 0 && chain.st[s].kind == ST_FLOAT && chain.st[s].ff.mode == R_NEAREST) {
+            // a bf16 (7 mantissa bits) / fp16 (10) source is already representable: rounding is the identity
+            int src_man = x->dtype == DMXQ_BF16 ? 7 : x->dtype == DMXQ_F16 ? 10 : 23;
+            if (23 - chain.st[s].ff.sh >= src_man) chain.st[s].ff.exact = 1;
+        }
         blocked |= stage_blocked(chain.st[s]);
         n_stoch += stage_mode(chain.st[s]) == R_STOCHASTIC;
         // consecutive CastTo.forward calls round to the tensor dtype in between (cast.py:306)

@@ -92,12 +92,18 @@ __global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_const
             if (st.kind == ST_BFP && st.mode == R_NEAREST) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    BfpBlock b = bfp_block(m[j], st.wl);
+                    if (st.fast && !st.asym && bfp_fast_ok(m[j])) {
+                        BfpFast b = bfp_fast_block(m[j], st.wl);
 #pragma unroll
-                    for (int r = 0; r < RPT; ++r) {
-                        float q = bfp_elem<R_NEAREST>(v[r][j], b, st.sh, st.mask, 0u);
-                        if (st.asym) q = bfp_asym_fix(q, v[r][j], b);
-                        v[r][j] = q;
+                        for (int r = 0; r < RPT; ++r) v[r][j] = bfp_fast_elem(v[r][j], b);
+                    } else {
+                        BfpBlock b = bfp_block(m[j], st.wl);
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            float q = bfp_elem<R_NEAREST>(v[r][j], b, st.sh, st.mask, 0u);
+                            if (st.asym) q = bfp_asym_fix(q, v[r][j], b);
+                            v[r][j] = q;
+                        }
                     }
                 }
             } else if (st.kind == ST_BFP) {
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_const
 #pragma unroll
                 for (int r = 0; r < RPT; ++r)
 #pragma unroll
-                    for (int j = 0; j < V; ++j) v[r][j] = float_elem<R_NEAREST>(v[r][j], st.ff, 0u);
+                    for (int j = 0; j < V; ++j) v[r][j] = float_elem_nearest(v[r][j], st.ff);
             } else {
 #pragma unroll
                 for (int r = 0; r < RPT; ++r)

@@ -20,6 +20,7 @@ struct StageDev {
                      //    (what consecutive CastTo.forward calls do, S/numerical/cast.py:306)
     // BFP
     int wl, sh, mode, asym;
+    int fast;        // wl <= 20: the float-add fast path of dmxq_numerics.cuh is valid
     uint32_t mask;
     // NM
     int n_prune;

@@ -93,9 +93,15 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             uint32_t m = lanes_max(vec_absmax<V>(v[u]), lanes);
-            BfpBlock b = bfp_block(m, st.wl);
+            if (st.fast && bfp_fast_ok(m)) {
+                BfpFast b = bfp_fast_block(m, st.wl);
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[u][j] = bfp_elem<R_NEAREST>(v[u][j], b, st.sh, st.mask, 0u);
+                for (int j = 0; j < V; ++j) v[u][j] = bfp_fast_elem(v[u][j], b);
+            } else {
+                BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[u][j] = bfp_elem<R_NEAREST>(v[u][j], b, st.sh, st.mask, 0u);
+            }
         }
     } else {
 #pragma unroll 1

@@ -158,7 +158,11 @@ __device__ __forceinline__ uint32_t lanes_max(uint32_t m, int lanes)
 template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const StageDev &st, int lanes, const uint32_t (&r)[V])
 {
     uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
-    if (st.mode == R_NEAREST) {
+    if (st.mode == R_NEAREST && st.fast && !st.asym && bfp_fast_ok(m)) {
+        BfpFast b = bfp_fast_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_fast_elem(v[j], b);
+    } else if (st.mode == R_NEAREST) {
         BfpBlock b = bfp_block(m, st.wl);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -189,7 +193,7 @@ template <int V> __device__ __forceinline__ void float_stage(float (&v)[V], cons
 {
     if (st.ff.mode == R_NEAREST) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = float_elem<R_NEAREST>(v[j], st.ff, 0u);
+        for (int j = 0; j < V; ++j) v[j] = float_elem_nearest(v[j], st.ff);
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = float_elem_slow(v[j], &st.ff, r[j]);

@@ -1,0 +1,24 @@
+"""Tiny driver for ncu captures: runs each profiled cast a few times (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dmx_compressor_b200 import ops
+from dmx_compressor_b200.numerical import Format
+dev = "cuda:0"
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
+n = 2**28
+st = [Format.from_shorthand("BFP[8|8]{64}(SN)").stage()]
+if which in ("all", "rows_f32"):
+    x = torch.randn(n // 4096, 4096, device=dev); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, st, -1, out=y)
+if which in ("all", "rows_bf16"):
+    x = torch.randn(n // 4096, 4096, device=dev).bfloat16(); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, st, -1, out=y)
+if which in ("all", "cols_f32"):
+    x = torch.randn(96, 2048, 1024, device=dev); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, st, -2, out=y)
+if which in ("all", "float16_f32"):
+    x = torch.randn(n // 4096, 4096, device=dev); y = torch.empty_like(x)
+    st2 = [Format.from_shorthand("FP[1|5|10,15](FN)").stage()]
+    for _ in range(3): ops.cast_chain(x, st2, -1, out=y)
+torch.cuda.synchronize()
