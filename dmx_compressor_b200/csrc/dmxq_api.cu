@@ -80,9 +80,10 @@ int decode_float(int man, int exp, int bias, int flush, int is_unsigned, int fp1
     f.flush = flush != 0;
     f.is_unsigned = is_unsigned != 0;
     f.fp16_flush = fp16_flush != 0;
-    // the extra fp16 pass (|q| < 2^-14 -> +0, format.py:223-232) is implied by flush_subnormal
-    // whenever the format's own smallest normal is >= 2^-14 and rounding is to nearest
-    if (f.flush && f.min_exp >= -14 && f.mode == R_NEAREST) f.fp16_flush = 0;
+    // fast path: nearest + flush + signed.  The extra fp16 pass (|q| < 2^-14 -> +0,
+    // format.py:223-232) is implied by flush_subnormal whenever the format's own smallest normal
+    // is >= 2^-14 (NaN inputs, the one exception, take the exact out-of-line path anyway).
+    f.fastpath = f.mode == R_NEAREST && f.flush && !f.is_unsigned && (!f.fp16_flush || f.min_exp >= -14);
     return DMXQ_OK;
 }
 
@@ -269,6 +270,14 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     for (int s = 0; s < n_stages; ++s) {
         int rc = decode_stage(stages[s], chain.st[s]);
         if (rc) return rc;
+        if (chain.st[s].kind == ST_BFP) {
+            // significant bits of the values this stage sees: the source dtype's for stage 0 (and
+            // after an N:M stage, which only zeroes elements), the output dtype's after a requant
+            int src = -1;
+            if (s == 0 || (s == 1 && chain.st[0].kind == ST_NM)) src = x->dtype;
+            else if (chain.st[s - 1].requant) src = y->dtype;
+            chain.st[s].fast16 = (src == DMXQ_BF16 && chain.st[s].wl <= 14) || (src == DMXQ_F16 && chain.st[s].wl <= 11);
+        }
         if (s == 0 && chain.st[s].kind == ST_FLOAT && chain.st[s].ff.mode == R_NEAREST) {
             // a bf16 (7 mantissa bits) / fp16 (10) source is already representable: rounding is the identity
             int src_man = x->dtype == DMXQ_BF16 ? 7 : x->dtype == DMXQ_F16 ? 10 : 23;
@@ -373,8 +382,17 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
             flat = c.k.rs == 1;
         }
         p.n_vec = flat ? rows * p.K / V : rows * vpr;
-        int special = (score_p || mask_p || rand) ? 0 : 1;
-        if (special == 1 && chain.n == 1 && chain.st[0].kind == ST_BFP && chain.st[0].mode == R_NEAREST && !chain.st[0].asym) special = 2;
+        // kernel specialisation (K_* of dmxq_rows.cuh)
+        auto bfp_ns = [](const StageDev &d) { return d.kind == ST_BFP && d.mode == R_NEAREST && !d.asym; };
+        auto float_fast = [](const StageDev &d) { return d.kind == ST_FLOAT && d.ff.fastpath; };
+        int kind = 1;  // K_CHAIN
+        if (score_p || mask_p || rand) kind = 0;  // K_AUX
+        else if (chain.n == 1 && bfp_ns(chain.st[0])) kind = 2;  // K_BFP
+        else if (chain.n == 1 && float_fast(chain.st[0])) kind = 3;  // K_FLOAT
+        else if (chain.n == 2 && float_fast(chain.st[0]) && bfp_ns(chain.st[1])) kind = 4;  // K_FLOAT_BFP
+        else if (chain.n == 2 && chain.st[0].kind == ST_NM && bfp_ns(chain.st[1])) kind = 5;  // K_NM_BFP
+        else if (chain.n == 1 && chain.st[0].kind == ST_SBFP && chain.st[0].sb.xp.mode == R_NEAREST && chain.st[0].sb.xp.tie == TIE_AWAY) kind = 6;  // K_SBFP
+        const int special = kind;
         if (rows_ok) {
             cudaError_t e = launch_rows(x->dtype, y->dtype, flat, special, p, st);
             if (e != cudaSuccess) return cuda_fail(e, "chain_rows_kernel");

@@ -37,7 +37,7 @@ template <typename T> __device__ __forceinline__ void store4(T *p, const float (
 }
 
 template <typename Tin, typename Tout, int RPT, int LK>
-__global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_constant__ ColsParams p)
+__global__ void __launch_bounds__(kThreads, (RPT <= 8 ? 3 : 2)) chain_cols_kernel(const __grid_constant__ ColsParams p)
 {
     constexpr int V = 4;
     constexpr int LI = 32 / LK;
@@ -47,15 +47,28 @@ __global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_const
     if (tile >= p.n_tiles) return;  // whole warp leaves together
     const int li = lane % LI, lk = lane / LI;
 
-    int64_t t = tile;
-    const int64_t chunk = t % p.nchunk; t /= p.nchunk;
-    const int64_t blk = t % p.nblk;
-    int64_t o = t / p.nblk;
-    int64_t xo = 0, yo = 0, ro = 0;
-    for (int d = p.nouter - 1; d >= 0; --d) {
-        int64_t i = (d == 0) ? o : o % p.odim[d];
-        if (d != 0) o /= p.odim[d];
-        xo += i * p.xs[d]; yo += i * p.ys[d]; ro += i * p.rs[d];
+    int64_t chunk, blk, xo = 0, yo = 0, ro = 0;
+    if (p.n_tiles <= 0xFFFFFFFFll) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
+        uint32_t t = (uint32_t)tile, nc = (uint32_t)p.nchunk, nb = (uint32_t)p.nblk;
+        uint32_t q = t / nc; chunk = t - q * nc; t = q;
+        q = t / nb; blk = t - q * nb;
+        uint32_t o = q;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            uint32_t od = (uint32_t)p.odim[d];
+            uint32_t i = (d == 0) ? o : o % od;
+            if (d != 0) o /= od;
+            xo += (int64_t)i * p.xs[d]; yo += (int64_t)i * p.ys[d]; ro += (int64_t)i * p.rs[d];
+        }
+    } else {
+        int64_t t = tile;
+        chunk = t % p.nchunk; t /= p.nchunk;
+        blk = t % p.nblk;
+        int64_t o = t / p.nblk;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            int64_t i = (d == 0) ? o : o % p.odim[d];
+            if (d != 0) o /= p.odim[d];
+            xo += i * p.xs[d]; yo += i * p.ys[d]; ro += i * p.rs[d];
+        }
     }
     const int64_t i0 = (chunk * LI + li) * V;
     const bool col_ok = i0 < p.inner;
@@ -94,8 +107,17 @@ __global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_const
                 for (int j = 0; j < V; ++j) {
                     if (st.fast && !st.asym && bfp_fast_ok(m[j])) {
                         BfpFast b = bfp_fast_block(m[j], st.wl);
+                        if (st.fast16) {
 #pragma unroll
-                        for (int r = 0; r < RPT; ++r) v[r][j] = bfp_fast_elem(v[r][j], b);
+                            for (int r = 0; r < RPT; ++r) v[r][j] = bfp_fast16_elem(v[r][j], b);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < RPT; ++r) v[r][j] = bfp_fast_elem(v[r][j], b);
+                        }
+                        if (b.clamp) {
+#pragma unroll
+                            for (int r = 0; r < RPT; ++r) v[r][j] = bfp_clamp(v[r][j], b);
+                        }
                     } else {
                         BfpBlock b = bfp_block(m[j], st.wl);
 #pragma unroll
@@ -164,7 +186,7 @@ __global__ void __launch_bounds__(kThreads) chain_cols_kernel(const __grid_const
 }
 
 struct ColsCfg { int B, RPT, LK; };
-static const ColsCfg kColsCfgs[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 16, 4}, {128, 16, 8}};
+static const ColsCfg kColsCfgs[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 8, 8}, {128, 16, 8}};
 
 bool cols_supported(int, int B)
 {
@@ -188,7 +210,7 @@ template <typename Tin, typename Tout> static cudaError_t launch_cols_t(int B, c
     case 8: chain_cols_kernel<Tin, Tout, 2, 4><<<g, b, 0, s>>>(p); break;
     case 16: chain_cols_kernel<Tin, Tout, 4, 4><<<g, b, 0, s>>>(p); break;
     case 32: chain_cols_kernel<Tin, Tout, 8, 4><<<g, b, 0, s>>>(p); break;
-    case 64: chain_cols_kernel<Tin, Tout, 16, 4><<<g, b, 0, s>>>(p); break;
+    case 64: chain_cols_kernel<Tin, Tout, 8, 8><<<g, b, 0, s>>>(p); break;
     case 128: chain_cols_kernel<Tin, Tout, 16, 8><<<g, b, 0, s>>>(p); break;
     default: return cudaErrorInvalidValue;
     }

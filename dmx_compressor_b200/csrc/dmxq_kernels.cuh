@@ -21,6 +21,7 @@ struct StageDev {
     // BFP
     int wl, sh, mode, asym;
     int fast;        // wl <= 20: the float-add fast path of dmxq_numerics.cuh is valid
+    int fast16;      // stage 0 on a 16-bit source with wl <= 14 (bf16) / 11 (fp16): two-add variant
     uint32_t mask;
     // NM
     int n_prune;
@@ -122,7 +123,7 @@ struct MinMaxParams {
 };
 
 // launchers (dmxq_kernels.cu)
-cudaError_t launch_rows(int in_dt, int out_dt, bool flat, int special, const RowsParams &p, cudaStream_t s);
+cudaError_t launch_rows(int in_dt, int out_dt, bool flat, int kind, const RowsParams &p, cudaStream_t s);  // kind: K_* of dmxq_rows.cuh
 cudaError_t launch_cols(int in_dt, int out_dt, int B, const ColsParams &p, cudaStream_t s);
 bool cols_supported(int in_dt, int B);
 int cols_tile_inner(int in_dt, int B);  // LI * V of the instantiation used for block size B

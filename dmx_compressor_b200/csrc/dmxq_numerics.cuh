@@ -101,6 +101,7 @@ __device__ __forceinline__ float bfp_elem(float x, const BfpBlock &b, int sh, ui
 // and checked against the integer path by tests/test_parity_gpu.py on adversarial ties.
 struct BfpFast {
     float base, C, maxval;
+    bool clamp;  // some element of the block can reach the clip (block max within 2 quanta of 2^(e+1))
 };
 __device__ __forceinline__ bool bfp_fast_ok(uint32_t maxabs_bits)
 {
@@ -113,16 +114,29 @@ __device__ __forceinline__ BfpFast bfp_fast_block(uint32_t maxabs_bits, int wl)
     b.base = __fmul_rn(u2f(E), 6.0f);
     b.C = u2f(E + (((uint32_t)(25 - wl) << 23) | 0x00400000u));
     int m = wl - 2;
-    b.maxval = u2f(E | ((0x007FFFFFu >> (23 - m)) << (23 - m)));
+    uint32_t maxnum = E | ((0x007FFFFFu >> (23 - m)) << (23 - m));
+    b.maxval = u2f(maxnum);
+    // |q| can exceed maxval = 2^(e+1) - Q only if |x| >= 2^(e+1) - Q/2 - (one ulp of the first
+    // add); testing the block max against maxval itself (a full quantum below 2^(e+1)) is a
+    // safe superset, and lets the common block skip the clamp altogether.
+    b.clamp = maxabs_bits >= maxnum;
     return b;
 }
 __device__ __forceinline__ float bfp_fast_elem(float x, const BfpFast &b)
 {
     float t = __fadd_rn(x, b.base);
     float r = __fsub_rn(__fadd_rn(t, b.C), b.C);
-    float q = __fsub_rn(r, b.base);
-    return fminf(fmaxf(q, -b.maxval), b.maxval);
+    return __fsub_rn(r, b.base);
 }
+// 16-bit sources (bf16: 8 significant bits, fp16: 11): x + base is exact whenever x is not
+// negligible (its LSB >= ulp(t) = 2^(e-21)), and negligible x (|x| < 2^(e-14) resp. 2^(e-11))
+// round to +0 either way as long as wl <= 14 (bf16) / 11 (fp16).  The reference's first add
+// therefore never changes the outcome and q = RNE_Q(x) = (x + C) - C: two adds per element.
+__device__ __forceinline__ float bfp_fast16_elem(float x, const BfpFast &b)
+{
+    return __fsub_rn(__fadd_rn(x, b.C), b.C);
+}
+__device__ __forceinline__ float bfp_clamp(float q, const BfpFast &b) { return fminf(fmaxf(q, -b.maxval), b.maxval); }
 
 // BlockFloatingPoint.make_mantissa_asymmetric, S/numerical/format.py:349-372: an element whose
 // integer mantissa is exactly -(2^(wl-1)-1) moves one quantum down to -2^(wl-1) when that does
@@ -153,6 +167,7 @@ struct FloatFmt {
     int is_unsigned;     // abs() afterwards
     int fp16_flush;      // extra |q| < 2^-14 -> +0
     int mode;
+    int fastpath;        // nearest + flush + signed (+ fp16 pass implied): float_elem_flush_nearest is valid for non-NaN inputs
 };
 
 template <int MODE>
@@ -180,11 +195,25 @@ __device__ __forceinline__ float float_elem(float x, const FloatFmt &f, uint32_t
     return q;
 }
 
-// nearest rounding, restated branch-light for the inlined fast path:
-//   * "exponent store > max" <=> |q| pattern > max_num (q is already rounded to man bits), so the
-//     saturation is an unsigned min on the magnitude; the sign is q's own (it can differ from
-//     x's only when a NaN mantissa carries out, and then nothing is clipped);
-//   * "target_exp < min_exp" <=> |x| pattern < shift_exp.
+// nearest rounding + flush_subnormal, signed: the FLOAT16 / BFLOAT16 "(FN)" formats every BASIC
+// module boundary uses.  Branch-free except for NaN inputs:
+//   * "target_exp < min_exp" <=> |x| pattern < shift_exp  -> +0;
+//   * "exponent store > max" <=> |q| pattern > max_num (q is already rounded to man bits), so
+//     the saturation is an unsigned min on the magnitude, re-signed with x's sign;
+//   * a NaN whose mantissa carries out of bit 30 when rounded is the one input where the sign
+//     bookkeeping above differs from the reference's pattern arithmetic: NaNs (pattern above
+//     0x7f800000) take the out-of-line exact path (never in real data; keeps bit parity).
+template <bool EXACT>
+__device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFmt &f)
+{
+    uint32_t target = f2u(x);
+    uint32_t ab = target & 0x7FFFFFFFu;
+    uint32_t qa = EXACT ? ab : round_bits<R_NEAREST>(ab, f.sh, f.mask, 0u);
+    uint32_t mag = min(qa, f.max_num);
+    return ab < f.shift_exp ? 0.0f : u2f(mag | (target & 0x80000000u));
+}
+
+// nearest rounding, all other flag combinations (FP8 formats keep subnormals; unsigned scalers)
 __device__ __forceinline__ float float_elem_nearest(float x, const FloatFmt &f)
 {
     uint32_t target = f2u(x);

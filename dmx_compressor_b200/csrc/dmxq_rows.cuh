@@ -1,0 +1,235 @@
+// dmxq_rows.cuh -- chain_rows_kernel: the blocked dim is contiguous in memory.
+//
+// This is the kernel of the headline casts (Linear inputs / weights, q, k^T views, attention
+// probabilities, whole-model weight casting).  One pass over HBM:
+//   * each thread owns kUnroll independent 16-byte vectors; all loads are issued (into raw
+//     registers) before the first use, so 64 B per thread / 16 KiB per CTA are in flight;
+//   * a block of B elements lives in B/V neighbouring lanes of one warp; its max|x| is an
+//     unsigned-integer max over bit patterns, reduced with log2(B/V) xor-shuffles;
+//   * the fused round / clamp / rescale (+ N:M mask) runs on registers and the result is
+//     written with one 16-byte streaming store.
+// Algorithmic traffic: sizeof(in) + sizeof(out) bytes per element, nothing else.
+//
+// KIND selects a compile-time specialisation of the stage list (static parameter offsets, no
+// stage loop / switch); the runtime-chain variants remain as the general path:
+//   K_AUX        runtime chain, score / mask / rand tensors honoured
+//   K_CHAIN      runtime chain, no auxiliary tensors
+//   K_BFP        [BFP nearest symmetric]                      BFP16 / BFP12 / MXINT casts
+//   K_FLOAT      [FLOAT nearest+flush+signed]                 FLOAT16 / BFLOAT16 boundary casts
+//   K_FLOAT_BFP  [FLOAT nearest+flush+signed -> BFP n.s.]     output cast fused with next input cast
+//   K_NM_BFP     [N:M with score |x| -> BFP n.s.]             sparsify -> weight cast (hypernet)
+//   K_SBFP       [SBFP, XP nearest half-away]                 SBFP weight storage cast
+#pragma once
+#include "dmxq_stages.cuh"
+
+namespace dmxq {
+
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_COUNT = 7 };
+
+struct RowAddr {
+    int64_t xo, yo, so, mo, ro;
+};
+
+__device__ __forceinline__ RowAddr row_addr(const RowsParams &p, int64_t row)
+{
+    RowAddr a;
+    if (p.nouter == 1) {
+        a.xo = row * p.xs[0]; a.yo = row * p.ys[0]; a.so = row * p.ss[0]; a.mo = row * p.ms[0]; a.ro = row * p.rs[0];
+        return a;
+    }
+    a.xo = a.yo = a.so = a.mo = a.ro = 0;
+    for (int d = p.nouter - 1; d >= 0; --d) {
+        int64_t i = (d == 0) ? row : row % p.odim[d];
+        if (d != 0) row /= p.odim[d];
+        a.xo += i * p.xs[d]; a.yo += i * p.ys[d]; a.so += i * p.ss[d]; a.mo += i * p.ms[d]; a.ro += i * p.rs[d];
+    }
+    return a;
+}
+
+// one symmetric nearest BFP stage on a register vector whose max|x| pattern is already known
+template <int V, bool SRC16>
+__device__ __forceinline__ void bfp_ns_apply(float (&v)[V], uint32_t m, const StageDev &st)
+{
+    if (st.fast && bfp_fast_ok(m)) {
+        BfpFast b = bfp_fast_block(m, st.wl);
+        if (SRC16 && st.fast16) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_fast_elem(v[j], b);
+        }
+        if (b.clamp) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+        }
+    } else {
+        BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem<R_NEAREST>(v[j], b, st.sh, st.mask, 0u);
+    }
+}
+
+template <int V> __device__ __forceinline__ void float_fast_apply(float (&v)[V], const StageDev &st)
+{
+    const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
+    float q[V];
+    if (st.ff.exact) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<true>(v[j], st.ff);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], st.ff);
+    }
+    if (any_nan) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_slow(v[j], &st.ff, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = q[j];
+}
+
+template <typename Tin, typename Tout, bool FLAT, int KIND>
+__global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_constant__ RowsParams p)
+{
+    constexpr int V = VecIO<Tin>::V;
+    constexpr bool SRC16 = sizeof(Tin) == 2;
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
+    Tout *__restrict__ y = static_cast<Tout *>(p.y);
+    const int lane = threadIdx.x & 31;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+
+    uint4 raw[kUnroll];
+    int64_t yoff[kUnroll];
+    int64_t aux_s[kUnroll], aux_m[kUnroll], aux_r[kUnroll];
+    bool valid[kUnroll];
+
+    // ---- phase 1: addresses + all loads (nothing here consumes loaded data)
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        int64_t g = g0 + (int64_t)u * kThreads;
+        int64_t xoff;
+        if (FLAT) {
+            valid[u] = g < p.n_vec;
+            xoff = g * V;
+            yoff[u] = xoff;
+            if (KIND == K_AUX) { aux_s[u] = xoff; aux_m[u] = xoff; aux_r[u] = xoff; }
+        } else {
+            int64_t row;
+            uint32_t kv;
+            if (p.n_vec <= 0xFFFFFFFFll) {
+                uint32_t g32 = (uint32_t)g;
+                uint32_t r32 = g32 / p.vpr;
+                kv = g32 - r32 * p.vpr;
+                row = r32;
+            } else {
+                row = g / p.vpr;
+                kv = (uint32_t)(g - row * p.vpr);
+            }
+            valid[u] = g < p.n_vec && kv < p.kvec;
+            RowAddr a = row_addr(p, valid[u] ? row : 0);
+            int64_t k = (int64_t)kv * V;
+            xoff = a.xo + k;
+            yoff[u] = a.yo + k;
+            if (KIND == K_AUX) { aux_s[u] = a.so + k; aux_m[u] = a.mo + k; aux_r[u] = a.ro + k * p.rks; }
+        }
+        raw[u] = valid[u] ? ldg_stream(x + xoff) : make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    // ---- phase 2: per vector: widen, stages, narrow, store
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        float v[V];
+        if (KIND == K_BFP) {
+            const StageDev &st = p.chain.st[0];
+            uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
+            bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_FLOAT) {
+            VecIO<Tin>::unpack(raw[u], v);
+            float_fast_apply<V>(v, p.chain.st[0]);
+        } else if (KIND == K_FLOAT_BFP) {
+            VecIO<Tin>::unpack(raw[u], v);
+            float_fast_apply<V>(v, p.chain.st[0]);
+            if (sizeof(Tout) == 2) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(v[j]);
+            }
+            const StageDev &st = p.chain.st[1];
+            uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
+            bfp_ns_apply<V, false>(v, m, st);
+        } else if (KIND == K_NM_BFP) {
+            VecIO<Tin>::unpack(raw[u], v);
+            nm_stage<V>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);
+            const StageDev &st = p.chain.st[1];
+            uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
+            bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_SBFP) {
+            const StageDev &st = p.chain.st[0];
+            uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
+            SbfpBlock b = sbfp_block_ol(m, st.sb);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = sbfp_elem_fast(v[j], b, st.sb);
+        } else {
+            VecIO<Tin>::unpack(raw[u], v);
+#pragma unroll 1
+            for (int s = 0; s < p.chain.n; ++s) {
+                const StageDev &st = p.chain.st[s];
+                const int lanes = st.block / V;
+                uint32_t r[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) r[j] = 0x3F000000u;  // 0.5f: deterministic FIXED
+                if (KIND == K_AUX && p.rnd != nullptr && valid[u]) {
+                    const int mode = st.kind == ST_FLOAT ? st.ff.mode : st.kind == ST_FIXED ? st.xf.mode : st.kind == ST_BFP ? st.mode : 0;
+                    if (mode == R_STOCHASTIC) {
+                        const uint32_t *rp = static_cast<const uint32_t *>(p.rnd) + aux_r[u];
+#pragma unroll
+                        for (int j = 0; j < V; ++j) r[j] = __ldg(rp + (FLAT ? (int64_t)j : j * p.rks));
+                    }
+                }
+                switch (st.kind) {
+                case ST_NM:
+                    nm_stage<V>(v, st, lane, (KIND == K_AUX && p.score) ? p.score + aux_s[u] : nullptr,
+                                (KIND == K_AUX && p.mask) ? p.mask + aux_m[u] : nullptr, valid[u]);
+                    break;
+                case ST_BFP: bfp_stage<V>(v, st, lanes, r); break;
+                case ST_SBFP: sbfp_stage<V>(v, st, lanes); break;
+                case ST_FLOAT: float_stage<V>(v, st, r); break;
+                case ST_FIXED: fixed_stage<V>(v, st, r); break;
+                default: break;
+                }
+                if (st.requant) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(v[j]);
+                }
+            }
+        }
+        if (valid[u]) VecIO<Tout>::template store<V>(y + yoff[u], v);
+    }
+}
+
+template <typename Tin, typename Tout, int KIND>
+static cudaError_t launch_rows_k(bool flat, const RowsParams &p, cudaStream_t s)
+{
+    int64_t per_cta = (int64_t)kThreads * kUnroll;
+    int64_t grid = (p.n_vec + per_cta - 1) / per_cta;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    dim3 g((unsigned)grid), b(kThreads);
+    if (flat) chain_rows_kernel<Tin, Tout, true, KIND><<<g, b, 0, s>>>(p);
+    else chain_rows_kernel<Tin, Tout, false, KIND><<<g, b, 0, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+// one translation unit per KIND group instantiates these (compile-time parallelism)
+template <int KIND> cudaError_t launch_rows_kind(int in_dt, int out_dt, bool flat, const RowsParams &p, cudaStream_t s)
+{
+    if (in_dt == 0 && out_dt == 0) return launch_rows_k<float, float, KIND>(flat, p, s);
+    if (in_dt == 1 && out_dt == 1) return launch_rows_k<__nv_bfloat16, __nv_bfloat16, KIND>(flat, p, s);
+    if (in_dt == 2 && out_dt == 2) return launch_rows_k<__half, __half, KIND>(flat, p, s);
+    if (in_dt == 1 && out_dt == 0) return launch_rows_k<__nv_bfloat16, float, KIND>(flat, p, s);
+    if (in_dt == 2 && out_dt == 0) return launch_rows_k<__half, float, KIND>(flat, p, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace dmxq

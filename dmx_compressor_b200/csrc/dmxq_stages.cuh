@@ -5,6 +5,8 @@
 // mode goes through one __noinline__ scalar function per format, so a kernel carries a single
 // copy of the rarely used paths instead of one per unrolled element.
 #pragma once
+#include <type_traits>
+
 #include "dmxq_kernels.cuh"
 
 namespace dmxq {
@@ -33,11 +35,11 @@ template <typename T> struct VecIO;  // V = 16 bytes of T on the input side
 
 template <> struct VecIO<float> {
     static constexpr int V = 4;
-    static __device__ __forceinline__ void load(const float *p, float (&v)[4])
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&v)[4])
     {
-        uint4 r = ldg_stream(p);
         v[0] = u2f(r.x); v[1] = u2f(r.y); v[2] = u2f(r.z); v[3] = u2f(r.w);
     }
+    static __device__ __forceinline__ void load(const float *p, float (&v)[4]) { unpack(ldg_stream(p), v); }
     template <int N> static __device__ __forceinline__ void store(float *p, const float (&v)[N])
     {
 #pragma unroll
@@ -46,13 +48,13 @@ template <> struct VecIO<float> {
 };
 template <> struct VecIO<__nv_bfloat16> {
     static constexpr int V = 8;
-    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8])
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8])
     {
-        uint4 r = ldg_stream(p);
         uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) { v[2 * i] = u2f(w[i] << 16); v[2 * i + 1] = u2f(w[i] & 0xFFFF0000u); }
     }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[8]) { unpack(ldg_stream(p), v); }
     template <int N> static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float (&v)[N])
     {
         static_assert(N == 8, "bf16 stores are 8 wide");
@@ -67,9 +69,8 @@ template <> struct VecIO<__nv_bfloat16> {
 };
 template <> struct VecIO<__half> {
     static constexpr int V = 8;
-    static __device__ __forceinline__ void load(const __half *p, float (&v)[8])
+    static __device__ __forceinline__ void unpack(const uint4 &r, float (&v)[8])
     {
-        uint4 r = ldg_stream(p);
         uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -77,6 +78,7 @@ template <> struct VecIO<__half> {
             v[2 * i] = f.x; v[2 * i + 1] = f.y;
         }
     }
+    static __device__ __forceinline__ void load(const __half *p, float (&v)[8]) { unpack(ldg_stream(p), v); }
     template <int N> static __device__ __forceinline__ void store(__half *p, const float (&v)[N])
     {
         static_assert(N == 8, "fp16 stores are 8 wide");
@@ -89,6 +91,25 @@ template <> struct VecIO<__half> {
         stg_stream(p, make_uint4(w[0], w[1], w[2], w[3]));
     }
 };
+
+// widen a raw 16-byte vector and return the max|x| pattern (as an fp32 bit pattern) of its
+// elements.  For 16-bit sources the max is taken on the packed words (2 elements per
+// instruction) before widening.
+template <typename T> __device__ __forceinline__ uint32_t unpack_absmax(const uint4 &r, float (&v)[VecIO<T>::V])
+{
+    VecIO<T>::unpack(r, v);
+    if constexpr (sizeof(T) == 4) {
+        uint32_t m = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m = max(m, f2u(v[j]) & 0x7FFFFFFFu);
+        return m;
+    } else {
+        uint32_t m2 = __vmaxu2(__vmaxu2(r.x & 0x7FFF7FFFu, r.y & 0x7FFF7FFFu), __vmaxu2(r.z & 0x7FFF7FFFu, r.w & 0x7FFF7FFFu));
+        uint32_t m16 = max(m2 & 0xFFFFu, m2 >> 16);
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) return m16 << 16;
+        else return f2u(__half2float(__ushort_as_half((unsigned short)m16)));
+    }
+}
 
 template <typename Tout> __device__ __forceinline__ float requant1(float v)
 {
@@ -160,8 +181,17 @@ template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const 
     uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
     if (st.mode == R_NEAREST && st.fast && !st.asym && bfp_fast_ok(m)) {
         BfpFast b = bfp_fast_block(m, st.wl);
+        if (st.fast16) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = bfp_fast_elem(v[j], b);
+            for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_fast_elem(v[j], b);
+        }
+        if (b.clamp) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+        }
     } else if (st.mode == R_NEAREST) {
         BfpBlock b = bfp_block(m, st.wl);
 #pragma unroll
@@ -191,7 +221,23 @@ template <int V> __device__ __forceinline__ void sbfp_stage(float (&v)[V], const
 
 template <int V> __device__ __forceinline__ void float_stage(float (&v)[V], const StageDev &st, const uint32_t (&r)[V])
 {
-    if (st.ff.mode == R_NEAREST) {
+    if (st.ff.fastpath) {
+        const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
+        float q[V];
+        if (st.ff.exact) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<true>(v[j], st.ff);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], st.ff);
+        }
+        if (any_nan) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) q[j] = float_elem_slow(v[j], &st.ff, 0u);
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = q[j];
+    } else if (st.ff.mode == R_NEAREST) {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = float_elem_nearest(v[j], st.ff);
     } else {

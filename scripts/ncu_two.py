@@ -1,0 +1,22 @@
+"""ncu driver #2: general-path kernels (development aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from dmx_compressor_b200 import ops
+from dmx_compressor_b200.numerical import Format
+dev = "cuda:0"
+n = 2**26
+F = lambda sh: Format.from_shorthand(sh).stage()
+x = torch.randn(n // 4096, 4096, device=dev); y = torch.empty_like(x)
+xs = torch.randn(n // 4096, 4096 + 64, device=dev)[:, :4096]
+ys = torch.empty(n // 4096, 4096 + 64, device=dev)[:, :4096]
+ops.cast_chain(xs, [F("BFP[8|8]{64}(SN)")], -1, out=ys)                 # 0 rows nonflat special2
+ops.cast_chain(x, [F("XP[8,0](CSN)")], -1, out=y)                       # 1 fixed
+ops.cast_chain(x, [F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}")], -1, out=y)   # 2 sbfp
+ops.cast_chain(x, [F("FP[1|5|10,15](FN)"), F("BFP[8|8]{64}(SN)")], -1, out=y)  # 3 fused pair
+ops.cast_chain(x, [ops.nm_stage(2, 4), F("BFP[4|8]{64}(SN)")], -1, out=y)      # 4 prune+bfp
+xb = x.bfloat16(); yb = torch.empty_like(xb)
+ops.cast_chain(xb, [F("FP[1|5|10,15](FN)")], -1, out=yb)                # 5 float16 on bf16
+v = torch.randn(96, 2048, 256, device=dev).bfloat16(); vy = torch.empty_like(v)
+ops.cast_chain(v, [F("BFP[8|8]{64}(SN)")], -2, out=vy)                  # 6 cols bf16
+torch.cuda.synchronize()
