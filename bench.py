@@ -44,11 +44,12 @@ CPU_SAMPLE_ELEMS = 1 << 22
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the model-level extras (OPT-125m forward, sharded weight casts)")
     return ap.parse_args()
 
 
@@ -163,7 +164,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -195,6 +196,128 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ extras
+LLAMA = {
+    "8b": dict(layers=32, d=4096, kv=1024, ffn=14336, vocab=128256),
+    "70b": dict(layers=80, d=8192, kv=1024, ffn=28672, vocab=128256),
+}
+
+
+def llama_shapes(name, layers=None):
+    c = LLAMA[name]
+    shapes = {}
+    for i in range(layers if layers is not None else c["layers"]):
+        for n, s in (("q", (c["d"], c["d"])), ("k", (c["kv"], c["d"])), ("v", (c["kv"], c["d"])), ("o", (c["d"], c["d"])),
+                     ("gate", (c["ffn"], c["d"])), ("up", (c["ffn"], c["d"])), ("down", (c["d"], c["ffn"]))):
+            shapes[f"layers.{i}.{n}"] = s
+    shapes["lm_head"] = (c["vocab"], c["d"])
+    return shapes
+
+
+def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_stats, dtype):
+    """Whole-model weight cast sharded by parameter / row range: every rank
+    materialises its shards (random, shard-local), optionally reduces per-tensor amax with ONE
+    batched all-reduce, and casts each shard with one fused kernel.  Timed on the device, max
+    over ranks; value = algorithmic bytes of all ranks / time."""
+    import torch
+
+    from dmx_compressor_b200 import parallel as P
+
+    shapes = llama_shapes(model, layers)
+    plan = P.plan_shards(shapes, world, row_align=1)
+    mine = plan[rank]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    ws = []
+    for sh in mine:
+        cols = shapes[sh.name][1]
+        ws.append(torch.randn(sh.row1 - sh.row0, cols, device=dev, dtype=torch.float32, generator=g).mul_(0.02).to(dtype))
+    outs = [torch.empty_like(w) for w in ws]
+    from dmx_compressor_b200 import ops
+
+    def run():
+        st = stages_fn(None)
+        if with_stats:
+            stats = P.sharded_minmax(ws)  # local dmxq_minmax per shard + ONE all_reduce(MAX)
+            amax = float(torch.cat([torch.maximum(-mn, mx).reshape(-1) for mn, mx in stats]).max())  # one host sync
+            st = stages_fn(amax)
+        for w, y in zip(ws, outs):
+            ops.cast_chain(w, st, -1, out=y)
+
+    run()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    run()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
+    t = torch.tensor([ms, float(nbytes)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_max, total = float(tm[0]), float(t[1])
+        ms_mean = float(t[0]) / world
+    else:
+        ms_max, total, ms_mean = ms, float(nbytes), ms
+    del ws, outs
+    torch.cuda.empty_cache()
+    return {"GB/s": round(total / (ms_max * 1e-3) / 1e9, 1), "ms": round(ms_max, 3), "bytes": int(total), "tensors": len(shapes),
+            "imbalance_max_over_mean_time": round(ms_max / ms_mean, 3), "plan_imbalance": round(P.plan_imbalance(plan, shapes), 3),
+            "dtype": str(dtype).split(".")[-1], "layers": layers if layers is not None else LLAMA[model]["layers"]}
+
+
+def extra_opt125m(dev):
+    """BASELINE config #3: OPT-125m-shaped random-init stack, batch 8 x seq 2048 forward, BASIC rule set.
+    tokens/s for the unquantised torch twin, the drop-in BASIC path, and BASIC with cast elision."""
+    import torch
+
+    from dmx_compressor_b200 import _lib, elide, opt
+
+    res = {}
+    B, S = 8, 2048
+    for dt in (torch.float32, torch.bfloat16):
+        q, p = opt.build_pair(device=dev, dtype=dt)
+        ids = torch.randint(0, 50272, (B, S), device=dev)
+
+        def timeit(fn, n=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        with torch.no_grad():
+            t_plain = timeit(lambda: p(ids))
+            n0 = _lib.launch_count()
+            y1 = q(ids)
+            n1 = _lib.launch_count()
+            t_basic = timeit(lambda: q(ids))
+            with elide.enabled():
+                y2 = q(ids)
+                n2 = _lib.launch_count()
+                q(ids)
+                n3 = _lib.launch_count()
+                t_el = timeit(lambda: q(ids))
+        res[str(dt).split(".")[-1]] = {
+            "tokens_per_s_unquantised": round(B * S / t_plain * 1e3), "tokens_per_s_basic": round(B * S / t_basic * 1e3),
+            "tokens_per_s_basic_elided": round(B * S / t_el * 1e3), "ms_unquantised": round(t_plain, 2), "ms_basic": round(t_basic, 2),
+            "ms_basic_elided": round(t_el, 2), "cast_overhead_basic": round((t_basic - t_plain) / t_plain, 3),
+            "cast_overhead_basic_elided": round((t_el - t_plain) / t_plain, 3), "dmxq_launches_basic": n1 - n0,
+            "dmxq_launches_elided": n3 - n2, "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2))}
+        del q, p, y1, y2
+        torch.cuda.empty_cache()
+    res["config"] = "OPT-125m shape (12 layers, d=768, ffn=3072, 12 heads, vocab 50272), random init, batch 8 x seq 2048, config_rules.BASIC"
+    return res
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -303,6 +426,30 @@ def run_ours(args):
                "api": "dmxq_cast_chain_host (pinned host in/out, 3-stream chunked pipeline)", "matches_device_path": bool(ok)}
         del xh32, xh16, yh32, yh16
 
+    # ---------------- extras: the model-level configs of BASELINE.json (not part of `value`)
+    extras = {}
+    if not args.no_extras:
+        from dmx_compressor_b200 import parallel as P
+
+        f12 = Format.from_shorthand("BFP[4|8]{64}(SN)").stage()
+        # config #4: Llama-3-8B-shaped weights, 2:4 sparsity (score |w|) -> BFP12, sharded over the ranks
+        extras["llama3_8b_24sparse_bfp12_weight_cast"] = extra_weight_cast(
+            dev, rank, world, dist, "8b", lambda amax: [ops.nm_stage(2, 4), f12], None, False, torch.bfloat16)
+
+        # config #5: Llama-3-70B-shaped weights, SBFP12_16 with the scaler bias chosen from the amax all-reduce
+        def sbfp(amax):
+            b = 7 if amax is None else P.sbfp_scaler_bias_from_amax(amax)
+            return [Format.from_shorthand(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}").stage()]
+
+        extras["llama3_70b_sbfp12_weight_cast"] = extra_weight_cast(
+            dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16)
+        extras["llama3_70b_sbfp12_weight_cast"]["note"] = "10 layers per GPU (weak scaling; 80 layers at 8 GPUs), one batched amax all-reduce"
+        if rank == 0:
+            try:
+                extras["opt125m_basic_forward"] = extra_opt125m(dev)
+            except Exception as e:  # pragma: no cover
+                extras["opt125m_basic_forward"] = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -350,7 +497,7 @@ def run_ours(args):
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_dict(world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "frac_of_hbm_peak": round(value / world / peak, 4),
+        "frac_of_hbm_peak": round(value / world / peak, 4), "extras": extras,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:

@@ -417,11 +417,11 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         ok = ok && vd >= 0 && B > 0 && cols_supported(x->dtype, B) && (int)c.outer.size() - 1 <= kMaxOuter;
         if (ok) {
             const Dim in = c.outer[vd];
-            const int vb_in = 4 * in_sz, vb_out = 4 * out_sz;
-            ok = in.n % 4 == 0 && aligned(x->data, vb_in) && aligned(y->data, vb_out) && (c.k.xs * in_sz) % vb_in == 0 &&
-                 (c.k.ys * out_sz) % vb_out == 0;
+            // 16-byte vectors of V input elements per lane; outputs are V * out_sz >= 16 bytes
+            ok = in.n % V == 0 && aligned(x->data, 16) && aligned(y->data, 16) && (c.k.xs * in_sz) % 16 == 0 &&
+                 (c.k.ys * out_sz) % 16 == 0;
             for (size_t i = 0; i < c.outer.size() && ok; ++i)
-                if ((int)i != vd) ok = (c.outer[i].xs * in_sz) % vb_in == 0 && (c.outer[i].ys * out_sz) % vb_out == 0;
+                if ((int)i != vd) ok = (c.outer[i].xs * in_sz) % 16 == 0 && (c.outer[i].ys * out_sz) % 16 == 0;
             if (ok) {
                 ColsParams p;
                 memset(&p, 0, sizeof(p));

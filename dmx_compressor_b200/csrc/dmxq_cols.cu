@@ -1,9 +1,10 @@
 // dmxq_cols.cu -- chain_cols_kernel: the blocked dim is strided, another dim is contiguous
 // (the PV multiplier v:[.., S, 64] blocked along S, conv inputs/weights blocked along channels).
 //
-// One warp per tile of B rows (along the blocked dim) x LI*4 contiguous inner elements.
-// lane = lk * LI + li; lane (lk, li) owns rows [lk*RPT, (lk+1)*RPT) of the tile and the 4
-// columns at li*4.  Every column is its own block, so a thread carries 4 running maxima and
+// One warp per tile of B rows (along the blocked dim) x LI*V contiguous inner elements, V = 16
+// bytes worth (4 fp32 / 8 bf16).  lane = lk * LI + li; lane (lk, li) owns rows
+// [lk*RPT, (lk+1)*RPT) of the tile and the V columns at li*V.  Every column is its own block,
+// so a thread carries V running maxima and
 // reduces them over the LK lanes that share li with xor-shuffles.  All RPT row loads of a
 // thread are issued back to back (RPT x 16 B in flight per thread); rows are LI*16 B (fp32)
 // contiguous segments, i.e. whole 128-byte lines for LI = 8.  Nothing is transposed in HBM.
@@ -11,35 +12,10 @@
 
 namespace dmxq {
 
-// 4-element accesses (16 B for fp32, 8 B for 16-bit types)
-template <typename T> __device__ __forceinline__ void load4(const T *p, float (&v)[4])
-{
-    if constexpr (sizeof(T) == 4) {
-        VecIO<float>::load(reinterpret_cast<const float *>(p), v);
-    } else {
-        uint2 w = *reinterpret_cast<const uint2 *>(p);
-        T h[4];
-        *reinterpret_cast<uint2 *>(h) = w;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = Cvt<T>::to_f32(h[j]);
-    }
-}
-template <typename T> __device__ __forceinline__ void store4(T *p, const float (&v)[4])
-{
-    if constexpr (sizeof(T) == 4) {
-        VecIO<float>::store<4>(reinterpret_cast<float *>(p), v);
-    } else {
-        T h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = Cvt<T>::from_f32(v[j]);
-        *reinterpret_cast<uint2 *>(p) = *reinterpret_cast<uint2 *>(h);
-    }
-}
-
 template <typename Tin, typename Tout, int RPT, int LK>
-__global__ void __launch_bounds__(kThreads, (RPT <= 8 ? 3 : 2)) chain_cols_kernel(const __grid_constant__ ColsParams p)
+__global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 : 2)) chain_cols_kernel(const __grid_constant__ ColsParams p)
 {
-    constexpr int V = 4;
+    constexpr int V = VecIO<Tin>::V;  // 16-byte row segments per lane: 4 fp32 or 8 bf16/fp16
     constexpr int LI = 32 / LK;
     constexpr int B = RPT * LK;
     const int lane = threadIdx.x & 31;
@@ -82,7 +58,7 @@ __global__ void __launch_bounds__(kThreads, (RPT <= 8 ? 3 : 2)) chain_cols_kerne
     for (int r = 0; r < RPT; ++r) {
         int64_t k = kb + r;
         if (col_ok && k < p.K) {
-            load4<Tin>(x + k * p.xks, v[r]);
+            VecIO<Tin>::load(x + k * p.xks, v[r]);
         } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[r][j] = 0.0f;
@@ -181,22 +157,26 @@ __global__ void __launch_bounds__(kThreads, (RPT <= 8 ? 3 : 2)) chain_cols_kerne
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         int64_t k = kb + r;
-        if (col_ok && k < p.K) store4<Tout>(y + k * p.yks, v[r]);
+        if (col_ok && k < p.K) VecIO<Tout>::template store<V>(y + k * p.yks, v[r]);
     }
 }
 
 struct ColsCfg { int B, RPT, LK; };
-static const ColsCfg kColsCfgs[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 8, 8}, {128, 16, 8}};
+// fp32 (V = 4) and 16-bit (V = 8) tilings; RPT * V <= 64 live values per thread
+static const ColsCfg kCfg32[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 8, 8}, {128, 16, 8}};
+static const ColsCfg kCfg16[] = {{8, 1, 8}, {16, 2, 8}, {32, 4, 8}, {64, 8, 8}, {128, 8, 16}};
 
-bool cols_supported(int, int B)
+static const ColsCfg *find_cfg(int in_dt, int B)
 {
-    for (auto &c : kColsCfgs) if (c.B == B) return true;
-    return false;
+    const ColsCfg *t = in_dt == 0 ? kCfg32 : kCfg16;
+    for (int i = 0; i < 5; ++i) if (t[i].B == B) return &t[i];
+    return nullptr;
 }
-int cols_tile_inner(int, int B)
+bool cols_supported(int in_dt, int B) { return find_cfg(in_dt, B) != nullptr; }
+int cols_tile_inner(int in_dt, int B)
 {
-    for (auto &c : kColsCfgs) if (c.B == B) return (32 / c.LK) * 4;
-    return 0;
+    const ColsCfg *c = find_cfg(in_dt, B);
+    return c ? (32 / c->LK) * (in_dt == 0 ? 4 : 8) : 0;
 }
 
 template <typename Tin, typename Tout> static cudaError_t launch_cols_t(int B, const ColsParams &p, cudaStream_t s)
@@ -206,13 +186,24 @@ template <typename Tin, typename Tout> static cudaError_t launch_cols_t(int B, c
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
     dim3 g((unsigned)grid), b(kThreads);
-    switch (B) {
-    case 8: chain_cols_kernel<Tin, Tout, 2, 4><<<g, b, 0, s>>>(p); break;
-    case 16: chain_cols_kernel<Tin, Tout, 4, 4><<<g, b, 0, s>>>(p); break;
-    case 32: chain_cols_kernel<Tin, Tout, 8, 4><<<g, b, 0, s>>>(p); break;
-    case 64: chain_cols_kernel<Tin, Tout, 8, 8><<<g, b, 0, s>>>(p); break;
-    case 128: chain_cols_kernel<Tin, Tout, 16, 8><<<g, b, 0, s>>>(p); break;
-    default: return cudaErrorInvalidValue;
+    if constexpr (sizeof(Tin) == 4) {
+        switch (B) {
+        case 8: chain_cols_kernel<Tin, Tout, 2, 4><<<g, b, 0, s>>>(p); break;
+        case 16: chain_cols_kernel<Tin, Tout, 4, 4><<<g, b, 0, s>>>(p); break;
+        case 32: chain_cols_kernel<Tin, Tout, 8, 4><<<g, b, 0, s>>>(p); break;
+        case 64: chain_cols_kernel<Tin, Tout, 8, 8><<<g, b, 0, s>>>(p); break;
+        case 128: chain_cols_kernel<Tin, Tout, 16, 8><<<g, b, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (B) {
+        case 8: chain_cols_kernel<Tin, Tout, 1, 8><<<g, b, 0, s>>>(p); break;
+        case 16: chain_cols_kernel<Tin, Tout, 2, 8><<<g, b, 0, s>>>(p); break;
+        case 32: chain_cols_kernel<Tin, Tout, 4, 8><<<g, b, 0, s>>>(p); break;
+        case 64: chain_cols_kernel<Tin, Tout, 8, 8><<<g, b, 0, s>>>(p); break;
+        case 128: chain_cols_kernel<Tin, Tout, 8, 16><<<g, b, 0, s>>>(p); break;
+        default: return cudaErrorInvalidValue;
+        }
     }
     count_launch();
     return cudaGetLastError();

@@ -193,6 +193,51 @@ __global__ void minmax_init_kernel(int *omin, int *omax, int64_t C)
     if (i < C) { omin[i] = 0x7F800000; omax[i] = ord(u2f(0xFF800000u)); }
 }
 
+// per-tensor fast path: contiguous data, 16-byte loads, 4 vectors in flight per thread
+template <typename T> __global__ void __launch_bounds__(kThreads) minmax_flat_kernel(const T *__restrict__ x, int64_t n, int *omin, int *omax)
+{
+    constexpr int V = VecIO<T>::V;
+    const int64_t nvec = n / V;
+    int lo = 0x7F800000, hi = ord(u2f(0xFF800000u));
+    auto upd = [&](float v) {
+        if (v != v) { lo = (int)0x80000000; hi = 0x7FFFFFFF; }
+        else { int k = ord(v); lo = min(lo, k); hi = max(hi, k); }
+    };
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = ldg_stream(x + (i + u * stride) * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[V];
+            VecIO<T>::unpack(r[u], v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) upd(v[j]);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        float v[V];
+        VecIO<T>::load(x + i * V, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) upd(v[j]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * V) upd(Cvt<T>::to_f32(x[nvec * V + threadIdx.x]));
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+    }
+    __shared__ int slo[kThreads / 32], shi[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) { lo = min(lo, slo[w]); hi = max(hi, shi[w]); }
+        atomicMin(omin, lo);
+        atomicMax(omax, hi);
+    }
+}
+
 template <typename T> __global__ void __launch_bounds__(kThreads) minmax_kernel(const __grid_constant__ MinMaxParams p)
 {
     // grid: (chunks, C); each CTA reduces a slice of channel c over (outer, inner)
@@ -240,7 +285,13 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
     unsigned ib = (unsigned)((C + 255) / 256);
     minmax_init_kernel<<<ib, 256, 0, s>>>(p.omin, p.omax, C);
     int64_t per = p.outer * p.inner;
-    if (per > 0) {
+    if (C == 1 && per > 0 && p.xi == 1 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0) {
+        int64_t nvec = per / (p.dtype == 0 ? 4 : 8);
+        unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nvec + kThreads * 4 - 1) / (kThreads * 4), 148 * 8));
+        if (p.dtype == 0) minmax_flat_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float *>(p.x), per, p.omin, p.omax);
+        else if (p.dtype == 1) minmax_flat_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(p.x), per, p.omin, p.omax);
+        else minmax_flat_kernel<__half><<<grid, kThreads, 0, s>>>(static_cast<const __half *>(p.x), per, p.omin, p.omax);
+    } else if (per > 0) {
         int64_t chunks = (per + (int64_t)kThreads * 8 - 1) / ((int64_t)kThreads * 8);
         int64_t cap = std::max<int64_t>(1, (148 * 8) / C);
         chunks = std::max<int64_t>(1, std::min(chunks, cap));

@@ -332,10 +332,9 @@ __device__ __forceinline__ uint32_t score_key(float s)
     if (b == 0x80000000u) b = 0u;                              // -0 == +0
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-__device__ __forceinline__ uint32_t absx_key(float x)  // score = |x|
+__device__ __forceinline__ uint32_t absx_key(float x)  // score = |x|: all NaNs collapse to one key above Inf
 {
-    uint32_t b = f2u(x) & 0x7FFFFFFFu;
-    return b > 0x7F800000u ? 0xFFFFFFFFu : b;
+    return min(f2u(x) & 0x7FFFFFFFu, 0x7F800001u);
 }
 __device__ __forceinline__ float nm_apply(float x, bool keep) { return keep ? x : __fmul_rn(x, 0.0f); }
 

@@ -261,22 +261,27 @@ template <int V> __device__ __forceinline__ void fixed_stage(float (&v)[V], cons
     }
 }
 
-// N:M inside one thread (M <= V): ranks by pairwise compares, ties -> lower index first.
+// N:M inside one thread (M <= V).  Stable ascending order: for a < b, "a sorts before b" iff
+// key[a] <= key[b]; one comparison per pair feeds both ranks (rank = number of elements that
+// sort before it); the n_prune lowest ranks are pruned.
 template <int V, int M> __device__ __forceinline__ void nm_local(const uint32_t (&key)[V], int n_prune, bool (&keep)[V])
 {
 #pragma unroll
-    for (int g0 = 0; g0 < V; g0 += M)
+    for (int g0 = 0; g0 < V; g0 += M) {
+        int rank[M];
 #pragma unroll
-        for (int a = 0; a < M; ++a) {
-            int rank = 0;
+        for (int a = 0; a < M; ++a) rank[a] = 0;
 #pragma unroll
-            for (int b = 0; b < M; ++b) {
-                if (b == a) continue;
-                bool less = key[g0 + b] < key[g0 + a] || (key[g0 + b] == key[g0 + a] && b < a);
-                rank += less ? 1 : 0;
+        for (int a = 0; a < M; ++a)
+#pragma unroll
+            for (int b = a + 1; b < M; ++b) {
+                int a_first = key[g0 + a] <= key[g0 + b] ? 1 : 0;
+                rank[b] += a_first;
+                rank[a] += 1 - a_first;
             }
-            keep[g0 + a] = rank >= n_prune;
-        }
+#pragma unroll
+        for (int a = 0; a < M; ++a) keep[g0 + a] = rank[a] >= n_prune;
+    }
 }
 
 // N:M across `lanes` = M / V neighbouring lanes (M > V): partner keys arrive by shuffle.

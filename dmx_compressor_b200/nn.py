@@ -1,0 +1,406 @@
+"""The callers of the cast path -- a compact mirror of the reference's ``DmxModule`` runtime for
+the module types the BASELINE configs exercise (reference
+src/dmx/compressor/modeling/nn/core.py:34-264, torch_modules.py).
+
+Same contract as the reference: every module owns ``input_casts`` / ``output_casts``
+(``CastToDict``), and parameterised modules also ``weight_storage_cast``, ``weight_cast``,
+``bias_cast``, ``accum_cast`` and a ``weight_sparsifier``; ``configure(dict)`` takes the same
+keys as ``DmxModule.configure`` (core.py:65-108); ``forward`` is
+``input_casts -> _forward (weight hypernet inside) -> output_casts -> back to the input dtype``
+(core.py:215-264); ``fold_weight_and_bias`` applies the parameter casts once (core.py:146-176).
+Graph tracing, approximation functions, SmoothQuant, plugins and perf proxies are out of scope
+(SURVEY.md section 2).
+
+Two opt-in accelerations that the reference does not have, both
+value-preserving, see dmx_compressor_b200/elide.py:
+  * weight-cast caching while parameters are unchanged,
+  * elision of casts that are provably no-ops (SAME clones, idempotent format repeats) and
+    sharing of one cast result between consumers of the same tensor.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import elide, ops
+from .numerical import CastTo, CastToDict, Format, Same
+from .sparse import BlockTopK, Dense, LazySparsify, Sparsify
+
+
+class DmxModule:
+    r"""Mixin that adds the boundary casts and the weight hypernet to a torch.nn.Module
+    (reference NumericalCastMixin cast.py:401-467 + WeightSparseMixin sparse.py:366-421 +
+    DmxModule core.py)."""
+
+    ch_axis = win_ch_axis = wout_ch_axis = None
+
+    def _init_dmx(self) -> None:
+        self.align_boundary_dtype = True
+        self.input_casts = CastToDict(OrderedDict({"input_cast": CastTo(ch_axis=self.ch_axis)}))
+        self.output_casts = CastToDict(OrderedDict({"output_cast": CastTo()}))
+        pnames = [n for n, _ in self.named_parameters(recurse=False)]
+        has_w = "weight" in pnames
+        self.accum_cast = CastTo() if isinstance(self, (torch.nn.Linear, torch.nn.modules.conv._ConvNd)) else None
+        self.weight_storage_cast = CastTo(ch_axis=self.wout_ch_axis) if has_w else None
+        self.weight_cast = CastTo(ch_axis=self.wout_ch_axis) if has_w else None
+        self.bias_cast = CastTo() if "bias" in pnames else None
+        self.weight_sparsifier = LazySparsify() if has_w else None
+        self._wcache = None
+
+    # ------------------------------------------------------------------ configuration (core.py:65-108)
+    def configure(self, config) -> None:
+        if "input_formats" in config:
+            self.input_casts.set_format(format=config["input_formats"])
+        if "pre_input_transform" in config:
+            self.input_casts.set_pre_transform(config["pre_input_transform"])
+        if "output_formats" in config:
+            self.output_casts.set_format(format=config["output_formats"])
+        if "pre_output_transform" in config:
+            self.output_casts.set_pre_transform(config["pre_output_transform"])
+        if self.accum_cast is not None and "accum_format" in config:
+            self.accum_cast.set_format(format=config["accum_format"])
+        if self.weight_storage_cast is not None and "weight_storage_format" in config:
+            self.weight_storage_cast.set_format(format=config["weight_storage_format"])
+        if self.weight_cast is not None and "weight_format" in config:
+            self.weight_cast.set_format(format=config["weight_format"])
+        if self.weight_cast is not None and "pre_weight_transform" in config:
+            self.weight_cast.set_pre_transform(config["pre_weight_transform"])
+        if self.bias_cast is not None and "bias_format" in config:
+            self.bias_cast.set_format(format=config["bias_format"])
+        if self.weight_sparsifier is not None and "weight_sparseness" in config:
+            self.weight_sparsifier.configure(sparseness=config["weight_sparseness"])
+        if self.weight_sparsifier is not None and "weight_score_func" in config:
+            self.weight_sparsifier.configure(score_func=config["weight_score_func"])
+        self._wcache = None
+
+    transform = configure
+
+    @property
+    def input_formats(self):
+        return [c.format for c in self.input_casts.values()]
+
+    @property
+    def output_formats(self):
+        return [c.format for c in self.output_casts.values()]
+
+    @property
+    def accum_format(self):
+        return self.accum_cast.format if self.accum_cast is not None else None
+
+    @property
+    def weight_format(self):
+        return self.weight_cast.format if self.weight_cast is not None else None
+
+    @property
+    def bias_format(self):
+        return self.bias_cast.format if self.bias_cast is not None else None
+
+    @property
+    def weight_sparseness(self):
+        return self.weight_sparsifier.sparseness if self.weight_sparsifier is not None else None
+
+    # ------------------------------------------------------------------ weight hypernet (core.py:178-213)
+    def _fusable_hypernet_stages(self):
+        """sparsify -> storage cast -> weight cast as dmxq stages, or None when some piece needs
+        the module-by-module path (score parameter, pre-transforms, observers, FixedPoint affine)."""
+        stages = []
+        sp = self.weight_sparsifier
+        if sp is not None and not isinstance(sp.sparseness, Dense):
+            from .sparse import abs_score
+
+            if not isinstance(sp.sparseness, BlockTopK) or sp.sparseness.block_dim not in (-1, self.weight.dim() - 1):
+                return None
+            if not (sp.plastic and sp.score_func is abs_score):
+                return None
+            stages.append(ops.nm_stage(sp.sparseness.K, sp.sparseness.block_size))
+        for c in (self.weight_storage_cast, self.weight_cast):
+            if c is None or isinstance(c.format, Same) or not c._fq_on:
+                continue
+            if c.pre_transform or c._obs_on or not isinstance(c.format, Format):
+                return None
+            st = c.format.stage() if not hasattr(c.format, "tie") else None  # FixedPoint carries affine state
+            if st is None or (c.format.blocked and c.block_dim not in (-1, self.weight.dim() - 1)):
+                return None
+            stages.append(st)
+        return stages
+
+    def weight_hypernet(self, _w):
+        if elide.active() and not torch.is_grad_enabled():
+            stages = self._fusable_hypernet_stages()
+            if stages is not None:
+                if not stages:
+                    return _w
+                if self.weight_sparsifier is not None and not isinstance(self.weight_sparsifier.sparseness, Dense):
+                    self.weight_sparsifier.plastic = False  # the reference rewires once, on this forward
+                return ops.cast_chain(_w, stages, -1)  # ONE kernel: prune -> storage cast -> weight cast
+        if self.weight_sparsifier is not None:
+            _w = self.weight_sparsifier(_w)
+        if self.weight_storage_cast is not None:
+            _w = self.weight_storage_cast(_w)
+        if self.weight_cast is not None:
+            _w = self.weight_cast(_w)
+        return _w
+
+    @property
+    def _weight(self):
+        if elide.active() and not torch.is_grad_enabled():
+            w = self.weight
+            key = (w.data_ptr(), w._version, tuple(w.shape), repr(self.weight_format),
+                   repr(self.weight_storage_cast.format) if self.weight_storage_cast is not None else None,
+                   repr(self.weight_sparseness))
+            if self._wcache is not None and self._wcache[0] == key:
+                return self._wcache[1]
+            out = self.weight_hypernet(w)
+            self._wcache = (key, out)
+            return out
+        return self.weight_hypernet(self.weight)
+
+    @property
+    def _bias(self):
+        if getattr(self, "bias", None) is None:
+            return None
+        return self.bias_cast(self.bias) if self.bias_cast is not None else self.bias
+
+    def fold_weight_and_bias(self) -> None:
+        with torch.no_grad():
+            if self.bias_cast is not None and not isinstance(self.bias_format, Same):
+                self.bias.data = self.bias_cast(self.bias.data)
+                self.bias_cast = CastTo(format=Same())
+            if self.weight_cast is not None:
+                self.weight.data = self.weight_hypernet(self.weight.data)
+                self.weight_sparsifier = LazySparsify(sparseness=Dense())
+                self.weight_storage_cast = CastTo(format=Same())
+                self.weight_cast = CastTo(format=Same())
+            self._wcache = None
+
+    # ------------------------------------------------------------------ forward (core.py:215-264)
+    def forward(self, input, *args, **kwargs):
+        _dtype = input.dtype
+        _input, args, kwargs = self.input_casts(input, *args, **kwargs)
+        _output = self._forward(_input, *args, **kwargs)
+        output = self.output_casts(_output, output=True)
+        if self.align_boundary_dtype:
+            output = type(output)(a.to(_dtype) for a in output) if isinstance(output, (tuple, list)) else output.to(_dtype)
+        return output
+
+
+class Linear(DmxModule, torch.nn.Linear):
+    ch_axis, win_ch_axis, wout_ch_axis = -1, -1, 0
+
+    def __init__(self, in_features, out_features, bias=True, **kw):
+        super().__init__(in_features, out_features, bias=bias, **kw)
+        self._init_dmx()
+        self.input_casts.input_cast.block_dim = -1
+        self.weight_cast.block_dim = -1
+        if self.bias_cast is not None:
+            self.bias_cast.block_dim = -1
+
+    def _forward(self, _input):  # reference torch_modules.py:346-360
+        if isinstance(self.accum_format, Same):
+            _weight = self._weight.to(_input.dtype)
+            _bias = None if self._bias is None else self._bias.to(_input.dtype)
+            return F.linear(_input, _weight, _bias)
+        _weight = self._weight
+        _product = self.accum_cast(torch.matmul(_input.to(_weight.dtype), _weight.t()))
+        return torch.add(_product, self._bias) if self.bias is not None else _product
+
+
+class Conv2d(DmxModule, torch.nn.Conv2d):
+    ch_axis, win_ch_axis, wout_ch_axis = 1, 1, 0
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+        self.input_casts.input_cast.block_dim = 1
+        self.weight_cast.block_dim = 1
+        if self.bias_cast is not None:
+            self.bias_cast.block_dim = -1
+
+    def _forward(self, _input):  # reference torch_modules.py:679-688
+        _weight = self._weight
+        _conv = self.accum_cast(self._conv_forward(_input.to(_weight.dtype), _weight, None))
+        return torch.add(_conv, self._bias.unsqueeze(-1).unsqueeze(-1)) if self.bias is not None else _conv
+
+
+class Embedding(DmxModule, torch.nn.Embedding):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+
+    def forward(self, input):
+        out = F.embedding(input, self._weight, self.padding_idx, self.max_norm, self.norm_type, self.scale_grad_by_freq, self.sparse)
+        return self.output_casts(out, output=True)
+
+
+class ResAdd(DmxModule, torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._init_dmx()
+        self.input_casts = CastToDict(OrderedDict({"input_cast": CastTo(), "residual_cast": CastTo()}))
+
+    def _forward(self, _input, _residual):
+        return _input + _residual
+
+
+class Mul(DmxModule, torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._init_dmx()
+        self.input_casts = CastToDict(OrderedDict({"input_cast": CastTo(), "multiplier_cast": CastTo()}))
+
+    def _forward(self, _input, multiplier):
+        return _input * multiplier
+
+
+class ActActMatMul(DmxModule, torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._init_dmx()
+        self.input_casts = CastToDict(OrderedDict({"input_cast": CastTo(block_dim=-1), "multiplier_cast": CastTo(block_dim=-2)}))
+
+    def _forward(self, _input, _multiplier):
+        return torch.matmul(_input, _multiplier)
+
+
+class Softmax(DmxModule, torch.nn.Softmax):
+    def __init__(self, dim: int = -1):
+        super().__init__(dim=dim)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.softmax(_input, dim=self.dim)
+
+
+class LayerNorm(DmxModule, torch.nn.LayerNorm):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.layer_norm(_input, self.normalized_shape, self._weight, self._bias, self.eps)
+
+
+class ReLU(DmxModule, torch.nn.ReLU):
+    def __init__(self, inplace: bool = False):
+        super().__init__(inplace=False)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.relu(_input)
+
+
+class GELU(DmxModule, torch.nn.GELU):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.gelu(_input, approximate=self.approximate)
+
+
+class Dropout(DmxModule, torch.nn.Dropout):
+    def __init__(self, p: float = 0.5, inplace: bool = False):
+        super().__init__(p=p, inplace=False)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.dropout(_input, self.p, self.training, False)
+
+
+class MaxPool2d(DmxModule, torch.nn.MaxPool2d):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.max_pool2d(_input, self.kernel_size, self.stride, self.padding, self.dilation, self.ceil_mode, self.return_indices)
+
+
+class AvgPool2d(DmxModule, torch.nn.AvgPool2d):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return F.avg_pool2d(_input, self.kernel_size, self.stride, self.padding, self.ceil_mode, self.count_include_pad, self.divisor_override)
+
+
+class Tanh(DmxModule, torch.nn.Tanh):
+    def __init__(self):
+        super().__init__()
+        self._init_dmx()
+
+    def _forward(self, _input):
+        return torch.tanh(_input)
+
+
+# --------------------------------------------------------------------------------------------
+# format aliases and rule sets (reference src/dmx/compressor/__init__.py:20-105, 142-483)
+_F = Format.from_shorthand
+format = SimpleNamespace(
+    SAME=_F("SAME"), FLOAT32=_F("FP[1|8|23,127](_N)"), FLOAT16=_F("FP[1|5|10,15](FN)"), BFLOAT16=_F("FP[1|8|7,127](FN)"),
+    AFLOAT8=_F("FP[1|4|3,7](_N)"), BFLOAT8=_F("FP[1|5|2,15](_N)"), INT8=_F("XP[8,0](CSN)"), INT4=_F("XP[4,0](CSN)"),
+    BFP32_1=_F("BFP[24|8]{1}(SN)"),
+    **{f"BFP{p + 8}_{b}": _F(f"BFP[{p}|8]{{{b}}}(SN)") for p in (16, 8, 6, 4) for b in (128, 64, 32, 16) if not (p == 16 and b == 128)},
+    **{f"BFP{p + 8}A_{b}": _F(f"BFP[{p}|8]{{{b}}}(_N)") for p in (8, 6, 4) for b in (128, 64, 32, 16)},
+    SBFP12_16=_F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"),
+    **{f"SBFP12_16_{b}": _F(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}") for b in range(4, 19)},
+    **{f"MXINT{p}_K{b}": _F(f"MXINT{p}{{{b}}}") for p in (8, 6, 4) for b in (128, 64, 32)},
+)
+sparseness = SimpleNamespace(BTK8_4_LD="BTOPK{4:8,-1}(U)", BTK8_4_FD="BTOPK{4:8,1}(U)", BTK8_2_LD="BTOPK{2:8,-1}(U)", BTK8_2_FD="BTOPK{2:8,1}(U)")
+
+
+class DmxConfigRule(SimpleNamespace):
+    r"""(module_types, name_re, module_config) -> applied to every matching submodule
+    (reference modeling/model.py:721-792)."""
+
+    def __init__(self, module_types=(), name_re: str = "", module_config: Optional[dict] = None):
+        super().__init__(module_types=tuple(module_types), name_re=name_re, module_config=module_config or {})
+
+    def apply_to(self, model: torch.nn.Module) -> None:
+        import re
+
+        for n, m in model.named_modules():
+            if isinstance(m, DmxModule) and isinstance(m, self.module_types) and re.match(self.name_re, n):
+                m.configure(self.module_config)
+
+
+_ACT = (ReLU, GELU, Tanh, Softmax, LayerNorm)
+config_rules = SimpleNamespace(
+    BASELINE=[
+        DmxConfigRule((Linear, Conv2d), module_config=dict(input_formats=[format.SAME], weight_format=format.SAME, bias_format=format.SAME, output_formats=[format.SAME])),
+        DmxConfigRule((ResAdd, ActActMatMul, Mul), module_config=dict(input_formats=[format.SAME, format.SAME], output_formats=[format.SAME])),
+        DmxConfigRule((Embedding,), module_config=dict(output_formats=[format.SAME])),
+        DmxConfigRule(_ACT + (MaxPool2d, AvgPool2d, Dropout), module_config=dict(input_formats=[format.SAME], output_formats=[format.SAME])),
+    ],
+    BASIC=[
+        DmxConfigRule((Linear, Conv2d), module_config=dict(input_formats=[format.BFP16_64], weight_format=format.BFP16_64, bias_format=format.BFP32_1, output_formats=[format.FLOAT16])),
+        DmxConfigRule((ResAdd,), module_config=dict(input_formats=[format.FLOAT16, format.FLOAT16], output_formats=[format.FLOAT16])),
+        DmxConfigRule((ActActMatMul,), module_config=dict(input_formats=[format.BFP16_64, format.BFP16_64], output_formats=[format.FLOAT16])),
+        DmxConfigRule((Embedding,), module_config=dict(output_formats=[format.FLOAT16])),
+        DmxConfigRule(_ACT + (MaxPool2d, AvgPool2d), module_config=dict(input_formats=[format.FLOAT16], output_formats=[format.FLOAT16])),
+    ],
+    SBFP_WEIGHT_STORAGE=[DmxConfigRule((Linear, Conv2d), module_config=dict(weight_storage_format=format.SBFP12_16))],
+)
+
+
+def configure(model: torch.nn.Module, *rules) -> torch.nn.Module:
+    """model.transform(None, *rules) of the reference (modeling/model.py:61-80)."""
+    for r in rules:
+        for rr in (r if isinstance(r, (list, tuple)) else [r]):
+            rr.apply_to(model)
+    return model
+
+
+def to_basic_mode(model: torch.nn.Module) -> torch.nn.Module:
+    return configure(model, config_rules.BASELINE, config_rules.BASIC)
+
+
+def fold_weights_and_biases(model: torch.nn.Module) -> None:
+    for m in model.modules():
+        if isinstance(m, DmxModule):
+            m.fold_weight_and_bias()

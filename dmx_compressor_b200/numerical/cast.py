@@ -20,7 +20,7 @@ import torch
 from torch.autograd import Function
 from torch.quantization.fake_quantize import FakeQuantize
 
-from .. import ops
+from .. import elide, ops
 from .format import FixedPoint, Format, Same
 from .observer import DummyObserver, MinMaxObserver, ObserverBase
 
@@ -243,8 +243,33 @@ class CastTo(FakeQuantize):
             return _FusedCast.apply(x, fmt, self.block_dim)
         return super().forward(x)  # plain torch.dtype fake-quant
 
+    def _forward_elided(self, x):
+        """value-identical fast path, only under elide.enabled() + no_grad (see elide.py)"""
+        fmt = self.format
+        if not self._fq_on or isinstance(fmt, Same):
+            elide.stats["elided"] += 1
+            return x
+        key = elide.format_key(fmt, self.block_dim if fmt.blocked else None)
+        if key is None:
+            return None
+        if elide.is_tagged(x, key) or (hasattr(fmt, "_identity_for") and fmt._identity_for(x.dtype) and not fmt.unsigned):
+            elide.stats["elided"] += 1
+            return x
+        y = elide.memo_get(x, key)
+        if y is None:
+            y = ops.cast_chain(x, [fmt.stage()], self.block_dim)
+            elide.stats["casts"] += 1
+            elide.memo_put(x, key, y)
+            elide.tag(y, key)
+        return y
+
     def forward(self, x):
         self.physical_dtype = x.dtype
+        if (elide.active() and not torch.is_grad_enabled() and not self.pre_transform and not self._obs_on
+                and isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point()):
+            y = self._forward_elided(x)
+            if y is not None:
+                return y
         undo = shortcut = None
         if "shaping" in self.pre_transform:
             x, undo = self.apply_shaping_seq(x, self.pre_transform["shaping"])

@@ -1,0 +1,190 @@
+"""Multi-GPU side of the path: whole-model weight casting sharded by
+parameter / row range, and calibration statistics reduced with ONE batched all-reduce.
+
+The reference has no distributed code at all; this is the capability BASELINE configs #4/#5
+name.  One process per GPU (``torchrun``), ``torch.distributed`` for the plumbing.
+
+* Every block (BFP/SBFP), element (FP/XP) and M-group (N:M) is independent, so a weight
+  ``[out, in]`` blocked along ``in`` can be cut at any row boundary and different parameters
+  are independent: sharding needs NO data-path collective.  ``plan_shards`` packs whole
+  tensors onto ranks (longest-processing-time first) and row-splits the few tensors that are
+  too big to balance (lm_head, embeddings).
+* The only exchange is calibration statistics (per-tensor / per-channel amin & amax feeding
+  ``MinMaxObserver._calculate_qparams``, or a tensor-wide amax): each rank reduces its shard
+  with ``dmxq_minmax``; all statistics of all tensors are packed into one fp32 buffer and
+  reduced with a single ``all_reduce(MAX)`` over ``[max..., -min...]`` (NCCL over NVLink on the
+  box, gloo in the CPU tests).  min/max are exact and order independent, so the sharded
+  result is bit-identical to the single-GPU result.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+
+@dataclass(frozen=True)
+class Shard:
+    name: str
+    row0: int   # first row (dim 0) owned by the rank
+    row1: int   # one past the last row
+    rows: int   # total rows of the tensor
+
+    @property
+    def whole(self) -> bool:
+        return self.row0 == 0 and self.row1 == self.rows
+
+
+def plan_shards(shapes: Dict[str, Sequence[int]], world_size: int, split_threshold: float = 0.5,
+                row_align: int = 1) -> List[List[Shard]]:
+    """-> per rank, the list of shards it owns.
+
+    Tensors with more than ``split_threshold * total / world_size`` elements are cut into
+    ``world_size`` contiguous row ranges (whole rows, multiples of ``row_align`` rows, so no
+    block or N:M group straddles ranks); the rest are assigned whole, largest first, to the
+    currently lightest rank."""
+    numel = {n: int(torch.Size(s).numel()) for n, s in shapes.items()}
+    total = sum(numel.values())
+    plan: List[List[Shard]] = [[] for _ in range(world_size)]
+    load = [0] * world_size
+    limit = split_threshold * total / max(world_size, 1)
+    whole = []
+    for n, s in shapes.items():
+        rows = int(s[0]) if len(s) > 0 else 1
+        if world_size > 1 and numel[n] > limit and rows >= world_size * row_align:
+            per_row = numel[n] // max(rows, 1)
+            units = rows // row_align
+            base, extra = divmod(units, world_size)
+            r0 = 0
+            for r in range(world_size):
+                take = (base + (1 if r < extra else 0)) * row_align
+                r1 = rows if r == world_size - 1 else r0 + take
+                plan[r].append(Shard(n, r0, r1, rows))
+                load[r] += (r1 - r0) * per_row
+                r0 = r1
+        else:
+            whole.append(n)
+    for n in sorted(whole, key=lambda k: (-numel[k], k)):
+        r = min(range(world_size), key=lambda i: (load[i], i))
+        rows = int(shapes[n][0]) if len(shapes[n]) > 0 else 1
+        plan[r].append(Shard(n, 0, rows, rows))
+        load[r] += numel[n]
+    return plan
+
+
+def plan_imbalance(plan: List[List[Shard]], shapes: Dict[str, Sequence[int]]) -> float:
+    """max rank load / mean rank load (1.0 = perfect)."""
+    loads = []
+    for shards in plan:
+        t = 0
+        for sh in shards:
+            s = shapes[sh.name]
+            t += (sh.row1 - sh.row0) * (int(torch.Size(s).numel()) // max(sh.rows, 1))
+        loads.append(t)
+    mean = sum(loads) / len(loads)
+    return max(loads) / mean if mean else 1.0
+
+
+def cast_shards(shards: Sequence[Shard], materialise: Callable[[Shard], torch.Tensor], stages, block_dim: int = -1,
+                keep: bool = False):
+    """Cast every shard this rank owns with one fused chain kernel each.  ``materialise`` returns
+    the shard's rows as a CUDA tensor (generated or loaded shard-locally).  Returns
+    (algorithmic bytes processed, {name: result} if keep)."""
+    from . import ops
+
+    out = {}
+    nbytes = 0
+    for sh in shards:
+        w = materialise(sh)
+        y = ops.cast_chain(w, stages, block_dim)
+        nbytes += 2 * w.numel() * w.element_size()
+        if keep:
+            out[(sh.name, sh.row0)] = y
+    return nbytes, out
+
+
+# ------------------------------------------------------------------------------------------------
+# batched statistics all-reduce
+def local_minmax(t: torch.Tensor, ch_axis: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """amin / amax of a local shard: the dmxq_minmax kernel on CUDA tensors."""
+    if t.is_cuda:
+        from . import ops
+
+        return ops.minmax(t, ch_axis)
+    # host tensors only appear in the gloo unit tests of the reduction logic (no cast math here)
+    if ch_axis is None:
+        return t.float().amin().reshape(1), t.float().amax().reshape(1)
+    dims = [d for d in range(t.dim()) if d != ch_axis % t.dim()]
+    return t.float().amin(dims), t.float().amax(dims)
+
+
+def allreduce_minmax(stats: Sequence[Tuple[torch.Tensor, torch.Tensor]], group=None):
+    """One collective for all tensors: pack [max_0.., -min_0..] and all_reduce(MAX).
+    ``stats``: per tensor (min, max) fp32 vectors (length 1 or #channels), identical lengths on
+    every rank.  Returns the reduced list in the same order.  NaN propagates (max of NaN)."""
+    import torch.distributed as dist
+
+    if not stats:
+        return []
+    dev = stats[0][0].device
+    sizes = [mn.numel() for mn, _ in stats]
+    buf = torch.cat([mx.reshape(-1).float() for _, mx in stats] + [(-mn.reshape(-1).float()) for mn, _ in stats]).to(dev)
+    nan = torch.isnan(buf)
+    buf = torch.where(nan, torch.full_like(buf, float("inf")), buf)  # NaN must win a MAX reduction
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
+    n = sum(sizes)
+    mx_all, mn_all = buf[:n], -buf[n:]
+    # +inf on the max side / -inf on the min side can only come from a NaN marker or a real inf;
+    # a NaN marker always sets BOTH sides of an entry to inf
+    was_nan = torch.isinf(mx_all) & torch.isinf(mn_all) & (mx_all > 0) & (mn_all < 0)
+    mx_all = torch.where(was_nan, torch.full_like(mx_all, float("nan")), mx_all)
+    mn_all = torch.where(was_nan, torch.full_like(mn_all, float("nan")), mn_all)
+    out, o = [], 0
+    for s in sizes:
+        out.append((mn_all[o:o + s].clone(), mx_all[o:o + s].clone()))
+        o += s
+    return out
+
+
+def sharded_minmax(tensors: Sequence[torch.Tensor], ch_axes: Optional[Sequence[Optional[int]]] = None, group=None):
+    """amin/amax of row-sharded tensors as if they were whole: local kernel + one all-reduce."""
+    ch_axes = ch_axes or [None] * len(tensors)
+    return allreduce_minmax([local_minmax(t, a) for t, a in zip(tensors, ch_axes)], group)
+
+
+def qparams_from_minmax(mn: torch.Tensor, mx: torch.Tensor, fmt, symmetric: bool = True, eps: float = torch.finfo(torch.float32).eps):
+    """scale / zero-point exactly as MinMaxObserver._calculate_qparams (reference
+    S/numerical/observer.py:59-115) computes them from (reduced) statistics."""
+    from .numerical.observer import _get_qmin_qmax
+
+    qmin, qmax = _get_qmin_qmax(fmt)
+    lo, hi = torch.clamp(mn, max=0.0), torch.clamp(mx, min=0.0)
+    e = torch.tensor([eps], device=mn.device)
+    if symmetric:
+        scale = torch.max(torch.max(-lo, hi) / (float(qmax - qmin) / 2), e)
+        zp = torch.zeros_like(scale, dtype=torch.int64)
+    else:
+        scale = torch.max((hi - lo) / float(qmax - qmin), e)
+        zp = torch.clamp(qmin - torch.round(lo / scale).to(torch.int), qmin, qmax)
+    return scale, zp
+
+
+def sbfp_scaler_bias_from_amax(amax: float, scaler_exponent_bits: int = 4, man_scaling: int = 7) -> int:
+    """Exponent bias of the SBFP scaler format from a tensor-wide amax.
+
+    The reference delegates this choice to d-Matrix's private ``numerics`` module
+    (S/numerical/format.py:13-20, 438-446), absent from the public repo -- parity is unpinned.
+    Rule used here (hardware-faithful reading of an E-bit exponent field): the largest block
+    scaler of the tensor, amax / man_scaling, must fall in the top binade the field can encode,
+    2^((2^E - 1) - bias); smaller block scalers then use the binades below it."""
+    import math
+
+    default = 2 ** (scaler_exponent_bits - 1) - 1
+    if not (amax > 0) or math.isinf(amax) or math.isnan(amax):
+        return default
+    top = math.floor(math.log2(amax / man_scaling))
+    bias = (2 ** scaler_exponent_bits - 1) - top
+    lo = 127 if scaler_exponent_bits == 8 else -128 + 2 ** scaler_exponent_bits
+    return int(max(lo, min(127, bias)))

@@ -1,0 +1,91 @@
+"""Host-side multi-GPU logic on CPU: shard planning and the batched statistics all-reduce over a
+world_size-2 gloo group (the N > 1 path of SURVEY.md section 8e).  No cast kernels run here."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from dmx_compressor_b200 import parallel as P
+
+LLAMA8B = {f"layers.{i}.{n}": s for i in range(4) for n, s in
+           (("q", (4096, 4096)), ("k", (1024, 4096)), ("v", (1024, 4096)), ("o", (4096, 4096)),
+            ("gate", (14336, 4096)), ("up", (14336, 4096)), ("down", (4096, 14336)))}
+LLAMA8B["lm_head"] = (128256, 4096)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_plan_covers_every_row_exactly_once(world):
+    plan = P.plan_shards(LLAMA8B, world, row_align=1)
+    seen = {}
+    for rank, shards in enumerate(plan):
+        for sh in shards:
+            assert 0 <= sh.row0 < sh.row1 <= sh.rows == LLAMA8B[sh.name][0]
+            seen.setdefault(sh.name, []).append((sh.row0, sh.row1))
+    assert set(seen) == set(LLAMA8B)
+    for n, rs in seen.items():
+        rs.sort()
+        assert rs[0][0] == 0 and rs[-1][1] == LLAMA8B[n][0]
+        assert all(a[1] == b[0] for a, b in zip(rs, rs[1:])), f"{n}: gaps or overlaps {rs}"
+    assert P.plan_imbalance(plan, LLAMA8B) < 1.15
+
+
+def test_plan_row_alignment_for_dim0_blocks():
+    # conv-style block_dim = 0 tensors must be cut at multiples of the block / group size
+    plan = P.plan_shards({"w": (1000, 64)}, 4, split_threshold=0.1, row_align=8)
+    for shards in plan:
+        for sh in shards:
+            assert sh.row0 % 8 == 0 and (sh.row1 % 8 == 0 or sh.row1 == 1000)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(7)
+    full = [torch.randn(64, 48, generator=g) * 3, torch.randn(32, 16, generator=g), torch.randn(10, 8, generator=g)]
+    full[2][3, 4] = float("nan")
+    shards = [t.chunk(world, 0)[rank] for t in full]
+    got = P.sharded_minmax(shards, [None, 1, None])
+    q.put((rank, [(a.clone(), b.clone()) for a, b in got]))
+    dist.destroy_process_group()
+
+
+def test_sharded_minmax_equals_single_device_bitwise():
+    world, port = 2, 29500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    g = torch.Generator().manual_seed(7)
+    full = [torch.randn(64, 48, generator=g) * 3, torch.randn(32, 16, generator=g), torch.randn(10, 8, generator=g)]
+    want = [(full[0].amin().reshape(1), full[0].amax().reshape(1)), (full[1].amin(0), full[1].amax(0))]
+    for rank in range(world):
+        for (mn, mx), (wmn, wmx) in zip(res[rank][:2], want):
+            assert torch.equal(mn, wmn) and torch.equal(mx, wmx)
+        assert torch.isnan(res[rank][2][0]).all() and torch.isnan(res[rank][2][1]).all()  # NaN propagates
+
+
+def test_qparams_match_observer_formula():
+    from dmx_compressor_b200.numerical import Format, MinMaxObserver
+
+    fmt = Format.from_shorthand("XP[8,0](CSN)")
+    x = torch.randn(1000) * 5
+    for scheme, sym in ((torch.per_tensor_symmetric, True), (torch.per_tensor_affine, False)):
+        obs = MinMaxObserver(dtype=fmt, qscheme=scheme)
+        obs.min_val, obs.max_val = x.amin(), x.amax()
+        s, z = obs.calculate_qparams()
+        s2, z2 = P.qparams_from_minmax(x.amin().reshape(1), x.amax().reshape(1), fmt, symmetric=sym)
+        assert torch.equal(s, s2) and torch.equal(z.to(torch.int64), z2.to(torch.int64))
+
+
+def test_sbfp_bias_rule():
+    assert P.sbfp_scaler_bias_from_amax(7 * 2.0**8) == 7       # top binade 2^8 <-> E4 bias 7
+    assert P.sbfp_scaler_bias_from_amax(7 * 2.0**-3) == 18
+    assert P.sbfp_scaler_bias_from_amax(0.0) == 7
