@@ -1,0 +1,174 @@
+"""GPU tests of the callers of the path: the DmxModule mirror, the BASIC
+rule set, weight folding, calibration, cast elision and the OPT-125m-shaped stack.  They read
+like the reference's own tests (tests/test_flexible_quant.py, test_fold_weights_and_biases.py,
+test_group_quant.py, test_sparse.py) and hold the same bit-equality bar."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from util import ROOT, bits
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+if torch.cuda.is_available():
+    from dmx_compressor_b200 import _lib, elide, opt
+    from dmx_compressor_b200 import nn as dmxnn
+    from dmx_compressor_b200.numerical import CastTo, MinMaxObserver
+    from dmx_compressor_b200.sparse import Sparsify, abs_score
+
+    fmt = dmxnn.format
+
+
+def test_linear_equals_hand_composed_casts():
+    """reference tests/test_flexible_quant.py:28-86: a configured module == the CastTo chain, bit for bit"""
+    torch.manual_seed(0)
+    lin = dmxnn.Linear(256, 128).to(DEV)
+    lin.configure(dict(input_formats=[fmt.BFP16A_64], weight_format=fmt.BFP16_64, bias_format=fmt.BFP32_1, output_formats=[fmt.FLOAT16]))
+    x = torch.randn(4, 17, 256, device=DEV)
+    y = lin(x)
+    xi = CastTo(fmt.BFP16A_64, block_dim=-1).to(DEV)(x)
+    w = CastTo(fmt.BFP16_64, block_dim=-1).to(DEV)(lin.weight)
+    b = CastTo(fmt.BFP32_1).to(DEV)(lin.bias)
+    want = CastTo(fmt.FLOAT16).to(DEV)(torch.nn.functional.linear(xi, w, b))
+    assert torch.equal(y, want)
+    # and the casts inside equal the oracle
+    assert (bits(xi.cpu().numpy()) == bits(O.cast(x.cpu().numpy(), "BFP[8|8]{64}(_N)"))).all()
+    assert (bits(w.detach().cpu().numpy()) == bits(O.cast(lin.weight.detach().cpu().numpy(), "BFP[8|8]{64}(SN)"))).all()
+    assert (bits(b.detach().cpu().numpy()) == bits(O.cast(lin.bias.detach().cpu().numpy(), "BFP[24|8]{1}(SN)"))).all()
+
+
+def test_int8_per_tensor_cast_module():
+    """reference tests/test_flexible_quant.py INT8 case: default scale 1 / zero-point 0 affine wrap"""
+    x = torch.randn(8, 64, device=DEV) * 40
+    y = CastTo(fmt.INT8).to(DEV)(x)
+    want = O.cast(x.cpu().numpy(), "XP[8,0](CSN)", tie=O.TIE_AWAY, scale=[1.0], zero_point=[0.0])
+    assert (bits(y.cpu().numpy()) == bits(want)).all()
+
+
+def test_group_quant_kat_with_minmax_calibration():
+    """reference tests/test_group_quant.py:49-63 (INT4, groups of 2 rows, symmetric MinMax)"""
+    cast = CastTo(format=fmt.INT4, observer=MinMaxObserver, group_size=2, qscheme=torch.per_tensor_symmetric, ch_axis=0).to(DEV)
+    cast.enable_observer()
+    x = torch.tensor([[0, 1], [3, 7], [5.1, 8], [10, 14], [0.1, 0.7]], device=DEV)
+    y = torch.tensor([[0, 1], [3, 7], [6, 8], [10, 14], [0.1, 0.7]], device=DEV)
+    assert torch.allclose(cast(x), y, rtol=0.0, atol=1e-6)
+
+
+def test_per_channel_calibration_equals_per_tensor_on_single_channel():
+    """reference tests/test_group_quant.py:144-369 style equivalence: per-channel on a 1-channel view"""
+    x = torch.randn(1, 4096, device=DEV) * 3
+    a = CastTo(format=fmt.INT8, observer=MinMaxObserver, qscheme=torch.per_tensor_symmetric).to(DEV)
+    b = CastTo(format=fmt.INT8, observer=MinMaxObserver, qscheme=torch.per_channel_symmetric, ch_axis=0).to(DEV)
+    a.enable_observer(); b.enable_observer()
+    assert torch.equal(a(x), b(x))
+    assert torch.equal(a.scale.view(-1), b.scale.view(-1))
+
+
+def test_sparsify_gradients_and_mask():
+    """reference tests/test_sparse.py:12-56: gradient routing for the backward modes"""
+    for mode, wg, mg in (("STE", True, False), ("supermask", False, True), ("joint", True, True)):
+        sp = Sparsify((64, 64), "BTOPK{4:8,-1}(U)", backward_mode=mode).to(DEV).train()
+        x = torch.randn(64, 64, device=DEV, requires_grad=True)
+        y = sp(x)
+        y.sum().backward()
+        assert (x.grad is not None) == wg
+        assert (sp.score.grad is not None) == mg
+        assert sp.mask.sum().item() == 64 * 64 // 2
+        if wg:
+            assert torch.equal(x.grad, sp.mask)
+    sp = Sparsify((8, 16), "BTOPK{2:4,-1}(U)").to(DEV).eval()
+    sp.configure(score_func=abs_score)
+    x = torch.randn(8, 16, device=DEV)
+    want = O.nm_prune(x.cpu().numpy(), 2, 4)
+    assert (bits(sp(x).cpu().numpy()) == bits(want)).all()
+
+
+def test_fold_weights_and_biases_is_a_fixed_point():
+    """reference tests/test_fold_weights_and_biases.py:139-148: folding leaves the output bit-identical"""
+    torch.manual_seed(1)
+    model = torch.nn.Sequential(dmxnn.Linear(256, 512), dmxnn.ReLU(), dmxnn.Linear(512, 64)).to(DEV).eval()
+    dmxnn.to_basic_mode(model)
+    for m in (model[0], model[2]):
+        m.configure(dict(weight_format=fmt.BFP12_128, weight_sparseness="BTOPK{2:4,-1}(U)", weight_score_func=abs_score))
+    x = torch.randn(32, 256, device=DEV)
+    with torch.no_grad():
+        m0 = model[0]
+        m0.weight_sparsifier.plastic = True
+        before_w = m0._weight.clone()
+        m0.weight_sparsifier.plastic = True
+        want = O.cast(O.nm_prune(m0.weight.detach().cpu().numpy(), 2, 4), "BFP[4|8]{128}(SN)")
+        assert (bits(before_w.cpu().numpy()) == bits(want)).all()
+        for m in (model[0], model[2]):
+            m.weight_sparsifier.plastic = True
+        y0 = model(x)
+        for m in (model[0], model[2]):
+            m.weight_sparsifier.plastic = True
+        dmxnn.fold_weights_and_biases(model)
+        y1 = model(x)
+    assert torch.equal(y0, y1)
+    assert repr(model[0].weight_format) == "SAME" and repr(model[0].weight_sparseness) == "DENSE"
+
+
+TINY = dict(vocab_size=512, max_position_embeddings=128, hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_opt_stack_basic_mode_elision_is_value_identical(dt):
+    q, p = opt.build_pair(TINY, device=DEV, dtype=dt)
+    ids = torch.randint(0, 512, (2, 96), device=DEV)
+    with torch.no_grad():
+        n0 = _lib.launch_count()
+        y1 = q(ids)
+        n1 = _lib.launch_count()
+        with elide.enabled():
+            y2 = q(ids)
+            n2 = _lib.launch_count()
+            y3 = q(ids)  # second pass: weights come from the cache
+            n3 = _lib.launch_count()
+        yp = p(ids)
+    assert torch.equal(y1, y2) and torch.equal(y1, y3)
+    assert n3 - n2 < n2 - n1 < n1 - n0
+    # BASIC-mode logits stay close to the unquantised twin (BFP16 / FLOAT16 noise only)
+    assert torch.isfinite(y1).all()
+    rel = (y1.float() - yp.float()).norm() / yp.float().norm()
+    assert rel < 0.1, rel
+
+
+def test_opt_layer_casts_match_oracle():
+    """first Linear of the stack, module boundary by module boundary against the CPU oracle"""
+    q, _ = opt.build_pair(TINY, device=DEV, dtype=torch.float32)
+    lin = q.layers[0].q_proj
+    x = torch.randn(2, 96, 128, device=DEV)
+    with torch.no_grad():
+        y = lin(x)
+    xi = O.cast(x.cpu().numpy(), "BFP[8|8]{64}(SN)")
+    w = O.cast(lin.weight.detach().cpu().numpy(), "BFP[8|8]{64}(SN)")
+    b = O.cast(lin.bias.detach().cpu().numpy(), "BFP[24|8]{1}(SN)")
+    pre = torch.nn.functional.linear(torch.from_numpy(xi).to(DEV), torch.from_numpy(w).to(DEV), torch.from_numpy(b).to(DEV))
+    want = O.cast(pre.cpu().numpy(), "FP[1|5|10,15](FN)")
+    assert (bits(y.cpu().numpy()) == bits(want)).all()
+
+
+def test_fused_hypernet_equals_module_by_module():
+    torch.manual_seed(3)
+    lin = dmxnn.Linear(512, 256).to(DEV).eval()
+    lin.configure(dict(weight_format=fmt.BFP16_64, weight_storage_format=fmt.SBFP12_16, weight_sparseness="BTOPK{4:8,-1}(U)",
+                       weight_score_func=abs_score))
+    with torch.no_grad():
+        a = lin._weight.clone()
+        lin.weight_sparsifier.plastic = True
+        n0 = _lib.launch_count()
+        with elide.enabled():
+            b = lin._weight
+        assert _lib.launch_count() - n0 == 1  # sparsify -> storage cast -> weight cast: ONE kernel
+    assert torch.equal(a, b)
+    want = O.cast(O.cast(O.nm_prune(lin.weight.detach().cpu().numpy(), 4, 8), "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", tie=O.TIE_AWAY),
+                  "BFP[8|8]{64}(SN)")
+    assert (bits(a.cpu().numpy()) == bits(want)).all()
