@@ -172,3 +172,34 @@ def test_fused_hypernet_equals_module_by_module():
     want = O.cast(O.cast(O.nm_prune(lin.weight.detach().cpu().numpy(), 4, 8), "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", tie=O.TIE_AWAY),
                   "BFP[8|8]{64}(SN)")
     assert (bits(a.cpu().numpy()) == bits(want)).all()
+
+
+def test_lenet5_example_config_against_reference_golden():
+    """BASELINE config #1: LeNet-5 with the example yaml's per-module config; every cast bit-equal to
+    the reference's CPU path given the same layer input, logits within conv/GEMM-order tolerance."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "lenet5_reference.npz"))
+    conv1, conv2 = dmxnn.Conv2d(1, 6, 5), dmxnn.Conv2d(6, 16, 5)
+    fc1, fc2, fc3 = dmxnn.Linear(400, 120), dmxnn.Linear(120, 84), dmxnn.Linear(84, 10)
+    mods = dict(conv1=conv1, conv2=conv2, fc1=fc1, fc2=fc2, fc3=fc3)
+    cfg = dict(input_formats=[fmt.BFP16_64], weight_format=fmt.BFP16_64, bias_format=fmt.SAME, output_formats=[fmt.FLOAT16])
+    for n, m in mods.items():
+        with torch.no_grad():
+            m.weight.copy_(torch.from_numpy(z[n + ".weight"]))
+            m.bias.copy_(torch.from_numpy(z[n + ".bias"]))
+        m.to(DEV).eval()
+        m.configure(cfg)
+    F = torch.nn.functional
+    with torch.no_grad():
+        for n, m in mods.items():
+            h = torch.from_numpy(z[n + ".in"]).to(DEV)
+            hi = m.input_casts.input_cast(h)
+            assert (bits(hi.cpu().numpy()) == z[n + ".in_cast"]).all(), f"{n} input cast"
+            assert (bits(m._weight.cpu().numpy()) == z[n + ".w_cast"]).all(), f"{n} weight cast"
+            pre = torch.from_numpy(z[n + ".pre"]).to(DEV)
+            assert (bits(m.output_casts.output_cast(pre).cpu().numpy()) == z[n + ".out"]).all(), f"{n} output cast"
+        x = torch.from_numpy(z["x"]).to(DEV)
+        h = F.max_pool2d(F.relu(conv1(x)), (2, 2))
+        h = F.max_pool2d(F.relu(conv2(h)), 2)
+        h = torch.flatten(h, 1)
+        h = fc3(F.relu(fc2(F.relu(fc1(h)))))
+    np.testing.assert_allclose(h.cpu().numpy(), z["logits"], rtol=0, atol=2e-3)
