@@ -237,13 +237,16 @@ def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_sta
     from dmx_compressor_b200 import ops
 
     def run():
-        st = stages_fn(None)
         if with_stats:
-            stats = P.sharded_minmax(ws)  # local dmxq_minmax per shard + ONE all_reduce(MAX)
-            amax = float(torch.cat([torch.maximum(-mn, mx).reshape(-1) for mn, mx in stats]).max())  # one host sync
-            st = stages_fn(amax)
-        for w, y in zip(ws, outs):
-            ops.cast_chain(w, st, -1, out=y)
+            # per-tensor amax: local dmxq_minmax per shard + ONE all_reduce(MAX) for the row-split tensors
+            stats = P.shard_stats(plan, rank, ws)
+            amax = torch.cat([torch.maximum(-mn, mx).reshape(-1) for mn, mx in stats]).cpu().tolist()  # one host sync
+            for w, y, a in zip(ws, outs, amax):
+                ops.cast_chain(w, stages_fn(a), -1, out=y)
+        else:
+            st = stages_fn(None)
+            for w, y in zip(ws, outs):
+                ops.cast_chain(w, st, -1, out=y)
 
     run()
     if dist is not None:

@@ -154,6 +154,28 @@ def sharded_minmax(tensors: Sequence[torch.Tensor], ch_axes: Optional[Sequence[O
     return allreduce_minmax([local_minmax(t, a) for t, a in zip(tensors, ch_axes)], group)
 
 
+def shard_stats(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tensor], group=None):
+    """Per-tensor (amin, amax) for the shards `tensors` that `plan[rank]` lists, as if every
+    tensor were whole.  Tensors owned entirely by one rank need no communication; the row-split
+    ones (the same set, in the same order, on every rank) share ONE all-reduce."""
+    mine = plan[rank]
+    local = [local_minmax(t) for t in tensors]
+    split_names = sorted({sh.name for shards in plan for sh in shards if not sh.whole})
+    if split_names:
+        pos = {n: i for i, n in enumerate(split_names)}
+        dev = tensors[0].device if tensors else torch.device("cpu")
+        mn = torch.full((len(split_names),), float("inf"), device=dev)
+        mx = torch.full((len(split_names),), float("-inf"), device=dev)
+        for sh, (a, b) in zip(mine, local):
+            if not sh.whole:
+                mn[pos[sh.name]] = a[0]
+                mx[pos[sh.name]] = b[0]
+        (rmn, rmx), = allreduce_minmax([(mn, mx)], group)
+        local = [(rmn[pos[sh.name]].reshape(1), rmx[pos[sh.name]].reshape(1)) if not sh.whole else st
+                 for sh, st in zip(mine, local)]
+    return local
+
+
 def qparams_from_minmax(mn: torch.Tensor, mx: torch.Tensor, fmt, symmetric: bool = True, eps: float = torch.finfo(torch.float32).eps):
     """scale / zero-point exactly as MinMaxObserver._calculate_qparams (reference
     S/numerical/observer.py:59-115) computes them from (reduced) statistics."""

@@ -89,3 +89,40 @@ def test_sbfp_bias_rule():
     assert P.sbfp_scaler_bias_from_amax(7 * 2.0**8) == 7       # top binade 2^8 <-> E4 bias 7
     assert P.sbfp_scaler_bias_from_amax(7 * 2.0**-3) == 18
     assert P.sbfp_scaler_bias_from_amax(0.0) == 7
+
+
+def _worker_stats(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {"big": (64, 32), "a": (8, 32), "b": (6, 32), "c": (4, 32)}
+    plan = P.plan_shards(shapes, world, split_threshold=0.5)
+    g = torch.Generator().manual_seed(11)
+    full = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+    mine = [full[sh.name][sh.row0:sh.row1] for sh in plan[rank]]
+    stats = P.shard_stats(plan, rank, mine)
+    q.put((rank, [(sh.name, float(a), float(b)) for sh, (a, b) in zip(plan[rank], stats)]))
+    dist.destroy_process_group()
+
+
+def test_shard_stats_mixed_whole_and_split_tensors():
+    """ranks own different whole tensors plus a slice of the split one: one all-reduce, exact result"""
+    world, port = 2, 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_stats, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    shapes = {"big": (64, 32), "a": (8, 32), "b": (6, 32), "c": (4, 32)}
+    g = torch.Generator().manual_seed(11)
+    full = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+    seen = set()
+    for rank in range(world):
+        for name, mn, mx in res[rank]:
+            assert mn == float(full[name].min()) and mx == float(full[name].max()), name
+            seen.add(name)
+    assert seen == set(shapes)
