@@ -251,8 +251,14 @@ int run_generic(const dmxq_tensor *x, const dmxq_tensor *y, const Canon &c, cons
     return DMXQ_OK;
 }
 
+// qscale / qzp (nullable): device-resident per-tensor FixedPoint affine parameters; only the vectorised rows
+// kernel consumes them -- when the layout needs another path the call returns kNeedFallback (no message) and
+// dmxq_fixed_qdq falls back to fixed_chan_kernel.
+constexpr int kNeedFallback = -100;
+
 int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const dmxq_stage *stages, int n_stages,
-               const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, cudaStream_t st)
+               const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, cudaStream_t st,
+               const float *qscale = nullptr, const float *qzp = nullptr)
 {
     if (!x || !y || !stages) return fail(DMXQ_ERR_BAD_ARG, "null argument");
     if (n_stages < 1 || n_stages > DMXQ_MAX_STAGES) return fail(DMXQ_ERR_BAD_ARG, "n_stages must be 1..%d, got %d", DMXQ_MAX_STAGES, n_stages);
@@ -392,6 +398,11 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         else if (chain.n == 2 && float_fast(chain.st[0]) && bfp_ns(chain.st[1])) kind = 4;  // K_FLOAT_BFP
         else if (chain.n == 2 && chain.st[0].kind == ST_NM && bfp_ns(chain.st[1])) kind = 5;  // K_NM_BFP
         else if (chain.n == 1 && chain.st[0].kind == ST_SBFP && chain.st[0].sb.xp.mode == R_NEAREST && chain.st[0].sb.xp.tie == TIE_AWAY) kind = 6;  // K_SBFP
+        else if (chain.n == 1 && chain.st[0].kind == ST_FIXED && chain.st[0].xf.mode == R_NEAREST && chain.st[0].xf.tie == TIE_AWAY) kind = 7;  // K_FIXED
+        if (qscale) {
+            if (kind != 7) return kNeedFallback;
+            p.qscale = qscale; p.qzp = qzp;
+        }
         const int special = kind;
         if (rows_ok) {
             cudaError_t e = launch_rows(x->dtype, y->dtype, flat, special, p, st);
@@ -399,6 +410,8 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
             return DMXQ_OK;
         }
     }
+
+    if (qscale) return kNeedFallback;
 
     // ---------------------------------------------------------------- cols path
     if (blocked && !score_p && !mask_p && c.k.n > 1) {
@@ -545,6 +558,15 @@ int dmxq_fixed_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int fl, i
         s.kind = DMXQ_STAGE_FIXED; s.precision = wl; s.fraction = fl; s.clamp = clamp; s.symmetric = symmetric;
         s.rounding = rounding; s.tie = tie; s.scale = 1.0f; s.zero_point = 0.0f;
         return chain_impl(x, y, -1, &s, 1, nullptr, nullptr, rand, st);
+    }
+    if (n_qparams == 1 && rounding == DMXQ_ROUND_NEAREST && tie == DMXQ_TIE_AWAY) {
+        // per-tensor parameters: the vectorised rows kernel reads them from device memory
+        dmxq_stage s;
+        memset(&s, 0, sizeof(s));
+        s.kind = DMXQ_STAGE_FIXED; s.precision = wl; s.fraction = fl; s.clamp = clamp; s.symmetric = symmetric;
+        s.rounding = rounding; s.tie = tie; s.scale = 1.0f; s.zero_point = 0.0f;
+        int rc = chain_impl(x, y, -1, &s, 1, nullptr, nullptr, nullptr, st, scale, zero_point);
+        if (rc != kNeedFallback) return rc;
     }
     // device-resident qparams: contiguous tensors only (what observers produce them for)
     if (!same_shape(x, y)) return fail(DMXQ_ERR_BAD_ARG, "x and y must have the same shape");

@@ -48,6 +48,7 @@ struct RowsParams {
     const float *score;  // nullable, NM stage
     float *mask;         // nullable, NM stage
     const void *rnd;     // nullable, stochastic stage (int32 or fp32)
+    const float *qscale, *qzp;  // nullable: per-tensor FixedPoint affine parameters in device memory (K_FIXED)
     int64_t n_vec;       // total (padded) vectors = rows * vpr
     int64_t rows;
     int64_t K;

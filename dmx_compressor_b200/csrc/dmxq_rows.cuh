@@ -19,12 +19,13 @@
 //   K_FLOAT_BFP  [FLOAT nearest+flush+signed -> BFP n.s.]     output cast fused with next input cast
 //   K_NM_BFP     [N:M with score |x| -> BFP n.s.]             sparsify -> weight cast (hypernet)
 //   K_SBFP       [SBFP, XP nearest half-away]                 SBFP weight storage cast
+//   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_COUNT = 7 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_COUNT = 8 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -156,13 +157,34 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             }
             const StageDev &st = p.chain.st[1];
             uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
-            bfp_ns_apply<V, false>(v, m, st);
+            bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, m, st);  // after the requant the values carry Tout's significand
         } else if (KIND == K_NM_BFP) {
             VecIO<Tin>::unpack(raw[u], v);
             nm_stage<V>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);
             const StageDev &st = p.chain.st[1];
             uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_FIXED) {
+            // CastTo.forward for FixedPoint (S/numerical/cast.py:279-296): x/sc + zp -> round -> clamp -> (q - zp)*sc,
+            // every step a separately rounded fp32 op.  sc == 1 makes the division and the final multiply exact
+            // identities, zp == 0 the final subtraction; the leading "+ zp" is kept (it turns -0 into +0).
+            const StageDev &st = p.chain.st[0];
+            const bool wrap = st.affine || p.qscale != nullptr;
+            const float sc = p.qscale ? __ldg(p.qscale) : st.sc;
+            const float zp = p.qzp ? __ldg(p.qzp) : st.zp;
+            const bool unit = sc == 1.0f, scaled = st.xf.up != 1.0f;
+            VecIO<Tin>::unpack(raw[u], v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float a = v[j];
+                if (wrap) a = __fadd_rn(unit ? a : __fdiv_rn(a, sc), zp);
+                if (scaled) a = __fmul_rn(a, st.xf.up);
+                a = roundf(a);
+                if (scaled) a = __fmul_rn(a, st.xf.down);
+                if (st.xf.clamp) a = a > st.xf.t_max ? st.xf.t_max : (a < st.xf.t_min ? st.xf.t_min : a);
+                if (wrap && !(unit && zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, zp), sc);
+                v[j] = a;
+            }
         } else if (KIND == K_SBFP) {
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);

@@ -142,14 +142,19 @@ __device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const S
 {
     SbfpBlock b;
     b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
-    b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
+    // scaler cast: cmax >= 0 (or NaN, in which case the block passes through and fs is unused), so the
+    // unsigned scaler formats of the SBFP aliases reduce to the signed nearest+flush fast path
+    if (f.sc.mode == R_NEAREST && f.sc.flush && (!f.sc.fp16_flush || f.sc.min_exp >= -14)) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
+    else b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
     b.on = b.cmax > 0.0f;
     return b;
 }
 __device__ __forceinline__ bool sbfp_fast(const SbfpFmt &f) { return f.xp.mode == R_NEAREST && f.xp.tie == TIE_AWAY; }
+// XP[p,0] nearest, half away (the reference's CUDA rule) of the IEEE quotient; fl = 0 => no scaling
+// multiplies.  (A reciprocal-estimate-and-verify variant was measured slower than the hardware
+// division sequence on B200 and dropped.)
 __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, const SbfpFmt &f)
 {
-    // XP[p,0] nearest, half away (the reference's CUDA behaviour): fl = 0 => no scaling multiplies
     float v = roundf(__fdiv_rn(x, b.cmax));
     if (f.xp.clamp) v = v > f.xp.t_max ? f.xp.t_max : (v < f.xp.t_min ? f.xp.t_min : v);
     return b.on ? __fmul_rn(v, b.fs) : x;

@@ -527,3 +527,43 @@ def test_host_entry_matches_device():
     ops.cast_chain_host(xh, yh, st, 0)
     want = ops.cast_chain(x.to(DEV), st, -1).cpu()
     assert torch.equal(yh.view(torch.int32), want.view(torch.int32))
+
+
+def test_sbfp_on_adversarial_ties():
+    """SBFP rounds fl(x / cmax) half-away: hammer exactly the boundaries (k + 0.5) * cmax +- a few ulps,
+    where any shortcut around the IEEE division would show."""
+    g = torch.Generator().manual_seed(77)
+    rows = []
+    for _ in range(512):
+        m = (torch.rand(1, generator=g) * 4 + 0.1) * 2.0 ** int(torch.randint(-20, 20, (1,), generator=g))
+        cmax = (m / 7.0).float()
+        k = torch.randint(0, 7, (15,), generator=g).float() + 0.5
+        x = (k * cmax).float()
+        ulps = torch.randint(-3, 4, (15,), generator=g)
+        x = (x.view(torch.int32) + ulps.int()).view(torch.float32)
+        x = x * (torch.randint(0, 2, (15,), generator=g).float() * 2 - 1)
+        rows.append(torch.cat([m.float(), x]))
+    x = torch.stack(rows)
+    for sh in ("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,12](FN)>{16}", "SBFP<XP[4,0](_SN)><FP[1|5|10,15](FN)>{16}"):
+        want = O.cast(x.numpy(), sh, -1, tie=O.TIE_AWAY)
+        check(gpu_cast(x.to(DEV), sh, -1), bits(want), sh)
+        xb = x.to(torch.bfloat16)
+        want = O.cast(xb.float().numpy(), sh, -1, tie=O.TIE_AWAY)
+        check(gpu_cast(xb.to(DEV), sh, -1), bits(want), sh + " bf16")
+
+
+def test_int8_device_qparams_fast_path():
+    """CastTo(INT8/INT4) per-tensor: vectorised kernel reading scale / zero-point from device memory"""
+    x = _rand((64, 1024), 91, spread=3) * 20
+    for sc, zp in ((1.0, 0.0), (0.05, 3.0), (0.37, -2.0)):
+        for fmt in ("XP[8,0](CSN)", "XP[4,0](CSN)", "XP[8,+2](C_N)"):
+            f = fmt_from(fmt)
+            want = O.cast(x.numpy(), fmt, tie=O.TIE_AWAY, scale=[sc], zero_point=[zp])
+            y = ops.fixed_qdq(x.to(DEV), f.precision, f.fraction, f.clamp, f.symmetric, "nearest", scale=torch.tensor([sc], device=DEV),
+                              zero_point=torch.tensor([zp], device=DEV))
+            check(y, bits(want), f"{fmt} sc={sc} zp={zp}")
+            xb = x.to(torch.bfloat16)
+            want = torch.from_numpy(O.cast(xb.float().numpy(), fmt, tie=O.TIE_AWAY, scale=[sc], zero_point=[zp])).to(torch.bfloat16)
+            y = ops.fixed_qdq(xb.to(DEV), f.precision, f.fraction, f.clamp, f.symmetric, "nearest", scale=torch.tensor([sc], device=DEV),
+                              zero_point=torch.tensor([zp], device=DEV))
+            check(y, want.view(torch.int16).numpy().view(np.uint16), f"{fmt} bf16 sc={sc}", dtype="bfloat16")
