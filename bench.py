@@ -275,6 +275,46 @@ def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_sta
             "dtype": str(dtype).split(".")[-1], "layers": layers if layers is not None else LLAMA[model]["layers"]}
 
 
+def extra_sweep(dev):
+    """configs[1] in full: BFP16_64 / BFP12_64 on fp32 / bf16 tensors of 2^20 .. 2^30 elements ([n/4096, 4096]).
+    Sizes whose input + output fit the 126 MB L2 are timed over 8 rotating buffer pairs so that every launch
+    streams from HBM (labelled hbm_rotating); CUDA events around 20 back-to-back launches, median of 5."""
+    import torch
+
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format
+
+    out = []
+    for dt, es in ((torch.float32, 4), (torch.bfloat16, 2)):
+        for e in (20, 22, 24, 26, 28, 30):
+            n = 1 << e
+            footprint = 2 * n * es
+            nbuf = 8 if footprint * 2 < (1 << 30) else 1
+            xs = [torch.randn(n // COLS, COLS, device=dev).to(dt) for _ in range(nbuf)]
+            ys = [torch.empty_like(x) for x in xs]
+            for name, sh, _ in FORMATS:
+                st = [Format.from_shorthand(sh).stage()]
+                reps = 20
+                for i in range(3):
+                    ops.cast_chain(xs[i % nbuf], st, -1, out=ys[i % nbuf])
+                ts = []
+                for _ in range(5):
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    a.record()
+                    for i in range(reps):
+                        ops.cast_chain(xs[i % nbuf], st, -1, out=ys[i % nbuf])
+                    b.record()
+                    torch.cuda.synchronize()
+                    ts.append(a.elapsed_time(b) / reps)
+                ts.sort()
+                out.append({"format": name, "dtype": str(dt).split(".")[-1], "log2_elements": e, "us_per_cast": round(ts[2] * 1e3, 2),
+                            "GB/s": round(footprint / ts[2] / 1e6, 1), "mode": "hbm_rotating" if nbuf > 1 else "hbm"})
+            del xs, ys
+            torch.cuda.empty_cache()
+    return out
+
+
 def extra_opt125m(dev):
     """BASELINE config #3: OPT-125m-shaped random-init stack, batch 8 x seq 2048 forward, BASIC rule set.
     tokens/s for the unquantised torch twin, the drop-in BASIC path, and BASIC with cast elision."""
@@ -284,20 +324,21 @@ def extra_opt125m(dev):
 
     res = {}
     B, S = 8, 2048
+
+    def timeit(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
     for dt in (torch.float32, torch.bfloat16):
         q, p = opt.build_pair(device=dev, dtype=dt)
         ids = torch.randint(0, 50272, (B, S), device=dev)
-
-        def timeit(fn, n=3):
-            fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(n):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / n
 
         with torch.no_grad():
             t_plain = timeit(lambda: p(ids))
@@ -319,6 +360,23 @@ def extra_opt125m(dev):
             "dmxq_launches_elided": n3 - n2, "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2))}
         del q, p, y1, y2
         torch.cuda.empty_cache()
+    # small-batch latency: launch-bound eagerly, so also as a captured CUDA graph
+    try:
+        from dmx_compressor_b200 import graph
+
+        q, p = opt.build_pair(device=dev, dtype=torch.float32)
+        ids = torch.randint(0, 50272, (4, 128), device=dev)
+        with torch.no_grad():
+            want = q(ids)
+            t_eager = timeit(lambda: q(ids), 5)
+        fq, fp = graph.capture(q, ids), graph.capture(p, ids)
+        res["small_batch_4x128_fp32"] = {"ms_basic_eager": round(t_eager, 2), "ms_basic_cuda_graph": round(timeit(lambda: fq(ids), 20), 2),
+                                         "ms_unquantised_cuda_graph": round(timeit(lambda: fp(ids), 20), 2),
+                                         "graph_equals_eager_bitwise": bool(torch.equal(fq(ids), want))}
+        del q, p, fq, fp
+        torch.cuda.empty_cache()
+    except Exception as e:  # pragma: no cover
+        res["small_batch_4x128_fp32"] = {"error": repr(e)}
     res["config"] = "OPT-125m shape (12 layers, d=768, ffn=3072, 12 heads, vocab 50272), random init, batch 8 x seq 2048, config_rules.BASIC"
     return res
 
@@ -448,6 +506,10 @@ def run_ours(args):
             dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16)
         extras["llama3_70b_sbfp12_weight_cast"]["note"] = "10 layers per GPU (weak scaling; 80 layers at 8 GPUs), one batched amax all-reduce"
         if rank == 0:
+            try:
+                extras["cast_sweep"] = extra_sweep(dev)
+            except Exception as e:  # pragma: no cover
+                extras["cast_sweep"] = {"error": repr(e)}
             try:
                 extras["opt125m_basic_forward"] = extra_opt125m(dev)
             except Exception as e:  # pragma: no cover

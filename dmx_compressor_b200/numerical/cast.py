@@ -234,12 +234,17 @@ class CastTo(FakeQuantize):
                 sc, zp = self.scale, self.zero_point
             else:
                 sc, zp = self.scale, self.zero_point
+            if not (torch.is_grad_enabled() and x.requires_grad):  # no tape needed: skip the autograd.Function hop
+                return ops.fixed_qdq(x, fmt.precision, fmt.fraction, fmt.clamp, fmt.symmetric, fmt.rounding, fmt.tie, sc, zp,
+                                     ch_axis=ch_axis, group_size=group)
             return _FusedFixedAffine.apply(x, fmt, sc, zp, ch_axis, group)
         if isinstance(fmt, Format):
             if fmt.stage() is None:
                 return CastToFormat.apply(x, fmt, self.block_dim)
             if hasattr(fmt, "_identity_for") and fmt._identity_for(x.dtype) and not fmt.unsigned:
                 return x
+            if not (torch.is_grad_enabled() and x.requires_grad):
+                return ops.cast_chain(x, [fmt.stage()], self.block_dim)
             return _FusedCast.apply(x, fmt, self.block_dim)
         return super().forward(x)  # plain torch.dtype fake-quant
 

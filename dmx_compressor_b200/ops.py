@@ -15,6 +15,23 @@ import torch
 from . import _lib as L
 
 
+class _guard:
+    """device guard that costs nothing when x already lives on the current device"""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None if device.index == torch.cuda.current_device() else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 def _out_like(x: torch.Tensor, dtype: Optional[torch.dtype]) -> torch.Tensor:
     dtype = dtype or x.dtype
     if x.is_contiguous() or x.numel() == 0:
@@ -85,7 +102,7 @@ def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, 
         if not rand.is_contiguous() or rand.shape != x.shape or rand.element_size() != 4:
             raise RuntimeError("dmxq: rand must be a contiguous 4-byte tensor with the shape of x")
         rp = rand.data_ptr()
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_cast_chain(C.byref(vx), C.byref(vy), block_dim, arr, n, vs, vm, rp, L.stream_ptr(x.device))
     L.check(rc, "dmxq_cast_chain")
     return y
@@ -99,7 +116,7 @@ def bfp_qdq(x, block_dim=-1, block_size=64, precision=8, symmetric=True, roundin
         rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:40
     y = out if out is not None else _out_like(x, out_dtype)
     vx, vy = L.view(x), L.view(y)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), block_dim, block_size, precision, int(symmetric),
                                 L.ROUND[rounding], rand.data_ptr() if rand is not None else None, L.stream_ptr(x.device))
     L.check(rc, "dmxq_bfp_qdq")
@@ -113,7 +130,7 @@ def sbfp_qdq(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_r
     L.require_cuda(x)
     y = out if out is not None else _out_like(x, out_dtype)
     vx, vy = L.view(x), L.view(y)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_sbfp_qdq(C.byref(vx), C.byref(vy), block_dim, block_size, xp_precision, int(xp_clamp),
                                  L.ROUND[xp_rounding], tie, sc_mantissa, sc_exponent, sc_bias, int(sc_flush),
                                  int(sc_unsigned), int(sc_fp16_flush), L.ROUND[sc_rounding], L.stream_ptr(x.device))
@@ -129,7 +146,7 @@ def float_qdq(x, mantissa, exponent, bias, flush_subnormal=True, unsigned=False,
         rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:160
     y = out if out is not None else _out_like(x, out_dtype)
     vx, vy = L.view(x), L.view(y)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_float_qdq(C.byref(vx), C.byref(vy), mantissa, exponent, bias, int(flush_subnormal), int(unsigned),
                                   int(fp16_flush), L.ROUND[rounding], rand.data_ptr() if rand is not None else None,
                                   L.stream_ptr(x.device))
@@ -155,7 +172,7 @@ def fixed_qdq(x, precision, fraction, clamp=True, symmetric=True, rounding="near
             x = x.contiguous()
     y = out if out is not None else _out_like(x, out_dtype)
     vx, vy = L.view(x), L.view(y)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_fixed_qdq(C.byref(vx), C.byref(vy), precision, fraction, int(clamp), int(symmetric), L.ROUND[rounding],
                                   tie, sp, zp, nq, ch_axis, group_size or 1, rand.data_ptr() if rand is not None else None,
                                   L.stream_ptr(x.device))
@@ -176,7 +193,7 @@ def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None
         vs = C.byref(L.view(score))
     if mask is not None:
         vm = C.byref(L.view(mask))
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_nm_prune(C.byref(vx), vs, C.byref(vy), vm, block_dim, n_keep, m, L.stream_ptr(x.device))
     L.check(rc, "dmxq_nm_prune")
     return (y, mask) if return_mask else y
@@ -190,7 +207,7 @@ def minmax(x, ch_axis: Optional[int] = None):
     mn = torch.empty(c, dtype=torch.float32, device=x.device)
     mx = torch.empty(c, dtype=torch.float32, device=x.device)
     vx = L.view(x)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_minmax(C.byref(vx), -1 if ch_axis is None else ch_axis % x.dim(), mn.data_ptr(), mx.data_ptr(),
                                L.stream_ptr(x.device))
     L.check(rc, "dmxq_minmax")
@@ -210,7 +227,7 @@ def block_quantize_l1(x, wl, dim=-1, symmetric=True, rounding="stochastic", rand
     c = 1 if dim == -1 else x.shape[dim]
     ws = torch.empty(3 * max(c, 1), dtype=torch.int32, device=x.device)
     vx, vy = L.view(x), L.view(y)
-    with torch.cuda.device(x.device):
+    with _guard(x.device):
         rc = L.lib.dmxq_block_quantize(C.byref(vx), C.byref(vy), wl, dim, int(symmetric), L.ROUND[rounding],
                                        rand.data_ptr() if rand is not None else None, ws.data_ptr(), L.stream_ptr(x.device))
     L.check(rc, "dmxq_block_quantize")

@@ -203,3 +203,21 @@ def test_lenet5_example_config_against_reference_golden():
         h = torch.flatten(h, 1)
         h = fc3(F.relu(fc2(F.relu(fc1(h)))))
     np.testing.assert_allclose(h.cpu().numpy(), z["logits"], rtol=0, atol=2e-3)
+
+
+def test_basic_forward_is_cuda_graph_capturable():
+    """kernels run on the current stream, never sync, never allocate: capture + replay == eager, bit for bit"""
+    from dmx_compressor_b200 import graph
+
+    q, _ = opt.build_pair(TINY, device=DEV, dtype=torch.float32)
+    ids = torch.randint(0, 512, (2, 64), device=DEV)
+    with torch.no_grad():
+        want = q(ids)
+    fwd = graph.capture(q, ids)
+    assert torch.equal(fwd(ids), want)
+    ids2 = torch.randint(0, 512, (2, 64), device=DEV)
+    with torch.no_grad():
+        want2 = q(ids2)
+    assert torch.equal(fwd(ids2), want2)
+    fwd_e = graph.capture(q, ids, elide_casts=True)
+    assert torch.equal(fwd_e(ids2), want2)
