@@ -399,6 +399,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         else if (chain.n == 2 && chain.st[0].kind == ST_NM && bfp_ns(chain.st[1])) kind = 5;  // K_NM_BFP
         else if (chain.n == 1 && chain.st[0].kind == ST_SBFP && chain.st[0].sb.xp.mode == R_NEAREST && chain.st[0].sb.xp.tie == TIE_AWAY) kind = 6;  // K_SBFP
         else if (chain.n == 1 && chain.st[0].kind == ST_FIXED && chain.st[0].xf.mode == R_NEAREST && chain.st[0].xf.tie == TIE_AWAY) kind = 7;  // K_FIXED
+        else if (chain.n == 1 && chain.st[0].kind == ST_NM) kind = 8;  // K_NM
         if (qscale) {
             if (kind != 7) return kNeedFallback;
             p.qscale = qscale; p.qzp = qzp;

@@ -19,13 +19,14 @@
 //   K_FLOAT_BFP  [FLOAT nearest+flush+signed -> BFP n.s.]     output cast fused with next input cast
 //   K_NM_BFP     [N:M with score |x| -> BFP n.s.]             sparsify -> weight cast (hypernet)
 //   K_SBFP       [SBFP, XP nearest half-away]                 SBFP weight storage cast
+//   K_NM         [N:M with score |x|]                          Sparsify alone (no mask output)
 //   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_COUNT = 8 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_COUNT = 9 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
 {
     constexpr int V = VecIO<Tin>::V;
     constexpr bool SRC16 = sizeof(Tin) == 2;
+    constexpr int SRCBITS = std::is_same<Tin, __nv_bfloat16>::value ? 16 : (std::is_same<Tin, __half>::value ? 11 : 32);
     const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
     Tout *__restrict__ y = static_cast<Tout *>(p.y);
     const int lane = threadIdx.x & 31;
@@ -160,10 +162,13 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, m, st);  // after the requant the values carry Tout's significand
         } else if (KIND == K_NM_BFP) {
             VecIO<Tin>::unpack(raw[u], v);
-            nm_stage<V>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);
+            nm_stage<V>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);  // (pairwise ranks measured faster here than the packed-key network)
             const StageDev &st = p.chain.st[1];
             uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_NM) {
+            VecIO<Tin>::unpack(raw[u], v);
+            nm_stage<V, SRCBITS>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);
         } else if (KIND == K_FIXED) {
             // CastTo.forward for FixedPoint (S/numerical/cast.py:279-296): x/sc + zp -> round -> clamp -> (q - zp)*sc,
             // every step a separately rounded fp32 op.  sc == 1 makes the division and the final multiply exact
@@ -210,8 +215,12 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                 }
                 switch (st.kind) {
                 case ST_NM:
-                    nm_stage<V>(v, st, lane, (KIND == K_AUX && p.score) ? p.score + aux_s[u] : nullptr,
-                                (KIND == K_AUX && p.mask) ? p.mask + aux_m[u] : nullptr, valid[u]);
+                    if (s == 0)  // values still carry the source dtype's significand
+                        nm_stage<V, SRCBITS>(v, st, lane, (KIND == K_AUX && p.score) ? p.score + aux_s[u] : nullptr,
+                                             (KIND == K_AUX && p.mask) ? p.mask + aux_m[u] : nullptr, valid[u]);
+                    else
+                        nm_stage<V>(v, st, lane, (KIND == K_AUX && p.score) ? p.score + aux_s[u] : nullptr,
+                                    (KIND == K_AUX && p.mask) ? p.mask + aux_m[u] : nullptr, valid[u]);
                     break;
                 case ST_BFP: bfp_stage<V>(v, st, lanes, r); break;
                 case ST_SBFP: sbfp_stage<V>(v, st, lanes); break;

@@ -8,6 +8,7 @@ cudaError_t launch_rows_c(int kind, int in_dt, int out_dt, bool flat, const Rows
     if (kind == K_FLOAT_BFP) return launch_rows_kind<K_FLOAT_BFP>(in_dt, out_dt, flat, p, s);
     if (kind == K_NM_BFP) return launch_rows_kind<K_NM_BFP>(in_dt, out_dt, flat, p, s);
     if (kind == K_FIXED) return launch_rows_kind<K_FIXED>(in_dt, out_dt, flat, p, s);
+    if (kind == K_NM) return launch_rows_kind<K_NM>(in_dt, out_dt, flat, p, s);
     return launch_rows_kind<K_SBFP>(in_dt, out_dt, flat, p, s);
 }
 

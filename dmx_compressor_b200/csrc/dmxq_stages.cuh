@@ -289,6 +289,43 @@ template <int V, int M> __device__ __forceinline__ void nm_local(const uint32_t 
     }
 }
 
+// N:M inside one thread for 16-bit sources scored by |x| (M <= 8): the |x| pattern of a bf16 / fp16
+// value fits 19 bits, so (pattern << 3) | index is a *unique* 22-bit key whose order is exactly the
+// stable ascending order.  A min/max sorting network on the keys yields the n_prune-th smallest;
+// everything at or above it is kept.  5 compare-exchanges for M = 4, 19 for M = 8.
+__device__ __forceinline__ void cex(uint32_t &a, uint32_t &b) { uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+template <int V, int M, int KEYSHIFT> __device__ __forceinline__ void nm_local16(const float (&v)[V], int n_prune, bool (&keep)[V])
+{
+#pragma unroll
+    for (int g0 = 0; g0 < V; g0 += M) {
+        uint32_t k[M], s[M];
+#pragma unroll
+        for (int a = 0; a < M; ++a) {
+            k[a] = (min((f2u(v[g0 + a]) & 0x7FFFFFFFu) >> KEYSHIFT, (0x7F800000u >> KEYSHIFT) + 1u) << 3) | (uint32_t)a;
+            s[a] = k[a];
+        }
+        if (M == 2) {
+            cex(s[0], s[1]);
+        } else if (M == 4) {
+            cex(s[0], s[1]); cex(s[2], s[3]); cex(s[0], s[2]); cex(s[1], s[3]); cex(s[1], s[2]);
+        } else {  // M == 8, 19-comparator network
+            cex(s[0], s[1]); cex(s[2], s[3]); cex(s[4], s[5]); cex(s[6], s[7]);
+            cex(s[0], s[2]); cex(s[1], s[3]); cex(s[4], s[6]); cex(s[5], s[7]);
+            cex(s[1], s[2]); cex(s[5], s[6]); cex(s[0], s[4]); cex(s[3], s[7]);
+            cex(s[1], s[5]); cex(s[2], s[6]);
+            cex(s[1], s[4]); cex(s[3], s[6]);
+            cex(s[2], s[4]); cex(s[3], s[5]);
+            cex(s[3], s[4]);
+        }
+        uint32_t thr = s[0];
+#pragma unroll
+        for (int a = 1; a < M; ++a) thr = (a == n_prune) ? s[a] : thr;
+#pragma unroll
+        for (int a = 0; a < M; ++a) keep[g0 + a] = n_prune == 0 || k[a] >= thr;
+    }
+}
+
 // N:M across `lanes` = M / V neighbouring lanes (M > V): partner keys arrive by shuffle.
 template <int V> __device__ __forceinline__ void nm_lanes(const uint32_t (&key)[V], int n_prune, int lanes, int lane, bool (&keep)[V])
 {
@@ -314,9 +351,26 @@ template <int V> __device__ __forceinline__ void nm_lanes(const uint32_t (&key)[
     for (int a = 0; a < V; ++a) keep[a] = rank[a] >= n_prune;
 }
 
-template <int V>
+template <int V, int SRCBITS = 32>
 __device__ __forceinline__ void nm_stage(float (&v)[V], const StageDev &st, int lane, const float *score_vec, float *mask_vec, bool valid)
 {
+    if (SRCBITS != 32 && V == 8 && score_vec == nullptr && st.block <= 8) {
+        // 16-bit source, score |x|: unique packed keys + sorting network
+        constexpr int KS = SRCBITS == 16 ? 16 : 13;  // bf16 keeps 8+7 bits, fp16 (widened) 8+10 bits
+        bool keep[V];
+        if (st.block == 2) nm_local16<V, 2, KS>(v, st.n_prune, keep);
+        else if (st.block == 4) nm_local16<V, 4, KS>(v, st.n_prune, keep);
+        else nm_local16<V, (V >= 8 ? 8 : V), KS>(v, st.n_prune, keep);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = nm_apply(v[j], keep[j]);
+        if (mask_vec != nullptr && valid) {
+            float mk[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) mk[j] = keep[j] ? 1.0f : 0.0f;
+            VecIO<float>::store<V>(mask_vec, mk);
+        }
+        return;
+    }
     uint32_t key[V];
     if (score_vec != nullptr) {
         if (valid) {
