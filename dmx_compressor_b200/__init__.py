@@ -2,7 +2,7 @@
 dmx-compressor, behind the reference's own Format / CastTo / Sparsify interface.
 
 CUDA only.  Importing the package loads dmx_compressor_b200/lib/libdmxq.so and raises
-ImportError if it has not been built (python -m dmx_compressor_b200.build).
+ImportError if it has not been built (python dmx_compressor_b200/build.py).
 """
 from . import _lib  # noqa: F401  (fails loudly when libdmxq.so is missing)
 from . import ops  # noqa: F401

@@ -44,7 +44,7 @@ class Stage(C.Structure):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            f"{LIB_PATH} is missing: build it with `python -m dmx_compressor_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python dmx_compressor_b200/build.py` "
             "(nvcc, sm_100a). dmx_compressor_b200 has no CPU / PyTorch fallback.")
     lib = C.CDLL(LIB_PATH)
     TP, SP, VP, I, I64 = C.POINTER(Tensor), C.POINTER(Stage), C.c_void_p, C.c_int, C.c_int64
@@ -59,6 +59,7 @@ def _load():
         "dmxq_float_qdq": ([TP, TP] + [I] * 7 + [VP, VP], I),
         "dmxq_fixed_qdq": ([TP, TP] + [I] * 6 + [VP, VP, I64, I, I64, VP, VP], I),
         "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, VP], I),
+        "dmxq_add_cast": ([TP, TP, TP, SP, SP, SP, VP], I),
         "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
         "dmxq_minmax": ([TP, I, VP, VP, VP], I),
         "dmxq_cast_chain_host": ([VP, VP, I, I, I64, I64, SP, I, I], I),

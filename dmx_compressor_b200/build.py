@@ -1,6 +1,6 @@
 """In-tree build of libdmxq.so (CUDA, sm_100a only).
 
-    python -m dmx_compressor_b200.build [--force] [--verbose]
+    python dmx_compressor_b200/build.py [--force] [--verbose]
 
 Plain nvcc command lines, one per translation unit, run in parallel; the shared library
 lands in dmx_compressor_b200/lib/libdmxq.so (git-ignored, shipped to the GPU box by gpurun).

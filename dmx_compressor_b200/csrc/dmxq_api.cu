@@ -613,6 +613,73 @@ int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_ten
     return chain_impl(x, y, block_dim, &s, 1, score, mask, nullptr, static_cast<cudaStream_t>(stream));
 }
 
+int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor *y, const dmxq_stage *stage_a,
+                  const dmxq_stage *stage_b, const dmxq_stage *stage_out, void *stream)
+{
+    if (!a || !b || !y) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (!same_shape(a, y) || a->dtype != y->dtype || a->dtype != b->dtype) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: a, b, y must share a dtype and a, y a shape");
+    if (a->dtype < 0 || a->dtype > 2 || b->ndim > a->ndim) return fail(DMXQ_ERR_BAD_ARG, "add_cast: bad dtype / rank");
+    AddParams p;
+    memset(&p, 0, sizeof(p));
+    const dmxq_stage *sts[3] = {stage_a, stage_b, stage_out};
+    FloatFmt *fmts[3] = {&p.fa, &p.fb, &p.fo};
+    int *has[3] = {&p.has_a, &p.has_b, &p.has_o};
+    for (int i = 0; i < 3; ++i) {
+        if (!sts[i]) continue;
+        StageDev d;
+        int rc = decode_stage(*sts[i], d);
+        if (rc) return rc;
+        if (d.kind != ST_FLOAT || !d.ff.fastpath) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: only nearest+flush FLOAT stages fuse");
+        *fmts[i] = d.ff;
+        *has[i] = 1;
+    }
+    const int nd = a->ndim, V = 16 / dtype_size(a->dtype);
+    int64_t n = 1, expect = 1;
+    for (int i = nd - 1; i >= 0; --i) {
+        if (a->shape[i] != 1 && (a->stride[i] != expect || y->stride[i] != expect)) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: a and y must be contiguous");
+        expect *= a->shape[i];
+        n *= a->shape[i];
+    }
+    if (n == 0) return DMXQ_OK;
+    // b right-aligned against a; broadcast dims get stride 0
+    std::vector<int64_t> bst(nd, 0);
+    for (int i = 0; i < b->ndim; ++i) {
+        int ai = nd - b->ndim + i;
+        if (b->shape[i] == a->shape[ai]) bst[ai] = b->shape[i] == 1 ? 0 : b->stride[i];
+        else if (b->shape[i] == 1) bst[ai] = 0;
+        else return fail(DMXQ_ERR_BAD_ARG, "add_cast: b is not broadcastable to a");
+    }
+    // inner: longest suffix over which b is contiguous like a
+    int64_t inner = 1;
+    int d = nd - 1;
+    for (; d >= 0; --d) {
+        if (a->shape[d] == 1) continue;
+        if (bst[d] != inner) break;
+        inner *= a->shape[d];
+    }
+    // remaining dims [0..d]: collapse into at most two (size, stride) pairs
+    std::vector<std::pair<int64_t, int64_t>> outer;  // outermost first
+    for (int i = 0; i <= d; ++i) {
+        if (a->shape[i] == 1) continue;
+        if (!outer.empty() && outer.back().second == bst[i] * a->shape[i]) { outer.back().first *= a->shape[i]; outer.back().second = bst[i]; }
+        else if (!outer.empty() && outer.back().second == 0 && bst[i] == 0) outer.back().first *= a->shape[i];
+        else outer.emplace_back(a->shape[i], bst[i]);
+    }
+    if (outer.size() > 2 || inner % V != 0 || !aligned(a->data, 16) || !aligned(b->data, 16) || !aligned(y->data, 16))
+        return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: layout not supported by the fused kernel");
+    for (auto &o : outer) if ((o.second * dtype_size(a->dtype)) % 16 != 0) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: misaligned broadcast stride");
+    if (inner / V > 0xFFFFFFFFll) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: inner run too long");
+    p.a = a->data; p.b = b->data; p.y = y->data;
+    p.n_vec = n / V;
+    p.inner_vec = (uint32_t)(inner / V);
+    p.d1 = 1; p.bs0 = 0; p.bs1 = 0;
+    if (outer.size() == 1) { p.d1 = (uint32_t)outer[0].first; p.bs1 = outer[0].second; }
+    if (outer.size() == 2) { p.d1 = (uint32_t)outer[1].first; p.bs1 = outer[1].second; p.bs0 = outer[0].second; }
+    cudaError_t e = launch_add(a->dtype, p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "add_cast_kernel");
+    return DMXQ_OK;
+}
+
 int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream)
 {
     if (!x || !out_min || !out_max) return fail(DMXQ_ERR_BAD_ARG, "null argument");

@@ -115,6 +115,18 @@ struct BlockQParams {
     uint32_t mask;
 };
 
+// fused add: y = out(A(a) + B(b)); a, y flat contiguous; b = [o0, o1, inner] with arbitrary outer strides
+struct AddParams {
+    const void *a, *b;
+    void *y;
+    int64_t n_vec;        // vectors of a
+    uint32_t inner_vec;   // vectors per contiguous inner run of b
+    uint32_t d1;          // size of the inner outer-dim (o = o0 * d1 + o1)
+    int64_t bs0, bs1;     // element strides of b for o0, o1
+    int has_a, has_b, has_o;
+    FloatFmt fa, fb, fo;
+};
+
 struct MinMaxParams {
     const void *x;
     int dtype;
@@ -132,6 +144,7 @@ cudaError_t launch_generic(int in_dt, int out_dt, const GenericParams &p, cudaSt
 cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, cudaStream_t s);
 cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s);
 cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s);
+cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
 cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s);
 int64_t launch_count();
 

@@ -305,6 +305,74 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// fused residual add with its boundary casts (see dmxq_add_cast in include/dmxq.h)
+template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], const FloatFmt &f)
+{
+    const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
+    float q[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], f);
+    if (any_nan) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_slow(v[j], &f, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = q[j];
+}
+
+template <typename T> __global__ void __launch_bounds__(kThreads) add_cast_kernel(const __grid_constant__ AddParams p)
+{
+    constexpr int V = VecIO<T>::V;
+    constexpr int U = 2;
+    const T *__restrict__ a = static_cast<const T *>(p.a);
+    const T *__restrict__ b = static_cast<const T *>(p.b);
+    T *__restrict__ y = static_cast<T *>(p.y);
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    uint4 ra[U], rb[U];
+    bool valid[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int64_t g = g0 + (int64_t)u * kThreads;
+        valid[u] = g < p.n_vec;
+        int64_t gg = valid[u] ? g : 0;
+        int64_t o = gg / p.inner_vec;
+        int64_t iv = gg - o * p.inner_vec;
+        int64_t o0 = o / p.d1, o1 = o - o0 * p.d1;
+        ra[u] = valid[u] ? ldg_stream(a + gg * V) : make_uint4(0, 0, 0, 0);
+        rb[u] = valid[u] ? ldg_stream(b + o0 * p.bs0 + o1 * p.bs1 + iv * V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float va[V], vb[V];
+        VecIO<T>::unpack(ra[u], va);
+        VecIO<T>::unpack(rb[u], vb);
+        if (p.has_a) { float_fast_vec<V>(va, p.fa);
+#pragma unroll
+            for (int j = 0; j < V; ++j) va[j] = requant1<T>(va[j]); }
+        if (p.has_b) { float_fast_vec<V>(vb, p.fb);
+#pragma unroll
+            for (int j = 0; j < V; ++j) vb[j] = requant1<T>(vb[j]); }
+#pragma unroll
+        for (int j = 0; j < V; ++j) va[j] = requant1<T>(__fadd_rn(va[j], vb[j]));  // torch adds in fp32, rounds to T
+        if (p.has_o) float_fast_vec<V>(va, p.fo);
+        if (valid[u]) VecIO<T>::template store<V>(y + (g0 + (int64_t)u * kThreads) * V, va);
+    }
+}
+
+cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s)
+{
+    int64_t per = (int64_t)kThreads * 2;
+    int64_t grid = (p.n_vec + per - 1) / per;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    if (dt == 0) add_cast_kernel<float><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else if (dt == 1) add_cast_kernel<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    else add_cast_kernel<__half><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void fold_absmax_kernel(const float *mn, const float *mx, uint32_t *out, int64_t C)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -245,6 +245,44 @@ class ResAdd(DmxModule, torch.nn.Module):
     def _forward(self, _input, _residual):
         return _input + _residual
 
+    def _fusable(self, a, b):
+        """(stage_a, stage_b, stage_out, out_key) when input casts + add + output cast can run as ONE kernel
+        (dmxq_add_cast): plain nearest+flush FLOAT formats (or SAME), no observers / pre-transforms."""
+        from .numerical.format import FloatingPoint
+
+        if not (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.is_cuda and b.is_cuda and a.dtype == b.dtype
+                and a.is_floating_point() and a.is_contiguous() and a.dim() >= b.dim()):
+            return None
+        casts = (self.input_casts.input_cast, self.input_casts.residual_cast, self.output_casts.output_cast)
+        stages = []
+        for c, t in zip(casts, (a, b, None)):
+            f = c.format
+            if c.pre_transform or c._obs_on:
+                return None
+            if isinstance(f, Same) or not c._fq_on:
+                stages.append(None)
+            elif isinstance(f, FloatingPoint) and f.rounding == "nearest" and f.flush_subnormal and not f.unsigned:
+                key = elide.format_key(f, None)
+                stages.append(None if (t is not None and elide.is_tagged(t, key)) else f.stage())  # already in format: skip
+            else:
+                return None
+        f_out = casts[2].format
+        return stages[0], stages[1], stages[2], (None if stages[2] is None else elide.format_key(f_out, None))
+
+    def forward(self, input, residual):
+        if elide.active() and not torch.is_grad_enabled():
+            plan = self._fusable(input, residual)
+            if plan is not None:
+                try:
+                    y = ops.add_cast(input, residual, plan[0], plan[1], plan[2])
+                except RuntimeError:
+                    y = None  # layout the fused kernel does not take: module-by-module path below
+                if y is not None:
+                    elide.stats["elided"] += 2
+                    elide.tag(y, plan[3])
+                    return y
+        return DmxModule.forward(self, input, residual)
+
 
 class Mul(DmxModule, torch.nn.Module):
     def __init__(self):

@@ -199,6 +199,20 @@ def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None
     return (y, mask) if return_mask else y
 
 
+def add_cast(a, b, stage_a=None, stage_b=None, stage_out=None, out=None):
+    """y = out(A(a) + B(b)): ResAdd with its boundary casts in one pass (dmxq_add_cast).  Raises
+    RuntimeError('unsupported') for layouts / stages the fused kernel does not take."""
+    L.require_cuda(a, "a")
+    L.require_cuda(b, "b")
+    y = out if out is not None else torch.empty(a.shape, dtype=a.dtype, device=a.device)
+    va, vb, vy = L.view(a), L.view(b), L.view(y)
+    ptr = lambda s: None if s is None else C.byref(s)
+    with _guard(a.device):
+        rc = L.lib.dmxq_add_cast(C.byref(va), C.byref(vb), C.byref(vy), ptr(stage_a), ptr(stage_b), ptr(stage_out), L.stream_ptr(a.device))
+    L.check(rc, "dmxq_add_cast")
+    return y
+
+
 def minmax(x, ch_axis: Optional[int] = None):
     """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax."""
     L.require_cuda(x)

@@ -22,6 +22,7 @@
  *   dmxq_cast_chain        DmxModule.weight_hypernet chain   S/modeling/nn/core.py:178-198
  *                          (sparsify -> storage cast -> weight cast in ONE pass), and any
  *                          back-to-back CastTo pair (output cast -> next input cast)
+ *   dmxq_add_cast          ResAdd.forward (casts + add fused)  S/modeling/nn/torch_modules.py:15-37
  *   dmxq_block_quantize    L1 block_quantize(x, wl, dim,...) Q/quant_cuda/quant.cu:14-112
  *   dmxq_minmax            MinMaxObserver.forward statistics S/numerical/observer.py:173-193
  *   dmxq_cast_chain_host   same as dmxq_cast_chain on HOST buffers (pipelined H2D/compute/D2H)
@@ -155,6 +156,14 @@ int dmxq_fixed_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int fl, i
                    const float *rand, void *stream);
 int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_tensor *y,
                   const dmxq_tensor *mask, int block_dim, int n_keep, int m, void *stream);
+
+/* ---- fused residual add: y = out( A(a) + B(b) ) in one pass (ResAdd.forward of the reference,
+ * S/modeling/nn/torch_modules.py:15-37, with its two input casts and its output cast folded into the
+ * add).  Stages are elementwise FLOAT stages or NULL (no cast).  a and y: same shape, contiguous,
+ * same dtype; b: same dtype, broadcastable to a (stride-0 dims allowed, e.g. an attention mask).
+ * Intermediates are rounded to the tensor dtype exactly where the unfused module sequence rounds. */
+int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor *y, const dmxq_stage *stage_a,
+                  const dmxq_stage *stage_b, const dmxq_stage *stage_out, void *stream);
 
 /* ---- L1 mirror: block_quantize(x, wl, dim, symmetric, rounding) of quant_cuda --------------
  * dim == -1: one exponent for the whole tensor; dim == 0: per row of view(size0,-1);

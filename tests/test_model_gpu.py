@@ -221,3 +221,35 @@ def test_basic_forward_is_cuda_graph_capturable():
     assert torch.equal(fwd(ids2), want2)
     fwd_e = graph.capture(q, ids, elide_casts=True)
     assert torch.equal(fwd_e(ids2), want2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_fused_resadd_equals_module_by_module(dt):
+    """ResAdd under elision = input casts + add + output cast in ONE kernel, incl. broadcast masks"""
+    from dmx_compressor_b200 import ops
+
+    torch.manual_seed(5)
+    add = dmxnn.ResAdd().to(DEV)
+    add.configure(dict(input_formats=[fmt.FLOAT16, fmt.FLOAT16], output_formats=[fmt.FLOAT16]))
+    a = (torch.randn(2, 3, 64, 64, device=DEV) * 300).to(dt)
+    a.view(-1)[::11] = 1e-6
+    S = 64
+    mask = torch.full((S, S), torch.finfo(dt).min, device=DEV, dtype=dt).triu(1)[None, None].expand(2, 1, S, S)
+    cases = ((mask, 1), ((torch.randn(2, 3, 64, 64, device=DEV) * 5).to(dt), 1), (torch.randn(64, device=DEV).to(dt), 1),
+             (torch.randn(3, 1, 64, device=DEV).to(dt), 3))  # last: 3 broadcast runs -> falls back to cast, cast, add+cast
+    for b, launches in cases:
+        with torch.no_grad():
+            want = add(a, b)
+            n0 = _lib.launch_count()
+            with elide.enabled():
+                got = add(a, b)
+            assert _lib.launch_count() - n0 == launches
+        assert torch.equal(got.view(torch.int16 if dt != torch.float32 else torch.int32), want.view(torch.int16 if dt != torch.float32 else torch.int32))
+    # oracle composition for the fp32 case
+    if dt == torch.float32:
+        b = torch.randn(2, 3, 64, 64, device=DEV) * 5
+        with torch.no_grad(), elide.enabled():
+            got = add(a, b)
+        F16 = "FP[1|5|10,15](FN)"
+        want = O.cast(O.cast(a.cpu().numpy(), F16) + O.cast(b.cpu().numpy(), F16), F16)
+        assert (bits(got.cpu().numpy()) == bits(want)).all()
