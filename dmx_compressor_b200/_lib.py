@@ -104,6 +104,8 @@ def require_cuda(t: torch.Tensor, name: str = "x") -> None:
 
 
 def view(t: torch.Tensor) -> Tensor:
+    if type(t) is not torch.Tensor and hasattr(t, "materialise"):
+        t = t.materialise()  # a deferred cast (elide.Lazy) reaching the ABI directly: run it first
     if t.dim() > MAX_DIMS:
         raise RuntimeError(f"dmxq: tensors of more than {MAX_DIMS} dims are not supported")
     v = Tensor()

@@ -30,6 +30,7 @@ from collections import OrderedDict
 import torch
 
 _ON = False
+defer_output_casts = True   # under elision, FLOAT output casts are handed to their consumer (see Lazy)
 _TAGS = {}   # id(tensor) -> (weakref, version, set(keys))
 _MEMO = OrderedDict()   # (id(x), version, key) -> (weakref(x), y)
 _MEMO_MAX = 8
@@ -94,6 +95,77 @@ def tag(y: torch.Tensor, key) -> None:
         t[2].add(key)
         return
     _TAGS[i] = (weakref.ref(y, lambda _r, i=i: _TAGS.pop(i, None)), y._version, {key})
+
+
+# ------------------------------------------------------------------------------------------------
+# deferred output casts
+_META_PROPS = ("shape", "dtype", "device", "is_cuda", "is_cpu", "ndim", "requires_grad", "_version", "layout", "is_leaf",
+               "grad_fn", "names", "is_sparse", "is_quantized", "is_meta", "is_nested", "is_mkldnn", "is_xpu")
+_META_METHODS = ("dim", "size", "stride", "numel", "nelement", "element_size", "is_contiguous", "is_floating_point", "is_complex",
+                 "storage_offset", "get_device", "ndimension", "is_pinned", "is_shared", "is_inference", "__len__", "__format__")
+_PASS = None
+
+
+def _passthrough():
+    global _PASS
+    if _PASS is None:
+        _PASS = {getattr(torch.Tensor, n).__get__ for n in _META_PROPS if hasattr(torch.Tensor, n)}
+        _PASS |= {getattr(torch.Tensor, n) for n in _META_METHODS if hasattr(torch.Tensor, n)}
+    return _PASS
+
+
+class Lazy(torch.Tensor):
+    """An output cast that has not run yet: carries the uncast tensor and the pending format.
+
+    A module's output cast is the producer half of a pair whose consumer half is the next module's
+    input cast.  Deferring it lets the consumer run ONE kernel: the same idempotent format ->
+    a single cast; a different format -> the fused chain [pending, own]; a ResAdd -> the pending
+    cast folds into the fused add.  Any *other* use -- any torch function or method that needs
+    values -- materialises the cast first through ``__torch_function__``, so code between modules
+    (views, scaling, user ops) always sees exactly the values the eager cast would have produced.
+    Only shape / dtype / device style metadata is answered without materialising."""
+
+    @staticmethod
+    def __new__(cls, raw, fmt, block_dim, key, materialise=None):
+        r = torch.Tensor._make_subclass(cls, raw, False)
+        r._raw, r._fmt, r._bd, r._key, r._real, r._mat = raw, fmt, block_dim, key, None, materialise
+        return r
+
+    def materialise(self) -> torch.Tensor:
+        if self._real is None:
+            if self._mat is not None:
+                self._real = self._mat(self._raw)
+            else:
+                from . import ops
+
+                self._real = ops.cast_chain(self._raw, [self._fmt.stage()], self._bd)
+            stats["casts"] += 1
+            tag(self._real, self._key)
+        return self._real
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        if func in _passthrough():
+            with torch._C.DisableTorchFunctionSubclass():
+                return func(*args, **kwargs)
+        stats["lazy_materialised_by_torch_op"] = stats.get("lazy_materialised_by_torch_op", 0) + 1
+        return func(*_unlazy(args), **_unlazy(kwargs))
+
+
+def _unlazy(o):
+    if isinstance(o, Lazy):
+        return o.materialise()
+    if isinstance(o, (list, tuple)):
+        return type(o)(_unlazy(e) for e in o)
+    if isinstance(o, dict):
+        return {k: _unlazy(v) for k, v in o.items()}
+    return o
+
+
+def materialise(x):
+    """the plain tensor behind a (possibly) deferred cast; tuples / lists / dicts are walked"""
+    return _unlazy(x)
 
 
 def memo_get(x: torch.Tensor, key):

@@ -184,7 +184,10 @@ class DmxModule:
         _output = self._forward(_input, *args, **kwargs)
         output = self.output_casts(_output, output=True)
         if self.align_boundary_dtype:
-            output = type(output)(a.to(_dtype) for a in output) if isinstance(output, (tuple, list)) else output.to(_dtype)
+            if isinstance(output, (tuple, list)):
+                output = type(output)(a if a.dtype == _dtype else a.to(_dtype) for a in output)
+            elif output.dtype != _dtype:  # (dtype is metadata: a deferred cast is not forced here)
+                output = output.to(_dtype)
         return output
 
 
@@ -254,34 +257,45 @@ class ResAdd(DmxModule, torch.nn.Module):
                 and a.is_floating_point() and a.is_contiguous() and a.dim() >= b.dim()):
             return None
         casts = (self.input_casts.input_cast, self.input_casts.residual_cast, self.output_casts.output_cast)
-        stages = []
+        stages, raws = [], []
         for c, t in zip(casts, (a, b, None)):
             f = c.format
             if c.pre_transform or c._obs_on:
                 return None
+            fast = isinstance(f, FloatingPoint) and f.rounding == "nearest" and f.flush_subnormal and not f.unsigned
+            key = elide.format_key(f, None) if fast else None
+            if isinstance(t, elide.Lazy):
+                # a deferred producer cast folds into the add when it is this very input format
+                # (F(F(x)) == F(x)); otherwise it has to run on its own first
+                if fast and t._key == key and c._fq_on:
+                    stages.append(f.stage())
+                    raws.append(t._raw)
+                    continue
+                t = t.materialise()
+            if t is not None:
+                raws.append(t)
             if isinstance(f, Same) or not c._fq_on:
                 stages.append(None)
-            elif isinstance(f, FloatingPoint) and f.rounding == "nearest" and f.flush_subnormal and not f.unsigned:
-                key = elide.format_key(f, None)
+            elif fast:
                 stages.append(None if (t is not None and elide.is_tagged(t, key)) else f.stage())  # already in format: skip
             else:
                 return None
         f_out = casts[2].format
-        return stages[0], stages[1], stages[2], (None if stages[2] is None else elide.format_key(f_out, None))
+        return stages[0], stages[1], stages[2], (None if stages[2] is None else elide.format_key(f_out, None)), raws[0], raws[1]
 
     def forward(self, input, residual):
         if elide.active() and not torch.is_grad_enabled():
             plan = self._fusable(input, residual)
             if plan is not None:
                 try:
-                    y = ops.add_cast(input, residual, plan[0], plan[1], plan[2])
+                    y = ops.add_cast(plan[4], plan[5], plan[0], plan[1], plan[2])
                 except RuntimeError:
                     y = None  # layout the fused kernel does not take: module-by-module path below
                 if y is not None:
                     elide.stats["elided"] += 2
                     elide.tag(y, plan[3])
                     return y
-        return DmxModule.forward(self, input, residual)
+        return DmxModule.forward(self, elide.materialise(input), elide.materialise(residual))
 
 
 class Mul(DmxModule, torch.nn.Module):
@@ -347,6 +361,14 @@ class Dropout(DmxModule, torch.nn.Dropout):
 
     def _forward(self, _input):
         return F.dropout(_input, self.p, self.training, False)
+
+    def forward(self, input):
+        # inference-mode dropout with SAME casts is the identity: under elision do not even touch the tensor
+        # (keeps a deferred producer cast alive for the real consumer)
+        if (elide.active() and not self.training and not torch.is_grad_enabled()
+                and all(isinstance(c.format, Same) or not c._fq_on for c in (self.input_casts.input_cast, self.output_casts.output_cast))):
+            return input
+        return DmxModule.forward(self, input)
 
 
 class MaxPool2d(DmxModule, torch.nn.MaxPool2d):

@@ -76,7 +76,7 @@ class CastToDict(torch.nn.ModuleDict):
         if output:
             if isinstance(x, (tuple, list)):
                 return type(x)(self[keys[i]](a) for i, a in enumerate(x))
-            return self[keys[0]](x)
+            return self[keys[0]](x, lazy_ok=True)  # an output cast may be deferred to its consumer under elision
         i = 1
         new_args, new_kwargs = [], {}
         for a in args:
@@ -248,18 +248,34 @@ class CastTo(FakeQuantize):
             return _FusedCast.apply(x, fmt, self.block_dim)
         return super().forward(x)  # plain torch.dtype fake-quant
 
-    def _forward_elided(self, x):
+    def _forward_elided(self, x, lazy_ok=False):
         """value-identical fast path, only under elide.enabled() + no_grad (see elide.py)"""
         fmt = self.format
         if not self._fq_on or isinstance(fmt, Same):
             elide.stats["elided"] += 1
-            return x
+            return x  # (a deferred cast passes through untouched)
+        pend = x if isinstance(x, elide.Lazy) else None
         key = elide.format_key(fmt, self.block_dim if fmt.blocked else None)
         if key is None:
             return None
+        if pend is not None:
+            if pend._key == key:  # producer's output format == this input format: cast once
+                elide.stats["elided"] += 1
+                return pend.materialise()
+            ckey = ("chain", pend._key, key)
+            y = elide.memo_get(pend._raw, ckey)
+            if y is None:  # output cast fused with this input cast: ONE pass over the tensor
+                y = ops.cast_chain(pend._raw, [pend._fmt.stage(), fmt.stage()], self.block_dim)
+                elide.stats["casts"] += 1
+                elide.stats["elided"] += 1
+                elide.memo_put(pend._raw, ckey, y)
+                elide.tag(y, key)
+            return y
         if elide.is_tagged(x, key) or (hasattr(fmt, "_identity_for") and fmt._identity_for(x.dtype) and not fmt.unsigned):
             elide.stats["elided"] += 1
             return x
+        if lazy_ok and key[0] == "FP" and fmt.flush_subnormal and not fmt.unsigned and type(x) is torch.Tensor:
+            return elide.Lazy(x, fmt, self.block_dim, key)  # defer: the consumer decides how to run it
         y = elide.memo_get(x, key)
         if y is None:
             y = ops.cast_chain(x, [fmt.stage()], self.block_dim)
@@ -268,13 +284,15 @@ class CastTo(FakeQuantize):
             elide.tag(y, key)
         return y
 
-    def forward(self, x):
+    def forward(self, x, lazy_ok=False):
         self.physical_dtype = x.dtype
         if (elide.active() and not torch.is_grad_enabled() and not self.pre_transform and not self._obs_on
                 and isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point()):
-            y = self._forward_elided(x)
+            y = self._forward_elided(x, lazy_ok and elide.defer_output_casts)
             if y is not None:
                 return y
+        if isinstance(x, elide.Lazy):
+            x = x.materialise()
         undo = shortcut = None
         if "shaping" in self.pre_transform:
             x, undo = self.apply_shaping_seq(x, self.pre_transform["shaping"])

@@ -91,7 +91,9 @@ class OPTStack(torch.nn.Module):
         mask = torch.full((S, S), torch.finfo(x.dtype).min, device=x.device, dtype=x.dtype).triu(1)[None, None].expand(B, 1, S, S)
         for layer in self.layers:
             x = layer(x, mask)
-        return self.lm_head(self.final_layer_norm(x))
+        from . import elide
+
+        return elide.materialise(self.lm_head(self.final_layer_norm(x)))  # (a deferred output cast runs here at the latest)
 
 
 def build_pair(cfg=None, device="cuda", dtype=torch.float32, seed=0):

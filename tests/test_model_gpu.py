@@ -242,14 +242,41 @@ def test_fused_resadd_equals_module_by_module(dt):
             want = add(a, b)
             n0 = _lib.launch_count()
             with elide.enabled():
-                got = add(a, b)
+                got = elide.materialise(add(a, b))  # (an output cast may come back deferred)
             assert _lib.launch_count() - n0 == launches
         assert torch.equal(got.view(torch.int16 if dt != torch.float32 else torch.int32), want.view(torch.int16 if dt != torch.float32 else torch.int32))
     # oracle composition for the fp32 case
     if dt == torch.float32:
         b = torch.randn(2, 3, 64, 64, device=DEV) * 5
         with torch.no_grad(), elide.enabled():
-            got = add(a, b)
+            got = elide.materialise(add(a, b))
         F16 = "FP[1|5|10,15](FN)"
         want = O.cast(O.cast(a.cpu().numpy(), F16) + O.cast(b.cpu().numpy(), F16), F16)
         assert (bits(got.cpu().numpy()) == bits(want)).all()
+
+
+def test_deferred_output_cast_is_safe_and_fuses():
+    """elide.Lazy: a deferred FLOAT16 output cast (a) fuses with a BFP16 consumer into ONE kernel, (b) is
+    materialised by any plain torch op, so arbitrary code between modules sees the eager values"""
+    lin = dmxnn.Linear(128, 128).to(DEV).eval()
+    nxt = dmxnn.Linear(128, 64).to(DEV).eval()
+    for m in (lin, nxt):
+        m.configure(dmxnn.config_rules.BASIC[0].module_config)
+    x = torch.randn(4, 33, 128, device=DEV)
+    with torch.no_grad():
+        h = lin(x)
+        want_next = nxt(h)
+        want_scaled = h * 0.125
+        with elide.enabled():
+            hl = lin(x)
+            assert isinstance(hl, elide.Lazy) and hl.shape == h.shape and hl.dtype == h.dtype  # metadata does not force it
+            assert hl._real is None
+            n0 = _lib.launch_count()
+            got_next = elide.materialise(nxt(hl))          # FLOAT16 -> BFP16 fused: one kernel for both casts (+ cached weights)
+            fused_launches = _lib.launch_count() - n0
+            assert hl._real is None                         # the consumer never needed the stand-alone FLOAT16 tensor
+            got_scaled = hl * 0.125                         # a plain torch op forces the cast
+            assert hl._real is not None and type(got_scaled) is torch.Tensor
+            assert torch.equal(hl.view(-1), h.view(-1))
+    assert torch.equal(got_next, want_next) and torch.equal(got_scaled, want_scaled)
+    assert fused_launches <= 4  # input chain, weight, bias, (deferred) output cast
