@@ -567,3 +567,38 @@ def test_int8_device_qparams_fast_path():
             y = ops.fixed_qdq(xb.to(DEV), f.precision, f.fraction, f.clamp, f.symmetric, "nearest", scale=torch.tensor([sc], device=DEV),
                               zero_point=torch.tensor([zp], device=DEV))
             check(y, want.view(torch.int16).numpy().view(np.uint16), f"{fmt} bf16 sc={sc}", dtype="bfloat16")
+
+
+def test_more_than_2_31_elements():
+    """The reference indexes with `int` and breaks above 2^31 elements; we index
+    with int64: a 2^31 + 2^20 element bf16 tensor, checked against the oracle at both ends."""
+    n = (1 << 31) + (1 << 20)
+    x = torch.empty(n // 4096, 4096, device=DEV, dtype=torch.bfloat16)
+    x.normal_()
+    st = [fmt_from("BFP[8|8]{64}(SN)").stage()]
+    y = ops.cast_chain(x, st, -1)
+    for rows in (slice(0, 8), slice(n // 4096 - 8, n // 4096), slice((1 << 31) // 4096 - 4, (1 << 31) // 4096 + 4)):
+        want = torch.from_numpy(O.cast(x[rows].float().cpu().numpy(), "BFP[8|8]{64}(SN)")).to(torch.bfloat16)
+        check(y[rows], want.view(torch.int16).numpy().view(np.uint16), f"rows {rows}", dtype="bfloat16")
+    # strided (non-flat) addressing beyond 2^31 as well
+    xs = x[:, :2048]
+    ys = ops.cast_chain(xs, st, -1)
+    rows = slice(n // 4096 - 8, n // 4096)
+    want = torch.from_numpy(O.cast(xs[rows].float().cpu().numpy(), "BFP[8|8]{64}(SN)")).to(torch.bfloat16)
+    check(ys[rows], want.view(torch.int16).numpy().view(np.uint16), "strided tail", dtype="bfloat16")
+
+
+def test_degenerate_shapes():
+    for shape in ((0, 64), (4, 0), (), (1,), (1, 1, 1)):
+        x = torch.randn(shape, device=DEV)
+        for sh in ("FP[1|5|10,15](FN)", "XP[8,0](CSN)"):
+            y = gpu_cast(x, sh)
+            want = O.cast(x.cpu().numpy().reshape(shape), sh, tie=O.TIE_AWAY)
+            assert y.shape == x.shape
+            if x.numel():
+                check(y, bits(want), f"{sh} {shape}")
+        if len(shape) >= 1:
+            y = gpu_cast(x, "BFP[8|8]{64}(SN)", -1)
+            assert y.shape == x.shape
+            if x.numel():
+                check(y, bits(O.cast(x.cpu().numpy(), "BFP[8|8]{64}(SN)", -1)), f"bfp {shape}")
