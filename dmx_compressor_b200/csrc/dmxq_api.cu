@@ -630,6 +630,10 @@ int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor 
         int rc = decode_stage(*sts[i], d);
         if (rc) return rc;
         if (d.kind != ST_FLOAT || !d.ff.fastpath) return fail(DMXQ_ERR_UNSUPPORTED, "add_cast: only nearest+flush FLOAT stages fuse");
+        // every value a stage sees here is representable in the tensor dtype (inputs, and the sum after its
+        // rounding to the dtype): with >= that many mantissa bits in the format, rounding is the identity
+        const int src_man = a->dtype == DMXQ_BF16 ? 7 : a->dtype == DMXQ_F16 ? 10 : 23;
+        if (23 - d.ff.sh >= src_man) d.ff.exact = 1;
         *fmts[i] = d.ff;
         *has[i] = 1;
     }

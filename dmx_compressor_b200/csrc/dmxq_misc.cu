@@ -311,8 +311,13 @@ template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], c
 {
     const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
     float q[V];
+    if (f.exact) {  // values already fit the format's mantissa (16-bit tensor dtype): flush + saturate only
 #pragma unroll
-    for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], f);
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<true>(v[j], f);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], f);
+    }
     if (any_nan) {
 #pragma unroll
         for (int j = 0; j < V; ++j) q[j] = float_elem_slow(v[j], &f, 0u);
@@ -321,10 +326,11 @@ template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], c
     for (int j = 0; j < V; ++j) v[j] = q[j];
 }
 
-template <typename T> __global__ void __launch_bounds__(kThreads) add_cast_kernel(const __grid_constant__ AddParams p)
+// BCAST 0: b has a's layout (no index arithmetic); 1: b = [o0, o1, inner] with arbitrary outer strides
+template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add_cast_kernel(const __grid_constant__ AddParams p)
 {
     constexpr int V = VecIO<T>::V;
-    constexpr int U = 2;
+    constexpr int U = 4;
     const T *__restrict__ a = static_cast<const T *>(p.a);
     const T *__restrict__ b = static_cast<const T *>(p.b);
     T *__restrict__ y = static_cast<T *>(p.y);
@@ -336,11 +342,21 @@ template <typename T> __global__ void __launch_bounds__(kThreads) add_cast_kerne
         int64_t g = g0 + (int64_t)u * kThreads;
         valid[u] = g < p.n_vec;
         int64_t gg = valid[u] ? g : 0;
-        int64_t o = gg / p.inner_vec;
-        int64_t iv = gg - o * p.inner_vec;
-        int64_t o0 = o / p.d1, o1 = o - o0 * p.d1;
+        int64_t boff;
+        if (BCAST == 0) {
+            boff = gg * V;
+        } else if (p.n_vec <= 0xFFFFFFFFll) {  // 32-bit index arithmetic
+            uint32_t g32 = (uint32_t)gg;
+            uint32_t o = g32 / p.inner_vec, iv = g32 - o * p.inner_vec;
+            uint32_t o0 = o / p.d1, o1 = o - o0 * p.d1;
+            boff = (int64_t)o0 * p.bs0 + (int64_t)o1 * p.bs1 + (int64_t)iv * V;
+        } else {
+            int64_t o = gg / p.inner_vec, iv = gg - o * p.inner_vec;
+            int64_t o0 = o / p.d1, o1 = o - o0 * p.d1;
+            boff = o0 * p.bs0 + o1 * p.bs1 + iv * V;
+        }
         ra[u] = valid[u] ? ldg_stream(a + gg * V) : make_uint4(0, 0, 0, 0);
-        rb[u] = valid[u] ? ldg_stream(b + o0 * p.bs0 + o1 * p.bs1 + iv * V) : make_uint4(0, 0, 0, 0);
+        rb[u] = valid[u] ? (BCAST == 0 ? ldg_stream(b + boff) : *reinterpret_cast<const uint4 *>(b + boff)) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -360,15 +376,22 @@ template <typename T> __global__ void __launch_bounds__(kThreads) add_cast_kerne
     }
 }
 
+template <typename T> static void launch_add_t(const AddParams &p, unsigned grid, cudaStream_t s)
+{
+    const bool same = p.d1 == 1 && p.bs0 == 0 && (int64_t)p.inner_vec == p.n_vec;
+    if (same) add_cast_kernel<T, 0><<<grid, kThreads, 0, s>>>(p);
+    else add_cast_kernel<T, 1><<<grid, kThreads, 0, s>>>(p);
+}
+
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s)
 {
-    int64_t per = (int64_t)kThreads * 2;
+    int64_t per = (int64_t)kThreads * 4;
     int64_t grid = (p.n_vec + per - 1) / per;
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
-    if (dt == 0) add_cast_kernel<float><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else if (dt == 1) add_cast_kernel<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else add_cast_kernel<__half><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    if (dt == 0) launch_add_t<float>(p, (unsigned)grid, s);
+    else if (dt == 1) launch_add_t<__nv_bfloat16>(p, (unsigned)grid, s);
+    else launch_add_t<__half>(p, (unsigned)grid, s);
     count_launch();
     return cudaGetLastError();
 }

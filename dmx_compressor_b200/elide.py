@@ -34,6 +34,8 @@ defer_output_casts = True   # under elision, FLOAT output casts are handed to th
 _TAGS = {}   # id(tensor) -> (weakref, version, set(keys))
 _MEMO = OrderedDict()   # (id(x), version, key) -> (weakref(x), y)
 _MEMO_MAX = 8
+_PINNED = OrderedDict()  # same, for small broadcast operands (masks) that must survive a whole forward
+_PINNED_MAX = 4
 stats = {"elided": 0, "memo_hits": 0, "casts": 0}
 
 
@@ -51,6 +53,7 @@ def enable(on: bool = True) -> None:
 def reset() -> None:
     _TAGS.clear()
     _MEMO.clear()
+    _PINNED.clear()
 
 
 @contextlib.contextmanager
@@ -169,15 +172,18 @@ def materialise(x):
 
 
 def memo_get(x: torch.Tensor, key):
-    ent = _MEMO.get((id(x), x._version, key))
-    if ent is not None and ent[0]() is x:
-        stats["memo_hits"] += 1
-        _MEMO.move_to_end((id(x), x._version, key))
-        return ent[1]
+    k = (id(x), x._version, key)
+    for table in (_MEMO, _PINNED):
+        ent = table.get(k)
+        if ent is not None and ent[0]() is x:
+            stats["memo_hits"] += 1
+            table.move_to_end(k)
+            return ent[1]
     return None
 
 
-def memo_put(x: torch.Tensor, key, y: torch.Tensor) -> None:
-    _MEMO[(id(x), x._version, key)] = (weakref.ref(x), y)
-    while len(_MEMO) > _MEMO_MAX:
-        _MEMO.popitem(last=False)
+def memo_put(x: torch.Tensor, key, y: torch.Tensor, pinned: bool = False) -> None:
+    table, cap = (_PINNED, _PINNED_MAX) if pinned else (_MEMO, _MEMO_MAX)
+    table[(id(x), x._version, key)] = (weakref.ref(x), y)
+    while len(table) > cap:
+        table.popitem(last=False)

@@ -277,6 +277,17 @@ class ResAdd(DmxModule, torch.nn.Module):
             if isinstance(f, Same) or not c._fq_on:
                 stages.append(None)
             elif fast:
+                if t is not None and not elide.is_tagged(t, key) and 0 in t.stride() and t.numel() > 0:
+                    # broadcast operand (e.g. the attention mask, the same object in every layer): cast its
+                    # un-expanded base once, remember it, and feed the kernel an already-cast operand
+                    tc = elide.memo_get(t, key)
+                    if tc is None:
+                        base = t[tuple(slice(0, 1) if (st == 0 and n > 1) else slice(None) for n, st in zip(t.shape, t.stride()))]
+                        tc = ops.cast_chain(base, [f.stage()], -1).expand(t.shape)
+                        elide.stats["casts"] += 1
+                        elide.memo_put(t, key, tc, pinned=True)
+                        elide.tag(tc, key)
+                    raws[-1] = t = tc
                 stages.append(None if (t is not None and elide.is_tagged(t, key)) else f.stage())  # already in format: skip
             else:
                 return None

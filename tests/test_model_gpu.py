@@ -235,7 +235,8 @@ def test_fused_resadd_equals_module_by_module(dt):
     a.view(-1)[::11] = 1e-6
     S = 64
     mask = torch.full((S, S), torch.finfo(dt).min, device=DEV, dtype=dt).triu(1)[None, None].expand(2, 1, S, S)
-    cases = ((mask, 1), ((torch.randn(2, 3, 64, 64, device=DEV) * 5).to(dt), 1), (torch.randn(64, device=DEV).to(dt), 1),
+    cases = ((mask, 2),  # broadcast operand: its un-expanded base is cast once (and remembered), then ONE fused add
+             ((torch.randn(2, 3, 64, 64, device=DEV) * 5).to(dt), 1), (torch.randn(64, device=DEV).to(dt), 1),
              (torch.randn(3, 1, 64, device=DEV).to(dt), 3))  # last: 3 broadcast runs -> falls back to cast, cast, add+cast
     for b, launches in cases:
         with torch.no_grad():
