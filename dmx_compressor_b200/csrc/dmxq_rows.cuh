@@ -209,8 +209,16 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                     const int mode = st.kind == ST_FLOAT ? st.ff.mode : st.kind == ST_FIXED ? st.xf.mode : st.kind == ST_BFP ? st.mode : 0;
                     if (mode == R_STOCHASTIC) {
                         const uint32_t *rp = static_cast<const uint32_t *>(p.rnd) + aux_r[u];
+                        if ((FLAT || p.rks == 1) && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {  // contiguous: 16-byte streaming loads
 #pragma unroll
-                        for (int j = 0; j < V; ++j) r[j] = __ldg(rp + (FLAT ? (int64_t)j : j * p.rks));
+                            for (int j = 0; j < V; j += 4) {
+                                uint4 q = ldg_stream(rp + j);
+                                r[j] = q.x; r[j + 1] = q.y; r[j + 2] = q.z; r[j + 3] = q.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < V; ++j) r[j] = __ldg(rp + (FLAT ? (int64_t)j : j * p.rks));
+                        }
                     }
                 }
                 switch (st.kind) {

@@ -205,6 +205,10 @@ template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const 
             if (st.asym) q = bfp_asym_fix(q, v[j], b);
             v[j] = q;
         }
+    } else if (st.mode == R_STOCHASTIC && !st.asym) {  // stochastic rounding is a first-class mode: inlined
+        BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem<R_STOCHASTIC>(v[j], b, st.sh, st.mask, r[j]);
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = bfp_elem_slow(v[j], m, st.wl, st.sh, st.mask, st.mode, st.asym, r[j]);
