@@ -131,15 +131,66 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_const
     }
 }
 
+// vectorised variant: inner % V == 0, so one 16-byte vector never straddles two channels
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p)
+{
+    constexpr int V = VecIO<Tin>::V;
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
+    Tout *__restrict__ y = static_cast<Tout *>(p.y);
+    const int64_t nvec = p.n / V;
+    const int64_t inner_vec = p.inner / V;
+    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * kThreads) {
+        int64_t c = (g / inner_vec) % p.C;
+        int64_t q = p.nq == 1 ? 0 : min(c / p.group, p.nq - 1);
+        const float sc = __ldg(p.scale + q), zp = __ldg(p.zp + q);
+        float v[V], r[V];
+        VecIO<Tin>::load(x + g * V, v);
+        if (p.rnd) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) r[j] = __ldg(p.rnd + g * V + j);
+        }
+        if (p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY) {
+            const bool scaled = p.xf.up != 1.0f;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float a = __fadd_rn(__fdiv_rn(v[j], sc), zp);
+                if (scaled) a = __fmul_rn(a, p.xf.up);
+                a = roundf(a);
+                if (scaled) a = __fmul_rn(a, p.xf.down);
+                if (p.xf.clamp) a = a > p.xf.t_max ? p.xf.t_max : (a < p.xf.t_min ? p.xf.t_min : a);
+                v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? r[j] : 0.5f);
+        }
+        VecIO<Tout>::template store<V>(y + g * V, v);
+    }
+}
+
+template <typename Tin, typename Tout> static void launch_fixed_chan_t(const FixedChanParams &p, cudaStream_t s)
+{
+    constexpr int V = VecIO<Tin>::V;
+    const bool vec = p.inner % V == 0 && p.n % V == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.y) % 16) == 0 &&
+                     (!p.rnd || (reinterpret_cast<uintptr_t>(p.rnd) % 16) == 0);
+    if (vec) {
+        int64_t grid = std::min<int64_t>((p.n / V + kThreads - 1) / kThreads, 148 * 32);
+        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(p);
+    } else {
+        int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
+        fixed_chan_kernel<Tin, Tout><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    }
+}
+
 cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, cudaStream_t s)
 {
     if (p.n <= 0) return cudaSuccess;
-    int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
-    if (in_dt == 0 && out_dt == 0) fixed_chan_kernel<float, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else if (in_dt == 1 && out_dt == 1) fixed_chan_kernel<__nv_bfloat16, __nv_bfloat16><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else if (in_dt == 2 && out_dt == 2) fixed_chan_kernel<__half, __half><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else if (in_dt == 1 && out_dt == 0) fixed_chan_kernel<__nv_bfloat16, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
-    else if (in_dt == 2 && out_dt == 0) fixed_chan_kernel<__half, float><<<(unsigned)grid, kThreads, 0, s>>>(p);
+    if (in_dt == 0 && out_dt == 0) launch_fixed_chan_t<float, float>(p, s);
+    else if (in_dt == 1 && out_dt == 1) launch_fixed_chan_t<__nv_bfloat16, __nv_bfloat16>(p, s);
+    else if (in_dt == 2 && out_dt == 2) launch_fixed_chan_t<__half, __half>(p, s);
+    else if (in_dt == 1 && out_dt == 0) launch_fixed_chan_t<__nv_bfloat16, float>(p, s);
+    else if (in_dt == 2 && out_dt == 0) launch_fixed_chan_t<__half, float>(p, s);
     else return cudaErrorInvalidValue;
     count_launch();
     return cudaGetLastError();

@@ -602,3 +602,22 @@ def test_degenerate_shapes():
             assert y.shape == x.shape
             if x.numel():
                 check(y, bits(O.cast(x.cpu().numpy(), "BFP[8|8]{64}(SN)", -1)), f"bfp {shape}")
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_per_channel_and_group_fixed_point_vectorised(dt):
+    """per-channel (ch_axis 0 and 1) and group qparams on shapes that take the 16-byte-vector kernel"""
+    g = torch.Generator().manual_seed(13)
+    x = (torch.randn(48, 64, 32, generator=g) * 30).to(dt)
+    xf = x.float().numpy()
+    for ch_axis, group in ((0, None), (1, None), (1, 16), (0, 5)):
+        C = x.shape[ch_axis]
+        nq = C if group is None else -(-C // group)
+        sc = torch.rand(nq, generator=g) * 0.5 + 0.02
+        zp = torch.round(torch.randn(nq, generator=g) * 4)
+        want = O.cast(xf, "XP[8,0](CSN)", tie=O.TIE_AWAY, scale=sc.tolist(), zero_point=zp.tolist(), ch_axis=ch_axis, group_size=group)
+        y = ops.fixed_qdq(x.to(DEV), 8, 0, True, True, "nearest", scale=sc.to(DEV), zero_point=zp.to(DEV), ch_axis=ch_axis, group_size=group)
+        if dt == torch.float32:
+            check(y, bits(want), f"ch_axis={ch_axis} group={group}")
+        else:
+            check(y, torch.from_numpy(want).to(dt).view(torch.int16).numpy().view(np.uint16), f"ch_axis={ch_axis} group={group}", dtype="bfloat16")
