@@ -308,8 +308,35 @@ def extra_sweep(dev):
                     torch.cuda.synchronize()
                     ts.append(a.elapsed_time(b) / reps)
                 ts.sort()
-                out.append({"format": name, "dtype": str(dt).split(".")[-1], "log2_elements": e, "us_per_cast": round(ts[2] * 1e3, 2),
-                            "GB/s": round(footprint / ts[2] / 1e6, 1), "mode": "hbm_rotating" if nbuf > 1 else "hbm"})
+                row = {"format": name, "dtype": str(dt).split(".")[-1], "log2_elements": e, "us_per_cast": round(ts[2] * 1e3, 2),
+                       "GB/s": round(footprint / ts[2] / 1e6, 1), "mode": "hbm_rotating" if nbuf > 1 else "hbm"}
+                if e <= 24:
+                    # below ~2^24 elements a cast is shorter than the python + launch path (~15 us): the same 20
+                    # launches replayed from a CUDA graph show the device-side time
+                    g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(side):
+                        ops.cast_chain(xs[0], st, -1, out=ys[0])
+                    torch.cuda.current_stream().wait_stream(side)
+                    with torch.cuda.graph(g):
+                        for i in range(reps):
+                            ops.cast_chain(xs[i % nbuf], st, -1, out=ys[i % nbuf])
+                    g.replay()
+                    tg = []
+                    for _ in range(5):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        torch.cuda.synchronize()
+                        a.record()
+                        g.replay()
+                        b.record()
+                        torch.cuda.synchronize()
+                        tg.append(a.elapsed_time(b) / reps)
+                    tg.sort()
+                    row["us_per_cast_cuda_graph"] = round(tg[2] * 1e3, 2)
+                    row["GB/s_cuda_graph"] = round(footprint / tg[2] / 1e6, 1)
+                    del g
+                out.append(row)
             del xs, ys
             torch.cuda.empty_cache()
     return out
