@@ -184,8 +184,13 @@ __device__ __forceinline__ uint32_t lanes_max(uint32_t m, int lanes)
 template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const StageDev &st, int lanes, const uint32_t (&r)[V])
 {
     uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
-    if (st.mode == R_NEAREST && st.fast && !st.asym && bfp_fast_ok(m)) {
+    if (st.mode == R_NEAREST && st.fast && bfp_fast_ok(m)) {
         BfpFast b = bfp_fast_block(m, st.wl);
+        float x0[V];
+        if (st.asym) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) x0[j] = v[j];
+        }
         if (st.fast16) {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
@@ -196,6 +201,15 @@ template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const 
         if (b.clamp) {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+        }
+        if (st.asym) {
+            // the edge mantissa -(2^(wl-1)-1) needs |x| >= maxval - Q/2: only blocks whose max is within one
+            // quantum of maxval (a safe superset) can hold it
+            BfpBlock bb = bfp_block(m, st.wl);
+            if (m >= bb.maxnum - (1u << (23 - (st.wl - 2)))) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = bfp_asym_fix(v[j], x0[j], bb);
+            }
         }
     } else if (st.mode == R_NEAREST) {
         BfpBlock b = bfp_block(m, st.wl);

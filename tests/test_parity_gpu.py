@@ -621,3 +621,30 @@ def test_per_channel_and_group_fixed_point_vectorised(dt):
             check(y, bits(want), f"ch_axis={ch_axis} group={group}")
         else:
             check(y, torch.from_numpy(want).to(dt).view(torch.int16).numpy().view(np.uint16), f"ch_axis={ch_axis} group={group}", dtype="bfloat16")
+
+
+def test_asymmetric_bfp_edge_blocks():
+    """BFP16A / BFP12A fast path: blocks whose most negative element sits on / next to the -(2^(wl-1)-1)
+    mantissa, with the block max just below, at and above the clamp threshold"""
+    g = torch.Generator().manual_seed(17)
+    rows = []
+    for wl in (8, 4):
+        q = 2.0 ** (2 - wl)
+        for top in (2 - q, 2 - 1.5 * q, 2 - 0.75 * q, 2 - 0.5 * q, 2 - 0.25 * q, 1.9999999, 2 - 2 * q):
+            for sign in (1.0, -1.0):
+                b = torch.randn(64, generator=g) * 0.3
+                b[0] = sign * top
+                b[1] = -(2 - q)
+                b[2] = -(2 - 0.5 * q)
+                b[3] = -(2 - 1.49 * q)
+                b[4] = -(2 - 0.51 * q)
+                rows.append(b * 2.0 ** int(torch.randint(-10, 10, (1,), generator=g)))
+    x = torch.stack(rows)
+    for sh in ("BFP[8|8]{64}(_N)", "BFP[4|8]{64}(_N)", "BFP[6|8]{16}(_N)"):
+        want = O.cast(x.numpy(), sh, -1)
+        check(gpu_cast(x.to(DEV), sh, -1), bits(want), sh)
+        xb = x.to(torch.bfloat16)
+        want = O.cast(xb.float().numpy(), sh, -1)
+        check(gpu_cast(xb.to(DEV), sh, -1), bits(want), sh + " bf16")
+        want = O.cast(x.numpy().T.copy(), sh, 0)
+        check(gpu_cast(x.t().contiguous().to(DEV), sh, 0), bits(want), sh + " cols")
