@@ -60,6 +60,8 @@ def _load():
         "dmxq_fixed_qdq": ([TP, TP] + [I] * 6 + [VP, VP, I64, I, I64, VP, VP], I),
         "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, VP], I),
         "dmxq_add_cast": ([TP, TP, TP, SP, SP, SP, VP], I),
+        "dmxq_bfp_pack": ([TP, VP, VP, I, I, VP], I),
+        "dmxq_bfp_unpack": ([VP, VP, TP, I, I, VP], I),
         "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
         "dmxq_minmax": ([TP, I, VP, VP, VP], I),
         "dmxq_cast_chain_host": ([VP, VP, I, I, I64, I64, SP, I, I], I),

@@ -684,6 +684,46 @@ int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor 
     return DMXQ_OK;
 }
 
+static int packed_args(const dmxq_tensor *t, const void *mant, const void *exps, int block_size, int precision, int64_t *n)
+{
+    if (!t || !mant || !exps) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (t->dtype < 0 || t->dtype > 2) return fail(DMXQ_ERR_BAD_ARG, "bad dtype");
+    if (precision < 2 || precision > 8) return fail(DMXQ_ERR_UNSUPPORTED, "packed BFP supports precision 2..8, got %d", precision);
+    const int V = 16 / dtype_size(t->dtype);
+    if (block_size < 16 || block_size % 16 != 0 || !pow2(block_size / V) || block_size / V > 32)
+        return fail(DMXQ_ERR_UNSUPPORTED, "packed BFP needs a power-of-two block size in 16..%d, got %d", 32 * V, block_size);
+    int64_t total = 1, expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {
+        if (t->shape[i] != 1 && t->stride[i] != expect) return fail(DMXQ_ERR_UNSUPPORTED, "packed BFP needs a contiguous tensor");
+        expect *= t->shape[i];
+        total *= t->shape[i];
+    }
+    if (t->ndim < 1 || t->shape[t->ndim - 1] % block_size != 0) return fail(DMXQ_ERR_BAD_ARG, "last dim must be a multiple of the block size");
+    if (total && !aligned(t->data, 16)) return fail(DMXQ_ERR_UNSUPPORTED, "packed BFP needs 16-byte aligned data");
+    *n = total;
+    return DMXQ_OK;
+}
+
+int dmxq_bfp_pack(const dmxq_tensor *x, void *mantissas, uint8_t *exponents, int block_size, int precision, void *stream)
+{
+    int64_t n = 0;
+    int rc = packed_args(x, mantissas, exponents, block_size, precision, &n);
+    if (rc || n == 0) return rc;
+    cudaError_t e = launch_bfp_pack(x->dtype, x->data, mantissas, exponents, n, block_size, precision, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "bfp_pack_kernel");
+    return DMXQ_OK;
+}
+
+int dmxq_bfp_unpack(const void *mantissas, const uint8_t *exponents, const dmxq_tensor *y, int block_size, int precision, void *stream)
+{
+    int64_t n = 0;
+    int rc = packed_args(y, mantissas, exponents, block_size, precision, &n);
+    if (rc || n == 0) return rc;
+    cudaError_t e = launch_bfp_unpack(y->dtype, mantissas, exponents, y->data, n, block_size, precision, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "bfp_unpack_kernel");
+    return DMXQ_OK;
+}
+
 int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream)
 {
     if (!x || !out_min || !out_max) return fail(DMXQ_ERR_BAD_ARG, "null argument");

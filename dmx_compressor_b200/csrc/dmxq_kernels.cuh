@@ -145,6 +145,8 @@ cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, c
 cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s);
 cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s);
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
+cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s);
+cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s);
 int64_t launch_count();
 

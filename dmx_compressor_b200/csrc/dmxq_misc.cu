@@ -447,6 +447,124 @@ cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s)
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed BFP storage (see dmxq_bfp_pack in include/dmxq.h).  Same tiling as the rows kernel; the
+// integer mantissa falls out of the float-add rounding trick for free: u = (x + base) + C has
+// ulp == Q, so bits(u) - bits(C) is t / Q as an integer and k = that - base / Q = ... - 3 * 2^(wl-1)
+// (16-bit sources skip the base: bits(x + C) - bits(C) is x / Q directly).
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ exps, int64_t n_vec, int lanes, int wl)
+{
+    constexpr int V = VecIO<T>::V;
+    constexpr int U = 4;
+    constexpr bool SRC16 = sizeof(T) == 2;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const int kmax = (1 << (wl - 1)) - 1;
+    const bool two_add = !(SRC16 && ((std::is_same<T, __nv_bfloat16>::value && wl <= 14) || (std::is_same<T, __half>::value && wl <= 11)));
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int64_t g = g0 + (int64_t)u * kThreads;
+        raw[u] = g < n_vec ? ldg_stream(x + g * V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        float v[V];
+        uint32_t m = lanes_max(unpack_absmax<T>(raw[u], v), lanes);
+        int k[V];
+        const bool ok = bfp_fast_ok(m);
+        if (ok) {
+            BfpFast b = bfp_fast_block(m, wl);
+            const int cb = (int)f2u(b.C);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float uu = two_add ? __fadd_rn(__fadd_rn(v[j], b.base), b.C) : __fadd_rn(v[j], b.C);
+                int q = (int)f2u(uu) - cb - (two_add ? 3 * (1 << (wl - 1)) : 0);
+                k[j] = max(-kmax, min(kmax, q));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) k[j] = 0;
+        }
+        if (g >= n_vec) continue;
+        if ((threadIdx.x & (lanes - 1)) == 0) exps[g / lanes] = ok ? (uint8_t)(m >> 23) : 0;
+        if (NIBBLE) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc |= ((uint32_t)k[j] & 0xFu) << (4 * j);
+            if (V == 8) reinterpret_cast<uint32_t *>(mant)[g] = acc;
+            else reinterpret_cast<uint16_t *>(mant)[g] = (uint16_t)acc;
+        } else {
+            uint32_t w[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < V; ++j) w[j / 4] |= ((uint32_t)k[j] & 0xFFu) << (8 * (j & 3));
+            if (V == 8) reinterpret_cast<uint2 *>(mant)[g] = make_uint2(w[0], w[1]);
+            else reinterpret_cast<uint32_t *>(mant)[g] = w[0];
+        }
+    }
+}
+
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_unpack_kernel(const uint8_t *__restrict__ mant, const uint8_t *__restrict__ exps, T *__restrict__ y, int64_t n_vec, int lanes, int wl)
+{
+    constexpr int V = VecIO<T>::V;
+    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (g >= n_vec) return;
+    const int ef = exps[g / lanes];
+    // quantum Q = 2^(ef - 127 + 2 - wl), applied as two exact power-of-two factors so that a denormal Q stays exact
+    const int qe = ef + 2 - wl;
+    const float s1 = u2f((uint32_t)max(qe, 1) << 23), s2 = qe >= 1 ? 1.0f : u2f((uint32_t)(127 + qe - 1) << 23);
+    int k[V];
+    if (NIBBLE) {
+        uint32_t acc = V == 8 ? reinterpret_cast<const uint32_t *>(mant)[g] : (uint32_t) reinterpret_cast<const uint16_t *>(mant)[g];
+#pragma unroll
+        for (int j = 0; j < V; ++j) k[j] = ((int)(acc << (28 - 4 * j))) >> 28;
+    } else {
+        uint32_t w[2];
+        if (V == 8) { uint2 t = reinterpret_cast<const uint2 *>(mant)[g]; w[0] = t.x; w[1] = t.y; }
+        else { w[0] = reinterpret_cast<const uint32_t *>(mant)[g]; w[1] = 0; }
+#pragma unroll
+        for (int j = 0; j < V; ++j) k[j] = ((int)(w[j / 4] << (24 - 8 * (j & 3)))) >> 24;
+    }
+    float v[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = ef == 0 ? 0.0f : __fmul_rn(__fmul_rn((float)k[j], s1), s2);
+    VecIO<T>::template store<V>(y + g * V, v);
+}
+
+cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s)
+{
+    const int V = dt == 0 ? 4 : 8;
+    int64_t n_vec = n / V;
+    int64_t grid = (n_vec + kThreads * 4 - 1) / (kThreads * 4);
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    const bool nib = wl <= 4;
+    uint8_t *m8 = static_cast<uint8_t *>(mant);
+#define DMXQ_PACK(T) do { if (nib) bfp_pack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, wl); \
+                          else bfp_pack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, wl); } while (0)
+    if (dt == 0) DMXQ_PACK(float); else if (dt == 1) DMXQ_PACK(__nv_bfloat16); else DMXQ_PACK(__half);
+#undef DMXQ_PACK
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s)
+{
+    const int V = dt == 0 ? 4 : 8;
+    int64_t n_vec = n / V;
+    int64_t grid = (n_vec + kThreads - 1) / kThreads;
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    const bool nib = wl <= 4;
+    const uint8_t *m8 = static_cast<const uint8_t *>(mant);
+#define DMXQ_UNPACK(T) do { if (nib) bfp_unpack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, B / V, wl); \
+                            else bfp_unpack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, B / V, wl); } while (0)
+    if (dt == 0) DMXQ_UNPACK(float); else if (dt == 1) DMXQ_UNPACK(__nv_bfloat16); else DMXQ_UNPACK(__half);
+#undef DMXQ_UNPACK
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void fold_absmax_kernel(const float *mn, const float *mx, uint32_t *out, int64_t C)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

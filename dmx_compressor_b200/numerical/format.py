@@ -247,6 +247,16 @@ class BlockFloatingPoint(Format):
     def stage(self):
         return ops.bfp_stage(self.block_size, self.precision, self.symmetric, self.rounding)
 
+    # packed storage: the real format whose size `bytes_per_elem` reports (reference format.py:345-347)
+    def pack(self, x: torch.Tensor):
+        """-> (mantissas, exponents); blocks along the last dim; symmetric nearest formats, precision <= 8"""
+        assert self.symmetric and self.rounding == "nearest" and self.precision <= 8, "packed storage: symmetric nearest, <= 8 bits"
+        return ops.bfp_pack(x, self.block_size, self.precision)
+
+    def unpack(self, mantissas: torch.Tensor, exponents: torch.Tensor, dtype=torch.float32):
+        """dequantise packed storage; equals ``cast`` of the original tensor bit for bit"""
+        return ops.bfp_unpack(mantissas, exponents, self.block_size, self.precision, dtype)
+
     @property
     def bytes_per_elem(self) -> float:
         return (self.precision + 8.0 / self.block_size) / 8.0

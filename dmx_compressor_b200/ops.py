@@ -213,6 +213,34 @@ def add_cast(a, b, stage_a=None, stage_b=None, stage_out=None, out=None):
     return y
 
 
+def bfp_pack(x, block_size=64, precision=8):
+    """-> (mantissas, exponents): packed BFP storage of a contiguous [..., K] tensor (dmxq_bfp_pack).
+    mantissas: int8 [..., K] (precision 5..8) or uint8 [..., K/2] (precision <= 4, two nibbles per byte);
+    exponents: uint8 [..., K / block_size]."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    K = x.shape[-1]
+    mant = torch.empty(x.shape[:-1] + ((K // 2,) if precision <= 4 else (K,)), dtype=torch.uint8 if precision <= 4 else torch.int8, device=x.device)
+    exps = torch.empty(x.shape[:-1] + (K // block_size,), dtype=torch.uint8, device=x.device)
+    vx = L.view(x)
+    with _guard(x.device):
+        rc = L.lib.dmxq_bfp_pack(C.byref(vx), mant.data_ptr(), exps.data_ptr(), block_size, precision, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_bfp_pack")
+    return mant, exps
+
+
+def bfp_unpack(mant, exps, block_size=64, precision=8, dtype=torch.float32):
+    """dequantise packed BFP storage (dmxq_bfp_unpack): bit-identical to bfp_qdq of the original tensor."""
+    L.require_cuda(mant, "mantissas")
+    K = mant.shape[-1] * (2 if precision <= 4 else 1)
+    y = torch.empty(mant.shape[:-1] + (K,), dtype=dtype, device=mant.device)
+    vy = L.view(y)
+    with _guard(mant.device):
+        rc = L.lib.dmxq_bfp_unpack(mant.data_ptr(), exps.data_ptr(), C.byref(vy), block_size, precision, L.stream_ptr(mant.device))
+    L.check(rc, "dmxq_bfp_unpack")
+    return y
+
+
 def minmax(x, ch_axis: Optional[int] = None):
     """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax."""
     L.require_cuda(x)

@@ -23,6 +23,7 @@
  *                          (sparsify -> storage cast -> weight cast in ONE pass), and any
  *                          back-to-back CastTo pair (output cast -> next input cast)
  *   dmxq_add_cast          ResAdd.forward (casts + add fused)  S/modeling/nn/torch_modules.py:15-37
+ *   dmxq_bfp_pack/unpack   packed BFP storage (QuantizeBFP/DequantizeBFP of the ONNX export, S/numerical/cast.py:34-55)
  *   dmxq_block_quantize    L1 block_quantize(x, wl, dim,...) Q/quant_cuda/quant.cu:14-112
  *   dmxq_minmax            MinMaxObserver.forward statistics S/numerical/observer.py:173-193
  *   dmxq_cast_chain_host   same as dmxq_cast_chain on HOST buffers (pipelined H2D/compute/D2H)
@@ -164,6 +165,20 @@ int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_ten
  * Intermediates are rounded to the tensor dtype exactly where the unfused module sequence rounds. */
 int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor *y, const dmxq_stage *stage_a,
                   const dmxq_stage *stage_b, const dmxq_stage *stage_out, void *stream);
+
+/* ---- packed BFP storage: the real format behind the simulation ------------
+ * The reference only ever materialises dequantised fp32 tensors, but it reports the packed size
+ * (BlockFloatingPoint.bytes_per_elem, S/numerical/format.py:345-347) and names the packed ops in its ONNX
+ * export (com.microsoft::QuantizeBFP / DequantizeBFP, S/numerical/cast.py:34-55).  These two entry points
+ * are that pair: per block of `block_size` consecutive elements one uint8 shared exponent (the biased
+ * fp32 exponent of the block max) and `block_size` signed mantissas of `precision` bits -- int8 each for
+ * precision 5..8, two per byte (low nibble first) for precision <= 4.
+ *   x / y: contiguous [rows, K], K % block_size == 0, block_size % 16 == 0; nearest rounding, symmetric.
+ *   dmxq_bfp_unpack(dmxq_bfp_pack(x)) == dmxq_bfp_qdq(x) bit for bit for every block whose max is a normal
+ *   number below 2^101; blocks outside that range (all-denormal, huge, non-finite) are stored as zeros. */
+int dmxq_bfp_pack(const dmxq_tensor *x, void *mantissas, uint8_t *exponents, int block_size, int precision, void *stream);
+int dmxq_bfp_unpack(const void *mantissas, const uint8_t *exponents, const dmxq_tensor *y, int block_size, int precision,
+                    void *stream);
 
 /* ---- L1 mirror: block_quantize(x, wl, dim, symmetric, rounding) of quant_cuda --------------
  * dim == -1: one exponent for the whole tensor; dim == 0: per row of view(size0,-1);

@@ -648,3 +648,37 @@ def test_asymmetric_bfp_edge_blocks():
         check(gpu_cast(xb.to(DEV), sh, -1), bits(want), sh + " bf16")
         want = O.cast(x.numpy().T.copy(), sh, 0)
         check(gpu_cast(x.t().contiguous().to(DEV), sh, 0), bits(want), sh + " cols")
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("wl,bs", [(8, 64), (4, 64), (8, 16), (6, 32), (4, 128), (2, 64), (8, 128)])
+def test_packed_bfp_storage_round_trip(dt, wl, bs):
+    """dmxq_bfp_unpack(dmxq_bfp_pack(x)) == the QDQ cast, bit for bit; packed size == Format.bytes_per_elem"""
+    from dmx_compressor_b200.numerical import BlockFloatingPoint
+
+    if dt != torch.float32 and bs // 8 > 32:
+        pytest.skip("block too wide for one warp")
+    x = _rand((96, 1024), 100 + wl + bs, spread=12 if dt != torch.float16 else 5).to(dt)  # (fp16 would overflow to inf)
+    x.view(-1)[::5] = torch.round(x.view(-1)[::5].float() * 16).to(dt) / 16
+    x[5] = 0
+    assert torch.isfinite(x).all()
+    xd = x.to(DEV)
+    f = BlockFloatingPoint(precision=wl, block_size=bs)
+    want = ops.cast_chain(xd, [f.stage()], -1)
+    mant, exps = ops.bfp_pack(xd, bs, wl)
+    stored_bits = 8 if wl > 4 else 4  # mantissas are byte- or nibble-aligned
+    assert mant.numel() * mant.element_size() + exps.numel() == x.numel() * stored_bits // 8 + x.numel() // bs
+    if wl in (8, 4):
+        assert mant.numel() * mant.element_size() + exps.numel() == int(f.bytes_per_elem * x.numel())
+    got = ops.bfp_unpack(mant, exps, bs, wl, dtype=dt)
+    v = torch.int32 if dt == torch.float32 else torch.int16
+    assert torch.equal(got.view(v), want.view(v))
+    # mantissas really are wl-bit integers and the exponent byte is the block exponent
+    if wl > 4:
+        assert int(mant.abs().max()) <= 2 ** (wl - 1) - 1
+    e = torch.floor(torch.log2(x.float().abs().view(96, -1, bs).amax(-1).clamp_min(1e-38))) + 127
+    nz = x.float().abs().view(96, -1, bs).amax(-1) > 0
+    assert torch.equal(exps.cpu().float()[nz], e[nz])
+    # and against the oracle
+    if dt == torch.float32:
+        check(got, bits(O.cast(x.numpy(), f"BFP[{wl}|8]{{{bs}}}(SN)", -1)), "packed vs oracle")
