@@ -24,7 +24,7 @@ ABI_VERSION = 1
 F32, BF16, F16 = 0, 1, 2
 ROUND = {"nearest": 0, "stochastic": 1, "up": 2, "down": 3}
 TIE_AWAY, TIE_EVEN = 0, 1
-ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED = 0, 1, 2, 3, 4, 5
+ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED, ST_MXFP = 0, 1, 2, 3, 4, 5, 6
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 

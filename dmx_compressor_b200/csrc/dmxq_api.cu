@@ -151,12 +151,20 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         d.affine = !(s.scale == 1.0f && s.zero_point == 0.0f);
         return DMXQ_OK;
     }
+    case DMXQ_STAGE_MXFP: {
+        if (s.block < 1) return fail(DMXQ_ERR_BAD_ARG, "block size has to be positive, got %d", s.block);
+        if (s.exp < 1 || s.exp > 7) return fail(DMXQ_ERR_UNSUPPORTED, "MXFP element exponent bits must be 1..7, got %d", s.exp);
+        int rc = decode_float(s.man, s.exp, (1 << (s.exp - 1)) - 1, 0, 0, 0, DMXQ_ROUND_NEAREST, d.ff);  // format.py:585-592
+        if (rc) return rc;
+        d.mx_largest = std::ldexp(1.0f, 1 << (s.exp - 1));  // FloatingPoint.largest_representable_power_of_two, format.py:235-237
+        return DMXQ_OK;
+    }
     default:
         return fail(DMXQ_ERR_BAD_ARG, "unknown stage kind %d", s.kind);
     }
 }
 
-inline bool stage_blocked(const StageDev &d) { return d.kind == ST_NM || d.kind == ST_BFP || d.kind == ST_SBFP; }
+inline bool stage_blocked(const StageDev &d) { return d.kind == ST_NM || d.kind == ST_BFP || d.kind == ST_SBFP || d.kind == ST_MXFP; }
 inline int stage_mode(const StageDev &d) { return d.kind == ST_FLOAT ? d.ff.mode : d.kind == ST_FIXED ? d.xf.mode : d.kind == ST_BFP ? d.mode : 0; }
 
 struct Dim {
@@ -349,7 +357,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         }
         for (int s = 0; s < chain.n && rows_ok; ++s) {
             const StageDev &sd = chain.st[s];
-            if (sd.kind == ST_BFP || sd.kind == ST_SBFP) {
+            if (sd.kind == ST_BFP || sd.kind == ST_SBFP || sd.kind == ST_MXFP) {
                 rows_ok &= sd.block % V == 0 && pow2(sd.block / V) && sd.block / V <= 32;
                 tile = std::max<int64_t>(tile, sd.block);
             } else if (sd.kind == ST_NM) {
@@ -421,7 +429,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         for (int s = 0; s < chain.n; ++s) {
             const StageDev &sd = chain.st[s];
             if (sd.kind == ST_NM) ok = false;
-            if (sd.kind == ST_BFP || sd.kind == ST_SBFP) {
+            if (sd.kind == ST_BFP || sd.kind == ST_SBFP || sd.kind == ST_MXFP) {
                 if (B == 0) B = sd.block; else if (B != sd.block) ok = false;
             }
         }

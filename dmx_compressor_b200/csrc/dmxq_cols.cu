@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 
 #pragma unroll 1
     for (int s = 0; s < p.chain.n; ++s) {
         const StageDev &st = p.chain.st[s];
-        if (st.kind == ST_BFP || st.kind == ST_SBFP) {
+        if (st.kind == ST_BFP || st.kind == ST_SBFP || st.kind == ST_MXFP) {
             uint32_t m[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
@@ -114,6 +114,13 @@ __global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 
                             rnd = __ldg(static_cast<const uint32_t *>(p.rnd) + ro + (kb + r) * p.rks + (i0 + j) * p.ris);
                         v[r][j] = bfp_elem_slow(v[r][j], m[j], st.wl, st.sh, st.mask, st.mode, st.asym, rnd);
                     }
+            } else if (st.kind == ST_MXFP) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    MxBlock b = mx_block(m[j], st.mx_largest);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) v[r][j] = mx_elem_ol(v[r][j], b.scale, &st.ff);
+                }
             } else {
                 const bool fast = sbfp_fast(st.sb);
 #pragma unroll

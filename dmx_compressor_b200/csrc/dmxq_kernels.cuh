@@ -33,6 +33,8 @@ struct StageDev {
     float sc, zp;
     // SBFP
     SbfpFmt sb;
+    // MXFP (element format in ff)
+    float mx_largest;  // 2^(2^(exp_bits-1))
 };
 
 struct ChainDev {

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kThreads) chain_generic_kernel(const __grid_co
     Tout *y = static_cast<Tout *>(p.y) + yo;
     const uint32_t *rnd = p.rnd ? static_cast<const uint32_t *>(p.rnd) + ro : nullptr;
 
-    if (st.kind == ST_BFP || st.kind == ST_SBFP) {
+    if (st.kind == ST_BFP || st.kind == ST_SBFP || st.kind == ST_MXFP) {
         uint32_t m = 0;
         for (int64_t k = k0; k < k1; ++k) m = max(m, f2u(Cvt<Tin>::to_f32(x[k * p.xks])) & 0x7FFFFFFFu);
         if (st.kind == ST_BFP) {
@@ -54,6 +54,10 @@ __global__ void __launch_bounds__(kThreads) chain_generic_kernel(const __grid_co
                 uint32_t r = (rnd && st.mode == R_STOCHASTIC) ? rnd[k * p.rks] : 0u;
                 y[k * p.yks] = Cvt<Tout>::from_f32(bfp_elem_slow(xv, m, st.wl, st.sh, st.mask, st.mode, st.asym, r));
             }
+        } else if (st.kind == ST_MXFP) {
+            MxBlock b = mx_block(m, st.mx_largest);
+            for (int64_t k = k0; k < k1; ++k)
+                y[k * p.yks] = Cvt<Tout>::from_f32(mx_elem_ol(Cvt<Tin>::to_f32(x[k * p.xks]), b.scale, &st.ff));
         } else {
             SbfpBlock b = sbfp_block_ol(m, st.sb);
             for (int64_t k = k0; k < k1; ++k)

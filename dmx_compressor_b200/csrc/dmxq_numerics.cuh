@@ -20,7 +20,7 @@ namespace dmxq {
 
 enum : int { R_NEAREST = 0, R_STOCHASTIC = 1, R_UP = 2, R_DOWN = 3 };
 enum : int { TIE_AWAY = 0, TIE_EVEN = 1 };
-enum : int { ST_NONE = 0, ST_NM = 1, ST_BFP = 2, ST_SBFP = 3, ST_FLOAT = 4, ST_FIXED = 5 };
+enum : int { ST_NONE = 0, ST_NM = 1, ST_BFP = 2, ST_SBFP = 3, ST_FLOAT = 4, ST_FIXED = 5, ST_MXFP = 6 };
 
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
@@ -318,6 +318,26 @@ __device__ __forceinline__ float sbfp_elem(float x, const SbfpBlock &b, const Sb
     float v = __fdiv_rn(x, b.cmax);
     v = fixed_elem(v, f.xp, 0.5f);
     return __fmul_rn(v, b.fs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MXFP.  Reference: MXFP.cast, S/numerical/format.py:545-564:
+//   scale = 2 ** floor(log2(max|chunk|)) / largest_representable_power_of_two      (:551-555)
+//   y     = element_format.cast(chunk / scale) * scale                             (:558)
+// with the very same float functions torch dispatches to on CUDA (log2f, floorf, exp2f, IEEE
+// division / multiplication), so an all-zero block becomes NaN (0 / 0) exactly as in the reference.
+struct MxBlock {
+    float scale;
+};
+__device__ __forceinline__ MxBlock mx_block(uint32_t maxabs_bits, float largest_pow2)
+{
+    MxBlock b;
+    b.scale = __fdiv_rn(exp2f(floorf(log2f(u2f(maxabs_bits)))), largest_pow2);
+    return b;
+}
+__device__ __forceinline__ float mx_elem(float x, const MxBlock &b, const FloatFmt &f)
+{
+    return __fmul_rn(float_elem_nearest(__fdiv_rn(x, b.scale), f), b.scale);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                 case ST_SBFP: sbfp_stage<V>(v, st, lanes); break;
                 case ST_FLOAT: float_stage<V>(v, st, r); break;
                 case ST_FIXED: fixed_stage<V>(v, st, r); break;
+                case ST_MXFP: mxfp_stage<V>(v, st, lanes); break;
                 default: break;
                 }
                 if (st.requant) {

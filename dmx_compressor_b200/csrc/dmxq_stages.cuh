@@ -242,6 +242,34 @@ template <int V> __device__ __forceinline__ void sbfp_stage(float (&v)[V], const
     }
 }
 
+static __device__ __noinline__ float mx_elem_ol(float x, float scale, const FloatFmt *f)
+{
+    MxBlock b{scale};
+    return mx_elem(x, b, *f);
+}
+template <int V> __device__ __forceinline__ void mxfp_stage(float (&v)[V], const StageDev &st, int lanes)
+{
+    uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
+    // floor(log2f(max)) is the exponent field whenever log2(max) is further than a few ulp from an integer,
+    // i.e. unless the mantissa is within 2^-16 of a power of two (log2f is only faithful, and the reference
+    // calls it: in that sliver -- and for denormal / non-finite maxima -- so do we).
+    const uint32_t man = m & 0x007FFFFFu, ef = m >> 23;
+    const int shift = (int)((f2u(st.mx_largest) >> 23) - 127u);
+    MxBlock b;
+    if (man >= 128u && man <= 0x007FFF00u && ef >= 1u && ef <= 254u && (int)ef - shift >= 2 && (int)ef - shift <= 252) b.scale = u2f((uint32_t)((int)ef - shift) << 23);
+    else b = mx_block(m, st.mx_largest);
+    const uint32_t sb = f2u(b.scale);
+    if ((sb & 0x807FFFFFu) == 0u && sb >= (2u << 23) && sb <= (252u << 23)) {
+        // ordinary block: the scale is a normal power of two, so x / scale == x * (1 / scale) exactly
+        const float inv = u2f((254u << 23) - sb);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = __fmul_rn(float_elem_nearest(__fmul_rn(v[j], inv), st.ff), b.scale);
+    } else {  // zero / denormal / huge / non-finite block: the literal op sequence
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = mx_elem_ol(v[j], b.scale, &st.ff);
+    }
+}
+
 template <int V> __device__ __forceinline__ void float_stage(float (&v)[V], const StageDev &st, const uint32_t (&r)[V])
 {
     if (st.ff.fastpath) {

@@ -6,6 +6,7 @@ from .format import (  # noqa: F401
     BlockFloatingPoint,
     ScaledBlockFloatingPoint,
     MXINT,
+    MXFP,
     ROUNDING_MODE,
 )
 from .observer import DMXObserverBase, DummyObserver, MinMaxObserver  # noqa: F401

@@ -67,7 +67,7 @@ class Format:
         elif sh.startswith("MXINT"):
             return MXINT.from_shorthand(sh)
         elif sh.startswith("MXFP"):
-            raise NotImplementedError(f"MXFP formats are not on the CUDA path yet: {sh}")
+            return MXFP.from_shorthand(sh)
         else:
             raise ValueError(f"unrecognized format shorthand: {sh}")
 
@@ -334,6 +334,58 @@ class ScaledBlockFloatingPoint(Format):
 
     def __repr__(self) -> str:
         return f"SBFP<{repr(self.block_format)}><{repr(self.scaler_format)}>{{{self.block_size}}}"
+
+
+class MXFP(Format):
+    r"""MXFP (reference format.py:514-602): low-bit float elements times a power-of-two block scale."""
+
+    blocked = True
+    _RX = re.compile(r"^MXFP(?P<precision>\d+)\[E(?P<exponent>\d+)M(?P<mantissa>\d+)\]\{(?P<block_size>\d+)\}$")
+
+    def __init__(self, element_format: FloatingPoint, block_size=32):
+        assert isinstance(element_format, FloatingPoint), "block format needs to be floating point"
+        assert block_size > 0, f"block size has to be positive, got {block_size}"
+        self.element_format = element_format
+        self.scaler_format = FloatingPoint(mantissa=0, exponent=8, bias=127, unsigned=True)
+        self.block_size = block_size
+
+    def cast(self, x: torch.Tensor, block_dim: int = -1) -> torch.Tensor:
+        return ops.cast_chain(x, [self.stage()], block_dim, out_dtype=torch.float32)
+
+    def stage(self):
+        e = self.element_format
+        assert e.bias == 2 ** (e.exponent - 1) - 1 and not e.flush_subnormal and not e.unsigned and e.rounding == "nearest", \
+            "MXFP element formats are E<e>M<m> with the default bias, subnormals kept, nearest rounding"
+        return ops.mxfp_stage(self.block_size, e.mantissa, e.exponent)
+
+    @property
+    def bytes_per_elem(self) -> float:
+        return self.element_format.bytes_per_elem + self.scaler_format.bytes_per_elem / self.block_size
+
+    @property
+    def bit_precision(self) -> float:
+        return self.element_format.bit_precision + 8.0 / self.block_size
+
+    @classmethod
+    def from_shorthand(cls, sh: str):
+        m = cls._RX.match(sh)
+        if m is None:
+            raise _bad(sh)
+        assert int(m["precision"]) == int(m["exponent"]) + int(m["mantissa"]) + 1
+        e = int(m["exponent"])
+        return cls(element_format=FloatingPoint(mantissa=int(m["mantissa"]), exponent=e, bias=2 ** (e - 1) - 1, flush_subnormal=False,
+                                                unsigned=False, rounding="nearest"), block_size=int(m["block_size"]))
+
+    def __str__(self) -> str:
+        return (f"Simulated MXFP format: element format = {self.element_format}, scaler format = {self.scaler_format},\n"
+                f" block size = {self.block_size}")
+
+    def __repr__(self) -> str:
+        e = self.element_format
+        return f"MXFP{e.exponent + e.mantissa + 1}[E{e.exponent}M{e.mantissa}]{{{self.block_size}}}"
+
+    def __reduce__(self):
+        return (self.__class__, (self.element_format, self.block_size))
 
 
 class MXINT(BlockFloatingPoint):

@@ -74,6 +74,10 @@ def sbfp_stage(block_size: int, xp_precision: int, xp_clamp: bool, xp_rounding: 
                       sc_rounding=L.ROUND[sc_rounding])
 
 
+def mxfp_stage(block_size: int, mantissa: int, exponent: int) -> L.Stage:
+    return make_stage(kind=L.ST_MXFP, block=block_size, man=mantissa, exp=exponent)
+
+
 def nm_stage(n_keep: int, m: int) -> L.Stage:
     return make_stage(kind=L.ST_NM, block=m, n_keep=n_keep)
 

@@ -98,8 +98,12 @@ typedef enum dmxq_stage_kind {
     DMXQ_STAGE_SBFP = 3,  /* scaled BFP       : block, precision(XP wl), clamp, rounding(XP), tie,   */
                           /*                    sc_* = scaler FloatingPoint format                   */
     DMXQ_STAGE_FLOAT = 4, /* low-bit float    : man, exp, bias, flush, is_unsigned, fp16_flush, rounding */
-    DMXQ_STAGE_FIXED = 5  /* fixed point      : precision(wl), fraction(fl), clamp, symmetric,       */
+    DMXQ_STAGE_FIXED = 5, /* fixed point      : precision(wl), fraction(fl), clamp, symmetric,       */
                           /*                    rounding, tie, scale, zero_point (per-tensor affine) */
+    DMXQ_STAGE_MXFP = 6   /* MX floating pt   : block, man, exp (element format E<exp>M<man>, bias    */
+                          /*                    2^(exp-1)-1, subnormals kept, nearest); power-of-two  */
+                          /*                    block scale 2^floor(log2 max) / 2^(2^(exp-1))         */
+                          /*                    (MXFP.cast, S/numerical/format.py:545-564)            */
 } dmxq_stage_kind;
 
 typedef struct dmxq_stage {

@@ -291,6 +291,33 @@ void orc_sbfp_cast(const float *x, float *y, int64_t outer, int64_t K, int64_t i
             }
 }
 
+/* MXFP.cast: S/numerical/format.py:545-564.
+ *   scale = 2 ** floor(log2(max|chunk|)) / largest_representable_power_of_two       (:551-555)
+ *   y     = element_format.cast(chunk / scale) * scale                               (:558)
+ * element format: E<exp>M<man>, bias 2^(exp-1)-1, subnormals kept, nearest (:585-592).  An all-zero
+ * chunk gives scale 0 and 0/0 = NaN, exactly as the torch ops do. */
+void orc_mxfp_cast(const float *x, float *y, int64_t outer, int64_t K, int64_t inner, int64_t bs, int man, int exp_bits)
+{
+    float largest = ldexpf(1.0f, 1 << (exp_bits - 1));
+    int bias = (1 << (exp_bits - 1)) - 1;
+    for (int64_t o = 0; o < outer; o++)
+        for (int64_t i = 0; i < inner; i++)
+            for (int64_t k0 = 0; k0 < K; k0 += bs) {
+                int64_t k1 = k0 + bs < K ? k0 + bs : K;
+                uint32_t m = 0;
+                for (int64_t k = k0; k < k1; k++) {
+                    uint32_t a = absbits(x[(o * K + k) * inner + i]);
+                    if (a > m) m = a;
+                }
+                float scale = exp2f(floorf(log2f(u2f(m)))) / largest;
+                for (int64_t k = k0; k < k1; k++) {
+                    int64_t idx = (o * K + k) * inner + i;
+                    float v = x[idx] / scale;
+                    y[idx] = float_elem(v, man, exp_bits, bias, 0, R_NEAREST, 0u) * scale;
+                }
+            }
+}
+
 /* BlockTopK.forward + Sparsify.forward: S/sparse.py:163-180, :287-301.
  * Per group of M consecutive k: ascending (stable, NaN largest) argsort of the score, the
  * first M - Kkeep indices get mask 0; y = x * mask (fp32 multiply: masked negatives become

@@ -54,6 +54,8 @@ def lib():
         L.orc_fixed_cast_affine.argtypes = [_fp, _fp, _i64, _i64, _i64] + [_int] * 6 + [_fp, _fp, _i64, _i64, _fp]
         L.orc_sbfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64] + [_int] * 11
         L.orc_nm_prune.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, _int, _int]
+        L.orc_mxfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64, _int, _int]
+        L.orc_mxfp_cast.restype = None
         L.orc_minmax.argtypes = [_fp, _i64, _i64, _i64, _fp, _fp]
         L.orc_bf16_to_f32.argtypes = [_fp, _fp, _i64]
         L.orc_f32_to_bf16.argtypes = [_fp, _fp, _i64]
@@ -206,6 +208,15 @@ def sbfp_cast(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_
     return y
 
 
+def mxfp_cast(x, block_dim=-1, block_size=32, mantissa=3, exponent=4):
+    """MXFP.cast (S/numerical/format.py:545-564) on an fp32 array."""
+    x = _f32(x)
+    o, K, i = _okI(x.shape, block_dim)
+    y = np.empty_like(x)
+    lib().orc_mxfp_cast(_p(x), _p(y), o, K, i, block_size, mantissa, exponent)
+    return y
+
+
 def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False):
     """Sparsify.forward with a BlockTopK sparseness (S/sparse.py:163-180, 287-301)."""
     x = _f32(x)
@@ -248,6 +259,8 @@ _RX_XP = re.compile(r"^XP\[(\d+),([-+]?\d+)\]\((\w)(\w)(\w)\)$")
 _RX_FP = re.compile(r"^FP\[(\d)\|(\d+)\|(\d+),([-+]?\d+)\]\((\w)([A-Za-z])\)$")
 _RX_BFP = re.compile(r"^BFP\[(\d+)\|8\]\{(\d+)\}\((\w)([A-Za-z])\)$")
 _RX_SBFP = re.compile(r"^SBFP<(.+?)><(.+?)>\{(\d+)\}$")
+_RX_MXFP = re.compile(r"^MXFP(\d+)\[E(\d+)M(\d+)\]\{(\d+)\}$")
+_RX_MXINT = re.compile(r"^MXINT(\d+)\{(\d+)\}$")
 _RMODE = {"N": "nearest", "S": "stochastic", "U": "up", "D": "down"}
 
 
@@ -270,4 +283,10 @@ def cast(x, shorthand, block_dim=-1, tie=TIE_EVEN, rand=None, **affine):
         xp, fp = _RX_XP.match(m[1]), _RX_FP.match(m[2])
         return sbfp_cast(x, block_dim, int(m[3]), int(xp[1]), xp[3] == "C", _RMODE[xp[5]], tie,
                          int(fp[3]), int(fp[2]), int(fp[4]), fp[5] == "F", fp[1] == "0", _RMODE[fp[6]])
+    m = _RX_MXFP.match(sh)
+    if m:
+        return mxfp_cast(x, block_dim, int(m[4]), int(m[3]), int(m[2]))
+    m = _RX_MXINT.match(sh)
+    if m:  # MXINT(BlockFloatingPoint), S/numerical/format.py:605-627
+        return bfp_cast(x, block_dim, int(m[2]), int(m[1]), True, "nearest")
     raise ValueError(f"unrecognized format shorthand: {sh}")

@@ -40,6 +40,7 @@ for dt in (torch.float32, torch.bfloat16):
     rnd = torch.randint(0, 2**31 - 1, x.shape, device=dev, dtype=torch.int32)
     report(f"BFP16 stochastic (ext. rand) {dt}", (2*es+4)*n, lambda: ops.cast_chain(x, [Format.from_shorthand("BFP[8|8]{64}(SS)").stage()], -1, out=y, rand=rnd))
     del rnd
+    report(f"MXFP8[E4M3]{{32}} {dt}", 2*n*es, lambda: ops.cast_chain(x, [Format.from_shorthand("MXFP8[E4M3]{32}").stage()], -1, out=y))
     report(f"2:4 prune {dt}", 2*n*es, lambda: ops.cast_chain(x, [ops.nm_stage(2, 4)], -1, out=y))
     report(f"2:4 -> BFP12 fused {dt}", 2*n*es, lambda: ops.cast_chain(x, [ops.nm_stage(2, 4), Format.from_shorthand('BFP[4|8]{64}(SN)').stage()], -1, out=y))
     report(f"FLOAT16 -> BFP16 fused {dt}", 2*n*es, lambda: ops.cast_chain(x, [Format.from_shorthand('FP[1|5|10,15](FN)').stage(), Format.from_shorthand('BFP[8|8]{64}(SN)').stage()], -1, out=y))

@@ -193,7 +193,8 @@ LAYOUTS = [
 ]
 FORMATS = ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)", "BFP[8|8]{16}(SN)", "BFP[6|8]{32}(SN)", "BFP[8|8]{128}(SN)",
            "BFP[8|8]{64}(_N)", "BFP[8|8]{64}(SU)", "BFP[8|8]{64}(SD)", "BFP[16|8]{64}(SN)", "BFP[8|8]{256}(SN)",
-           "BFP[8|8]{24}(SN)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,7](FN)>{64}"]
+           "BFP[8|8]{24}(SN)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,7](FN)>{64}",
+           "MXFP8[E4M3]{32}", "MXFP8[E5M2]{64}", "MXFP4[E2M1]{32}", "MXINT8{32}"]
 
 
 @pytest.mark.parametrize("fmt", FORMATS)
@@ -682,3 +683,16 @@ def test_packed_bfp_storage_round_trip(dt, wl, bs):
     # and against the oracle
     if dt == torch.float32:
         check(got, bits(O.cast(x.numpy(), f"BFP[{wl}|8]{{{bs}}}(SN)", -1)), "packed vs oracle")
+
+
+def test_golden_mxfp():
+    """MXFP: the reference's own MXFP.cast on CPU vs the CUDA path"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mxfp_reference.npz"))
+    for n in [str(t) for t in z["names"]]:
+        i, sh, shp = n.split("|")
+        shp = tuple(int(t) for t in shp.split(","))
+        x = f32(z[f"{i}.x"]).reshape(shp)
+        check(gpu_cast(torch.from_numpy(x).to(DEV), sh, -1), z[f"{i}.y"].reshape(shp), n)
+        xb = torch.from_numpy(x).to(torch.bfloat16)
+        want = O.cast(xb.float().numpy(), sh, -1)
+        check(gpu_cast(xb.to(DEV), sh, -1), bits(want), n + " bf16")
