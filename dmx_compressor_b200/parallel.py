@@ -107,16 +107,11 @@ def cast_shards(shards: Sequence[Shard], materialise: Callable[[Shard], torch.Te
 # ------------------------------------------------------------------------------------------------
 # batched statistics all-reduce
 def local_minmax(t: torch.Tensor, ch_axis: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """amin / amax of a local shard: the dmxq_minmax kernel on CUDA tensors."""
-    if t.is_cuda:
-        from . import ops
+    """amin / amax of a local shard: the dmxq_minmax kernel (CUDA tensors only; there is no CPU path --
+    the gloo unit tests of the reduction logic inject their own statistic through ``local=``)."""
+    from . import ops
 
-        return ops.minmax(t, ch_axis)
-    # host tensors only appear in the gloo unit tests of the reduction logic (no cast math here)
-    if ch_axis is None:
-        return t.float().amin().reshape(1), t.float().amax().reshape(1)
-    dims = [d for d in range(t.dim()) if d != ch_axis % t.dim()]
-    return t.float().amin(dims), t.float().amax(dims)
+    return ops.minmax(t, ch_axis)
 
 
 def allreduce_minmax(stats: Sequence[Tuple[torch.Tensor, torch.Tensor]], group=None):
@@ -148,18 +143,19 @@ def allreduce_minmax(stats: Sequence[Tuple[torch.Tensor, torch.Tensor]], group=N
     return out
 
 
-def sharded_minmax(tensors: Sequence[torch.Tensor], ch_axes: Optional[Sequence[Optional[int]]] = None, group=None):
+def sharded_minmax(tensors: Sequence[torch.Tensor], ch_axes: Optional[Sequence[Optional[int]]] = None, group=None,
+                   local: Callable = local_minmax):
     """amin/amax of row-sharded tensors as if they were whole: local kernel + one all-reduce."""
     ch_axes = ch_axes or [None] * len(tensors)
-    return allreduce_minmax([local_minmax(t, a) for t, a in zip(tensors, ch_axes)], group)
+    return allreduce_minmax([local(t, a) for t, a in zip(tensors, ch_axes)], group)
 
 
-def shard_stats(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tensor], group=None):
+def shard_stats(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tensor], group=None, local: Callable = local_minmax):
     """Per-tensor (amin, amax) for the shards `tensors` that `plan[rank]` lists, as if every
     tensor were whole.  Tensors owned entirely by one rank need no communication; the row-split
     ones (the same set, in the same order, on every rank) share ONE all-reduce."""
     mine = plan[rank]
-    local = [local_minmax(t) for t in tensors]
+    local = [local(t, None) for t in tensors]
     split_names = sorted({sh.name for shards in plan for sh in shards if not sh.whole})
     if split_names:
         pos = {n: i for i, n in enumerate(split_names)}

@@ -9,6 +9,14 @@ import torch.multiprocessing as mp
 
 from dmx_compressor_b200 import parallel as P
 
+def _cpu_minmax(t, ch_axis=None):
+    """stand-in for the dmxq_minmax kernel so that the *reduction logic* can be exercised over gloo without a GPU"""
+    if ch_axis is None:
+        return t.float().amin().reshape(1), t.float().amax().reshape(1)
+    dims = [d for d in range(t.dim()) if d != ch_axis % t.dim()]
+    return t.float().amin(dims), t.float().amax(dims)
+
+
 LLAMA8B = {f"layers.{i}.{n}": s for i in range(4) for n, s in
            (("q", (4096, 4096)), ("k", (1024, 4096)), ("v", (1024, 4096)), ("o", (4096, 4096)),
             ("gate", (14336, 4096)), ("up", (14336, 4096)), ("down", (4096, 14336)))}
@@ -48,7 +56,7 @@ def _worker(rank, world, port, q):
     full = [torch.randn(64, 48, generator=g) * 3, torch.randn(32, 16, generator=g), torch.randn(10, 8, generator=g)]
     full[2][3, 4] = float("nan")
     shards = [t.chunk(world, 0)[rank] for t in full]
-    got = P.sharded_minmax(shards, [None, 1, None])
+    got = P.sharded_minmax(shards, [None, 1, None], local=_cpu_minmax)
     q.put((rank, [(a.clone(), b.clone()) for a, b in got]))
     dist.destroy_process_group()
 
@@ -101,7 +109,7 @@ def _worker_stats(rank, world, port, q):
     g = torch.Generator().manual_seed(11)
     full = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
     mine = [full[sh.name][sh.row0:sh.row1] for sh in plan[rank]]
-    stats = P.shard_stats(plan, rank, mine)
+    stats = P.shard_stats(plan, rank, mine, local=_cpu_minmax)
     q.put((rank, [(sh.name, float(a), float(b)) for sh, (a, b) in zip(plan[rank], stats)]))
     dist.destroy_process_group()
 
