@@ -64,6 +64,7 @@ def _load():
         "dmxq_bfp_unpack": ([VP, VP, TP, I, I, VP], I),
         "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
         "dmxq_minmax": ([TP, I, VP, VP, VP], I),
+        "dmxq_histc": ([TP, I, C.c_float, C.c_float, VP, VP, VP, VP], I),
         "dmxq_cast_chain_host": ([VP, VP, I, I, I64, I64, SP, I, I], I),
         "dmxq_host_alloc": ([I64], VP),
         "dmxq_host_free": ([VP], None),

@@ -763,6 +763,27 @@ int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_ma
     return DMXQ_OK;
 }
 
+int dmxq_histc(const dmxq_tensor *x, int bins, float lo, float hi, unsigned long long *counts, float *out_min, float *out_max,
+               void *stream)
+{
+    if (!x || !counts) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if ((out_min == nullptr) != (out_max == nullptr)) return fail(DMXQ_ERR_BAD_ARG, "out_min and out_max go together");
+    if (x->dtype < 0 || x->dtype > 2) return fail(DMXQ_ERR_BAD_ARG, "bad dtype");
+    if (bins < 1 || bins > 12288) return fail(DMXQ_ERR_UNSUPPORTED, "bins must be in [1, 12288] (got %d)", bins);
+    if (!(lo < hi) || std::isinf(lo) || std::isinf(hi))
+        return fail(DMXQ_ERR_BAD_ARG, "histogram range [%g, %g] must be finite and non-empty", (double)lo, (double)hi);
+    int64_t n = 1, expect = 1;
+    for (int i = x->ndim - 1; i >= 0; --i) {
+        if (x->shape[i] != 1 && x->stride[i] != expect) return fail(DMXQ_ERR_UNSUPPORTED, "dmxq_histc needs a contiguous tensor");
+        expect *= x->shape[i];
+        n *= x->shape[i];
+    }
+    if (n > 0 && reinterpret_cast<uintptr_t>(x->data) % 16) return fail(DMXQ_ERR_UNSUPPORTED, "dmxq_histc needs 16-byte aligned data");
+    cudaError_t e = launch_histc(x->dtype, x->data, n, lo, hi, bins, counts, out_min, out_max, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "histc_kernel");
+    return DMXQ_OK;
+}
+
 int dmxq_block_quantize(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int dim, int symmetric, int rounding,
                         const int32_t *rand, void *workspace, void *stream)
 {

@@ -146,6 +146,8 @@ cudaError_t launch_generic(int in_dt, int out_dt, const GenericParams &p, cudaSt
 cudaError_t launch_fixed_chan(int in_dt, int out_dt, const FixedChanParams &p, cudaStream_t s);
 cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s);
 cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s);
+cudaError_t launch_histc(int dt, const void *x, int64_t n, float lo, float hi, int bins, unsigned long long *counts, float *out_min,
+                         float *out_max, cudaStream_t s);
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
 cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s);

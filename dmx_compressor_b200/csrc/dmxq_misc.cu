@@ -361,6 +361,135 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------------
+// calibration histogram (see dmxq_histc in include/dmxq.h): torch.histc's bin rule evaluated in fp32,
+//   bin = (int)((v - lo) * bins / (hi - lo)), bin == bins -> bins - 1, values outside [lo, hi] and NaN dropped,
+// counted in per-CTA shared-memory bins (u32) that are flushed to 64-bit global counters once per CTA.
+// MM additionally folds the tensor's amin/amax into ordered-int accumulators in the same pass.
+template <typename T, bool MM>
+__global__ void __launch_bounds__(kThreads) histc_kernel(const T *__restrict__ x, int64_t n, float lo, float hi, int bins,
+                                                         unsigned long long *counts, int *omin, int *omax)
+{
+    extern __shared__ unsigned int sbin[];
+    constexpr int V = VecIO<T>::V;
+    for (int i = threadIdx.x; i < bins; i += kThreads) sbin[i] = 0u;
+    __syncthreads();
+    const float nb = (float)bins, w = __fsub_rn(hi, lo);
+    // Correctly rounded t / w without a division per element: with rw = RN(1/w), two Newton steps on the quotient
+    //   q0 = t*rw;  q1 = q0 + (t - q0*w)*rw;  q2 = q1 + (t - q1*w)*rw      (each residual one FMA)
+    // leave q2 == RN(t/w): q1 is within one ulp, its residual is then exact, and the last step rounds correctly
+    // (Markstein's theorem; it needs w's significand not to be all ones and everything well inside the normal range,
+    // otherwise `recip_ok` is false and every element takes the IEEE division).
+    const float rw = __fdiv_rn(1.0f, w);
+    const bool recip_ok = w > 0x1p-60f && w < 0x1p60f && (f2u(w) & 0x7FFFFFu) != 0x7FFFFFu;
+    float fmn = u2f(0x7F800000u), fmx = u2f(0xFF800000u);
+    bool saw_nan = false;
+    auto bin_exact = [&](float v) {  // next to a bin edge (or rw unusable): the reference's own expression
+        int b = (int)__fdiv_rn(__fmul_rn(__fsub_rn(v, lo), nb), w);
+        return min(b, bins - 1);
+    };
+    auto put = [&](float v) {
+        if (v >= lo && v <= hi) {
+            int b = bin_exact(v);
+            if (b >= 0) atomicAdd(&sbin[b], 1u);
+        }
+    };
+    auto put_vec = [&](const float (&v)[V]) {
+        int b[V];
+        bool in[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (MM) {
+                fmn = fminf(fmn, v[j]);
+                fmx = fmaxf(fmx, v[j]);
+                saw_nan |= v[j] != v[j];
+            }
+            in[j] = v[j] >= lo && v[j] <= hi;
+            const float t = __fmul_rn(__fsub_rn(v[j], lo), nb);
+            float q = __fmul_rn(t, rw);
+            q = __fmaf_rn(__fmaf_rn(-q, w, t), rw, q);
+            q = __fmaf_rn(__fmaf_rn(-q, w, t), rw, q);
+            b[j] = min((int)q, bins - 1);  // right edge -> last bin
+        }
+        if (!recip_ok) {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (in[j]) b[j] = bin_exact(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+            if (in[j] && b[j] >= 0) atomicAdd(&sbin[b[j]], 1u);
+    };
+    const int64_t nvec = n / V;
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = ldg_stream(x + (i + u * stride) * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[V];
+            VecIO<T>::unpack(r[u], v);
+            put_vec(v);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        float v[V];
+        VecIO<T>::load(x + i * V, v);
+        put_vec(v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * V) {
+        const float v = Cvt<T>::to_f32(x[nvec * V + threadIdx.x]);
+        if (MM) {
+            fmn = fminf(fmn, v);
+            fmx = fmaxf(fmx, v);
+            saw_nan |= v != v;
+        }
+        put(v);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < bins; b += kThreads) {
+        unsigned int c = sbin[b];
+        if (c) atomicAdd(counts + b, (unsigned long long)c);
+    }
+    if (MM) {
+        int mlo = saw_nan ? (int)0x80000000 : ord(fmn), mhi = saw_nan ? 0x7FFFFFFF : ord(fmx);
+        for (int off = 16; off > 0; off >>= 1) {
+            mlo = min(mlo, __shfl_xor_sync(0xFFFFFFFFu, mlo, off));
+            mhi = max(mhi, __shfl_xor_sync(0xFFFFFFFFu, mhi, off));
+        }
+        if ((threadIdx.x & 31) == 0) { atomicMin(omin, mlo); atomicMax(omax, mhi); }
+    }
+}
+
+template <typename T>
+static void histc_dispatch(const void *x, int64_t n, float lo, float hi, int bins, unsigned long long *counts, int *omin, int *omax,
+                           unsigned grid, cudaStream_t s)
+{
+    size_t sh = (size_t)bins * sizeof(unsigned int);
+    if (omin) histc_kernel<T, true><<<grid, kThreads, sh, s>>>(static_cast<const T *>(x), n, lo, hi, bins, counts, omin, omax);
+    else histc_kernel<T, false><<<grid, kThreads, sh, s>>>(static_cast<const T *>(x), n, lo, hi, bins, counts, omin, omax);
+}
+
+cudaError_t launch_histc(int dt, const void *x, int64_t n, float lo, float hi, int bins, unsigned long long *counts, float *out_min,
+                         float *out_max, cudaStream_t s)
+{
+    int *omin = reinterpret_cast<int *>(out_min), *omax = reinterpret_cast<int *>(out_max);
+    if (omin) minmax_init_kernel<<<1, 256, 0, s>>>(omin, omax, 1);
+    if (n > 0) {
+        const int V = dt == 0 ? 4 : 8;
+        int64_t nvec = n / V;
+        unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((nvec + kThreads * 4 - 1) / (kThreads * 4), 148 * 8));
+        if (dt == 0) histc_dispatch<float>(x, n, lo, hi, bins, counts, omin, omax, grid, s);
+        else if (dt == 1) histc_dispatch<__nv_bfloat16>(x, n, lo, hi, bins, counts, omin, omax, grid, s);
+        else histc_dispatch<__half>(x, n, lo, hi, bins, counts, omin, omax, grid, s);
+    }
+    if (omin) minmax_final_kernel<<<1, 256, 0, s>>>(omin, omax, 1);
+    count_launch((n > 0 ? 1 : 0) + (omin ? 2 : 0));
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused residual add with its boundary casts (see dmxq_add_cast in include/dmxq.h)
 template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], const FloatFmt &f)
 {

@@ -8,8 +8,8 @@ Same contract as the reference: every module owns ``input_casts`` / ``output_cas
 keys as ``DmxModule.configure`` (core.py:65-108); ``forward`` is
 ``input_casts -> _forward (weight hypernet inside) -> output_casts -> back to the input dtype``
 (core.py:215-264); ``fold_weight_and_bias`` applies the parameter casts once (core.py:146-176).
-Graph tracing, approximation functions, SmoothQuant, plugins and perf proxies are out of scope
-(SURVEY.md section 2).
+SmoothQuant (statistics on the dmxq_minmax kernel) hooks in where the reference puts it (core.py:188-191,
+227-230).  Graph tracing, approximation functions, plugins and perf proxies are out of scope.
 
 Two opt-in accelerations that the reference does not have, both
 value-preserving, see dmx_compressor_b200/elide.py:
@@ -28,6 +28,7 @@ import torch.nn.functional as F
 
 from . import elide, ops
 from .numerical import CastTo, CastToDict, Format, Same
+from .numerical.smoothquant import ActivationWeightSmoothQuant
 from .sparse import BlockTopK, Dense, LazySparsify, Sparsify
 
 
@@ -49,6 +50,8 @@ class DmxModule:
         self.weight_cast = CastTo(ch_axis=self.wout_ch_axis) if has_w else None
         self.bias_cast = CastTo() if "bias" in pnames else None
         self.weight_sparsifier = LazySparsify() if has_w else None
+        self.smoothquant = (ActivationWeightSmoothQuant(self.ch_axis, self.win_ch_axis)
+                            if has_w and self.ch_axis is not None and self.win_ch_axis is not None else None)
         self._wcache = None
 
     # ------------------------------------------------------------------ configuration (core.py:65-108)
@@ -75,6 +78,8 @@ class DmxModule:
             self.weight_sparsifier.configure(sparseness=config["weight_sparseness"])
         if self.weight_sparsifier is not None and "weight_score_func" in config:
             self.weight_sparsifier.configure(score_func=config["weight_score_func"])
+        if self.smoothquant is not None and "smoothquant_scale_format" in config:
+            self.smoothquant.set_scale_format(format=config["smoothquant_scale_format"])
         self._wcache = None
 
     transform = configure
@@ -128,7 +133,22 @@ class DmxModule:
             stages.append(st)
         return stages
 
+    @property
+    def effective_weight(self):  # reference sparse.py:389-395
+        return self.weight_sparsifier(self.weight) if self.weight_sparsifier is not None else self.weight
+
+    def _smoothing_weight(self) -> bool:
+        sq = self.smoothquant
+        return sq is not None and sq._on and not sq._fused
+
     def weight_hypernet(self, _w):
+        if self._smoothing_weight():  # sparsify -> smoothquant scale -> storage cast -> weight cast (core.py:184-196)
+            if self.weight_sparsifier is not None:
+                _w = self.weight_sparsifier(_w)
+            _w = self.smoothquant.scale_weight(_w)
+            if self.weight_storage_cast is not None:
+                _w = self.weight_storage_cast(_w)
+            return self.weight_cast(_w) if self.weight_cast is not None else _w
         if elide.active() and not torch.is_grad_enabled():
             stages = self._fusable_hypernet_stages()
             if stages is not None:
@@ -147,7 +167,7 @@ class DmxModule:
 
     @property
     def _weight(self):
-        if elide.active() and not torch.is_grad_enabled():
+        if elide.active() and not torch.is_grad_enabled() and not self._smoothing_weight():
             w = self.weight
             key = (w.data_ptr(), w._version, tuple(w.shape), repr(self.weight_format),
                    repr(self.weight_storage_cast.format) if self.weight_storage_cast is not None else None,
@@ -172,6 +192,9 @@ class DmxModule:
                 self.bias_cast = CastTo(format=Same())
             if self.weight_cast is not None:
                 self.weight.data = self.weight_hypernet(self.weight.data)
+                if self.smoothquant is not None:  # its scale is now part of the stored weight (core.py:161-166)
+                    self.smoothquant.fused_to_weight[0] = 1
+                    self.smoothquant._fused = True
                 self.weight_sparsifier = LazySparsify(sparseness=Dense())
                 self.weight_storage_cast = CastTo(format=Same())
                 self.weight_cast = CastTo(format=Same())
@@ -180,6 +203,12 @@ class DmxModule:
     # ------------------------------------------------------------------ forward (core.py:215-264)
     def forward(self, input, *args, **kwargs):
         _dtype = input.dtype
+        sq = self.smoothquant
+        if sq is not None and (sq._on or sq._dyn or sq.calibrating):  # core.py:227-230
+            input = elide.materialise(input)
+            if sq._dyn or sq.calibrating:
+                sq(input, self.effective_weight)
+            input = sq.scale_input(input)
         _input, args, kwargs = self.input_casts(input, *args, **kwargs)
         _output = self._forward(_input, *args, **kwargs)
         output = self.output_casts(_output, output=True)

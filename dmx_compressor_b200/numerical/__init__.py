@@ -9,5 +9,5 @@ from .format import (  # noqa: F401
     MXFP,
     ROUNDING_MODE,
 )
-from .observer import DMXObserverBase, DummyObserver, MinMaxObserver  # noqa: F401
+from .observer import DMXObserverBase, DummyObserver, HistogramObserver, MinMaxObserver  # noqa: F401
 from .cast import CastTo, CastToDict, CastToFormat  # noqa: F401

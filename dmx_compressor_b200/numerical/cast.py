@@ -22,7 +22,7 @@ from torch.quantization.fake_quantize import FakeQuantize
 
 from .. import elide, ops
 from .format import FixedPoint, Format, Same
-from .observer import DummyObserver, MinMaxObserver, ObserverBase
+from .observer import DummyObserver, HistogramObserver, MinMaxObserver, ObserverBase  # noqa: F401
 
 
 class CastToFormat(Function):
@@ -311,10 +311,9 @@ class CastTo(FakeQuantize):
             x, _ = self.apply_shaping_seq(x, undo)
         return x.to(self.physical_dtype)
 
-    def enable_calibration(self, state: bool = True, observer_cls: ObserverBase = MinMaxObserver,
+    def enable_calibration(self, state: bool = True, observer_cls: ObserverBase = HistogramObserver,
                            qscheme_to_overload: Optional[torch.qscheme] = None, group_size: int = None, ch_axis: int = None) -> None:
-        """reference cast.py:308-340 (its default observer is the HistogramObserver, which is outside
-        the CUDA path; MinMaxObserver is the default here)."""
+        """reference cast.py:308-340; the default observer is the HistogramObserver, as there."""
         if state:
             if ch_axis is not None:
                 self.ch_axis = self.activation_post_process.ch_axis = ch_axis

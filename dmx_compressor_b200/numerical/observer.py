@@ -1,14 +1,17 @@
 """Calibration observers feeding FixedPoint casts their scale / zero-point -- host-side mirror
 of the reference's observer surface (reference src/dmx/compressor/numerical/observer.py:59-210).
 
-Only the min/max family is on the CUDA path: the running amin/amax statistics come from
-``dmxq_minmax`` (exact, order independent => a sharded reduction + all-reduce(MIN/MAX) equals
-the single-device result bit for bit, see dmx_compressor_b200/parallel.py).  The histogram
-search of the reference (observer.py:213-582) is a host-side calibration-time loop and is out
-of scope.
+The passes over the observed tensor are CUDA kernels: running amin/amax come from ``dmxq_minmax``
+(exact, order independent => a sharded reduction + all-reduce(MIN/MAX) equals the single-device
+result bit for bit, see dmx_compressor_b200/parallel.py) and the HistogramObserver's
+``torch.aminmax`` + ``torch.histc`` pair from ``dmxq_histc`` (one fused pass in steady state).
+What happens to the 2048 bins afterwards (re-binning onto a wider range, the clipping-range
+search) is O(bins) host logic on small torch tensors, as in the reference (observer.py:213-582).
 """
 from __future__ import annotations
 
+import bisect
+import struct
 from typing import Optional, Tuple
 
 import torch
@@ -136,3 +139,202 @@ class MinMaxObserver(DMXObserverBase):
     def reset_min_max_vals(self):
         self.min_val.copy_(torch.tensor(float("inf")))
         self.max_val.copy_(torch.tensor(float("-inf")))
+
+
+def _f32(v: float) -> float:
+    return struct.unpack("f", struct.pack("f", v))[0]
+
+
+class HistogramObserver(DMXObserverBase):
+    r"""Running histogram of the observed values + an L2-optimal clipping range for the
+    quantizer (reference observer.py:213-582, itself after torch.ao's HistogramObserver;
+    per-tensor schemes only).  The default observer of ``CastTo.enable_calibration``.
+
+    Per step the reference makes three passes over ``x`` (``x.float()``, ``aminmax``,
+    ``histc``).  Here the first step is ``dmxq_minmax`` + ``dmxq_histc`` on ``x`` in its own
+    dtype, and every later step ONE ``dmxq_histc`` launch that bins into the range the
+    running min/max predict while folding the new amin/amax in the same pass; only when the new
+    batch widens the range is the histogram pass repeated over the widened range.  Range
+    quirks are the reference's: the bin range is ``[int(min), int(max)]`` (truncated toward
+    zero, observer.py:470,488) with torch.histc's "min == max => use the data's range" rule.
+    """
+
+    histogram: torch.Tensor
+    min_val: torch.Tensor
+    max_val: torch.Tensor
+
+    # kernel entry points; the CPU unit tests of the host logic swap these for the oracle's
+    _histc = staticmethod(ops.histc)
+    _minmax = staticmethod(ops.minmax)
+
+    def __init__(self, bins: int = 2048, upsample_rate: int = 128, dtype: Format = None,
+                 qscheme: Optional[torch.qscheme] = torch.per_tensor_affine, ch_axis: int = -1, factory_kwargs=None,
+                 eps=torch.finfo(torch.float32).eps, **kwargs) -> None:
+        if qscheme not in (torch.per_tensor_affine, torch.per_tensor_symmetric):
+            raise NotImplementedError(
+                "HistogramObserver's qscheme only support torch.per_tensor_symmetric or torch.per_tensor_affine.")
+        if dtype is None:
+            dtype = Format.from_shorthand("XP[8,0](CSN)")
+        super().__init__(dtype=dtype, qscheme=qscheme, factory_kwargs=factory_kwargs, eps=eps, **kwargs)
+        fk = torch.nn.factory_kwargs(factory_kwargs)
+        self.bins = bins
+        self.upsample_rate = upsample_rate
+        self.ch_axis = ch_axis
+        self.register_buffer("histogram", torch.zeros(bins, **fk))
+        self.register_buffer("min_val", torch.tensor(float("inf"), **fk))
+        self.register_buffer("max_val", torch.tensor(float("-inf"), **fk))
+        self.stats = {"fused_steps": 0, "rebinned_steps": 0}
+
+    # ---- accumulate -------------------------------------------------------------------------
+    def _widened(self, lo: torch.Tensor, hi: torch.Tensor):
+        """Grow [lo, hi] (only upwards) so that its width is a whole multiple of the current bin grid refined
+        ``upsample_rate`` times; returns the new bounds, that multiple and the fine-grid offset of the old
+        minimum (reference observer.py:390-413).  All arithmetic on 0-d fp32 tensors, as there."""
+        fine = (self.max_val - self.min_val) / (self.bins * self.upsample_rate)
+        span = self.bins * fine
+        factor = int(torch.ceil((hi - lo) / span).item())
+        hi = hi + (factor * span - (hi - lo))
+        first = int(torch.round((self.min_val - lo) / fine).item())
+        return lo, hi, factor, first
+
+    def _rebinned(self, fresh: torch.Tensor, factor: int, first: int) -> torch.Tensor:
+        """Spread the stored histogram uniformly onto the fine grid, drop it at its offset inside the widened range
+        and re-integrate it ``factor`` fine cells per new bin (double-precision prefix sums), then add the fresh
+        batch's histogram (reference observer.py:415-452)."""
+        n, up = self.bins, self.upsample_rate
+        dense = torch.zeros(n * factor, device=fresh.device)
+        dense[first:n * up + first] = self.histogram.repeat_interleave(up)
+        prefix = torch.cumsum(dense, 0, dtype=torch.double)[factor - 1::factor]
+        before = torch.zeros(n, device=fresh.device)
+        before[1:n] = prefix[0:-1]
+        return fresh + ((prefix - before) / up).to(torch.float)
+
+    @staticmethod
+    def _trunc(v: torch.Tensor) -> int:
+        return int(v)  # toward zero; OverflowError / ValueError on inf / NaN exactly as in the reference
+
+    def forward(self, x_orig: torch.Tensor) -> torch.Tensor:
+        if x_orig.numel() == 0:
+            return x_orig
+        x = x_orig.detach()
+        lo0, hi0 = self.min_val.item(), self.max_val.item()
+        if (lo0 == float("inf") and hi0 == float("-inf")) or lo0 == hi0:
+            mn, mx = self._minmax(x)
+            mn, mx = mn.reshape(()), mx.reshape(())
+            hist = self._histc(x, self.bins, min=self._trunc(mn), max=self._trunc(mx))
+            self._store(hist, mn, mx)
+            return x_orig
+        # steady state: bin into the range the running min/max predict and learn the batch's amin/amax in the same pass
+        lo, hi, factor, first = self._widened(self.min_val, self.max_val)
+        a, b = self._trunc(lo), self._trunc(hi)
+        hist = None
+        if a != b:
+            hist, mn, mx = self._histc(x, self.bins, min=a, max=b, return_minmax=True)
+        else:  # empty integer range: histc falls back on this batch's own range, which needs its amin/amax first
+            mn, mx = self._minmax(x)
+            mn, mx = mn.reshape(()), mx.reshape(())
+        mn, mx = mn.to(self.min_val.device), mx.to(self.max_val.device)
+        new_lo, new_hi = torch.min(mn, self.min_val), torch.max(mx, self.max_val)
+        if hist is not None and new_lo.item() == lo0 and new_hi.item() == hi0:
+            self.stats["fused_steps"] += 1
+        else:
+            lo, hi, factor, first = self._widened(new_lo, new_hi)
+            hist = self._histc(x, self.bins, min=self._trunc(lo), max=self._trunc(hi))
+            self.stats["rebinned_steps"] += 1
+        hist = hist.to(self.histogram.device)
+        if lo.item() == lo0 and hi.item() == hi0:
+            hist = hist + self.histogram
+        else:
+            hist = self._rebinned(hist, factor, first)
+        self._store(hist, lo, hi)
+        return x_orig
+
+    def _store(self, hist, lo, hi):
+        self.histogram.detach_().resize_(hist.shape)
+        self.histogram.copy_(hist)
+        self.min_val.detach_().resize_(lo.shape)
+        self.min_val.copy_(lo)
+        self.max_val.detach_().resize_(hi.shape)
+        self.max_val.copy_(hi)
+
+    # ---- clipping-range search ----------------------------------------------------------------
+    @staticmethod
+    def _cube_span(a, b, density):
+        """density * integral_a^b t^2 dt"""
+        return density * ((b * b * b - a * a * a) / 3)
+
+    def _clip_error(self, first: int, last: int) -> float:
+        """Expected squared quantization error when source bins first..last span the quantizer's 2^precision
+        levels, every source bin taken as a uniform density (reference observer.py:269-329)."""
+        levels = 2 ** self.dtype.precision
+        w = (self.max_val.item() - self.min_val.item()) / self.bins
+        q = w * (last - first + 1) / levels
+        if q == 0.0:
+            return 0.0
+        dev = self.histogram.device
+        idx = torch.arange(self.bins, device=dev)
+        left = (idx - first) * w
+        right = left + w
+        lv_left = torch.clamp(torch.div(left, q, rounding_mode="floor"), 0, levels - 1)
+        lv_right = torch.clamp(torch.div(right, q, rounding_mode="floor"), 0, levels - 1)
+        density = self.histogram / w
+        half = q / 2
+        # the part of the bin inside its first level, the whole levels in between, the part inside its last level
+        err = torch.zeros(self.bins, device=dev)
+        err += self._cube_span(left - (lv_left + 0.5) * q, torch.ones(self.bins, device=dev) * half, density)
+        err += (lv_right - lv_left - 1) * self._cube_span(torch.tensor(-half), torch.tensor(half), density)
+        err += self._cube_span(torch.tensor(-half), right - (lv_right * q + half), density)
+        return err.sum().item()
+
+    def _non_linear_param_search(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Greedy outlier clipping: shave 1e-5 of the probability mass off whichever tail gives up more bins, as
+        long as the L2 error estimate keeps falling (reference observer.py:331-388).  The quantile scans run on a
+        host copy of the prefix sums (bisect instead of one device read per bin)."""
+        assert self.histogram.size()[0] == self.bins, "bins mistmatch"
+        w = (self.max_val - self.min_val) / self.bins
+        total = torch.sum(self.histogram).item()
+        cdf = torch.cumsum(self.histogram, dim=0).tolist()
+        monotone = all(a <= b for a, b in zip(cdf, cdf[1:]))  # parallel prefix sums may wobble by an ulp
+
+        def scan_up(thr, i):  # first i' >= i with i' == last or cdf[i'] >= thr
+            if monotone:
+                return min(bisect.bisect_left(cdf, thr, i), last)
+            while i < last and cdf[i] < thr:
+                i += 1
+            return i
+
+        def scan_down(thr, i):  # last i' <= i with i' == first or cdf[i'] <= thr
+            if monotone:
+                return max(bisect.bisect_right(cdf, thr, first, i + 1) - 1, first)
+            while i > first and cdf[i] > thr:
+                i -= 1
+            return i
+
+        step, lo_q, hi_q = 1e-5, 0.0, 1.0
+        first, last = 0, self.bins - 1
+        best = float("inf")
+        while lo_q < hi_q:
+            nlo, nhi = lo_q + step, hi_q - step
+            # tensor-vs-python comparisons round the scalar to fp32 first
+            l, r = scan_up(_f32(nlo * total), first), scan_down(_f32(nhi * total), last)
+            cand = (first, last)
+            if (l - first) > (last - r):
+                cand, lo_q = (l, last), nlo
+            else:
+                cand, hi_q = (first, r), nhi
+            if cand == (first, last):
+                continue
+            e = self._clip_error(*cand)
+            if e > best:
+                break
+            best, (first, last) = e, cand
+        return self.min_val + w * first, self.min_val + w * (last + 1)
+
+    def calculate_qparams(self):
+        if self.min_val == float("inf") and self.max_val == float("-inf"):
+            return torch.tensor([1.0], device=self.min_val.device.type), torch.tensor([0], device=self.min_val.device.type)
+        assert self.bins == len(self.histogram), "histogram length does not match the observer's bins"
+        return self._calculate_qparams(*self._non_linear_param_search())
+
+    def extra_repr(self):
+        return super().extra_repr() + f", min_val = {self.min_val}, max_val = {self.max_val}"

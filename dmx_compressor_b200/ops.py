@@ -8,6 +8,8 @@ Output allocation policy (the reference returns a fresh tensor, Q/quant_cuda/qua
 from __future__ import annotations
 
 import ctypes as C
+import math
+import struct
 from typing import Optional, Sequence
 
 import torch
@@ -258,6 +260,48 @@ def minmax(x, ch_axis: Optional[int] = None):
                                L.stream_ptr(x.device))
     L.check(rc, "dmxq_minmax")
     return mn, mx
+
+
+def _f32(v) -> float:
+    """a python number rounded to fp32 (what a torch Scalar becomes inside an fp32 kernel)"""
+    return struct.unpack("f", struct.pack("f", float(v)))[0]
+
+
+def histc(x, bins: int = 100, min=0, max=0, return_minmax: bool = False):
+    """``torch.histc(x.float(), bins, min, max)`` via dmxq_histc (the call HistogramObserver.forward makes,
+    reference S/numerical/observer.py:470-491): fp32 histogram of ``bins`` equal-width bins over [min, max], values
+    outside the range and NaN dropped, ``min == max`` -> the data's own range (and +-1 if that is empty too).
+    ``return_minmax``: also return amin / amax of ``x`` (0-d fp32 tensors) computed in the same pass."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    lo, hi = _f32(min), _f32(max)
+    mn = mx = None
+    if lo == hi and x.numel():
+        mn, mx = minmax(x)
+        lo, hi = torch.cat([mn, mx]).tolist()  # one 8-byte read-back
+        have_minmax = True
+    else:
+        have_minmax = False
+    if lo == hi:
+        lo, hi = _f32(lo - 1), _f32(hi + 1)
+    if math.isinf(lo) or math.isinf(hi) or lo != lo or hi != hi:
+        raise RuntimeError(f"range of [{lo}, {hi}] is not finite")
+    if lo > hi:
+        raise RuntimeError("max must be larger than min")
+    counts = torch.zeros(bins, dtype=torch.int64, device=x.device)
+    want = return_minmax and not have_minmax
+    if want:
+        mn = torch.empty(1, dtype=torch.float32, device=x.device)
+        mx = torch.empty(1, dtype=torch.float32, device=x.device)
+    vx = L.view(x)
+    with _guard(x.device):
+        rc = L.lib.dmxq_histc(C.byref(vx), bins, lo, hi, counts.data_ptr(), mn.data_ptr() if want else None,
+                              mx.data_ptr() if want else None, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_histc")
+    hist = counts.to(torch.float32)
+    if return_minmax:
+        return hist, mn.reshape(()), mx.reshape(())
+    return hist
 
 
 def block_quantize_l1(x, wl, dim=-1, symmetric=True, rounding="stochastic", rand=None):

@@ -26,6 +26,7 @@
  *   dmxq_bfp_pack/unpack   packed BFP storage (QuantizeBFP/DequantizeBFP of the ONNX export, S/numerical/cast.py:34-55)
  *   dmxq_block_quantize    L1 block_quantize(x, wl, dim,...) Q/quant_cuda/quant.cu:14-112
  *   dmxq_minmax            MinMaxObserver.forward statistics S/numerical/observer.py:173-193
+ *   dmxq_histc             HistogramObserver.forward: torch.histc (+ aminmax) S/numerical/observer.py:454-499
  *   dmxq_cast_chain_host   same as dmxq_cast_chain on HOST buffers (pipelined H2D/compute/D2H)
  *
  * Conventions
@@ -197,6 +198,17 @@ int dmxq_block_quantize(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int 
  * order independent, so a sharded reduction followed by an all-reduce(MIN/MAX) is
  * bit-identical to the single-device result. */
 int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream);
+
+/* ---- calibration histogram: the torch.histc call of HistogramObserver.forward (S/numerical/observer.py:470-491)
+ * counts[b] += #{ v in x : lo <= v <= hi, b == min((int)((v - lo) * bins / (hi - lo)), bins - 1) }, the bin expression
+ * evaluated in fp32 exactly as torch does; NaN and out-of-range values are dropped.  `counts`: device array of `bins`
+ * 64-bit counters, ACCUMULATED into (zero it first for a fresh histogram; torch's float histogram is float(counts),
+ * exact wherever torch's own float accumulation is).  lo < hi, both finite (torch's "min == max -> use the data's
+ * range" rule needs the data's range first: the python wrapper resolves it with dmxq_minmax).
+ * out_min / out_max (both or neither, device float[1]): also return amin / amax of x from the same pass -- the
+ * torch.aminmax(x) every observer step needs -- NaN propagates.  x contiguous, 16-byte aligned, bins <= 12288. */
+int dmxq_histc(const dmxq_tensor *x, int bins, float lo, float hi, unsigned long long *counts, float *out_min, float *out_max,
+               void *stream);
 
 /* ---- host-buffer entry (the e2e path): x_host / y_host are HOST pointers to contiguous
  * [rows, K] matrices blocked along K (pinned memory gives full PCIe speed).  The call

@@ -366,6 +366,24 @@ void orc_minmax(const float *x, int64_t outer, int64_t C, int64_t inner, float *
             }
 }
 
+/* torch.histc(x, bins, min, max) as HistogramObserver.forward calls it (S/numerical/observer.py:470-491); the bin
+ * rule is ATen's (aten/src/ATen/native/cpu/.. histc and cuda/SummaryOps.cu getBin, torch 2.x -- a dependency of the
+ * reference, not vendored): values outside [lo, hi] (and NaN) are skipped, bin = (int)((v - lo) * bins / (hi - lo))
+ * evaluated in fp32 left to right, the right edge falls into the last bin.  lo < hi is resolved by the caller
+ * (histc's "min == max -> data range, still equal -> +-1" rule lives in oracle.py). counts are accumulated. */
+void orc_histc(const float *x, int64_t n, int bins, float lo, float hi, int64_t *counts)
+{
+    const float nb = (float)bins, w = hi - lo;
+    for (int64_t i = 0; i < n; i++) {
+        float v = x[i];
+        if (!(v >= lo && v <= hi)) continue;
+        volatile float t = (v - lo) * nb;
+        int64_t b = (int64_t)(t / w);
+        if (b == bins) b -= 1;
+        if (b >= 0 && b < bins) counts[b] += 1;
+    }
+}
+
 /* bf16 <-> fp32 as torch does it (`x.float()` exact widening; `.to(bfloat16)` RNE with NaN
  * quieting) -- S/numerical/cast.py:262,306 wrap every cast in these conversions. */
 void orc_bf16_to_f32(const uint16_t *x, float *y, int64_t n)

@@ -57,6 +57,8 @@ def lib():
         L.orc_mxfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64, _int, _int]
         L.orc_mxfp_cast.restype = None
         L.orc_minmax.argtypes = [_fp, _i64, _i64, _i64, _fp, _fp]
+        L.orc_histc.argtypes = [_fp, _i64, _int, C.c_float, C.c_float, _fp]
+        L.orc_histc.restype = None
         L.orc_bf16_to_f32.argtypes = [_fp, _fp, _i64]
         L.orc_f32_to_bf16.argtypes = [_fp, _fp, _i64]
         L.orc_fixed_min_max.argtypes = [_int, _int, _int, _fp, _fp]
@@ -238,6 +240,22 @@ def minmax(x, ch_axis=None):
     mn, mx = np.empty(Cc, np.float32), np.empty(Cc, np.float32)
     lib().orc_minmax(_p(x), o, Cc, i, _p(mn), _p(mx))
     return mn, mx
+
+
+def histc(x, bins=100, min=0, max=0):
+    """torch.histc(x, bins, min, max) on fp32 data -> float32 histogram (min == max: the data's own range; still
+    equal: widened by one either side -- ATen's rule)."""
+    x = _f32(x).reshape(-1)
+    lo, hi = np.float32(min), np.float32(max)
+    if lo == hi and x.size:
+        lo, hi = x.min(), x.max()
+    if lo == hi:
+        lo, hi = np.float32(lo - 1), np.float32(hi + 1)
+    if not (np.isfinite(lo) and np.isfinite(hi)):
+        raise RuntimeError(f"range of [{lo}, {hi}] is not finite")
+    counts = np.zeros(bins, np.int64)
+    lib().orc_histc(_p(x), x.size, bins, float(lo), float(hi), _p(counts))
+    return counts.astype(np.float32)
 
 
 def bf16_to_f32(u16):

@@ -281,3 +281,42 @@ def test_deferred_output_cast_is_safe_and_fuses():
             assert torch.equal(hl.view(-1), h.view(-1))
     assert torch.equal(got_next, want_next) and torch.equal(got_scaled, want_scaled)
     assert fused_launches <= 4  # input chain, weight, bias, (deferred) output cast
+
+
+def test_smoothquant_gpu_matches_reference_golden():
+    """maxabs through dmxq_minmax on the device; scale within powf's CPU/GPU ulp difference of the reference's"""
+    from test_observer_cpu import replay_smoothquant
+    from dmx_compressor_b200 import ops
+
+    replay_smoothquant(ops.minmax, device=DEV, ulps=8)
+
+
+def test_linear_with_smoothquant():
+    """reference core.py:184-196,227-230: input / s before the input cast, weight * s between sparsifier and storage cast"""
+    torch.manual_seed(3)
+    lin = dmxnn.Linear(256, 96).to(DEV)
+    lin.configure(dict(input_formats=[fmt.BFP16_64], weight_format=fmt.BFP16_64, output_formats=[fmt.FLOAT16]))
+    x = torch.randn(2, 33, 256, device=DEV) * torch.rand(256, device=DEV).mul(6).exp2()
+    y_plain = lin(x)
+    sq = lin.smoothquant
+    sq.calibrating = True
+    assert torch.equal(lin(x), y_plain)  # calibrating: statistics only, nothing scaled yet
+    sq.calibrating = False
+    s = sq.scale
+    assert s.shape == (256,)
+    mx_a = x.abs().amax((0, 1))
+    mx_w = lin.weight.abs().amax(0).clamp(min=1e-5)
+    torch.testing.assert_close(s, (mx_a**0.5 / mx_w**0.5).clamp(min=1e-5), rtol=1e-6, atol=0)
+    sq.enable()
+    y = lin(x)
+    xi = CastTo(fmt.BFP16_64, block_dim=-1).to(DEV)(x / s)
+    w = CastTo(fmt.BFP16_64, block_dim=-1).to(DEV)(lin.weight * s)
+    want = CastTo(fmt.FLOAT16).to(DEV)(torch.nn.functional.linear(xi, w, lin.bias))
+    assert torch.equal(y, want)
+    assert not torch.equal(y, y_plain)
+    with torch.no_grad(), elide.enabled():
+        assert torch.equal(elide.materialise(lin(x)), want)
+    lin.fold_weight_and_bias()
+    assert sq.fused_to_weight.item() == 1
+    assert torch.equal(lin.weight, w)
+    assert torch.equal(lin(x), want)

@@ -696,3 +696,101 @@ def test_golden_mxfp():
         xb = torch.from_numpy(x).to(torch.bfloat16)
         want = O.cast(xb.float().numpy(), sh, -1)
         check(gpu_cast(xb.to(DEV), sh, -1), bits(want), n + " bf16")
+
+
+# ---- (f3) calibration histogram: dmxq_histc / HistogramObserver ---------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("bins,lo,hi", [(2048, -3, 4), (1000, -7, 10), (7, -1, 1), (2048, 0, 0), (12288, -40, 41), (1, -2, 2)])
+def test_histc_vs_oracle(dtype, bins, lo, hi):
+    """torch.histc semantics bit for bit: oracle (pinned to torch's CPU histc) and torch's own CUDA histc."""
+    x = (_rand((37, 1031), 71, spread=2)).to(dtype)  # 38147 elements: ragged vector tail
+    x.view(-1)[5] = float("nan")
+    x.view(-1)[6] = float("inf")
+    x.view(-1)[7] = lo if lo != hi else 0.25  # left edge
+    x.view(-1)[8] = hi if lo != hi else 0.5  # right edge -> last bin
+    if lo == hi:  # "use the data's range" needs finite data
+        x.view(-1)[5] = 0.0
+        x.view(-1)[6] = 0.0
+    got, mn, mx = ops.histc(x.to(DEV), bins, min=lo, max=hi, return_minmax=True)
+    want = O.histc(x.float().numpy(), bins, lo, hi)
+    assert np.array_equal(got.cpu().numpy(), want)
+    if lo != hi:
+        assert torch.isnan(mn) and torch.isnan(mx)
+        assert torch.equal(got, torch.histc(x.float().to(DEV), bins, min=lo, max=hi))
+    else:
+        assert mn.item() == x.float().min().item() and mx.item() == x.float().max().item()
+    assert torch.equal(ops.histc(x.to(DEV), bins, min=lo, max=hi), got)  # without the fused min/max
+
+
+def test_histc_errors_and_degenerate():
+    x = torch.randn(1000, device=DEV)
+    with pytest.raises(RuntimeError, match="larger"):
+        ops.histc(x, 16, min=2, max=1)
+    with pytest.raises(RuntimeError, match="finite"):
+        ops.histc(x, 16, min=0, max=float("inf"))
+    with pytest.raises(RuntimeError, match="bins"):
+        ops.histc(x, 100000, min=-1, max=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.histc(x.cpu(), 16, min=-1, max=1)
+    c = torch.full((64,), 2.5, device=DEV)  # constant data and no range: [1.5, 3.5]
+    assert torch.equal(ops.histc(c, 8), torch.histc(c, 8))
+    assert ops.histc(torch.empty(0, device=DEV), 8, min=-1, max=1).sum().item() == 0
+
+
+def test_histc_full_size():
+    """2^28 elements: every in-range value lands in exactly one bin, and the result equals torch's CUDA histc."""
+    n = 2**28
+    x = torch.randn(n, device=DEV) * 3
+    got, mn, mx = ops.histc(x, 2048, min=-7, max=9, return_minmax=True)
+    assert got.double().sum().item() == ((x >= -7) & (x <= 9)).sum().item()
+    assert torch.equal(got, torch.histc(x, 2048, min=-7, max=9))
+    assert mn.item() == x.min().item() and mx.item() == x.max().item()
+    xb = x.to(torch.bfloat16)
+    assert torch.equal(ops.histc(xb, 2048, min=-7, max=9), torch.histc(xb.float(), 2048, min=-7, max=9))
+
+
+@pytest.mark.parametrize("name", ["widening", "steady", "unit_interval", "one_sided", "int4_sym", "bins_1000", "constant_then_data"])
+def test_histogram_observer_gpu(name):
+    """the reference's golden calibration sequences through dmxq_histc / dmxq_minmax on the device"""
+    from test_observer_cpu import check_sequence
+    from dmx_compressor_b200.numerical import HistogramObserver
+
+    obs = check_sequence(HistogramObserver, name, device=DEV, exact_search=False)
+    if name == "steady":
+        assert obs.stats == {"fused_steps": 3, "rebinned_steps": 0}
+
+
+def test_castto_calibration_default_observer():
+    """CastTo.enable_calibration() -> HistogramObserver (reference cast.py:308-340), then quantise with its qparams"""
+    from dmx_compressor_b200.numerical import CastTo, HistogramObserver
+
+    c = CastTo("XP[8,0](CSN)").to(DEV)
+    c.enable_calibration(True)
+    assert isinstance(c.activation_post_process, HistogramObserver)
+    x = torch.randn(256, 512, device=DEV) * 4
+    for _ in range(3):
+        assert torch.equal(c(x), x)  # observing only
+    c.enable_calibration(False)
+    sc, zp = c.scale.item(), c.zero_point.item()
+    assert 0.02 < sc < 0.2
+    y = c(x)
+    want = O.cast(x.cpu().numpy(), "XP[8,0](CSN)", -1, tie=O.TIE_AWAY, scale=np.array([sc], np.float32), zero_point=np.array([zp], np.float32))
+    assert_bits_equal(bits(y.cpu().numpy()), bits(want))
+
+
+def test_histc_division_free_bins_are_exact():
+    """the kernel replaces (v - lo) * bins / (hi - lo) by a reciprocal + two FMA refinements: it must truncate like the
+    IEEE division for values on and next to every bin edge, for awkward widths and bin counts (torch's CUDA histc divides)"""
+    g = torch.Generator().manual_seed(5)
+    for bins, lo, hi in [(2048, -7, 9), (2048, -3, 4), (1000, -7, 10), (12288, -41, 45), (7, 0, 3), (2047, -1, 2), (4096, -100, 27)]:
+        k = torch.arange(0, bins + 1, dtype=torch.float64)
+        edges = (lo + k * (hi - lo) / bins).float()
+        near = torch.cat([edges, torch.nextafter(edges, torch.tensor(float("inf"))), torch.nextafter(edges, torch.tensor(float("-inf")))])
+        x = torch.cat([near.repeat(40), torch.rand(1 << 20, generator=g) * (hi - lo) + lo]).to(DEV)
+        assert torch.equal(ops.histc(x, bins, min=lo, max=hi), torch.histc(x, bins, min=lo, max=hi)), (bins, lo, hi)
+        xb = x.to(torch.bfloat16)  # coarse values: very many sit exactly on a bin edge
+        assert torch.equal(ops.histc(xb, bins, min=lo, max=hi), torch.histc(xb.float(), bins, min=lo, max=hi)), (bins, lo, hi)
+    # a width whose significand is all ones, a huge and a tiny one: the IEEE-division path
+    for lo, hi in [(0.0, float(np.float32(2.0) - np.float32(2.0**-23))), (-1e30, 1e30), (0.0, 1e-20)]:
+        x = (torch.rand(1 << 18, generator=g) * (hi - lo) + lo).to(DEV)
+        assert torch.equal(ops.histc(x, 100, min=lo, max=hi), torch.histc(x, 100, min=lo, max=hi))
