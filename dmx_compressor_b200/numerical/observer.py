@@ -145,6 +145,85 @@ def _f32(v: float) -> float:
     return struct.unpack("f", struct.pack("f", v))[0]
 
 
+# ---- one HistogramObserver step (module level: dmx_compressor_b200.plugin binds it onto the reference's own class) ----
+def _widened(obs, lo: torch.Tensor, hi: torch.Tensor):
+    """Grow [lo, hi] (only upwards) so that its width is a whole multiple of the current bin grid refined
+    ``upsample_rate`` times; returns the new bounds, that multiple and the fine-grid offset of the old
+    minimum (reference observer.py:390-413).  All arithmetic on 0-d fp32 tensors, as there."""
+    fine = (obs.max_val - obs.min_val) / (obs.bins * obs.upsample_rate)
+    span = obs.bins * fine
+    factor = int(torch.ceil((hi - lo) / span).item())
+    hi = hi + (factor * span - (hi - lo))
+    first = int(torch.round((obs.min_val - lo) / fine).item())
+    return lo, hi, factor, first
+
+
+def _rebinned(obs, fresh: torch.Tensor, factor: int, first: int) -> torch.Tensor:
+    """Spread the stored histogram uniformly onto the fine grid, drop it at its offset inside the widened range
+    and re-integrate it ``factor`` fine cells per new bin (double-precision prefix sums), then add the fresh
+    batch's histogram (reference observer.py:415-452)."""
+    n, up = obs.bins, obs.upsample_rate
+    dense = torch.zeros(n * factor, device=fresh.device)
+    dense[first:n * up + first] = obs.histogram.repeat_interleave(up)
+    prefix = torch.cumsum(dense, 0, dtype=torch.double)[factor - 1::factor]
+    before = torch.zeros(n, device=fresh.device)
+    before[1:n] = prefix[0:-1]
+    return fresh + ((prefix - before) / up).to(torch.float)
+
+
+def _store(obs, hist, lo, hi):
+    obs.histogram.detach_().resize_(hist.shape)
+    obs.histogram.copy_(hist)
+    obs.min_val.detach_().resize_(lo.shape)
+    obs.min_val.copy_(lo)
+    obs.max_val.detach_().resize_(hi.shape)
+    obs.max_val.copy_(hi)
+
+
+def _count(obs, what):
+    stats = getattr(obs, "stats", None)
+    if stats is not None:
+        stats[what] += 1
+
+
+def histogram_step(obs, x_orig: torch.Tensor, histc=ops.histc, minmax=ops.minmax) -> torch.Tensor:
+    """HistogramObserver.forward (reference observer.py:454-499) on the dmxq kernels.  ``int(tensor)`` truncates toward
+    zero and raises OverflowError / ValueError on inf / NaN exactly as it does in the reference."""
+    if x_orig.numel() == 0:
+        return x_orig
+    x = x_orig.detach()
+    lo0, hi0 = obs.min_val.item(), obs.max_val.item()
+    if (lo0 == float("inf") and hi0 == float("-inf")) or lo0 == hi0:
+        mn, mx = minmax(x)
+        mn, mx = mn.reshape(()), mx.reshape(())
+        _store(obs, histc(x, obs.bins, min=int(mn), max=int(mx)), mn, mx)
+        return x_orig
+    # steady state: bin into the range the running min/max predict and learn the batch's amin/amax in the same pass
+    lo, hi, factor, first = _widened(obs, obs.min_val, obs.max_val)
+    a, b = int(lo), int(hi)
+    hist = None
+    if a != b:
+        hist, mn, mx = histc(x, obs.bins, min=a, max=b, return_minmax=True)
+    else:  # empty integer range: histc falls back on this batch's own range, which needs its amin/amax first
+        mn, mx = minmax(x)
+        mn, mx = mn.reshape(()), mx.reshape(())
+    mn, mx = mn.to(obs.min_val.device), mx.to(obs.max_val.device)
+    new_lo, new_hi = torch.min(mn, obs.min_val), torch.max(mx, obs.max_val)
+    if hist is not None and new_lo.item() == lo0 and new_hi.item() == hi0:
+        _count(obs, "fused_steps")
+    else:
+        lo, hi, factor, first = _widened(obs, new_lo, new_hi)
+        hist = histc(x, obs.bins, min=int(lo), max=int(hi))
+        _count(obs, "rebinned_steps")
+    hist = hist.to(obs.histogram.device)
+    if lo.item() == lo0 and hi.item() == hi0:
+        hist = hist + obs.histogram
+    else:
+        hist = _rebinned(obs, hist, factor, first)
+    _store(obs, hist, lo, hi)
+    return x_orig
+
+
 class HistogramObserver(DMXObserverBase):
     r"""Running histogram of the observed values + an L2-optimal clipping range for the
     quantizer (reference observer.py:213-582, itself after torch.ao's HistogramObserver;
@@ -186,76 +265,8 @@ class HistogramObserver(DMXObserverBase):
         self.stats = {"fused_steps": 0, "rebinned_steps": 0}
 
     # ---- accumulate -------------------------------------------------------------------------
-    def _widened(self, lo: torch.Tensor, hi: torch.Tensor):
-        """Grow [lo, hi] (only upwards) so that its width is a whole multiple of the current bin grid refined
-        ``upsample_rate`` times; returns the new bounds, that multiple and the fine-grid offset of the old
-        minimum (reference observer.py:390-413).  All arithmetic on 0-d fp32 tensors, as there."""
-        fine = (self.max_val - self.min_val) / (self.bins * self.upsample_rate)
-        span = self.bins * fine
-        factor = int(torch.ceil((hi - lo) / span).item())
-        hi = hi + (factor * span - (hi - lo))
-        first = int(torch.round((self.min_val - lo) / fine).item())
-        return lo, hi, factor, first
-
-    def _rebinned(self, fresh: torch.Tensor, factor: int, first: int) -> torch.Tensor:
-        """Spread the stored histogram uniformly onto the fine grid, drop it at its offset inside the widened range
-        and re-integrate it ``factor`` fine cells per new bin (double-precision prefix sums), then add the fresh
-        batch's histogram (reference observer.py:415-452)."""
-        n, up = self.bins, self.upsample_rate
-        dense = torch.zeros(n * factor, device=fresh.device)
-        dense[first:n * up + first] = self.histogram.repeat_interleave(up)
-        prefix = torch.cumsum(dense, 0, dtype=torch.double)[factor - 1::factor]
-        before = torch.zeros(n, device=fresh.device)
-        before[1:n] = prefix[0:-1]
-        return fresh + ((prefix - before) / up).to(torch.float)
-
-    @staticmethod
-    def _trunc(v: torch.Tensor) -> int:
-        return int(v)  # toward zero; OverflowError / ValueError on inf / NaN exactly as in the reference
-
     def forward(self, x_orig: torch.Tensor) -> torch.Tensor:
-        if x_orig.numel() == 0:
-            return x_orig
-        x = x_orig.detach()
-        lo0, hi0 = self.min_val.item(), self.max_val.item()
-        if (lo0 == float("inf") and hi0 == float("-inf")) or lo0 == hi0:
-            mn, mx = self._minmax(x)
-            mn, mx = mn.reshape(()), mx.reshape(())
-            hist = self._histc(x, self.bins, min=self._trunc(mn), max=self._trunc(mx))
-            self._store(hist, mn, mx)
-            return x_orig
-        # steady state: bin into the range the running min/max predict and learn the batch's amin/amax in the same pass
-        lo, hi, factor, first = self._widened(self.min_val, self.max_val)
-        a, b = self._trunc(lo), self._trunc(hi)
-        hist = None
-        if a != b:
-            hist, mn, mx = self._histc(x, self.bins, min=a, max=b, return_minmax=True)
-        else:  # empty integer range: histc falls back on this batch's own range, which needs its amin/amax first
-            mn, mx = self._minmax(x)
-            mn, mx = mn.reshape(()), mx.reshape(())
-        mn, mx = mn.to(self.min_val.device), mx.to(self.max_val.device)
-        new_lo, new_hi = torch.min(mn, self.min_val), torch.max(mx, self.max_val)
-        if hist is not None and new_lo.item() == lo0 and new_hi.item() == hi0:
-            self.stats["fused_steps"] += 1
-        else:
-            lo, hi, factor, first = self._widened(new_lo, new_hi)
-            hist = self._histc(x, self.bins, min=self._trunc(lo), max=self._trunc(hi))
-            self.stats["rebinned_steps"] += 1
-        hist = hist.to(self.histogram.device)
-        if lo.item() == lo0 and hi.item() == hi0:
-            hist = hist + self.histogram
-        else:
-            hist = self._rebinned(hist, factor, first)
-        self._store(hist, lo, hi)
-        return x_orig
-
-    def _store(self, hist, lo, hi):
-        self.histogram.detach_().resize_(hist.shape)
-        self.histogram.copy_(hist)
-        self.min_val.detach_().resize_(lo.shape)
-        self.min_val.copy_(lo)
-        self.max_val.detach_().resize_(hi.shape)
-        self.max_val.copy_(hi)
+        return histogram_step(self, x_orig, self._histc, self._minmax)
 
     # ---- clipping-range search ----------------------------------------------------------------
     @staticmethod

@@ -118,6 +118,20 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
             if hasattr(mod, name):
                 _patch(mod, name, routed)
 
+    # HistogramObserver.forward: aminmax + histc over the observed tensor on dmxq_histc / dmxq_minmax
+    # (one fused pass per steady-state step); the state it leaves in histogram / min_val / max_val and
+    # everything downstream (calculate_qparams, the clipping search) stay the reference's own code.
+    obs = importlib.import_module(package + ".numerical.observer")
+    o_hfwd = obs.HistogramObserver.forward
+    from .numerical.observer import histogram_step
+
+    def histogram_forward(self, x_orig):
+        if not x_orig.is_cuda:
+            return o_hfwd(self, x_orig)
+        return histogram_step(self, x_orig)
+
+    _patch(obs.HistogramObserver, "forward", histogram_forward)
+
     if fuse_castto:
         # CastTo.forward's x.float() ... .to(dtype) round trip fused into the kernel for the plain
         # (no pre-transform, no observer, non-FixedPoint) case; everything else: reference code.

@@ -44,3 +44,31 @@ def test_install_patches_plugin_points_and_keeps_cpu_path():
     finally:
         plugin.uninstall()
     assert fmt.BlockFloatingPoint.cast is orig[0] and sp.Sparsify.forward is orig[4] and not plugin.installed()
+
+
+def test_histogram_step_drives_the_reference_observer_class():
+    """plugin.install() binds numerical.observer.histogram_step onto the reference's HistogramObserver for CUDA tensors;
+    here the same function drives a *reference* observer instance with the oracle standing in for the two kernels, and
+    must leave exactly the state (and qparams) the reference's own forward leaves"""
+    num, _, _ = load_reference.load()
+    from dmx.compressor.numerical.observer import HistogramObserver as RefObserver
+
+    from dmx_compressor_b200 import plugin
+    from dmx_compressor_b200.numerical.observer import histogram_step
+    from test_observer_cpu import G, oracle_histc, oracle_minmax
+
+    plugin.install("dmx.compressor")
+    try:
+        for name in ("widening", "steady", "unit_interval"):
+            fmt, qs, bins, recipe = G.SEQUENCES[name]
+            ours = RefObserver(bins=bins, dtype=num.Format.from_shorthand(fmt), qscheme=G.QS[qs])
+            theirs = RefObserver(bins=bins, dtype=num.Format.from_shorthand(fmt), qscheme=G.QS[qs])
+            for x in G.batches(recipe):
+                histogram_step(ours, torch.from_numpy(x), oracle_histc, oracle_minmax)
+                theirs(torch.from_numpy(x))  # CPU tensor: the patched forward falls through to the reference's own
+                assert torch.equal(ours.histogram, theirs.histogram)
+                assert ours.min_val.item() == theirs.min_val.item() and ours.max_val.item() == theirs.max_val.item()
+            a, b = ours.calculate_qparams(), theirs.calculate_qparams()
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    finally:
+        plugin.uninstall()
