@@ -204,13 +204,17 @@ __device__ __forceinline__ float float_elem(float x, const FloatFmt &f, uint32_t
 //     bookkeeping above differs from the reference's pattern arithmetic: NaNs (pattern above
 //     0x7f800000) take the out-of-line exact path (never in real data; keeps bit parity).
 template <bool EXACT>
-__device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFmt &f)
+__device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFmt &f, uint32_t max_num)
 {
     uint32_t target = f2u(x);
     uint32_t ab = target & 0x7FFFFFFFu;
     uint32_t qa = EXACT ? ab : round_bits<R_NEAREST>(ab, f.sh, f.mask, 0u);
-    uint32_t mag = min(qa, f.max_num);
+    uint32_t mag = min(qa, max_num);
     return ab < f.shift_exp ? 0.0f : u2f(mag | (target & 0x80000000u));
+}
+template <bool EXACT> __device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFmt &f)
+{
+    return float_elem_flush_nearest<EXACT>(x, f, f.max_num);
 }
 
 // nearest rounding, all other flag combinations (FP8 formats keep subnormals; unsigned scalers)

@@ -72,9 +72,8 @@ __device__ __forceinline__ void bfp_ns_apply(float (&v)[V], uint32_t m, const St
     }
 }
 
-template <int V> __device__ __forceinline__ void float_fast_apply(float (&v)[V], const StageDev &st)
+template <int V> __device__ __forceinline__ void float_fast_apply(float (&v)[V], const StageDev &st, bool any_nan)
 {
-    const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
     float q[V];
     if (st.ff.exact) {
 #pragma unroll
@@ -99,8 +98,11 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
     constexpr int SRCBITS = std::is_same<Tin, __nv_bfloat16>::value ? 16 : (std::is_same<Tin, __half>::value ? 11 : 32);
     const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
     Tout *__restrict__ y = static_cast<Tout *>(p.y);
+    constexpr bool SAME16 = SRC16 && std::is_same<Tin, Tout>::value;
     const int lane = threadIdx.x & 31;
     const int64_t g0 = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    // FLOAT -> BFP pair on a 16-bit tensor: the float format's saturation value as Tout stores it
+    const uint32_t fmax_rq = (KIND == K_FLOAT_BFP && SAME16) ? f2u(requant1<Tout>(u2f(p.chain.st[0].ff.max_num))) : 0u;
 
     uint4 raw[kUnroll];
     int64_t yoff[kUnroll];
@@ -148,27 +150,78 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
         } else if (KIND == K_FLOAT) {
-            VecIO<Tin>::unpack(raw[u], v);
-            float_fast_apply<V>(v, p.chain.st[0]);
+            const bool any_nan = unpack_absmax<Tin>(raw[u], v) > 0x7F800000u;
+            float_fast_apply<V>(v, p.chain.st[0], any_nan);
         } else if (KIND == K_FLOAT_BFP) {
-            VecIO<Tin>::unpack(raw[u], v);
-            float_fast_apply<V>(v, p.chain.st[0]);
-            if (sizeof(Tout) == 2) {
+            // The float stage (nearest, flush, saturate) and the rounding to Tout are monotone in |x|, so the block
+            // maximum the BFP stage needs is the stage applied to the maximum of the inputs: one scalar evaluation
+            // instead of a second max over the vector.
+            const StageDev &sf = p.chain.st[0];
+            const StageDev &st = p.chain.st[1];
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
+            uint32_t m_thr;
+            if (m_in > 0x7F800000u) {  // a NaN in this vector: literal path
 #pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(v[j]);
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_slow(v[j], &sf.ff, 0u));
+                m_thr = vec_absmax<V>(v);
+            } else if (SAME16 && sf.ff.exact) {
+                // the values already sit on Tout's grid and the format keeps their significand: only flush and
+                // saturate act, and the saturation value is the one constant that needs Tout's rounding
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = float_elem_flush_nearest<true>(v[j], sf.ff, fmax_rq);
+                m_thr = f2u(float_elem_flush_nearest<true>(u2f(m_in), sf.ff, fmax_rq));
+            } else if (sf.ff.exact) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<true>(v[j], sf.ff));
+                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<true>(u2f(m_in), sf.ff)));
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<false>(v[j], sf.ff));
+                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<false>(u2f(m_in), sf.ff)));
             }
-            const StageDev &st = p.chain.st[1];
-            uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
-            bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, m, st);  // after the requant the values carry Tout's significand
+            bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, lanes_max(m_thr, st.block / V), st);  // the values now carry Tout's significand
         } else if (KIND == K_NM_BFP) {
-            VecIO<Tin>::unpack(raw[u], v);
-            nm_stage<V>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);  // (pairwise ranks measured faster here than the packed-key network)
+            // score = |x|: the largest magnitude of every group survives the pruning, so the block maximum is the
+            // maximum of the inputs (packed 16-bit max on the raw words for 16-bit sources)
+            const StageDev &sn = p.chain.st[0];
             const StageDev &st = p.chain.st[1];
-            uint32_t m = lanes_max(vec_absmax<V>(v), st.block / V);
-            bfp_ns_apply<V, SRC16>(v, m, st);
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
+            bool pruned = false;
+            if constexpr (SRC16) {
+                if (sn.block == 4 && sn.n_prune >= 1 && sn.n_prune <= 3 && m_in < 0x7F800000u) {
+                    bool keep[8];
+                    nm4_keep_raw16(raw[u], sn.n_prune, keep);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = keep[j] ? v[j] : __fmul_rn(v[j], 0.0f);  // x * mask (finite x)
+                    pruned = true;
+                }
+            }
+            if (!pruned) nm_stage<V>(v, sn, lane, nullptr, nullptr, valid[u]);  // (pairwise ranks measured faster here than the packed-key network)
+            const uint32_t m_thr = m_in > 0x7F800000u ? vec_absmax<V>(v) : m_in;  // NaN: whatever the pruning left
+            bfp_ns_apply<V, SRC16>(v, lanes_max(m_thr, st.block / V), st);
         } else if (KIND == K_NM) {
-            VecIO<Tin>::unpack(raw[u], v);
-            nm_stage<V, SRCBITS>(v, p.chain.st[0], lane, nullptr, nullptr, valid[u]);
+            const StageDev &sn = p.chain.st[0];
+            bool pruned = false;
+            if constexpr (SRC16) {
+                constexpr uint32_t kInf16 = std::is_same<Tin, __nv_bfloat16>::value ? 0x7F80u : 0x7C00u;
+                if (sn.block == 4 && sn.n_prune >= 1 && sn.n_prune <= 3 && raw16_absmax(raw[u]) < kInf16) {
+                    bool keep[8];
+                    nm4_keep_raw16(raw[u], sn.n_prune, keep);
+                    if constexpr (SAME16) {  // no widening at all: mask the packed words and store them
+                        if (valid[u]) stg_stream(y + yoff[u], nm_apply_raw16(raw[u], keep));
+                        continue;
+                    } else {
+                        VecIO<Tin>::unpack(raw[u], v);
+#pragma unroll
+                        for (int j = 0; j < V; ++j) v[j] = keep[j] ? v[j] : __fmul_rn(v[j], 0.0f);
+                        pruned = true;
+                    }
+                }
+            }
+            if (!pruned) {
+                VecIO<Tin>::unpack(raw[u], v);
+                nm_stage<V, SRCBITS>(v, sn, lane, nullptr, nullptr, valid[u]);
+            }
         } else if (KIND == K_FIXED) {
             // CastTo.forward for FixedPoint (S/numerical/cast.py:279-296): x/sc + zp -> round -> clamp -> (q - zp)*sc,
             // every step a separately rounded fp32 op.  sc == 1 makes the division and the final multiply exact

@@ -175,8 +175,23 @@ template <int V> __device__ __forceinline__ uint32_t vec_absmax(const float (&v)
     for (int j = 0; j < V; ++j) m = max(m, f2u(v[j]) & 0x7FFFFFFFu);
     return m;
 }
+template <int LANES> __device__ __forceinline__ uint32_t lanes_max_n(uint32_t m)
+{
+#pragma unroll
+    for (int off = 1; off < LANES; off <<= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    return m;
+}
 __device__ __forceinline__ uint32_t lanes_max(uint32_t m, int lanes)
 {
+    // (warp-uniform) the usual block sizes get straight-line shuffles; the loop form costs ~6 instructions per step
+    switch (lanes) {
+    case 1: return m;
+    case 2: return lanes_max_n<2>(m);
+    case 4: return lanes_max_n<4>(m);
+    case 8: return lanes_max_n<8>(m);
+    case 16: return lanes_max_n<16>(m);
+    default: break;
+    }
     for (int off = 1; off < lanes; off <<= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
     return m;
 }
@@ -370,6 +385,53 @@ template <int V, int M, int KEYSHIFT> __device__ __forceinline__ void nm_local16
 #pragma unroll
         for (int a = 0; a < M; ++a) keep[g0 + a] = n_prune == 0 || k[a] >= thr;
     }
+}
+
+// N:4 with score |x| straight on the RAW 16-bit patterns of a 16-byte vector (bf16 or fp16, eight finite values): the
+// magnitude pattern of either format orders like the magnitude, so ((pattern & 0x7FFF) << 3) | index is a unique key
+// in stable ascending order.  The n_prune-th smallest key of a group (1 <= n_prune <= 3) comes from six min/max
+// operations on the two sorted pairs; everything at or above it is kept.
+// Inf / NaN (where x * 0 is not a signed zero, and NaN payloads must not order) are excluded by the caller.
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c)  // a * b + c kept as one FMA-pipe IMAD
+{
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t raw16_absmax(const uint4 &r)
+{
+    uint32_t m2 = __vmaxu2(__vmaxu2(r.x & 0x7FFF7FFFu, r.y & 0x7FFF7FFFu), __vmaxu2(r.z & 0x7FFF7FFFu, r.w & 0x7FFF7FFFu));
+    return max(m2 & 0xFFFFu, m2 >> 16);
+}
+__device__ __forceinline__ void nm4_keep_raw16(const uint4 &r, int n_prune, bool (&keep)[8])
+{
+    // keys: magnitude pattern in bits 17..31, index in the low bits.  The multiplications are shifts that drop the
+    // sign (and, for the low half, the other element) and run on the FMA pipe; the kernels these serve are bound by
+    // the integer ALU pipe, so every LOP3 / VIMNMX saved counts.
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        uint32_t k[4];
+        k[0] = imad(w[2 * g], 0x20000u, 0u);
+        k[1] = imad(w[2 * g] & 0x7FFF0000u, 2u, 1u);
+        k[2] = imad(w[2 * g + 1], 0x20000u, 2u);
+        k[3] = imad(w[2 * g + 1] & 0x7FFF0000u, 2u, 3u);
+        const uint32_t lo1 = min(k[0], k[1]), hi1 = max(k[0], k[1]), lo2 = min(k[2], k[3]), hi2 = max(k[2], k[3]);
+        uint32_t thr;  // the n_prune-th smallest key (0-based): everything from it upwards is kept
+        if (n_prune == 2) thr = __vimax3_u32(min(hi1, hi2), lo1, lo2);
+        else if (n_prune == 1) thr = __vimin3_u32(max(lo1, lo2), hi1, hi2);
+        else thr = max(hi1, hi2);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) keep[4 * g + a] = k[a] >= thr;
+    }
+}
+// x * mask on the packed words: a pruned finite value becomes a zero of its own sign
+__device__ __forceinline__ uint4 nm_apply_raw16(const uint4 &r, const bool (&keep)[8])
+{
+    uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] &= (keep[2 * i] ? 0x0000FFFFu : 0x00008000u) | (keep[2 * i + 1] ? 0xFFFF0000u : 0x80000000u);
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // N:M across `lanes` = M / V neighbouring lanes (M > V): partner keys arrive by shuffle.

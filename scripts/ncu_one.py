@@ -22,3 +22,13 @@ if which in ("all", "float16_f32"):
     st2 = [Format.from_shorthand("FP[1|5|10,15](FN)").stage()]
     for _ in range(3): ops.cast_chain(x, st2, -1, out=y)
 torch.cuda.synchronize()
+if which in ("nm_bf16",):
+    x = torch.randn(n // 4096, 4096, device=dev).bfloat16(); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, [ops.nm_stage(2, 4)], -1, out=y)
+if which in ("nm_bfp_bf16",):
+    x = torch.randn(n // 4096, 4096, device=dev).bfloat16(); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, [ops.nm_stage(2, 4), Format.from_shorthand("BFP[4|8]{64}(SN)").stage()], -1, out=y)
+if which in ("float_bfp_bf16",):
+    x = torch.randn(n // 4096, 4096, device=dev).bfloat16(); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, [Format.from_shorthand("FP[1|5|10,15](FN)").stage(), Format.from_shorthand("BFP[8|8]{64}(SN)").stage()], -1, out=y)
+torch.cuda.synchronize()
