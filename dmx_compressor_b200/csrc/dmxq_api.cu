@@ -139,6 +139,7 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         if (rc) return rc;
         if (d.sb.sc.mode == R_STOCHASTIC) return fail(DMXQ_ERR_UNSUPPORTED, "stochastic SBFP scaler format is not supported");
         d.sb.man_scaling = (float)((1 << (s.precision - 1)) - 1);
+        d.sb.inv_man = 1.0f / d.sb.man_scaling;
         return DMXQ_OK;
     }
     case DMXQ_STAGE_FLOAT:

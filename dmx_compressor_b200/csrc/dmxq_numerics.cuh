@@ -299,12 +299,15 @@ struct SbfpFmt {
     FixedFmt xp;        // XP[p,0] block format (fl = 0: up = down = 1)
     FloatFmt sc;        // scaler FloatingPoint format
     float man_scaling;  // 2^(p-1) - 1
+    float inv_man;      // RN(1 / man_scaling)
 };
 
 struct SbfpBlock {
     float cmax;  // max|x| / man_scaling   (NaN when the block holds a NaN)
     float fs;    // FP_cast(cmax)
+    float rc;    // RN(1 / cmax), for the division-free quotient (dmxq_stages.cuh sbfp_elem_fast)
     bool on;     // cmax > 0 (false => pass the block through, format.py:467-472)
+    bool rok;    // rc usable: cmax well inside the normal range and its significand not all ones
 };
 
 __device__ __forceinline__ SbfpBlock sbfp_block(uint32_t maxabs_bits, const SbfpFmt &f)
@@ -313,6 +316,8 @@ __device__ __forceinline__ SbfpBlock sbfp_block(uint32_t maxabs_bits, const Sbfp
     b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
     b.fs = float_elem_rt(b.cmax, f.sc, 0u);
     b.on = b.cmax > 0.0f;
+    b.rc = 0.0f;
+    b.rok = false;
     return b;
 }
 

@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             SbfpBlock b = sbfp_block_ol(m, st.sb);
-#pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = sbfp_elem_fast(v[j], b, st.sb);
+            sbfp_apply<V>(v, b, st.sb);
         } else {
             VecIO<Tin>::unpack(raw[u], v);
 #pragma unroll 1

@@ -138,26 +138,64 @@ static __device__ __noinline__ float fixed_elem_slow(float x, const FixedFmt *f,
 }
 
 // SBFP block header (once per block per lane) and element
+// Correctly rounded a / b without the division sequence, given rb = RN(1/b): q0 = a*rb is within 2 ulp, one Newton
+// step q += (a - q*b)*rb (residual by FMA) makes it faithful and a second one rounds correctly (Markstein), i.e. the
+// result equals __fdiv_rn(a, b) bit for bit -- for a >= 0, b > 0 both well inside the normal range and b's significand
+// not all ones (the callers check; they fall back on __fdiv_rn otherwise).  (A -0 numerator would come out as +0.)
+__device__ __forceinline__ float div_by_recip(float a, float b, float rb)
+{
+    float q = __fmul_rn(a, rb);
+    q = __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+    return __fmaf_rn(__fmaf_rn(-q, b, a), rb, q);
+}
+__device__ __forceinline__ bool recip_safe(float b) { return b > 0x1p-60f && b < 0x1p60f && (f2u(b) & 0x7FFFFFu) != 0x7FFFFFu; }
+
 __device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const SbfpFmt &f)
 {
     SbfpBlock b;
-    b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
+    const float m = u2f(maxabs_bits);
+    // max / man_scaling: man_scaling = 2^(p-1) - 1 never has an all-ones significand, its reciprocal comes from the host
+    b.cmax = (m > 0x1p-60f && m < 0x1p60f) ? div_by_recip(m, f.man_scaling, f.inv_man) : __fdiv_rn(m, f.man_scaling);
     // scaler cast: cmax >= 0 (or NaN, in which case the block passes through and fs is unused), so the
     // unsigned scaler formats of the SBFP aliases reduce to the signed nearest+flush fast path
     if (f.sc.mode == R_NEAREST && f.sc.flush && (!f.sc.fp16_flush || f.sc.min_exp >= -14)) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
     else b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
     b.on = b.cmax > 0.0f;
+    b.rok = recip_safe(b.cmax);
+    b.rc = __frcp_rn(b.cmax);
     return b;
 }
 __device__ __forceinline__ bool sbfp_fast(const SbfpFmt &f) { return f.xp.mode == R_NEAREST && f.xp.tie == TIE_AWAY; }
-// XP[p,0] nearest, half away (the reference's CUDA rule) of the IEEE quotient; fl = 0 => no scaling
-// multiplies.  (A reciprocal-estimate-and-verify variant was measured slower than the hardware
-// division sequence on B200 and dropped.)
+// XP[p,0] nearest, half away (the reference's CUDA rule) of the IEEE quotient; fl = 0 => no scaling multiplies.
 __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, const SbfpFmt &f)
 {
     float v = roundf(__fdiv_rn(x, b.cmax));
     if (f.xp.clamp) v = v > f.xp.t_max ? f.xp.t_max : (v < f.xp.t_min ? f.xp.t_min : v);
     return b.on ? __fmul_rn(v, b.fs) : x;
+}
+// The same on a register vector of one block, division free for ordinary blocks.  Works on magnitudes (|x| is a free
+// operand modifier): the quotient |x| / cmax is in [0, 7.0000005] (cmax = RN(max|x| / man_scaling)), so
+//   * round-to-nearest-even is (q + 2^23) - 2^23, and half-away differs from it only on exact ties, where the
+//     remainder q - r is exactly +0.5 after rounding down: one compare and a predicated add;
+//   * the clamp to [t_min, t_max] cannot trigger when |t_min|, t_max >= man_scaling (every SBFP format), so it is skipped;
+//   * the result carries x's sign (cmax, fs >= 0).
+template <int V> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const SbfpBlock &b, const SbfpFmt &f)
+{
+    if (!b.on) return;  // all-zero (or NaN) block: passes through
+    const bool no_clamp = !f.xp.clamp || (f.xp.t_max >= f.man_scaling && f.xp.t_min <= -f.man_scaling);
+    if (b.rok && no_clamp) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float a = fabsf(v[j]);
+            const float q = div_by_recip(a, b.cmax, b.rc);
+            float r = __fsub_rn(__fadd_rn(q, 8388608.0f), 8388608.0f);
+            if (__fsub_rn(q, r) == 0.5f) r = __fadd_rn(r, 1.0f);
+            v[j] = copysignf(__fmul_rn(r, b.fs), v[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = sbfp_elem_fast(v[j], b, f);
+    }
 }
 static __device__ __noinline__ float sbfp_elem_slow(float x, float cmax, float fs, const FixedFmt *xp)
 {
@@ -249,8 +287,7 @@ template <int V> __device__ __forceinline__ void sbfp_stage(float (&v)[V], const
     uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
     SbfpBlock b = sbfp_block_ol(m, st.sb);
     if (sbfp_fast(st.sb)) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = sbfp_elem_fast(v[j], b, st.sb);
+        sbfp_apply<V>(v, b, st.sb);
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = sbfp_elem_slow(v[j], b.cmax, b.fs, &st.sb.xp);

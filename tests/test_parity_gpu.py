@@ -553,6 +553,32 @@ def test_sbfp_on_adversarial_ties():
         check(gpu_cast(xb.to(DEV), sh, -1), bits(want), sh + " bf16")
 
 
+def test_sbfp_division_free_quotient_at_scale():
+    """the kernel's x / cmax is a reciprocal with two FMA refinements: 2^23 tie-adjacent quotients (vectorised version of
+    the test above, every block its own scale) and 2^22 ordinary values must match the dividing oracle bit for bit,
+    including blocks whose cmax forces the IEEE-division path (significand all ones, tiny, huge)"""
+    g = torch.Generator().manual_seed(78)
+    nblk = 1 << 19
+    m = (torch.rand(nblk, 1, generator=g) * 4 + 0.1) * torch.pow(2.0, torch.randint(-30, 30, (nblk, 1), generator=g).float())
+    m[0::1001] = (7.0 * (2.0 - 2.0**-23))  # cmax = 2 - ulp: all-ones significand
+    m[1::1001] *= 2.0**-90
+    m[2::1001] *= 2.0**80
+    cmax = m / 7.0
+    k = torch.randint(0, 7, (nblk, 15), generator=g).float() + 0.5
+    x = k * cmax
+    x = (x.view(torch.int32) + torch.randint(-2, 3, (nblk, 15), generator=g, dtype=torch.int32)).view(torch.float32)
+    x = x * (torch.randint(0, 2, (nblk, 15), generator=g).float() * 2 - 1)
+    x = torch.cat([m, x], 1).reshape(-1, 4096)
+    for sh in ("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,12](FN)>{16}"):
+        check(gpu_cast(x.to(DEV), sh, -1), bits(O.cast(x.numpy(), sh, -1, tie=O.TIE_AWAY)), sh)
+    y = _rand((1024, 4096), 79, spread=20)
+    sh = "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"
+    check(gpu_cast(y.to(DEV), sh, -1), bits(O.cast(y.numpy(), sh, -1, tie=O.TIE_AWAY)), sh)
+    yb = y.to(torch.bfloat16)
+    check(gpu_cast(yb.to(DEV), sh, -1), bits(O.cast(yb.float().numpy(), sh, -1, tie=O.TIE_AWAY)), sh + " bf16")
+    check(gpu_cast(y.to(DEV), sh, 0), bits(O.cast(y.numpy(), sh, 0, tie=O.TIE_AWAY)), sh + " cols")
+
+
 def test_int8_device_qparams_fast_path():
     """CastTo(INT8/INT4) per-tensor: vectorised kernel reading scale / zero-point from device memory"""
     x = _rand((64, 1024), 91, spread=3) * 20
