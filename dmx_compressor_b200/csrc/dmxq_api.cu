@@ -84,6 +84,8 @@ int decode_float(int man, int exp, int bias, int flush, int is_unsigned, int fp1
     // format.py:223-232) is implied by flush_subnormal whenever the format's own smallest normal
     // is >= 2^-14 (NaN inputs, the one exception, take the exact out-of-line path anyway).
     f.fastpath = f.mode == R_NEAREST && f.flush && !f.is_unsigned && (!f.fp16_flush || f.min_exp >= -14);
+    f.nsub = f.mode == R_NEAREST && !f.flush && !f.is_unsigned && !f.fp16_flush && f.sh >= 2;
+    f.magic = ((uint32_t)f.sh << 23) | 0x00400000u;
     return DMXQ_OK;
 }
 
@@ -409,6 +411,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         else if (chain.n == 1 && chain.st[0].kind == ST_SBFP && chain.st[0].sb.xp.mode == R_NEAREST && chain.st[0].sb.xp.tie == TIE_AWAY) kind = 6;  // K_SBFP
         else if (chain.n == 1 && chain.st[0].kind == ST_FIXED && chain.st[0].xf.mode == R_NEAREST && chain.st[0].xf.tie == TIE_AWAY) kind = 7;  // K_FIXED
         else if (chain.n == 1 && chain.st[0].kind == ST_NM) kind = 8;  // K_NM
+        else if (chain.n == 1 && chain.st[0].kind == ST_MXFP) kind = 9;  // K_MXFP
         if (qscale) {
             if (kind != 7) return kNeedFallback;
             p.qscale = qscale; p.qzp = qzp;

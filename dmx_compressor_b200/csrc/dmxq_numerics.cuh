@@ -168,6 +168,8 @@ struct FloatFmt {
     int fp16_flush;      // extra |q| < 2^-14 -> +0
     int mode;
     int fastpath;        // nearest + flush + signed (+ fp16 pass implied): float_elem_flush_nearest is valid for non-NaN inputs
+    int nsub;            // nearest, subnormals kept, signed, man <= 21: float_elem_nearest_sub is valid for finite inputs
+    uint32_t magic;      // (sh << 23) | 0x00400000: exponent-field offset + mantissa of the rounding constant 1.5 * 2^(e + sh)
 };
 
 template <int MODE>
@@ -215,6 +217,22 @@ __device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFm
 template <bool EXACT> __device__ __forceinline__ float float_elem_flush_nearest(float x, const FloatFmt &f)
 {
     return float_elem_flush_nearest<EXACT>(x, f, f.max_num);
+}
+
+// nearest rounding with subnormals kept (the MX element formats), branch free, for finite x.  The reference
+// (float_kernel.cu:147-160) rounds values below 2^min_exp by adding +-2^min_exp first (val = x + shift, itself a rounded
+// fp32 add), rounding val's mantissa to `man` bits and subtracting the shift again; ordinary values are rounded in
+// place.  Both are "round val to a multiple of 2^(exponent(val) - man), ties to even", which one more fp32 add of
+// C = 1.5 * 2^(exponent(val) + 23 - man) performs: (val + C) - C.  With shift = +-0 for ordinary values the two cases
+// share one instruction sequence; the saturation is an unsigned min on the magnitude, as in float_elem_flush_nearest.
+__device__ __forceinline__ float float_elem_nearest_sub(float x, const FloatFmt &f)
+{
+    const uint32_t t = f2u(x), ab = t & 0x7FFFFFFFu;
+    const float shift = u2f((ab < f.shift_exp ? f.shift_exp : 0u) | (t & 0x80000000u));
+    const float val = __fadd_rn(x, shift);
+    const float C = u2f((f2u(val) & 0x7F800000u) + f.magic);
+    const uint32_t qb = f2u(__fsub_rn(__fsub_rn(__fadd_rn(val, C), C), shift));
+    return u2f(min(qb & 0x7FFFFFFFu, f.max_num) | (qb & 0x80000000u));
 }
 
 // nearest rounding, all other flag combinations (FP8 formats keep subnormals; unsigned scalers)

@@ -21,12 +21,13 @@
 //   K_SBFP       [SBFP, XP nearest half-away]                 SBFP weight storage cast
 //   K_NM         [N:M with score |x|]                          Sparsify alone (no mask output)
 //   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
+//   K_MXFP       [MXFP]                                       OCP-MX style power-of-two block scale + low-bit float elements
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_COUNT = 9 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_COUNT = 10 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -243,6 +244,9 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                 if (wrap && !(unit && zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, zp), sc);
                 v[j] = a;
             }
+        } else if (KIND == K_MXFP) {
+            const StageDev &st = p.chain.st[0];
+            mxfp_apply<V>(v, lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V), st);
         } else if (KIND == K_SBFP) {
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);

@@ -299,9 +299,9 @@ static __device__ __noinline__ float mx_elem_ol(float x, float scale, const Floa
     MxBlock b{scale};
     return mx_elem(x, b, *f);
 }
-template <int V> __device__ __forceinline__ void mxfp_stage(float (&v)[V], const StageDev &st, int lanes)
+// MXFP on one register vector whose block max|x| pattern `m` is known
+template <int V> __device__ __forceinline__ void mxfp_apply(float (&v)[V], uint32_t m, const StageDev &st)
 {
-    uint32_t m = lanes_max(vec_absmax<V>(v), lanes);
     // floor(log2f(max)) is the exponent field whenever log2(max) is further than a few ulp from an integer,
     // i.e. unless the mantissa is within 2^-16 of a power of two (log2f is only faithful, and the reference
     // calls it: in that sliver -- and for denormal / non-finite maxima -- so do we).
@@ -314,12 +314,21 @@ template <int V> __device__ __forceinline__ void mxfp_stage(float (&v)[V], const
     if ((sb & 0x807FFFFFu) == 0u && sb >= (2u << 23) && sb <= (252u << 23)) {
         // ordinary block: the scale is a normal power of two, so x / scale == x * (1 / scale) exactly
         const float inv = u2f((254u << 23) - sb);
+        if (st.ff.nsub) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = __fmul_rn(float_elem_nearest(__fmul_rn(v[j], inv), st.ff), b.scale);
+            for (int j = 0; j < V; ++j) v[j] = __fmul_rn(float_elem_nearest_sub(__fmul_rn(v[j], inv), st.ff), b.scale);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = __fmul_rn(float_elem_nearest(__fmul_rn(v[j], inv), st.ff), b.scale);
+        }
     } else {  // zero / denormal / huge / non-finite block: the literal op sequence
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = mx_elem_ol(v[j], b.scale, &st.ff);
     }
+}
+template <int V> __device__ __forceinline__ void mxfp_stage(float (&v)[V], const StageDev &st, int lanes)
+{
+    mxfp_apply<V>(v, lanes_max(vec_absmax<V>(v), lanes), st);
 }
 
 template <int V> __device__ __forceinline__ void float_stage(float (&v)[V], const StageDev &st, const uint32_t (&r)[V])

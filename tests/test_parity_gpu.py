@@ -724,6 +724,29 @@ def test_golden_mxfp():
         check(gpu_cast(xb.to(DEV), sh, -1), bits(want), n + " bf16")
 
 
+@pytest.mark.parametrize("sh", ["MXFP8[E4M3]{32}", "MXFP8[E5M2]{32}", "MXFP6[E2M3]{32}", "MXFP6[E3M2]{64}", "MXFP4[E2M1]{32}", "MXFP8[E4M3]{128}"])
+def test_mxfp_vs_oracle_at_scale(sh):
+    """the branch-free element rounding (shared op sequence for subnormal and normal values) against the oracle on
+    2^21 values whose in-block spread reaches deep into the element format's subnormals, plus exact rounding ties,
+    for rows, strided-rows and cols layouts and 16-bit sources"""
+    g = torch.Generator().manual_seed(97)
+    x = torch.randn(512, 4096, generator=g) * torch.pow(2.0, torch.randint(-24, 3, (512, 4096), generator=g).float())
+    x = x * torch.pow(2.0, torch.randint(-20, 20, (512, 1), generator=g).float())
+    x.view(-1)[::5] = torch.round(x.view(-1)[::5] * 16) / 16  # coarse values: many exact ties
+    x.view(-1)[3::17] = 0.0
+    x.view(-1)[4::17] *= -1
+    x[7] = 0.0  # an all-zero row: 0 / 0 -> NaN blocks, as in the reference
+    check(gpu_cast(x.to(DEV), sh, -1), bits(O.cast(x.numpy(), sh, -1)), sh)
+    for dt, name in ((torch.bfloat16, "bf16"), (torch.float16, "fp16")):
+        xh = x.to(dt)
+        xh = torch.where(torch.isfinite(xh), xh, torch.zeros_like(xh))
+        check(gpu_cast(xh.to(DEV), sh, -1), bits(O.cast(xh.float().numpy(), sh, -1)), f"{sh} {name}")
+    xs = x.to(DEV)[:, :2048]  # strided rows
+    check(gpu_cast(xs, sh, -1), bits(O.cast(x[:, :2048].contiguous().numpy(), sh, -1)), sh + " strided")
+    xc = x[:256].to(DEV)  # blocks along dim 0
+    check(gpu_cast(xc, sh, 0), bits(O.cast(x[:256].contiguous().numpy(), sh, 0)), sh + " cols")
+
+
 # ---- (f3) calibration histogram: dmxq_histc / HistogramObserver ---------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("bins,lo,hi", [(2048, -3, 4), (1000, -7, 10), (7, -1, 1), (2048, 0, 0), (12288, -40, 41), (1, -2, 2)])
