@@ -168,6 +168,144 @@ __global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 16-bit specialisation: ONE symmetric nearest BFP stage, Tin == Tout (bf16 or fp16), wl small enough for the two-add
+// element form (bfp_fast16_elem).  Same tiling as above, but the tile stays PACKED in registers: RPT raw 16-byte rows
+// (4 registers each) instead of RPT x 8 floats, the per-column maxima are taken two columns at a time on the packed
+// words (also through the shuffles), and every word is widened, rounded and narrowed in place.  Half the registers of
+// the generic kernel (twice the resident warps) and half its instructions.
+template <typename T> struct Pack16;
+template <> struct Pack16<__nv_bfloat16> {
+    static __device__ __forceinline__ void widen(uint32_t w, float &lo, float &hi) { lo = u2f(w << 16); hi = u2f(w & 0xFFFF0000u); }
+    static __device__ __forceinline__ uint32_t narrow(float lo, float hi)
+    {
+        __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    static __device__ __forceinline__ uint32_t max_bits(uint32_t m16) { return m16 << 16; }
+};
+template <> struct Pack16<__half> {
+    static __device__ __forceinline__ void widen(uint32_t w, float &lo, float &hi)
+    {
+        float2 f = __half22float2(*reinterpret_cast<__half2 *>(&w));
+        lo = f.x; hi = f.y;
+    }
+    static __device__ __forceinline__ uint32_t narrow(float lo, float hi)
+    {
+        __half2 h = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    static __device__ __forceinline__ uint32_t max_bits(uint32_t m16) { return f2u(__half2float(__ushort_as_half((unsigned short)m16))); }
+};
+
+template <typename T> static __device__ __noinline__ uint32_t bfp_word16_slow(uint32_t w, uint32_t ma, uint32_t mb, int wl, int sh, uint32_t mask)
+{
+    float lo, hi;
+    Pack16<T>::widen(w, lo, hi);
+    return Pack16<T>::narrow(bfp_elem_slow(lo, ma, wl, sh, mask, R_NEAREST, 0, 0u), bfp_elem_slow(hi, mb, wl, sh, mask, R_NEAREST, 0, 0u));
+}
+
+template <typename T, int RPT, int LK>
+__global__ void __launch_bounds__(kThreads, 4) bfp_cols16_kernel(const __grid_constant__ ColsParams p)
+{
+    constexpr int V = 8;
+    constexpr int LI = 32 / LK;
+    constexpr int B = RPT * LK;
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= p.n_tiles) return;  // whole warp leaves together
+    const int li = lane % LI, lk = lane / LI;
+
+    int64_t chunk, blk, xo = 0, yo = 0;
+    if (p.n_tiles <= 0xFFFFFFFFll) {
+        uint32_t t = (uint32_t)tile, nc = (uint32_t)p.nchunk, nb = (uint32_t)p.nblk;
+        uint32_t q = t / nc; chunk = t - q * nc; t = q;
+        q = t / nb; blk = t - q * nb;
+        uint32_t o = q;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            uint32_t od = (uint32_t)p.odim[d];
+            uint32_t i = (d == 0) ? o : o % od;
+            if (d != 0) o /= od;
+            xo += (int64_t)i * p.xs[d]; yo += (int64_t)i * p.ys[d];
+        }
+    } else {
+        int64_t t = tile;
+        chunk = t % p.nchunk; t /= p.nchunk;
+        blk = t % p.nblk;
+        int64_t o = t / p.nblk;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            int64_t i = (d == 0) ? o : o % p.odim[d];
+            if (d != 0) o /= p.odim[d];
+            xo += i * p.xs[d]; yo += i * p.ys[d];
+        }
+    }
+    const int64_t i0 = (chunk * LI + li) * V;
+    const bool col_ok = i0 < p.inner;
+    const int64_t kb = blk * B + (int64_t)lk * RPT;
+    const T *__restrict__ x = static_cast<const T *>(p.x) + xo + i0;
+    T *__restrict__ y = static_cast<T *>(p.y) + yo + i0;
+    const StageDev &st = p.chain.st[0];
+
+    uint32_t w[RPT][4];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const uint4 t = (col_ok && kb + r < p.K) ? ldg_stream(x + (kb + r) * p.xks) : make_uint4(0u, 0u, 0u, 0u);
+        w[r][0] = t.x; w[r][1] = t.y; w[r][2] = t.z; w[r][3] = t.w;
+    }
+    // per-column max|x| patterns, two columns per register
+    uint32_t m2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        m2[c] = 0u;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) m2[c] = __vmaxu2(m2[c], w[r][c] & 0x7FFF7FFFu);
+#pragma unroll
+        for (int off = LI; off < 32; off <<= 1) m2[c] = __vmaxu2(m2[c], __shfl_xor_sync(0xFFFFFFFFu, m2[c], off));
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t ma = Pack16<T>::max_bits(m2[c] & 0xFFFFu), mb = Pack16<T>::max_bits(m2[c] >> 16);
+        if (bfp_fast_ok(ma) && bfp_fast_ok(mb)) {
+            const BfpFast ba = bfp_fast_block(ma, st.wl), bb = bfp_fast_block(mb, st.wl);
+            if (ba.clamp || bb.clamp) {
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    float lo, hi;
+                    Pack16<T>::widen(w[r][c], lo, hi);
+                    w[r][c] = Pack16<T>::narrow(bfp_clamp(bfp_fast16_elem(lo, ba), ba), bfp_clamp(bfp_fast16_elem(hi, bb), bb));
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    float lo, hi;
+                    Pack16<T>::widen(w[r][c], lo, hi);
+                    w[r][c] = Pack16<T>::narrow(bfp_fast16_elem(lo, ba), bfp_fast16_elem(hi, bb));
+                }
+            }
+        } else {  // a denormal / huge / non-finite block in this column pair: the literal integer path
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) w[r][c] = bfp_word16_slow<T>(w[r][c], ma, mb, st.wl, st.sh, st.mask);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r)
+        if (col_ok && kb + r < p.K) stg_stream(y + (kb + r) * p.yks, make_uint4(w[r][0], w[r][1], w[r][2], w[r][3]));
+}
+
+template <typename T> static bool launch_cols16(int B, const ColsParams &p, dim3 g, dim3 b, cudaStream_t s)
+{
+    const StageDev &st = p.chain.st[0];
+    if (!(p.chain.n == 1 && st.kind == ST_BFP && st.mode == R_NEAREST && !st.asym && st.fast && st.fast16)) return false;
+    switch (B) {
+    case 8: bfp_cols16_kernel<T, 1, 8><<<g, b, 0, s>>>(p); return true;
+    case 16: bfp_cols16_kernel<T, 2, 8><<<g, b, 0, s>>>(p); return true;
+    case 32: bfp_cols16_kernel<T, 4, 8><<<g, b, 0, s>>>(p); return true;
+    case 64: bfp_cols16_kernel<T, 8, 8><<<g, b, 0, s>>>(p); return true;
+    case 128: bfp_cols16_kernel<T, 8, 16><<<g, b, 0, s>>>(p); return true;
+    default: return false;
+    }
+}
+
 struct ColsCfg { int B, RPT, LK; };
 // fp32 (V = 4) and 16-bit (V = 8) tilings; RPT * V <= 64 live values per thread
 static const ColsCfg kCfg32[] = {{8, 2, 4}, {16, 4, 4}, {32, 8, 4}, {64, 8, 8}, {128, 16, 8}};
@@ -193,6 +331,12 @@ template <typename Tin, typename Tout> static cudaError_t launch_cols_t(int B, c
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
     dim3 g((unsigned)grid), b(kThreads);
+    if constexpr (sizeof(Tin) == 2 && std::is_same<Tin, Tout>::value) {
+        if (launch_cols16<Tin>(B, p, g, b, s)) {
+            count_launch();
+            return cudaGetLastError();
+        }
+    }
     if constexpr (sizeof(Tin) == 4) {
         switch (B) {
         case 8: chain_cols_kernel<Tin, Tout, 2, 4><<<g, b, 0, s>>>(p); break;

@@ -32,6 +32,9 @@ if which in ("float_bfp_bf16",):
     x = torch.randn(n // 4096, 4096, device=dev).bfloat16(); y = torch.empty_like(x)
     for _ in range(3): ops.cast_chain(x, [Format.from_shorthand("FP[1|5|10,15](FN)").stage(), Format.from_shorthand("BFP[8|8]{64}(SN)").stage()], -1, out=y)
 torch.cuda.synchronize()
+if which in ("cols_bf16",):
+    x = torch.randn(96, 2048, 2048, device=dev).bfloat16(); y = torch.empty_like(x)
+    for _ in range(3): ops.cast_chain(x, st, -2, out=y)
 if which in ("sbfp_bf16", "sbfp_f32"):
     x = torch.randn(n // 4096, 4096, device=dev)
     if which == "sbfp_bf16": x = x.bfloat16()

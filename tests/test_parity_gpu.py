@@ -277,6 +277,31 @@ def test_oracle_16bit_io(dt, fmt, bd):
     check(y, want16, f"{fmt} {dt}->{dt}", dtype=dt)
 
 
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("bs", [8, 16, 32, 64, 128])
+@pytest.mark.parametrize("wl", [8, 4])
+def test_packed_16bit_cols_kernel(dt, bs, wl):
+    """bfp_cols16_kernel (strided blocks of a 16-bit tensor, tile kept packed in registers): every tiling, ragged K and
+    inner extents, and columns whose block is all-zero / denormal / huge / non-finite (literal path inside the kernel)"""
+    tdt = getattr(torch, dt)
+    fmt = f"BFP[{wl}|8]{{{bs}}}(SN)"
+    for shape in ((3, 2 * bs + bs // 2, 72), (2, 256, 200), (5, bs, 8)):
+        x = _rand(shape, 31 + bs + wl, spread=6 if dt == "bfloat16" else 3, dtype=tdt)
+        x[0, :, 1] = 0.0
+        x[0, :, 2] = x[0, :, 2] * (2.0**-120 if dt == "bfloat16" else 2.0**-12)  # denormal-range column
+        if dt == "bfloat16":
+            x[1, :, 3] = x[1, :, 3] * 2.0**110  # exponent field >= 228: off the fast path
+            x[1, 0, 5] = 3.0e38
+        x[1, 1, 4] = float("inf")
+        x[1, 2, 6] = float("nan")
+        xf = x.float().numpy()
+        want32 = O.cast(xf, fmt, -2)
+        y = ops.cast_chain(x.to(DEV), [fmt_from(fmt).stage()], -2)
+        assert y.dtype == tdt
+        want16 = torch.from_numpy(want32).to(tdt).float().numpy()
+        check(y.float(), bits(want16), f"{fmt} {dt} {shape}", x=xf, fmt=fmt, block_dim=-2)
+
+
 @pytest.mark.parametrize("shape,bd", [((32, 256), -1), ((4, 128, 16), 1), ((16, 70), -1)])
 @pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SS)", "BFP[4|8]{16}(SS)", "FP[1|4|3,7](_S)", "XP[8,0](CSS)"])
 def test_oracle_stochastic_same_random_tensor(shape, bd, fmt):
