@@ -248,16 +248,68 @@ __global__ void minmax_init_kernel(int *omin, int *omax, int64_t C)
     if (i < C) { omin[i] = 0x7F800000; omax[i] = ord(u2f(0xFF800000u)); }
 }
 
-// per-tensor fast path: contiguous data, 16-byte loads, 4 vectors in flight per thread
+// per-tensor fast path: contiguous data, 16-byte loads, 4 vectors in flight per thread.  Running extrema are kept in
+// the source's own arithmetic -- FMNMX for fp32 with a sticky NaN flag, NaN-propagating packed HMNMX2 for bf16 / fp16
+// (two elements per instruction, no widening) -- and only the per-thread results go through the ordered-int reduction.
+template <typename T> struct MinMaxAcc;
+template <> struct MinMaxAcc<float> {
+    float lo = u2f(0x7F800000u), hi = u2f(0xFF800000u);
+    bool nan = false;
+    __device__ __forceinline__ void add(const uint4 &r)
+    {
+        const float v[4] = {u2f(r.x), u2f(r.y), u2f(r.z), u2f(r.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo = fminf(lo, v[j]); hi = fmaxf(hi, v[j]); nan |= v[j] != v[j]; }
+    }
+    __device__ __forceinline__ void add1(float v) { lo = fminf(lo, v); hi = fmaxf(hi, v); nan |= v != v; }
+    __device__ __forceinline__ void finish(int &olo, int &ohi) const
+    {
+        olo = nan ? (int)0x80000000 : ord(lo);
+        ohi = nan ? 0x7FFFFFFF : ord(hi);
+    }
+};
+template <typename H2, typename H> struct MinMaxAcc16 {
+    H2 lo, hi;
+    __device__ __forceinline__ MinMaxAcc16()
+    {
+        lo = __float2half2_rn_any(u2f(0x7F800000u));
+        hi = __float2half2_rn_any(u2f(0xFF800000u));
+    }
+    static __device__ __forceinline__ H2 __float2half2_rn_any(float f);
+    __device__ __forceinline__ void add(const uint4 &r)
+    {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const H2 v = *reinterpret_cast<const H2 *>(&w[j]);
+            lo = __hmin2_nan(lo, v);
+            hi = __hmax2_nan(hi, v);
+        }
+    }
+    __device__ __forceinline__ void add1(float v)
+    {
+        const H2 t = __float2half2_rn_any(v);  // exact: v came from a 16-bit element
+        lo = __hmin2_nan(lo, t);
+        hi = __hmax2_nan(hi, t);
+    }
+    __device__ __forceinline__ void finish(int &olo, int &ohi) const
+    {
+        const float l0 = Cvt<H>::to_f32(lo.x), l1 = Cvt<H>::to_f32(lo.y), h0 = Cvt<H>::to_f32(hi.x), h1 = Cvt<H>::to_f32(hi.y);
+        const bool nan = l0 != l0 || l1 != l1 || h0 != h0 || h1 != h1;
+        olo = nan ? (int)0x80000000 : min(ord(l0), ord(l1));
+        ohi = nan ? 0x7FFFFFFF : max(ord(h0), ord(h1));
+    }
+};
+template <> __device__ __forceinline__ __nv_bfloat162 MinMaxAcc16<__nv_bfloat162, __nv_bfloat16>::__float2half2_rn_any(float f) { return __float2bfloat162_rn(f); }
+template <> __device__ __forceinline__ __half2 MinMaxAcc16<__half2, __half>::__float2half2_rn_any(float f) { return __float2half2_rn(f); }
+template <> struct MinMaxAcc<__nv_bfloat16> : MinMaxAcc16<__nv_bfloat162, __nv_bfloat16> {};
+template <> struct MinMaxAcc<__half> : MinMaxAcc16<__half2, __half> {};
+
 template <typename T> __global__ void __launch_bounds__(kThreads) minmax_flat_kernel(const T *__restrict__ x, int64_t n, int *omin, int *omax)
 {
     constexpr int V = VecIO<T>::V;
     const int64_t nvec = n / V;
-    int lo = 0x7F800000, hi = ord(u2f(0xFF800000u));
-    auto upd = [&](float v) {
-        if (v != v) { lo = (int)0x80000000; hi = 0x7FFFFFFF; }
-        else { int k = ord(v); lo = min(lo, k); hi = max(hi, k); }
-    };
+    MinMaxAcc<T> acc;
     const int64_t stride = (int64_t)gridDim.x * kThreads;
     int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     for (; i + 3 * stride < nvec; i += 4 * stride) {
@@ -265,20 +317,12 @@ template <typename T> __global__ void __launch_bounds__(kThreads) minmax_flat_ke
 #pragma unroll
         for (int u = 0; u < 4; ++u) r[u] = ldg_stream(x + (i + u * stride) * V);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            float v[V];
-            VecIO<T>::unpack(r[u], v);
-#pragma unroll
-            for (int j = 0; j < V; ++j) upd(v[j]);
-        }
+        for (int u = 0; u < 4; ++u) acc.add(r[u]);
     }
-    for (; i < nvec; i += stride) {
-        float v[V];
-        VecIO<T>::load(x + i * V, v);
-#pragma unroll
-        for (int j = 0; j < V; ++j) upd(v[j]);
-    }
-    if (blockIdx.x == 0 && threadIdx.x < n - nvec * V) upd(Cvt<T>::to_f32(x[nvec * V + threadIdx.x]));
+    for (; i < nvec; i += stride) acc.add(ldg_stream(x + i * V));
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * V) acc.add1(Cvt<T>::to_f32(x[nvec * V + threadIdx.x]));
+    int lo, hi;
+    acc.finish(lo, hi);
     for (int off = 16; off > 0; off >>= 1) {
         lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
         hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
