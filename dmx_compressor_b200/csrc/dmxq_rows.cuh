@@ -104,6 +104,11 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
     const int64_t g0 = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
     // FLOAT -> BFP pair on a 16-bit tensor: the float format's saturation value as Tout stores it
     const uint32_t fmax_rq = (KIND == K_FLOAT_BFP && SAME16) ? f2u(requant1<Tout>(u2f(p.chain.st[0].ff.max_num))) : 0u;
+    // FLOAT stage on a 16-bit tensor whose significand the format keeps: a vector whose magnitudes all lie between the
+    // flush threshold and the saturation value passes through the stage unchanged (16-bit pattern bounds, inclusive)
+    const bool f16_same = (KIND == K_FLOAT_BFP || KIND == K_FLOAT) && SAME16 && p.chain.st[0].ff.exact && !p.chain.st[0].ff.is_unsigned;
+    const uint32_t f16_lo = f16_same ? pattern16_ru<Tin>(u2f(p.chain.st[0].ff.shift_exp)) : 0u;
+    const uint32_t f16_hi = f16_same ? min(pattern16_rn<Tin>(u2f(p.chain.st[0].ff.max_num)), (uint32_t)(std::is_same<Tin, __half>::value ? 0x7BFFu : 0x7F7Fu)) : 0u;
 
     uint4 raw[kUnroll];
     int64_t yoff[kUnroll];
@@ -151,6 +156,12 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
         } else if (KIND == K_FLOAT) {
+            if constexpr (SAME16) {
+                if (f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {  // identity on this vector
+                    if (valid[u]) stg_stream(y + yoff[u], raw[u]);
+                    continue;
+                }
+            }
             const bool any_nan = unpack_absmax<Tin>(raw[u], v) > 0x7F800000u;
             float_fast_apply<V>(v, p.chain.st[0], any_nan);
         } else if (KIND == K_FLOAT_BFP) {
@@ -165,6 +176,8 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_slow(v[j], &sf.ff, 0u));
                 m_thr = vec_absmax<V>(v);
+            } else if (SAME16 && f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {
+                m_thr = m_in;  // every magnitude inside [flush threshold, saturation value]: the float stage is the identity
             } else if (SAME16 && sf.ff.exact) {
                 // the values already sit on Tout's grid and the format keeps their significand: only flush and
                 // saturate act, and the saturation value is the one constant that needs Tout's rounding

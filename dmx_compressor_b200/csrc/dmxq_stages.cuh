@@ -449,6 +449,21 @@ __device__ __forceinline__ uint32_t raw16_absmax(const uint4 &r)
     uint32_t m2 = __vmaxu2(__vmaxu2(r.x & 0x7FFF7FFFu, r.y & 0x7FFF7FFFu), __vmaxu2(r.z & 0x7FFF7FFFu, r.w & 0x7FFF7FFFu));
     return max(m2 & 0xFFFFu, m2 >> 16);
 }
+__device__ __forceinline__ uint32_t raw16_absmin(const uint4 &r)
+{
+    uint32_t m2 = __vminu2(__vminu2(r.x & 0x7FFF7FFFu, r.y & 0x7FFF7FFFu), __vminu2(r.z & 0x7FFF7FFFu, r.w & 0x7FFF7FFFu));
+    return min(m2 & 0xFFFFu, m2 >> 16);
+}
+// 16-bit magnitude patterns of a 16-bit dtype: order == order of the values they encode
+template <typename T> __device__ __forceinline__ uint32_t pattern16_ru(float f);  // smallest pattern whose value is >= f (f > 0)
+template <> __device__ __forceinline__ uint32_t pattern16_ru<__nv_bfloat16>(float f) { return (f2u(f) + 0xFFFFu) >> 16; }
+template <> __device__ __forceinline__ uint32_t pattern16_ru<__half>(float f) { return (uint32_t)__half_as_ushort(__float2half_ru(f)); }
+template <> __device__ __forceinline__ uint32_t pattern16_ru<float>(float) { return 0u; }
+template <typename T> __device__ __forceinline__ uint32_t pattern16_rn(float f);  // pattern of f rounded to T (f >= 0)
+template <> __device__ __forceinline__ uint32_t pattern16_rn<__nv_bfloat16>(float f) { return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+template <> __device__ __forceinline__ uint32_t pattern16_rn<__half>(float f) { return (uint32_t)__half_as_ushort(__float2half_rn(f)); }
+template <> __device__ __forceinline__ uint32_t pattern16_rn<float>(float) { return 0u; }
+
 __device__ __forceinline__ void nm4_keep_raw16(const uint4 &r, int n_prune, bool (&keep)[8])
 {
     // keys: magnitude pattern in bits 17..31, index in the low bits.  The multiplications are shifts that drop the
