@@ -245,17 +245,39 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             const float sc = p.qscale ? __ldg(p.qscale) : st.sc;
             const float zp = p.qzp ? __ldg(p.qzp) : st.zp;
             const bool unit = sc == 1.0f, scaled = st.xf.up != 1.0f;
+            const float t_min = st.xf.t_min, t_max = st.xf.t_max;
             VecIO<Tin>::unpack(raw[u], v);
+            // straight-line variants for the shapes that occur (the flags are kernel-uniform)
+            if (!wrap && !scaled && st.xf.clamp) {  // INT8 / INT4 with unit scale
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                float a = v[j];
-                if (wrap) a = __fadd_rn(unit ? a : __fdiv_rn(a, sc), zp);
-                if (scaled) a = __fmul_rn(a, st.xf.up);
-                a = roundf(a);
-                if (scaled) a = __fmul_rn(a, st.xf.down);
-                if (st.xf.clamp) a = a > st.xf.t_max ? st.xf.t_max : (a < st.xf.t_min ? st.xf.t_min : a);
-                if (wrap && !(unit && zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, zp), sc);
-                v[j] = a;
+                for (int j = 0; j < V; ++j) {
+                    const float a = roundf(v[j]);
+                    v[j] = a > t_max ? t_max : (a < t_min ? t_min : a);
+                }
+            } else if (wrap && !unit && !scaled && st.xf.clamp) {  // calibrated INT8 / INT4: scale and zero-point
+                // x / sc, correctly rounded: reciprocal + two FMA refinements when scale and data are well inside the
+                // normal range (a -0 quotient comes out as +0, which the "+ zp" produces anyway)
+                const bool div_free = recip_safe(sc) && vec_absmax<V>(v) < 0x5D800000u;
+                const float rsc = __frcp_rn(sc);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float a = div_free ? div_by_recip(v[j], sc, rsc) : __fdiv_rn(v[j], sc);
+                    a = roundf(__fadd_rn(a, zp));
+                    a = a > t_max ? t_max : (a < t_min ? t_min : a);
+                    v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float a = v[j];
+                    if (wrap) a = __fadd_rn(unit ? a : __fdiv_rn(a, sc), zp);
+                    if (scaled) a = __fmul_rn(a, st.xf.up);
+                    a = roundf(a);
+                    if (scaled) a = __fmul_rn(a, st.xf.down);
+                    if (st.xf.clamp) a = a > t_max ? t_max : (a < t_min ? t_min : a);
+                    if (wrap && !(unit && zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, zp), sc);
+                    v[j] = a;
+                }
             }
         } else if (KIND == K_MXFP) {
             const StageDev &st = p.chain.st[0];

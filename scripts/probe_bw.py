@@ -36,7 +36,7 @@ for dt in (torch.float32, torch.bfloat16):
     _m, _e = ops.bfp_pack(x, 64, 8)
     report(f"BFP16 unpack {dt}", n*es + n + n//64, lambda: ops.bfp_unpack(_m, _e, 64, 8, dtype=dt))
     del _m, _e
-    report(f"INT8 CastTo (device qparams) {dt}", 2*n*es, lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=torch.ones(1, device=dev), zero_point=torch.zeros(1, device=dev), out=y))
+    report(f"INT8 CastTo (device qparams) {dt}", 2*n*es, lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=torch.full((1,), 0.037, device=dev), zero_point=torch.full((1,), 3.0, device=dev), out=y))
     rnd = torch.randint(0, 2**31 - 1, x.shape, device=dev, dtype=torch.int32)
     report(f"BFP16 stochastic (ext. rand) {dt}", (2*es+4)*n, lambda: ops.cast_chain(x, [Format.from_shorthand("BFP[8|8]{64}(SS)").stage()], -1, out=y, rand=rnd))
     del rnd
