@@ -19,4 +19,12 @@ xb = x.bfloat16(); yb = torch.empty_like(xb)
 ops.cast_chain(xb, [F("FP[1|5|10,15](FN)")], -1, out=yb)                # 5 float16 on bf16
 v = torch.randn(96, 2048, 256, device=dev).bfloat16(); vy = torch.empty_like(v)
 ops.cast_chain(v, [F("BFP[8|8]{64}(SN)")], -2, out=vy)                  # 6 cols bf16
+ops.cast_chain(xb, [ops.nm_stage(2, 4)], -1, out=yb)                    # 7 2:4 on bf16 (raw packed path)
+ops.cast_chain(xb, [ops.nm_stage(2, 4), F("BFP[4|8]{64}(SN)")], -1, out=yb)   # 8 2:4 -> BFP12 bf16
+ops.cast_chain(xb, [F("FP[1|5|10,15](FN)"), F("BFP[8|8]{64}(SN)")], -1, out=yb)  # 9 FLOAT16 -> BFP16 bf16
+ops.cast_chain(xb, [F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}")], -1, out=yb)   # 10 sbfp bf16
+ops.cast_chain(x, [F("MXFP8[E4M3]{32}")], -1, out=y)                    # 11 mxfp fp32
+ops.cast_chain(xb, [F("MXFP8[E4M3]{32}")], -1, out=yb)                  # 12 mxfp bf16
+ops.histc(x, 2048, min=-7, max=9, return_minmax=True)                   # 13 histc (+ init / final helper kernels)
+ops.minmax(xb)                                                          # 14 minmax bf16
 torch.cuda.synchronize()
