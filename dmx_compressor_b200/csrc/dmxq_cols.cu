@@ -12,6 +12,39 @@
 
 namespace dmxq {
 
+// tile -> (inner chunk, block index along K, element offsets of the outer coordinate in x / y / rand)
+struct ColsTile {
+    int64_t chunk, blk, xo, yo, ro;
+};
+__device__ __forceinline__ ColsTile cols_tile(const ColsParams &p, int64_t tile)
+{
+    ColsTile c;
+    c.xo = c.yo = c.ro = 0;
+    if (p.n_tiles <= 0xFFFFFFFFll) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
+        uint32_t t = (uint32_t)tile, nc = (uint32_t)p.nchunk, nb = (uint32_t)p.nblk;
+        uint32_t q = t / nc; c.chunk = t - q * nc; t = q;
+        q = t / nb; c.blk = t - q * nb;
+        uint32_t o = q;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            uint32_t od = (uint32_t)p.odim[d];
+            uint32_t i = (d == 0) ? o : o % od;
+            if (d != 0) o /= od;
+            c.xo += (int64_t)i * p.xs[d]; c.yo += (int64_t)i * p.ys[d]; c.ro += (int64_t)i * p.rs[d];
+        }
+    } else {
+        int64_t t = tile;
+        c.chunk = t % p.nchunk; t /= p.nchunk;
+        c.blk = t % p.nblk;
+        int64_t o = t / p.nblk;
+        for (int d = p.nouter - 1; d >= 0; --d) {
+            int64_t i = (d == 0) ? o : o % p.odim[d];
+            if (d != 0) o /= p.odim[d];
+            c.xo += i * p.xs[d]; c.yo += i * p.ys[d]; c.ro += i * p.rs[d];
+        }
+    }
+    return c;
+}
+
 template <typename Tin, typename Tout, int RPT, int LK>
 __global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 : 2)) chain_cols_kernel(const __grid_constant__ ColsParams p)
 {
@@ -23,29 +56,8 @@ __global__ void __launch_bounds__(kThreads, (RPT * (16 / sizeof(Tin)) <= 32 ? 3 
     if (tile >= p.n_tiles) return;  // whole warp leaves together
     const int li = lane % LI, lk = lane / LI;
 
-    int64_t chunk, blk, xo = 0, yo = 0, ro = 0;
-    if (p.n_tiles <= 0xFFFFFFFFll) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
-        uint32_t t = (uint32_t)tile, nc = (uint32_t)p.nchunk, nb = (uint32_t)p.nblk;
-        uint32_t q = t / nc; chunk = t - q * nc; t = q;
-        q = t / nb; blk = t - q * nb;
-        uint32_t o = q;
-        for (int d = p.nouter - 1; d >= 0; --d) {
-            uint32_t od = (uint32_t)p.odim[d];
-            uint32_t i = (d == 0) ? o : o % od;
-            if (d != 0) o /= od;
-            xo += (int64_t)i * p.xs[d]; yo += (int64_t)i * p.ys[d]; ro += (int64_t)i * p.rs[d];
-        }
-    } else {
-        int64_t t = tile;
-        chunk = t % p.nchunk; t /= p.nchunk;
-        blk = t % p.nblk;
-        int64_t o = t / p.nblk;
-        for (int d = p.nouter - 1; d >= 0; --d) {
-            int64_t i = (d == 0) ? o : o % p.odim[d];
-            if (d != 0) o /= p.odim[d];
-            xo += i * p.xs[d]; yo += i * p.ys[d]; ro += i * p.rs[d];
-        }
-    }
+    const ColsTile tc = cols_tile(p, tile);
+    const int64_t chunk = tc.chunk, blk = tc.blk, xo = tc.xo, yo = tc.yo, ro = tc.ro;
     const int64_t i0 = (chunk * LI + li) * V;
     const bool col_ok = i0 < p.inner;
     const int64_t kb = blk * B + (int64_t)lk * RPT;
@@ -216,29 +228,8 @@ __global__ void __launch_bounds__(kThreads, 4) bfp_cols16_kernel(const __grid_co
     if (tile >= p.n_tiles) return;  // whole warp leaves together
     const int li = lane % LI, lk = lane / LI;
 
-    int64_t chunk, blk, xo = 0, yo = 0;
-    if (p.n_tiles <= 0xFFFFFFFFll) {
-        uint32_t t = (uint32_t)tile, nc = (uint32_t)p.nchunk, nb = (uint32_t)p.nblk;
-        uint32_t q = t / nc; chunk = t - q * nc; t = q;
-        q = t / nb; blk = t - q * nb;
-        uint32_t o = q;
-        for (int d = p.nouter - 1; d >= 0; --d) {
-            uint32_t od = (uint32_t)p.odim[d];
-            uint32_t i = (d == 0) ? o : o % od;
-            if (d != 0) o /= od;
-            xo += (int64_t)i * p.xs[d]; yo += (int64_t)i * p.ys[d];
-        }
-    } else {
-        int64_t t = tile;
-        chunk = t % p.nchunk; t /= p.nchunk;
-        blk = t % p.nblk;
-        int64_t o = t / p.nblk;
-        for (int d = p.nouter - 1; d >= 0; --d) {
-            int64_t i = (d == 0) ? o : o % p.odim[d];
-            if (d != 0) o /= p.odim[d];
-            xo += i * p.xs[d]; yo += i * p.ys[d];
-        }
-    }
+    const ColsTile tc = cols_tile(p, tile);
+    const int64_t chunk = tc.chunk, blk = tc.blk, xo = tc.xo, yo = tc.yo;
     const int64_t i0 = (chunk * LI + li) * V;
     const bool col_ok = i0 < p.inner;
     const int64_t kb = blk * B + (int64_t)lk * RPT;
