@@ -337,6 +337,142 @@ template <typename T> __global__ void __launch_bounds__(kThreads) minmax_flat_ke
     }
 }
 
+// per-channel statistics, channel = a contiguous run: the tensor is rows of `inner` contiguous elements, row r belongs
+// to channel r % C ((outer, C, inner) addressing; MinMaxObserver per_channel on weights, conv activations).  One warp
+// per (row, segment); 16-byte loads, four in flight per lane.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) minmax_rows_kernel(const T *__restrict__ x, int64_t rows, int64_t C, int64_t inner_vec, int segs,
+                                                               int64_t per_seg_vec, int *omin, int *omax)
+{
+    constexpr int V = VecIO<T>::V;
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    if (tile >= rows * segs) return;
+    const int64_t row = tile / segs, seg = tile - row * segs;
+    const T *base = x + row * inner_vec * V;
+    const int64_t i1 = min(inner_vec, (seg + 1) * per_seg_vec);
+    MinMaxAcc<T> acc;
+    int64_t i = seg * per_seg_vec + lane;
+    for (; i + 96 < i1; i += 128) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = ldg_stream(base + (i + 32 * u) * V);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc.add(r[u]);
+    }
+    for (; i < i1; i += 32) acc.add(ldg_stream(base + i * V));
+    int lo, hi;
+    acc.finish(lo, hi);
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, off));
+    }
+    if (lane == 0) {
+        const int64_t c = row % C;
+        atomicMin(omin + c, lo);
+        atomicMax(omax + c, hi);
+    }
+}
+
+// per-channel statistics, channel = position along the contiguous dim: x = [R, C] row-major, channel = column
+// (activations observed per feature, SmoothQuant maxabs).  A lane owns the V columns of one 16-byte segment and walks
+// down the rows (a warp reads 512 contiguous bytes per row); per-column extrema stay in the source's arithmetic
+// (packed for 16-bit), the 8 warps of a CTA combine through shared memory, one pair of atomics per column and CTA.
+template <typename T> struct MinMaxColAcc;
+template <> struct MinMaxColAcc<float> {
+    float lo[4], hi[4];
+    unsigned nan = 0u;
+    __device__ __forceinline__ MinMaxColAcc()
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo[j] = u2f(0x7F800000u); hi[j] = u2f(0xFF800000u); }
+    }
+    __device__ __forceinline__ void add(const uint4 &r)
+    {
+        const float v[4] = {u2f(r.x), u2f(r.y), u2f(r.z), u2f(r.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo[j] = fminf(lo[j], v[j]); hi[j] = fmaxf(hi[j], v[j]); nan |= (v[j] != v[j] ? 1u : 0u) << j; }
+    }
+    __device__ __forceinline__ void finish(int (&olo)[4], int (&ohi)[4]) const
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool n = (nan >> j) & 1u;
+            olo[j] = n ? (int)0x80000000 : ord(lo[j]);
+            ohi[j] = n ? 0x7FFFFFFF : ord(hi[j]);
+        }
+    }
+};
+template <typename H2, typename H> struct MinMaxColAcc16 {
+    H2 lo[4], hi[4];
+    __device__ __forceinline__ MinMaxColAcc16()
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { lo[j] = MinMaxAcc16<H2, H>::__float2half2_rn_any(u2f(0x7F800000u)); hi[j] = MinMaxAcc16<H2, H>::__float2half2_rn_any(u2f(0xFF800000u)); }
+    }
+    __device__ __forceinline__ void add(const uint4 &r)
+    {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const H2 v = *reinterpret_cast<const H2 *>(&w[j]);
+            lo[j] = __hmin2_nan(lo[j], v);
+            hi[j] = __hmax2_nan(hi[j], v);
+        }
+    }
+    __device__ __forceinline__ void finish(int (&olo)[8], int (&ohi)[8]) const
+    {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float l[2] = {Cvt<H>::to_f32(lo[j].x), Cvt<H>::to_f32(lo[j].y)}, h[2] = {Cvt<H>::to_f32(hi[j].x), Cvt<H>::to_f32(hi[j].y)};
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool n = l[k] != l[k] || h[k] != h[k];
+                olo[2 * j + k] = n ? (int)0x80000000 : ord(l[k]);
+                ohi[2 * j + k] = n ? 0x7FFFFFFF : ord(h[k]);
+            }
+        }
+    }
+};
+template <> struct MinMaxColAcc<__nv_bfloat16> : MinMaxColAcc16<__nv_bfloat162, __nv_bfloat16> {};
+template <> struct MinMaxColAcc<__half> : MinMaxColAcc16<__half2, __half> {};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) minmax_cols_kernel(const T *__restrict__ x, int64_t R, int64_t C, int *omin, int *omax)
+{
+    constexpr int V = VecIO<T>::V;
+    constexpr int W = kThreads / 32;
+    __shared__ int slo[W][V][32], shi[W][V][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * V;
+    MinMaxColAcc<T> acc;
+    if (c0 < C) {
+        const int64_t step = (int64_t)gridDim.y * W;
+        int64_t r = (int64_t)blockIdx.y * W + warp;
+        for (; r + 3 * step < R; r += 4 * step) {
+            uint4 t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = ldg_stream(x + (r + u * step) * C + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc.add(t[u]);
+        }
+        for (; r < R; r += step) acc.add(ldg_stream(x + r * C + c0));
+    }
+    int lo[V], hi[V];
+    acc.finish(lo, hi);
+#pragma unroll
+    for (int j = 0; j < V; ++j) { slo[warp][j][lane] = lo[j]; shi[warp][j][lane] = hi[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * V; i += kThreads) {
+        const int j = i >> 5, l = i & 31;
+        int a = slo[0][j][l], b = shi[0][j][l];
+#pragma unroll
+        for (int w = 1; w < W; ++w) { a = min(a, slo[w][j][l]); b = max(b, shi[w][j][l]); }
+        const int64_t c = ((int64_t)blockIdx.x * 32 + l) * V + j;
+        if (c < C) { atomicMin(omin + c, a); atomicMax(omax + c, b); }
+    }
+}
+
 template <typename T> __global__ void __launch_bounds__(kThreads) minmax_kernel(const __grid_constant__ MinMaxParams p)
 {
     // grid: (chunks, C); each CTA reduces a slice of channel c over (outer, inner)
@@ -380,7 +516,6 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
 {
     int64_t C = p.C;
     if (C <= 0) return cudaSuccess;
-    if (C > 65535) return cudaErrorInvalidConfiguration;
     unsigned ib = (unsigned)((C + 255) / 256);
     minmax_init_kernel<<<ib, 256, 0, s>>>(p.omin, p.omax, C);
     int64_t per = p.outer * p.inner;
@@ -390,7 +525,30 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s)
         if (p.dtype == 0) minmax_flat_kernel<float><<<grid, kThreads, 0, s>>>(static_cast<const float *>(p.x), per, p.omin, p.omax);
         else if (p.dtype == 1) minmax_flat_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(p.x), per, p.omin, p.omax);
         else minmax_flat_kernel<__half><<<grid, kThreads, 0, s>>>(static_cast<const __half *>(p.x), per, p.omin, p.omax);
+    } else if (per > 0 && p.inner == 1 && C % (p.dtype == 0 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0) {
+        // channel = column of the row-major [outer, C] matrix
+        const int V = p.dtype == 0 ? 4 : 8;
+        const int64_t gx = (C + 32 * V - 1) / (32 * V);
+        int64_t gy = std::max<int64_t>(1, std::min<int64_t>((p.outer + 31) / 32, std::max<int64_t>(1, (148 * 8) / gx)));
+        dim3 g((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535));
+        if (p.dtype == 0) minmax_cols_kernel<float><<<g, kThreads, 0, s>>>(static_cast<const float *>(p.x), p.outer, C, p.omin, p.omax);
+        else if (p.dtype == 1) minmax_cols_kernel<__nv_bfloat16><<<g, kThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(p.x), p.outer, C, p.omin, p.omax);
+        else minmax_cols_kernel<__half><<<g, kThreads, 0, s>>>(static_cast<const __half *>(p.x), p.outer, C, p.omin, p.omax);
+    } else if (per > 0 && p.inner % (p.dtype == 0 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0) {
+        // channel = contiguous run of `inner` elements
+        const int V = p.dtype == 0 ? 4 : 8;
+        const int64_t rows = p.outer * C, inner_vec = p.inner / V;
+        const int64_t want = (148 * 32 + rows - 1) / rows;                       // segments per row that fill the GPU
+        const int64_t most = std::max<int64_t>(1, inner_vec / 128);              // ... but at least 128 vectors each
+        const int segs = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, most), 1 << 20));
+        const int64_t per_seg = (inner_vec + segs - 1) / segs;
+        const int64_t grid = (rows * segs + kThreads / 32 - 1) / (kThreads / 32);
+        if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+        if (p.dtype == 0) minmax_rows_kernel<float><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const float *>(p.x), rows, C, inner_vec, segs, per_seg, p.omin, p.omax);
+        else if (p.dtype == 1) minmax_rows_kernel<__nv_bfloat16><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const __nv_bfloat16 *>(p.x), rows, C, inner_vec, segs, per_seg, p.omin, p.omax);
+        else minmax_rows_kernel<__half><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const __half *>(p.x), rows, C, inner_vec, segs, per_seg, p.omin, p.omax);
     } else if (per > 0) {
+        if (C > 65535) return cudaErrorInvalidConfiguration;
         int64_t chunks = (per + (int64_t)kThreads * 8 - 1) / ((int64_t)kThreads * 8);
         int64_t cap = std::max<int64_t>(1, (148 * 8) / C);
         chunks = std::max<int64_t>(1, std::min(chunks, cap));

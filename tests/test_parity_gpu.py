@@ -376,6 +376,27 @@ def test_minmax_exact():
     assert torch.isnan(mn).all() and torch.isnan(mx).all()
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("shape,axis", [((96, 4096), 0), ((96, 4096), 1), ((513, 1032), 1), ((4, 24, 2048), 1), ((3, 7, 64), 2),
+                                        ((8, 100, 768), 2), ((2000, 8), 1), ((5, 6, 49), 1), ((70000, 8), 0), ((16, 40), 1)])
+def test_minmax_per_channel_kernels(dt, shape, axis):
+    """vectorised per-channel statistics (channel = contiguous run / channel = column) and the scalar fallback, exact,
+    NaN confined to its own channel"""
+    x = _rand(shape, 57, spread=4).to(dt)
+    dims = tuple(d for d in range(len(shape)) if d != axis)
+    mn, mx = ops.minmax(x.to(DEV), ch_axis=axis)
+    assert torch.equal(mn.cpu(), x.float().amin(dims)) and torch.equal(mx.cpu(), x.float().amax(dims))
+    idx = [0] * len(shape)
+    idx[axis] = shape[axis] // 2
+    x[tuple(idx)] = float("nan")
+    mn, mx = ops.minmax(x.to(DEV), ch_axis=axis)
+    want_mn, want_mx = x.float().amin(dims), x.float().amax(dims)
+    assert torch.isnan(mn[shape[axis] // 2]) and torch.isnan(mx[shape[axis] // 2])
+    keep = torch.ones(shape[axis], dtype=torch.bool)
+    keep[shape[axis] // 2] = False
+    assert torch.equal(mn.cpu()[keep], want_mn[keep]) and torch.equal(mx.cpu()[keep], want_mx[keep])
+
+
 @pytest.mark.parametrize("dim", [-1, 0, 1])
 @pytest.mark.parametrize("mode", ["nearest", "up", "down", "stochastic"])
 @pytest.mark.parametrize("symmetric", [True, False])
