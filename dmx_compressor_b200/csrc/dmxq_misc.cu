@@ -135,52 +135,143 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_const
     }
 }
 
-// vectorised variant: inner % V == 0, so one 16-byte vector never straddles two channels
-template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p)
+// The affine wrap on one value: x / sc + zp -> round half away -> clamp -> (q - zp) * sc, every step a separately
+// rounded fp32 operation (S/numerical/cast.py:279-296 around fixed_point_quantize_nearest_cuda).  `rsc` = RN(1 / sc);
+// div_free: the exact reciprocal-based quotient may be used (scale and data well inside the normal range).
+__device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, float rsc, bool div_free, const FixedFmt &xf, bool scaled)
 {
+    float a = __fadd_rn(div_free ? div_by_recip(x, sc, rsc) : __fdiv_rn(x, sc), zp);
+    if (scaled) a = __fmul_rn(a, xf.up);
+    a = roundf(a);
+    if (scaled) a = __fmul_rn(a, xf.down);
+    if (xf.clamp) {
+        // div_free implies finite inputs and parameters, so no NaN can reach the clamp and min/max instructions do;
+        // otherwise the compare form, which lets a NaN through as the reference's does
+        if (div_free) a = fminf(fmaxf(a, xf.t_min), xf.t_max);
+        else a = a > xf.t_max ? xf.t_max : (a < xf.t_min ? xf.t_min : a);
+    }
+    return __fmul_rn(__fsub_rn(a, zp), sc);
+}
+
+// vectorised variant 1: one 16-byte vector never straddles two qparam groups (inner % V == 0, or the channel runs
+// along the contiguous dim in groups that are multiples of V).  256 threads x 4 vectors, all loads before first use.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p, int64_t cvec, int64_t gvec)
+{
+    // qparam index of vector g: ((g / cvec) % C') / gvec with the caller's (cvec, C', gvec) -- see launch_fixed_chan_t
     constexpr int V = VecIO<Tin>::V;
+    constexpr int U = 4;
     const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
     Tout *__restrict__ y = static_cast<Tout *>(p.y);
     const int64_t nvec = p.n / V;
-    const int64_t inner_vec = p.inner / V;
-    for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * kThreads) {
-        int64_t c = (g / inner_vec) % p.C;
-        int64_t q = p.nq == 1 ? 0 : min(c / p.group, p.nq - 1);
-        const float sc = __ldg(p.scale + q), zp = __ldg(p.zp + q);
-        float v[V], r[V];
-        VecIO<Tin>::load(x + g * V, v);
-        if (p.rnd) {
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const bool fast = p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY, scaled = p.xf.up != 1.0f;
+    uint4 raw[U];
 #pragma unroll
-            for (int j = 0; j < V; ++j) r[j] = __ldg(p.rnd + g * V + j);
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        raw[u] = g < nvec ? ldg_stream(x + g * V) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    int64_t q_cur = -1;
+    float sc = 1.0f, zp = 0.0f, rsc = 1.0f;
+    bool sc_ok = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        if (g >= nvec) continue;
+        int64_t q;
+        if (nvec <= 0xFFFFFFFFll) {
+            const uint32_t t = (uint32_t)g / (uint32_t)cvec;
+            q = (t % (uint32_t)p.C) / (uint32_t)gvec;
+        } else {
+            q = ((g / cvec) % p.C) / gvec;
         }
-        if (p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY) {
-            const bool scaled = p.xf.up != 1.0f;
+        q = p.nq == 1 ? 0 : min(q, p.nq - 1);
+        if (q != q_cur) {  // (neighbouring vectors mostly share their channel: parameters are refreshed on change only)
+            q_cur = q;
+            sc = __ldg(p.scale + q);
+            zp = __ldg(p.zp + q);
+            rsc = __frcp_rn(sc);
+            sc_ok = recip_safe(sc) && fabsf(zp) < 0x1p60f;
+        }
+        float v[V];
+        const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
+        if (fast) {
+            const bool div_free = sc_ok && m_in < 0x5D800000u;
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                float a = __fadd_rn(__fdiv_rn(v[j], sc), zp);
-                if (scaled) a = __fmul_rn(a, p.xf.up);
-                a = roundf(a);
-                if (scaled) a = __fmul_rn(a, p.xf.down);
-                if (p.xf.clamp) a = a > p.xf.t_max ? p.xf.t_max : (a < p.xf.t_min ? p.xf.t_min : a);
-                v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
-            }
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc, zp, rsc, div_free, p.xf, scaled);
         } else {
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? r[j] : 0.5f);
+            for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
         }
         VecIO<Tout>::template store<V>(y + g * V, v);
+    }
+}
+
+// vectorised variant 2: the channel runs along the contiguous dim ([R, C] row-major, channel = column) with arbitrary
+// group size: a lane owns the V columns of one 16-byte segment, keeps their scale / zero-point / reciprocal in
+// registers and walks down the rows, four loads in flight.
+template <typename Tin, typename Tout>
+__global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_constant__ FixedChanParams p, int64_t R)
+{
+    constexpr int V = VecIO<Tin>::V;
+    constexpr int W = kThreads / 32;
+    const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
+    Tout *__restrict__ y = static_cast<Tout *>(p.y);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * V;
+    if (c0 >= p.C) return;
+    const bool scaled = p.xf.up != 1.0f;
+    float sc[V], zp[V], rsc[V];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int64_t q = p.nq == 1 ? 0 : min((c0 + j) / p.group, p.nq - 1);
+        sc[j] = __ldg(p.scale + q);
+        zp[j] = __ldg(p.zp + q);
+        rsc[j] = __frcp_rn(sc[j]);
+        ok = ok && recip_safe(sc[j]) && fabsf(zp[j]) < 0x1p60f;
+    }
+    const int64_t step = (int64_t)gridDim.y * W;
+    for (int64_t r0 = (int64_t)blockIdx.y * W + warp; r0 < R; r0 += 4 * step) {
+        uint4 raw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) raw[u] = r0 + u * step < R ? ldg_stream(x + (r0 + u * step) * p.C + c0) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (r0 + u * step >= R) continue;
+            float v[V];
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (also fills v: keep it out of the && chain)
+            const bool div_free = ok && m_in < 0x5D800000u;
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc[j], zp[j], rsc[j], div_free, p.xf, scaled);
+            VecIO<Tout>::template store<V>(y + (r0 + u * step) * p.C + c0, v);
+        }
     }
 }
 
 template <typename Tin, typename Tout> static void launch_fixed_chan_t(const FixedChanParams &p, cudaStream_t s)
 {
     constexpr int V = VecIO<Tin>::V;
-    const bool vec = p.inner % V == 0 && p.n % V == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.y) % 16) == 0 &&
-                     (!p.rnd || (reinterpret_cast<uintptr_t>(p.rnd) % 16) == 0);
-    if (vec) {
-        int64_t grid = std::min<int64_t>((p.n / V + kThreads - 1) / kThreads, 148 * 32);
-        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(p);
+    const bool aligned = p.n % V == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.y) % 16) == 0 &&
+                         (!p.rnd || (reinterpret_cast<uintptr_t>(p.rnd) % 16) == 0);
+    const bool fast = p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY;
+    if (aligned && p.inner % V == 0) {
+        // channel constant inside a vector: qparam = ((g / inner_vec) % C) / group
+        FixedChanParams q = p;
+        int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
+        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, p.inner / V, p.group);
+    } else if (aligned && p.inner == 1 && p.C % V == 0 && p.group % V == 0) {
+        // channel along the contiguous dim, groups are whole vectors: qparam = (g % (C / V)) / (group / V)
+        FixedChanParams q = p;
+        q.C = p.C / V;
+        int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
+        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, 1, p.group / V);
+    } else if (aligned && fast && !p.rnd && p.inner == 1 && p.C % V == 0) {
+        const int64_t R = p.n / p.C, gx = (p.C + 32 * V - 1) / (32 * V);
+        int64_t gy = std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, std::max<int64_t>(1, (148 * 8) / gx)));
+        dim3 g((unsigned)gx, (unsigned)std::min<int64_t>(gy, 65535));
+        fixed_chan_cols_kernel<Tin, Tout><<<g, kThreads, 0, s>>>(p, R);
     } else {
         int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
         fixed_chan_kernel<Tin, Tout><<<(unsigned)grid, kThreads, 0, s>>>(p);

@@ -257,14 +257,22 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             } else if (wrap && !unit && !scaled && st.xf.clamp) {  // calibrated INT8 / INT4: scale and zero-point
                 // x / sc, correctly rounded: reciprocal + two FMA refinements when scale and data are well inside the
                 // normal range (a -0 quotient comes out as +0, which the "+ zp" produces anyway)
-                const bool div_free = recip_safe(sc) && vec_absmax<V>(v) < 0x5D800000u;
+                // (finite data and parameters: no NaN can reach the clamp, so min/max instructions do)
+                const bool div_free = recip_safe(sc) && fabsf(zp) < 0x1p60f && vec_absmax<V>(v) < 0x5D800000u;
                 const float rsc = __frcp_rn(sc);
+                if (div_free) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    float a = div_free ? div_by_recip(v[j], sc, rsc) : __fdiv_rn(v[j], sc);
-                    a = roundf(__fadd_rn(a, zp));
-                    a = a > t_max ? t_max : (a < t_min ? t_min : a);
-                    v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
+                    for (int j = 0; j < V; ++j) {
+                        const float a = roundf(__fadd_rn(div_by_recip(v[j], sc, rsc), zp));
+                        v[j] = __fmul_rn(__fsub_rn(fminf(fmaxf(a, t_min), t_max), zp), sc);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        float a = roundf(__fadd_rn(__fdiv_rn(v[j], sc), zp));
+                        a = a > t_max ? t_max : (a < t_min ? t_min : a);
+                        v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
+                    }
                 }
             } else {
 #pragma unroll

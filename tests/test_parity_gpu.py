@@ -696,6 +696,38 @@ def test_per_channel_and_group_fixed_point_vectorised(dt):
             check(y, torch.from_numpy(want).to(dt).view(torch.int16).numpy().view(np.uint16), f"ch_axis={ch_axis} group={group}", dtype="bfloat16")
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_fixed_point_qparams_along_contiguous_dim(dt):
+    """per-channel / group qparams where the channel runs along the contiguous dim (activations per feature): the
+    column kernel (any group size), the vector-uniform kernel (groups of whole vectors), ragged column counts, quotient
+    rounding ties (x / scale is reciprocal-based), non-finite and huge inputs (IEEE-division path), other fraction bits"""
+    g = torch.Generator().manual_seed(29)
+    for shape, group in (((257, 328), None), ((64, 512), 128), ((64, 512), 3), ((33, 40), 8), ((1000, 8), None), ((4, 9, 264), None), ((16, 96), 24)):
+        C = shape[-1]
+        nq = C if group is None else -(-C // group)
+        sc = torch.rand(nq, generator=g) * 0.5 + 0.02
+        sc[0] = float(np.float32(2.0) - np.float32(2.0**-23)) / 16  # significand all ones: must divide
+        zp = torch.round(torch.randn(nq, generator=g) * 4)
+        x = torch.randn(shape, generator=g) * 20
+        q = sc.repeat_interleave(group or 1)[:C]
+        ties = (torch.randint(-120, 120, shape, generator=g).float() + 0.5) * q  # x / scale on (and an ulp around) a tie
+        ties = (ties.view(torch.int32) + torch.randint(-1, 2, shape, generator=g, dtype=torch.int32)).view(torch.float32)
+        x = torch.where(torch.rand(shape, generator=g) < 0.3, ties, x).to(dt)
+        if dt != torch.float16:
+            x.view(-1)[5] = 3.0e38
+        x.view(-1)[6] = float("inf")
+        x.view(-1)[7] = float("nan")
+        x.view(-1)[8] = -0.0
+        xf = x.float().numpy()
+        for fmt, (wl, fl, sym) in (("XP[8,0](CSN)", (8, 0, True)), ("XP[4,0](C_N)", (4, 0, False)), ("XP[8,+2](CSN)", (8, 2, True))):
+            want = O.cast(xf, fmt, tie=O.TIE_AWAY, scale=sc.tolist(), zero_point=zp.tolist(), ch_axis=len(shape) - 1, group_size=group)
+            y = ops.fixed_qdq(x.to(DEV), wl, fl, True, sym, "nearest", scale=sc.to(DEV), zero_point=zp.to(DEV), ch_axis=-1, group_size=group)
+            if dt == torch.float32:
+                check(y, bits(want), f"{fmt} {shape} group={group}")
+            else:
+                check(y.float(), bits(torch.from_numpy(want).to(dt).float().numpy()), f"{fmt} {shape} group={group} {dt}")
+
+
 def test_asymmetric_bfp_edge_blocks():
     """BFP16A / BFP12A fast path: blocks whose most negative element sits on / next to the -(2^(wl-1)-1)
     mantissa, with the block max just below, at and above the clamp threshold"""
