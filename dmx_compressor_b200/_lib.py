@@ -106,22 +106,40 @@ def require_cuda(t: torch.Tensor, name: str = "x") -> None:
         raise RuntimeError(f"{name} must be a CUDA tensor (dmx_compressor_b200 is CUDA-only: no CPU fallback)")
 
 
+_VIEW_TEMPLATES: dict = {}
+
+
 def view(t: torch.Tensor) -> Tensor:
+    """dmxq_tensor descriptor of ``t``.  The (dtype, shape, stride) part is memoised -- a model issues the same few
+    layouts over and over -- so a call costs one struct copy plus the data pointer."""
     if type(t) is not torch.Tensor and hasattr(t, "materialise"):
         t = t.materialise()  # a deferred cast (elide.Lazy) reaching the ABI directly: run it first
-    if t.dim() > MAX_DIMS:
-        raise RuntimeError(f"dmxq: tensors of more than {MAX_DIMS} dims are not supported")
-    v = Tensor()
+    key = (t.dtype, t.shape, t.stride())
+    tmpl = _VIEW_TEMPLATES.get(key)
+    if tmpl is None:
+        if t.dim() > MAX_DIMS:
+            raise RuntimeError(f"dmxq: tensors of more than {MAX_DIMS} dims are not supported")
+        tmpl = Tensor()
+        tmpl.dtype = dtype_code(t.dtype)
+        tmpl.ndim = t.dim()
+        for i, (n, s) in enumerate(zip(t.shape, t.stride())):
+            tmpl.shape[i] = n
+            tmpl.stride[i] = s
+        if len(_VIEW_TEMPLATES) > 4096:
+            _VIEW_TEMPLATES.clear()
+        _VIEW_TEMPLATES[key] = tmpl
+    v = Tensor.from_buffer_copy(tmpl)
     v.data = t.data_ptr()
-    v.dtype = dtype_code(t.dtype)
-    v.ndim = t.dim()
-    for i, (n, s) in enumerate(zip(t.shape, t.stride())):
-        v.shape[i] = n
-        v.stride[i] = s
     return v
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr(device) -> int:
+    """the caller's current CUDA stream on ``device`` as a raw handle"""
+    if _raw_stream is not None:
+        return _raw_stream(device.index if device.index is not None else torch.cuda.current_device())
     return torch.cuda.current_stream(device).cuda_stream
 
 

@@ -285,7 +285,7 @@ class CastTo(FakeQuantize):
         return y
 
     def forward(self, x, lazy_ok=False):
-        self.physical_dtype = x.dtype
+        self.__dict__["physical_dtype"] = x.dtype  # (plain attribute; nn.Module.__setattr__ costs microseconds per call)
         if (elide.active() and not torch.is_grad_enabled() and not self.pre_transform and not self._obs_on
                 and isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point()):
             y = self._forward_elided(x, lazy_ok and elide.defer_output_casts)

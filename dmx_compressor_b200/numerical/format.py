@@ -44,6 +44,16 @@ class Format:
         """dmxq_stage describing this format, or None when it is a no-op (SAME)."""
         raise NotImplementedError
 
+    def _memo_stage(self, key, build):
+        """the ctypes stage struct is rebuilt only when one of the attributes it encodes changed (a cast is issued per
+        module call: building the struct -- and formatting ``repr`` for the FLOAT16 special case -- every time showed
+        up in the host-side cost of small casts)"""
+        c = self.__dict__.get("_stage_memo")
+        if c is None or c[0] != key:
+            c = (key, build())
+            self.__dict__["_stage_memo"] = c
+        return c[1]
+
     @property
     def bytes_per_elem(self) -> Optional[float]:
         raise NotImplementedError
@@ -132,8 +142,8 @@ class FixedPoint(Format):
                              out_dtype=torch.float32)
 
     def stage(self, scale: float = 1.0, zero_point: float = 0.0):
-        return ops.fixed_stage(self.precision, self.fraction, self.clamp, self.symmetric, self.rounding, self.tie, scale,
-                               zero_point)
+        key = (self.precision, self.fraction, self.clamp, self.symmetric, self.rounding, self.tie, scale, zero_point)
+        return self._memo_stage(key, lambda: ops.fixed_stage(*key))
 
     @property
     def bytes_per_elem(self) -> float:
@@ -192,8 +202,9 @@ class FloatingPoint(Format):
                              repr(self) == "FP[1|5|10,15](FN)", self.rounding, out_dtype=torch.float32)
 
     def stage(self):
-        return ops.float_stage(self.mantissa, self.exponent, self.bias, self.flush_subnormal, self.unsigned,
-                               repr(self) == "FP[1|5|10,15](FN)", self.rounding)
+        key = (self.mantissa, self.exponent, self.bias, self.flush_subnormal, self.unsigned, self.rounding)
+        return self._memo_stage(key, lambda: ops.float_stage(self.mantissa, self.exponent, self.bias, self.flush_subnormal, self.unsigned,
+                                                             repr(self) == "FP[1|5|10,15](FN)", self.rounding))
 
     @property
     def largest_representable_power_of_two(self):
@@ -245,7 +256,8 @@ class BlockFloatingPoint(Format):
                            out_dtype=torch.float32)
 
     def stage(self):
-        return ops.bfp_stage(self.block_size, self.precision, self.symmetric, self.rounding)
+        key = (self.block_size, self.precision, self.symmetric, self.rounding)
+        return self._memo_stage(key, lambda: ops.bfp_stage(*key))
 
     # packed storage: the real format whose size `bytes_per_elem` reports (reference format.py:345-347)
     def pack(self, x: torch.Tensor):
@@ -309,8 +321,11 @@ class ScaledBlockFloatingPoint(Format):
 
     def stage(self):
         b, s = self.block_format, self.scaler_format
-        return ops.sbfp_stage(self.block_size, b.precision, b.clamp, b.rounding, b.tie, s.mantissa, s.exponent, s.bias,
-                              s.flush_subnormal, s.unsigned, repr(s) == "FP[1|5|10,15](FN)", s.rounding)
+        key = (self.block_size, b.precision, b.clamp, b.rounding, b.tie, s.mantissa, s.exponent, s.bias, s.flush_subnormal, s.unsigned,
+               s.rounding)
+        return self._memo_stage(key, lambda: ops.sbfp_stage(self.block_size, b.precision, b.clamp, b.rounding, b.tie, s.mantissa,
+                                                            s.exponent, s.bias, s.flush_subnormal, s.unsigned,
+                                                            repr(s) == "FP[1|5|10,15](FN)", s.rounding))
 
     @property
     def bytes_per_elem(self) -> float:
@@ -356,7 +371,8 @@ class MXFP(Format):
         e = self.element_format
         assert e.bias == 2 ** (e.exponent - 1) - 1 and not e.flush_subnormal and not e.unsigned and e.rounding == "nearest", \
             "MXFP element formats are E<e>M<m> with the default bias, subnormals kept, nearest rounding"
-        return ops.mxfp_stage(self.block_size, e.mantissa, e.exponent)
+        key = (self.block_size, e.mantissa, e.exponent)
+        return self._memo_stage(key, lambda: ops.mxfp_stage(*key))
 
     @property
     def bytes_per_elem(self) -> float:

@@ -93,7 +93,7 @@ def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, 
     if not 1 <= n <= L.MAX_STAGES:
         raise RuntimeError(f"dmxq: a chain holds 1..{L.MAX_STAGES} stages, got {n}")
     y = out if out is not None else _out_like(x, out_dtype)
-    arr = (L.Stage * n)(*stages)
+    arr = C.byref(stages[0]) if n == 1 else (L.Stage * n)(*stages)  # one stage: its own struct is the array
     vx, vy = L.view(x), L.view(y)
     vs = vm = None
     if score is not None:
