@@ -206,6 +206,58 @@ def test_oracle_blocked_layouts(fmt, shape, bd, desc):
     check(y, bits(want), f"{fmt} {desc}")
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_random_views_formats_dtypes(seed):
+    """seeded differential fuzzing: random rank / extents / permutation / slicing (so rows, cols and generic kernels all
+    get odd strides, offsets and ragged tails), random format, block dim and source dtype, against the oracle"""
+    rng = np.random.default_rng(1000 + seed)
+    fmts = FORMATS + ELEMENTWISE
+    for _ in range(40):
+        rank = int(rng.integers(1, 5))
+        shape = [int(rng.choice([1, 2, 3, 5, 8, 16, 24, 33, 64, 96, 130, 256])) for _ in range(rank)]
+        while int(np.prod(shape)) > 1 << 18:
+            shape[int(np.argmax(shape))] //= 2
+        base = _rand(tuple(shape), int(rng.integers(1 << 30)), spread=int(rng.integers(1, 10)))
+        view = base
+        if rank >= 2 and rng.random() < 0.5:
+            view = view.permute(*[int(i) for i in rng.permutation(rank)])
+        if rng.random() < 0.5:  # slice one dim (offset + shorter extent)
+            d = int(rng.integers(rank))
+            n = view.shape[d]
+            if n > 2:
+                lo = int(rng.integers(0, n // 2))
+                view = view.narrow(d, lo, int(rng.integers(1, n - lo + 1)))
+        if rng.random() < 0.2 and view.shape[-1] > 3:
+            view = view[..., ::2]
+        fmt = fmts[int(rng.integers(len(fmts)))]
+        bd = int(rng.integers(-view.dim(), view.dim()))
+        if fmt.startswith("MXFP") and bd not in (-1, view.dim() - 1):
+            pass  # (the oracle follows the reference's definition on any dim; the reference itself only runs dim -1)
+        dt = [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(3))]
+        xv = view.to(dt) if dt == torch.float32 else view.to(dt)
+        if dt != torch.float32:
+            xv = torch.where(torch.isfinite(xv), xv, torch.zeros_like(xv))
+            # (.to() of a strided view returns a dense tensor: rebuild the same striding on the 16-bit copy)
+            dense = base.to(dt)
+            dense = torch.where(torch.isfinite(dense), dense, torch.zeros_like(dense))
+            xv = dense.as_strided(view.shape, view.stride(), view.storage_offset())
+        want = O.cast(xv.float().contiguous().numpy(), fmt, bd, tie=O.TIE_AWAY)
+        if dt == torch.float16 and fmt == "FP[1|5|10,15](_N)":
+            want = xv.float().contiguous().numpy()  # native format of the tensor: handed back unchanged (reference format.py:209-212)
+        if fmt.startswith("XP"):
+            # the oracle's XP entry is CastTo.forward, i.e. with the (unit) affine wrap around the quantiser, which turns
+            # a -0 input into +0 before rounding: run the same entry on the device
+            f = fmt_from(fmt, "away")
+            got = ops.fixed_qdq(_same_layout(xv), f.precision, f.fraction, f.clamp, f.symmetric, f.rounding, f.tie,
+                                scale=torch.ones(1, device=DEV), zero_point=torch.zeros(1, device=DEV), out_dtype=torch.float32)
+        else:
+            got = gpu_cast(_same_layout(xv), fmt, bd, "away")
+        what = f"seed {seed}: {fmt} bd={bd} shape={tuple(view.shape)} stride={view.stride()} {dt}"
+        blocked = (fmt.startswith("BFP") and "{1}" not in fmt)
+        # (.float(): FloatingPoint.cast hands a native fp16 / fp32 tensor back unchanged, reference format.py:209-212)
+        check(got.float(), bits(want), what, x=xv.float().contiguous().numpy() if blocked else None, fmt=fmt if blocked else None, block_dim=bd)
+
+
 @pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(_N)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"])
 def test_oracle_strided_views(fmt):
     """Views must be consumed in place: transposes, slices, attention-head views."""
