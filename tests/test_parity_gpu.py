@@ -414,6 +414,50 @@ def test_fused_chain_matches_sequential():
     check(y, t.view(torch.int16).numpy().view(np.uint16), "bf16 chain", dtype="bfloat16")
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_fuzz_fused_chains(seed):
+    """seeded fuzzing of the fused kernels (N:M -> BFP, N:M alone, FLOAT -> BFP and three-stage chains) on fp32 / bf16 /
+    fp16 tensors with ties in |x| (stable N:M order), zeros, negative zeros and out-of-range values, against the
+    oracle applied stage by stage with the tensor dtype's rounding in between (consecutive CastTo.forward calls)"""
+    rng = np.random.default_rng(2000 + seed)
+    floats = ["FP[1|5|10,15](FN)", "FP[1|8|7,127](FN)", "FP[1|4|3,7](_N)"]
+    bfps = ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)", "BFP[8|8]{16}(SN)", "BFP[4|8]{128}(SN)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "MXFP8[E4M3]{32}"]
+    for _ in range(24):
+        rows, K = int(rng.choice([1, 3, 64, 257])), int(rng.choice([128, 256, 384, 1024]))
+        dt = [torch.float32, torch.bfloat16, torch.float16][int(rng.integers(3))]
+        x = _rand((rows, K), int(rng.integers(1 << 30)), spread=int(rng.integers(1, 8)))
+        x = torch.round(x * 8) / 8 if rng.random() < 0.5 else x  # many equal magnitudes
+        flat = x.view(-1)
+        flat[1::13] = -flat[0::13][: flat[1::13].numel()]  # +-pairs: ties in |x|
+        flat[2::29] = -0.0
+        if rng.random() < 0.3:
+            flat[3::31] *= 2.0**-20  # below the FLOAT16 flush threshold
+        x = x.to(dt)
+        x = torch.where(torch.isfinite(x), x, torch.zeros_like(x))
+        kind = int(rng.integers(4))
+        m = int(rng.choice([2, 4, 8]))
+        nk = int(rng.integers(1, m))
+        if kind == 0:
+            chain = [("nm", nk, m), bfps[int(rng.integers(len(bfps)))]]
+        elif kind == 1:
+            chain = [("nm", nk, m)]
+        elif kind == 2:
+            chain = [floats[int(rng.integers(len(floats)))], bfps[int(rng.integers(4))]]
+        else:
+            chain = [("nm", nk, m), bfps[int(rng.integers(len(bfps)))], "BFP[8|8]{64}(SN)"]
+        stages, t = [], x
+        for st in chain:
+            if isinstance(st, tuple):
+                stages.append(ops.nm_stage(st[1], st[2]))
+                t = torch.from_numpy(O.nm_prune(t.float().numpy(), st[1], st[2])).to(dt)
+            else:
+                stages.append(fmt_from(st).stage())
+                t = torch.from_numpy(O.cast(t.float().numpy(), st, -1, tie=O.TIE_AWAY)).to(dt)
+        y = ops.cast_chain(x.to(DEV), stages, -1)
+        assert y.dtype == dt
+        check(y.float(), bits(t.float().numpy()), f"seed {seed}: {chain} [{rows},{K}] {dt}")
+
+
 def test_minmax_exact():
     x = _rand((7, 33, 50), 51)
     mn, mx = ops.minmax(x.to(DEV))
