@@ -878,7 +878,7 @@ cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s)
 // integer mantissa falls out of the float-add rounding trick for free: u = (x + base) + C has
 // ulp == Q, so bits(u) - bits(C) is t / Q as an integer and k = that - base / Q = ... - 3 * 2^(wl-1)
 // (16-bit sources skip the base: bits(x + C) - bits(C) is x / Q directly).
-template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ exps, int64_t n_vec, int lanes, int wl)
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ exps, int64_t n_vec, int lanes, int lshift, int wl)
 {
     constexpr int V = VecIO<T>::V;
     constexpr int U = 4;
@@ -913,7 +913,7 @@ template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) b
             for (int j = 0; j < V; ++j) k[j] = 0;
         }
         if (g >= n_vec) continue;
-        if ((threadIdx.x & (lanes - 1)) == 0) exps[g / lanes] = ok ? (uint8_t)(m >> 23) : 0;
+        if ((threadIdx.x & (lanes - 1)) == 0) exps[g >> lshift] = ok ? (uint8_t)(m >> 23) : 0;  // lanes is a power of two
         if (NIBBLE) {
             uint32_t acc = 0;
 #pragma unroll
@@ -923,38 +923,60 @@ template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) b
         } else {
             uint32_t w[2] = {0u, 0u};
 #pragma unroll
-            for (int j = 0; j < V; ++j) w[j / 4] |= ((uint32_t)k[j] & 0xFFu) << (8 * (j & 3));
+            for (int j = 0; j < V; j += 4)  // low bytes of four ints -> one word: three byte permutes
+                w[j / 4] = __byte_perm(__byte_perm((uint32_t)k[j], (uint32_t)k[j + 1], 0x0040), __byte_perm((uint32_t)k[j + 2], (uint32_t)k[j + 3], 0x0040), 0x5410);
             if (V == 8) reinterpret_cast<uint2 *>(mant)[g] = make_uint2(w[0], w[1]);
             else reinterpret_cast<uint32_t *>(mant)[g] = w[0];
         }
     }
 }
 
-template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_unpack_kernel(const uint8_t *__restrict__ mant, const uint8_t *__restrict__ exps, T *__restrict__ y, int64_t n_vec, int lanes, int wl)
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) bfp_unpack_kernel(const uint8_t *__restrict__ mant, const uint8_t *__restrict__ exps, T *__restrict__ y, int64_t n_vec, int lshift, int wl)
 {
     constexpr int V = VecIO<T>::V;
-    const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (g >= n_vec) return;
-    const int ef = exps[g / lanes];
-    // quantum Q = 2^(ef - 127 + 2 - wl), applied as two exact power-of-two factors so that a denormal Q stays exact
-    const int qe = ef + 2 - wl;
-    const float s1 = u2f((uint32_t)max(qe, 1) << 23), s2 = qe >= 1 ? 1.0f : u2f((uint32_t)(127 + qe - 1) << 23);
-    int k[V];
-    if (NIBBLE) {
-        uint32_t acc = V == 8 ? reinterpret_cast<const uint32_t *>(mant)[g] : (uint32_t) reinterpret_cast<const uint16_t *>(mant)[g];
+    constexpr int U = 4;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    uint32_t w[U][2];
+    int ef[U];
 #pragma unroll
-        for (int j = 0; j < V; ++j) k[j] = ((int)(acc << (28 - 4 * j))) >> 28;
-    } else {
-        uint32_t w[2];
-        if (V == 8) { uint2 t = reinterpret_cast<const uint2 *>(mant)[g]; w[0] = t.x; w[1] = t.y; }
-        else { w[0] = reinterpret_cast<const uint32_t *>(mant)[g]; w[1] = 0; }
-#pragma unroll
-        for (int j = 0; j < V; ++j) k[j] = ((int)(w[j / 4] << (24 - 8 * (j & 3)))) >> 24;
+    for (int u = 0; u < U; ++u) {  // all loads first
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        w[u][0] = w[u][1] = 0u;
+        ef[u] = 0;
+        if (g < n_vec) {
+            ef[u] = __ldg(exps + (g >> lshift));
+            if (NIBBLE) {
+                w[u][0] = V == 8 ? __ldg(reinterpret_cast<const uint32_t *>(mant) + g) : (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(mant) + g);
+            } else if (V == 8) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(mant) + g);
+                w[u][0] = t.x; w[u][1] = t.y;
+            } else {
+                w[u][0] = __ldg(reinterpret_cast<const uint32_t *>(mant) + g);
+            }
+        }
     }
-    float v[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) v[j] = ef == 0 ? 0.0f : __fmul_rn(__fmul_rn((float)k[j], s1), s2);
-    VecIO<T>::template store<V>(y + g * V, v);
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        if (g >= n_vec) continue;
+        // quantum Q = 2^(ef - 127 + 2 - wl), applied as two exact power-of-two factors so that a denormal Q stays exact
+        const int qe = ef[u] + 2 - wl;
+        const float s1 = u2f((uint32_t)max(qe, 1) << 23), s2 = qe >= 1 ? 1.0f : u2f((uint32_t)(127 + qe - 1) << 23);
+        float v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int k = NIBBLE ? ((int)(w[u][0] << (28 - 4 * j))) >> 28 : ((int)(w[u][j / 4] << (24 - 8 * (j & 3)))) >> 24;
+            v[j] = ef[u] == 0 ? 0.0f : __fmul_rn(__fmul_rn((float)k, s1), s2);
+        }
+        VecIO<T>::template store<V>(y + g * V, v);
+    }
+}
+
+static int log2_pow2(int v)
+{
+    int s = 0;
+    while ((1 << s) < v) ++s;
+    return s;
 }
 
 cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s)
@@ -966,8 +988,8 @@ cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, in
     if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
     const bool nib = wl <= 4;
     uint8_t *m8 = static_cast<uint8_t *>(mant);
-#define DMXQ_PACK(T) do { if (nib) bfp_pack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, wl); \
-                          else bfp_pack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, wl); } while (0)
+#define DMXQ_PACK(T) do { if (nib) bfp_pack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, log2_pow2(B / V), wl); \
+                          else bfp_pack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, exps, n_vec, B / V, log2_pow2(B / V), wl); } while (0)
     if (dt == 0) DMXQ_PACK(float); else if (dt == 1) DMXQ_PACK(__nv_bfloat16); else DMXQ_PACK(__half);
 #undef DMXQ_PACK
     count_launch();
@@ -978,13 +1000,13 @@ cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, voi
 {
     const int V = dt == 0 ? 4 : 8;
     int64_t n_vec = n / V;
-    int64_t grid = (n_vec + kThreads - 1) / kThreads;
+    int64_t grid = (n_vec + kThreads * 4 - 1) / (kThreads * 4);
     if (grid <= 0) return cudaSuccess;
     if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
     const bool nib = wl <= 4;
     const uint8_t *m8 = static_cast<const uint8_t *>(mant);
-#define DMXQ_UNPACK(T) do { if (nib) bfp_unpack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, B / V, wl); \
-                            else bfp_unpack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, B / V, wl); } while (0)
+#define DMXQ_UNPACK(T) do { if (nib) bfp_unpack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, log2_pow2(B / V), wl); \
+                            else bfp_unpack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(m8, exps, static_cast<T *>(y), n_vec, log2_pow2(B / V), wl); } while (0)
     if (dt == 0) DMXQ_UNPACK(float); else if (dt == 1) DMXQ_UNPACK(__nv_bfloat16); else DMXQ_UNPACK(__half);
 #undef DMXQ_UNPACK
     count_launch();
