@@ -318,11 +318,100 @@ __global__ void __launch_bounds__(kThreads) blockq_kernel(const __grid_constant_
     }
 }
 
+// one element of the L1 apply, any mode (the literal integer path of block_kernel.cu)
+__device__ __forceinline__ float blockq_elem(float xv, uint32_t mb, const BlockQParams &p, uint32_t r)
+{
+    if (!p.symmetric) {
+        float mf = u2f(mb);
+        if (xv == -mf && ((mb >> 16) << 25) == 0xFE000000u) mb = ((mb >> 23) + 1u) << 23;
+    }
+    BfpBlock b = bfp_block(mb, p.wl);
+    switch (p.mode) {
+    case R_NEAREST: return bfp_elem<R_NEAREST>(xv, b, p.sh, p.mask, r);
+    case R_STOCHASTIC: return bfp_elem<R_STOCHASTIC>(xv, b, p.sh, p.mask, r);
+    case R_UP: return bfp_elem<R_UP>(xv, b, p.sh, p.mask, r);
+    default: return bfp_elem<R_DOWN>(xv, b, p.sh, p.mask, r);
+    }
+}
+
+// vectorised apply: 16-byte vectors, four in flight per thread.  PER_ELEM = false: the slice ("channel") is constant
+// inside a vector (whole tensor, or inner % 4 == 0); true: the slices run along the contiguous dim (inner == 1, C % 4 == 0).
+// Symmetric nearest slices whose max is an ordinary number take the four-add form of the rows kernel.
+template <bool PER_ELEM> __global__ void __launch_bounds__(kThreads) blockq_vec_kernel(const __grid_constant__ BlockQParams p)
+{
+    constexpr int V = 4, U = 4;
+    const int64_t nvec = p.n / V;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const bool fast_mode = p.mode == R_NEAREST && p.symmetric && p.wl <= 20;
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        raw[u] = g < nvec ? ldg_stream(p.x + g * V) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        if (g >= nvec) continue;
+        float v[V];
+        VecIO<float>::unpack(raw[u], v);
+        uint32_t r[V] = {0u, 0u, 0u, 0u};
+        if (p.rnd) {
+            const uint4 t = ldg_stream(p.rnd + g * V);
+            r[0] = t.x; r[1] = t.y; r[2] = t.z; r[3] = t.w;
+        }
+        if (!PER_ELEM) {
+            int64_t c = 0;
+            if (p.C != 1) {
+                const int64_t iv = p.inner / V;
+                c = nvec <= 0xFFFFFFFFll ? (int64_t)(((uint32_t)g / (uint32_t)iv) % (uint32_t)p.C) : (g / iv) % p.C;
+            }
+            const uint32_t mb = __ldg(p.maxbits + c);
+            if (fast_mode && bfp_fast_ok(mb)) {
+                const BfpFast b = bfp_fast_block(mb, p.wl);
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = bfp_fast_elem(v[j], b);
+                if (b.clamp) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = blockq_elem(v[j], mb, p, r[j]);
+            }
+        } else {
+            const int64_t c0 = nvec <= 0xFFFFFFFFll ? (int64_t)((uint32_t)g % (uint32_t)(p.C / V)) * V : (g % (p.C / V)) * V;
+            const uint4 m4 = *reinterpret_cast<const uint4 *>(p.maxbits + c0);
+            const uint32_t mb[V] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if (fast_mode && bfp_fast_ok(mb[j])) {
+                    const BfpFast b = bfp_fast_block(mb[j], p.wl);
+                    const float q = bfp_fast_elem(v[j], b);
+                    v[j] = b.clamp ? bfp_clamp(q, b) : q;
+                } else {
+                    v[j] = blockq_elem(v[j], mb[j], p, r[j]);
+                }
+            }
+        }
+        VecIO<float>::store<V>(p.y + g * V, v);
+    }
+}
+
 cudaError_t launch_blockq(const BlockQParams &p, cudaStream_t s)
 {
     if (p.n <= 0) return cudaSuccess;
-    int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
-    blockq_kernel<<<(unsigned)grid, kThreads, 0, s>>>(p);
+    const bool aligned = p.n % 4 == 0 && (reinterpret_cast<uintptr_t>(p.x) % 16) == 0 && (reinterpret_cast<uintptr_t>(p.y) % 16) == 0 &&
+                         (!p.rnd || (reinterpret_cast<uintptr_t>(p.rnd) % 16) == 0);
+    const int64_t vgrid = (p.n / 4 + kThreads * 4 - 1) / (kThreads * 4);
+    if (aligned && vgrid <= 0x7FFFFFFFll && (p.C == 1 || p.inner % 4 == 0)) {
+        blockq_vec_kernel<false><<<(unsigned)vgrid, kThreads, 0, s>>>(p);
+    } else if (aligned && vgrid <= 0x7FFFFFFFll && p.inner == 1 && p.C % 4 == 0 && (reinterpret_cast<uintptr_t>(p.maxbits) % 16) == 0) {
+        blockq_vec_kernel<true><<<(unsigned)vgrid, kThreads, 0, s>>>(p);
+    } else {
+        int64_t grid = std::min<int64_t>((p.n + kThreads - 1) / kThreads, 148 * 16);
+        blockq_kernel<<<(unsigned)grid, kThreads, 0, s>>>(p);
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -30,3 +30,9 @@ for dt in (torch.float32, torch.bfloat16):
         zp = torch.randint(-3, 4, (nq,), device="cuda").float()
         ms = timeit(lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=sc, zero_point=zp, ch_axis=ax, group_size=gs, out=y))
         print(f"{str(dt):16s} INT8 {name:30s} {ms:8.3f} ms  {nbytes / ms / 1e6:8.1f} GB/s")
+
+# L1 block_quantize(x, wl, dim) (quant_cuda.block_quantize_nearest mirror)
+x = torch.randn(16384, 4096, device="cuda")
+for dim in (-1, 0, 1):
+    ms = timeit(lambda: ops.block_quantize_l1(x, 8, dim, True, "nearest"))
+    print(f"L1 block_quantize dim={dim:2d} fp32 [16384,4096]   {ms:8.3f} ms  {2 * x.numel() * 4 / ms / 1e6:8.1f} GB/s (8 B/elem)")

@@ -493,7 +493,7 @@ def test_minmax_per_channel_kernels(dt, shape, axis):
     assert torch.equal(mn.cpu()[keep], want_mn[keep]) and torch.equal(mx.cpu()[keep], want_mx[keep])
 
 
-@pytest.mark.parametrize("dim", [-1, 0, 1])
+@pytest.mark.parametrize("dim", [-1, 0, 1, 2])
 @pytest.mark.parametrize("mode", ["nearest", "up", "down", "stochastic"])
 @pytest.mark.parametrize("symmetric", [True, False])
 def test_l1_block_quantize(dim, mode, symmetric):
@@ -509,10 +509,14 @@ def test_l1_block_quantize(dim, mode, symmetric):
         want = O.block_quantize_rows(rows, 8, symmetric, mode, rand=rr).reshape(xn.shape)
     elif dim == 0:
         want = O.block_quantize_rows(xn.reshape(12, -1), 8, symmetric, mode, rand=r.numpy().reshape(12, -1)).reshape(xn.shape)
-    else:
+    elif dim == 1:
         xt = np.ascontiguousarray(np.swapaxes(xn, 0, 1)).reshape(20, -1)
         rt = np.ascontiguousarray(np.swapaxes(r.numpy(), 0, 1)).reshape(20, -1)
         want = np.swapaxes(O.block_quantize_rows(xt, 8, symmetric, mode, rand=rt).reshape(20, 12, 16), 0, 1)
+    else:  # slices along the contiguous dim
+        xt = np.ascontiguousarray(np.moveaxis(xn, 2, 0)).reshape(16, -1)
+        rt = np.ascontiguousarray(np.moveaxis(r.numpy(), 2, 0)).reshape(16, -1)
+        want = np.moveaxis(O.block_quantize_rows(xt, 8, symmetric, mode, rand=rt).reshape(16, 12, 20), 0, 2)
     y = ops.block_quantize_l1(x.to(DEV), 8, dim, symmetric, mode, rand=r.to(DEV))
     check(y, bits(np.ascontiguousarray(want)), f"block_quantize dim={dim} {mode} sym={symmetric}")
 
