@@ -412,6 +412,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         else if (chain.n == 1 && chain.st[0].kind == ST_FIXED && chain.st[0].xf.mode == R_NEAREST && chain.st[0].xf.tie == TIE_AWAY) kind = 7;  // K_FIXED
         else if (chain.n == 1 && chain.st[0].kind == ST_NM) kind = 8;  // K_NM
         else if (chain.n == 1 && chain.st[0].kind == ST_MXFP) kind = 9;  // K_MXFP
+        else if (chain.n == 1 && chain.st[0].kind == ST_BFP && chain.st[0].mode == R_NEAREST && chain.st[0].asym) kind = 10;  // K_BFP_ASYM
         if (qscale) {
             if (kind != 7) return kNeedFallback;
             p.qscale = qscale; p.qzp = qzp;

@@ -22,12 +22,13 @@
 //   K_NM         [N:M with score |x|]                          Sparsify alone (no mask output)
 //   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
 //   K_MXFP       [MXFP]                                       OCP-MX style power-of-two block scale + low-bit float elements
+//   K_BFP_ASYM   [BFP nearest, asymmetric mantissa]            BFP16A / BFP12A (kept apart from K_BFP: it needs a copy of the inputs)
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_COUNT = 10 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_BFP_ASYM = 10, K_COUNT = 11 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -155,6 +156,21 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_BFP_ASYM) {
+            // symmetric nearest result first, then make_mantissa_asymmetric (S/numerical/format.py:349-372): the edge
+            // mantissa -(2^(wl-1)-1) needs |x| >= maxval - Q/2, so only blocks whose max is within one quantum of
+            // maxval (a safe superset) -- or blocks off the fast path -- can hold it
+            const StageDev &st = p.chain.st[0];
+            uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
+            float x0[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) x0[j] = v[j];
+            bfp_ns_apply<V, SRC16>(v, m, st);
+            const BfpBlock bb = bfp_block(m, st.wl);
+            if (!(st.fast && bfp_fast_ok(m)) || m >= bb.maxnum - (1u << (23 - (st.wl - 2)))) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = bfp_asym_fix(v[j], x0[j], bb);
+            }
         } else if (KIND == K_FLOAT) {
             if constexpr (SAME16) {
                 if (f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {  // identity on this vector
