@@ -23,12 +23,13 @@
 //   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
 //   K_MXFP       [MXFP]                                       OCP-MX style power-of-two block scale + low-bit float elements
 //   K_BFP_ASYM   [BFP nearest, asymmetric mantissa]            BFP16A / BFP12A (kept apart from K_BFP: it needs a copy of the inputs)
+//   K_BFP_STOCH  [BFP stochastic, external random tensor, FLAT]  the reference's default rounding; random words loaded with the data
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_BFP_ASYM = 10, K_COUNT = 11 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_BFP_ASYM = 10, K_BFP_STOCH = 11, K_COUNT = 12 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
     const uint32_t f16_hi = f16_same ? min(pattern16_rn<Tin>(u2f(p.chain.st[0].ff.max_num)), (uint32_t)(std::is_same<Tin, __half>::value ? 0x7BFFu : 0x7F7Fu)) : 0u;
 
     uint4 raw[kUnroll];
+    uint4 rraw[kUnroll][V / 4];  // K_BFP_STOCH only
     int64_t yoff[kUnroll];
     int64_t aux_s[kUnroll], aux_m[kUnroll], aux_r[kUnroll];
     bool valid[kUnroll];
@@ -146,6 +148,11 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             if (KIND == K_AUX) { aux_s[u] = a.so + k; aux_m[u] = a.mo + k; aux_r[u] = a.ro + k * p.rks; }
         }
         raw[u] = valid[u] ? ldg_stream(x + xoff) : make_uint4(0u, 0u, 0u, 0u);
+        if (KIND == K_BFP_STOCH) {  // (FLAT only) one int32 random word per element, same offsets as the data
+#pragma unroll
+            for (int j = 0; j < V / 4; ++j)
+                rraw[u][j] = valid[u] ? ldg_stream(static_cast<const uint32_t *>(p.rnd) + xoff + 4 * j) : make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 
     // ---- phase 2: per vector: widen, stages, narrow, store
@@ -156,6 +163,18 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
+        } else if (KIND == K_BFP_STOCH) {
+            const StageDev &st = p.chain.st[0];
+            const uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
+            const BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+            for (int j = 0; j < V; j += 4) {
+                const uint4 q = rraw[u][j / 4];
+                v[j] = bfp_elem<R_STOCHASTIC>(v[j], b, st.sh, st.mask, q.x);
+                v[j + 1] = bfp_elem<R_STOCHASTIC>(v[j + 1], b, st.sh, st.mask, q.y);
+                v[j + 2] = bfp_elem<R_STOCHASTIC>(v[j + 2], b, st.sh, st.mask, q.z);
+                v[j + 3] = bfp_elem<R_STOCHASTIC>(v[j + 3], b, st.sh, st.mask, q.w);
+            }
         } else if (KIND == K_BFP_ASYM) {
             // symmetric nearest result first, then make_mantissa_asymmetric (S/numerical/format.py:349-372): the edge
             // mantissa -(2^(wl-1)-1) needs |x| >= maxval - Q/2, so only blocks whose max is within one quantum of

@@ -15,7 +15,8 @@ cudaError_t launch_rows(int in_dt, int out_dt, bool flat, int kind, const RowsPa
     case K_BFP:
     case K_FLOAT: return launch_rows_b(kind, in_dt, out_dt, flat, p, s);
     case K_MXFP:
-    case K_BFP_ASYM: return launch_rows_d(kind, in_dt, out_dt, flat, p, s);
+    case K_BFP_ASYM:
+    case K_BFP_STOCH: return launch_rows_d(kind, in_dt, out_dt, flat, p, s);
     default: return launch_rows_c(kind, in_dt, out_dt, flat, p, s);
     }
 }
