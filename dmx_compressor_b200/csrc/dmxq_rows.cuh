@@ -190,6 +190,16 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[j] = bfp_asym_fix(v[j], x0[j], bb);
             }
+        } else if (KIND == K_FLOAT && p.chain.st[0].ff.nsub) {
+            // nearest with subnormals kept (FP8 E4M3 / E5M2 ...): the branch-free form; Inf / NaN vectors take the literal path
+            const StageDev &st = p.chain.st[0];
+            if (unpack_absmax<Tin>(raw[u], v) < 0x7F800000u) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = float_elem_nearest_sub(v[j], st.ff);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = float_elem_slow(v[j], &st.ff, 0u);
+            }
         } else if (KIND == K_FLOAT) {
             if constexpr (SAME16) {
                 if (f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {  // identity on this vector

@@ -28,7 +28,7 @@ for dt in (torch.float32, torch.bfloat16):
     y = torch.empty_like(x)
     es = x.element_size()
     report(f"torch copy_ {dt}", 2*n*es, lambda: y.copy_(x))
-    for sh in ("BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)", "BFP[8|8]{64}(_N)", "BFP[8|8]{64}(SU)", "FP[1|5|10,15](FN)", "XP[8,0](CSN)",
+    for sh in ("BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)", "BFP[8|8]{64}(_N)", "BFP[8|8]{64}(SU)", "FP[1|5|10,15](FN)", "FP[1|4|3,7](_N)", "FP[1|5|2,15](_N)", "XP[8,0](CSN)",
                "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"):
         st = [Format.from_shorthand(sh).stage()]
         report(f"{sh} {dt} flat", 2*n*es, lambda: ops.cast_chain(x, st, -1, out=y))
