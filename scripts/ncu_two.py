@@ -27,4 +27,13 @@ ops.cast_chain(x, [F("MXFP8[E4M3]{32}")], -1, out=y)                    # 11 mxf
 ops.cast_chain(xb, [F("MXFP8[E4M3]{32}")], -1, out=yb)                  # 12 mxfp bf16
 ops.histc(x, 2048, min=-7, max=9, return_minmax=True)                   # 13 histc (+ init / final helper kernels)
 ops.minmax(xb)                                                          # 14 minmax bf16
+ops.cast_chain(xb, [F("BFP[8|8]{64}(_N)")], -1, out=yb)                 # 15 asymmetric BFP16A bf16 (K_BFP_ASYM)
+rnd = torch.randint(0, 2**31 - 1, xb.shape, device=dev, dtype=torch.int32)
+ops.cast_chain(xb, [F("BFP[8|8]{64}(SS)")], -1, out=yb, rand=rnd)       # 16 stochastic BFP16 bf16 (K_BFP_STOCH)
+ops.cast_chain(xb, [F("FP[1|4|3,7](_N)")], -1, out=yb)                  # 17 FP8 E4M3 on bf16 (K_FLOAT, subnormals kept)
+_m, _e = ops.bfp_pack(x, 64, 8)                                         # 18 pack fp32 -> int8 + exponent bytes
+ops.bfp_unpack(_m, _e, 64, 8, dtype=torch.float32)                      # 19 unpack
+sc = torch.rand(4096, device=dev) * 0.05 + 0.01
+ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=sc, zero_point=torch.zeros(4096, device=dev), ch_axis=1, out=y)   # 20 INT8 per column
+ops.minmax(x, 1)                                                        # 21 per-column amin / amax
 torch.cuda.synchronize()

@@ -36,3 +36,15 @@ x = torch.randn(16384, 4096, device="cuda")
 for dim in (-1, 0, 1):
     ms = timeit(lambda: ops.block_quantize_l1(x, 8, dim, True, "nearest"))
     print(f"L1 block_quantize dim={dim:2d} fp32 [16384,4096]   {ms:8.3f} ms  {2 * x.numel() * 4 / ms / 1e6:8.1f} GB/s (8 B/elem)")
+
+# Sparsify with a learnable score tensor and the mask written out (training-time path, K_AUX)
+for dt in (torch.float32, torch.bfloat16):
+    w = torch.randn(16384, 4096, device="cuda").to(dt)
+    sc = torch.rand(16384, 4096, device="cuda")
+    n = w.numel()
+    ms = timeit(lambda: ops.nm_prune(w, 2, 4, -1, score=sc, return_mask=True))
+    print(f"{str(dt):16s} 2:4 prune, fp32 score in, fp32 mask out   {ms:8.3f} ms  {(2 * n * w.element_size() + 8 * n) / ms / 1e6:8.1f} GB/s")
+    ms = timeit(lambda: ops.nm_prune(w, 2, 4, -1, score=sc))
+    print(f"{str(dt):16s} 2:4 prune, fp32 score in                  {ms:8.3f} ms  {(2 * n * w.element_size() + 4 * n) / ms / 1e6:8.1f} GB/s")
+    ms = timeit(lambda: ops.nm_prune(w, 4, 8, -1))
+    print(f"{str(dt):16s} 4:8 prune (score |x|)                     {ms:8.3f} ms  {(2 * n * w.element_size()) / ms / 1e6:8.1f} GB/s")
