@@ -893,6 +893,39 @@ template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], c
 }
 
 // BCAST 0: b has a's layout (no index arithmetic); 1: b = [o0, o1, inner] with arbitrary outer strides
+// 16-bit helpers: pack a register vector to T (round to nearest: the tensor dtype's rounding) and the "this FLOAT stage
+// is the identity on the whole vector" test on the packed patterns (see f16_same in dmxq_rows.cuh)
+template <typename T> __device__ __forceinline__ uint4 pack16(const float (&v)[8])
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        } else {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+struct Range16 {
+    uint32_t lo, hi;
+    bool on;  // the stage exists, keeps T's significand, and is the signed nearest+flush kind
+};
+template <typename T> __device__ __forceinline__ Range16 range16(int has, const FloatFmt &f)
+{
+    Range16 r;
+    r.on = has && f.exact && !f.is_unsigned;
+    r.lo = pattern16_ru<T>(u2f(f.shift_exp));
+    r.hi = min(pattern16_rn<T>(u2f(f.max_num)), (uint32_t)(std::is_same<T, __half>::value ? 0x7BFFu : 0x7F7Fu));
+    return r;
+}
+__device__ __forceinline__ bool inside16(const uint4 &w, const Range16 &r) { return r.on && raw16_absmin(w) >= r.lo && raw16_absmax(w) <= r.hi; }
+
+// BCAST 0: b has a's layout (no index arithmetic); 1: b = [o0, o1, inner] with arbitrary outer strides; 2: the same, with
+// every inner run a whole number of CTA tiles, so the outer index is CTA-uniform (the attention-mask add: no per-vector division)
 template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add_cast_kernel(const __grid_constant__ AddParams p)
 {
     constexpr int V = VecIO<T>::V;
@@ -901,6 +934,12 @@ template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add
     const T *__restrict__ b = static_cast<const T *>(p.b);
     T *__restrict__ y = static_cast<T *>(p.y);
     const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    int64_t cta_boff = 0;
+    if (BCAST == 2) {
+        const int64_t o = ((int64_t)blockIdx.x * (kThreads * U)) / p.inner_vec;
+        const int64_t o0 = o / p.d1, o1 = o - o0 * p.d1;
+        cta_boff = o0 * p.bs0 + o1 * p.bs1 - o * (int64_t)p.inner_vec * V;  // + g * V gives the element offset in b
+    }
     uint4 ra[U], rb[U];
     bool valid[U];
 #pragma unroll
@@ -911,6 +950,8 @@ template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add
         int64_t boff;
         if (BCAST == 0) {
             boff = gg * V;
+        } else if (BCAST == 2) {
+            boff = cta_boff + gg * V;
         } else if (p.n_vec <= 0xFFFFFFFFll) {  // 32-bit index arithmetic
             uint32_t g32 = (uint32_t)gg;
             uint32_t o = g32 / p.inner_vec, iv = g32 - o * p.inner_vec;
@@ -924,21 +965,48 @@ template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add
         ra[u] = valid[u] ? ldg_stream(a + gg * V) : make_uint4(0, 0, 0, 0);
         rb[u] = valid[u] ? (BCAST == 0 ? ldg_stream(b + boff) : *reinterpret_cast<const uint4 *>(b + boff)) : make_uint4(0, 0, 0, 0);
     }
+    if constexpr (sizeof(T) == 2) {
+        // 16-bit tensors: a FLOAT stage that keeps T's significand only flushes / saturates, so a vector whose magnitudes all
+        // lie inside [flush threshold, saturation value] passes through it untouched -- two packed compares per stage
+        const Range16 qa = range16<T>(p.has_a, p.fa), qb = range16<T>(p.has_b, p.fb), qo = range16<T>(p.has_o, p.fo);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        float va[V], vb[V];
-        VecIO<T>::unpack(ra[u], va);
-        VecIO<T>::unpack(rb[u], vb);
-        if (p.has_a) { float_fast_vec<V>(va, p.fa);
+        for (int u = 0; u < U; ++u) {
+            float va[V], vb[V];
+            VecIO<T>::unpack(ra[u], va);
+            VecIO<T>::unpack(rb[u], vb);
+            if (p.has_a && !inside16(ra[u], qa)) {
+                float_fast_vec<V>(va, p.fa);
 #pragma unroll
-            for (int j = 0; j < V; ++j) va[j] = requant1<T>(va[j]); }
-        if (p.has_b) { float_fast_vec<V>(vb, p.fb);
+                for (int j = 0; j < V; ++j) va[j] = requant1<T>(va[j]);
+            }
+            if (p.has_b && !inside16(rb[u], qb)) {
+                float_fast_vec<V>(vb, p.fb);
 #pragma unroll
-            for (int j = 0; j < V; ++j) vb[j] = requant1<T>(vb[j]); }
+                for (int j = 0; j < V; ++j) vb[j] = requant1<T>(vb[j]);
+            }
 #pragma unroll
-        for (int j = 0; j < V; ++j) va[j] = requant1<T>(__fadd_rn(va[j], vb[j]));  // torch adds in fp32, rounds to T
-        if (p.has_o) float_fast_vec<V>(va, p.fo);
-        if (valid[u]) VecIO<T>::template store<V>(y + (g0 + (int64_t)u * kThreads) * V, va);
+            for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);  // torch adds in fp32, rounds to T
+            uint4 w = pack16<T>(va);
+            if (p.has_o && !inside16(w, qo)) {
+                VecIO<T>::unpack(w, va);
+                float_fast_vec<V>(va, p.fo);
+                w = pack16<T>(va);
+            }
+            if (valid[u]) stg_stream(y + (g0 + (int64_t)u * kThreads) * V, w);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float va[V], vb[V];
+            VecIO<T>::unpack(ra[u], va);
+            VecIO<T>::unpack(rb[u], vb);
+            if (p.has_a) float_fast_vec<V>(va, p.fa);
+            if (p.has_b) float_fast_vec<V>(vb, p.fb);
+#pragma unroll
+            for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);
+            if (p.has_o) float_fast_vec<V>(va, p.fo);
+            if (valid[u]) VecIO<T>::template store<V>(y + (g0 + (int64_t)u * kThreads) * V, va);
+        }
     }
 }
 
@@ -946,6 +1014,7 @@ template <typename T> static void launch_add_t(const AddParams &p, unsigned grid
 {
     const bool same = p.d1 == 1 && p.bs0 == 0 && (int64_t)p.inner_vec == p.n_vec;
     if (same) add_cast_kernel<T, 0><<<grid, kThreads, 0, s>>>(p);
+    else if (p.inner_vec % (kThreads * 4) == 0) add_cast_kernel<T, 2><<<grid, kThreads, 0, s>>>(p);
     else add_cast_kernel<T, 1><<<grid, kThreads, 0, s>>>(p);
 }
 
