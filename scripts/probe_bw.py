@@ -49,6 +49,12 @@ for dt in (torch.float32, torch.bfloat16):
     ys = torch.empty(n // 4096, 4096 + 64, device=dev, dtype=dt)[:, :4096]
     st = [Format.from_shorthand("BFP[8|8]{64}(SN)").stage()]
     report(f"BFP16 {dt} strided rows", 2*n*es, lambda: ops.cast_chain(xs, st, -1, out=ys))
+    # per-head view of a fused projection: [B, H, S, 64] view of [B, S, H*64] (two outer dims with odd strides)
+    qkv = torch.randn(64, 2048, 12 * 64, device=dev).to(dt)
+    qv = qkv.view(64, 2048, 12, 64).transpose(1, 2)
+    qy = torch.empty(64, 12, 2048, 64, device=dev, dtype=dt)
+    report(f"BFP16 {dt} per-head view [64,12,2048,64] of [64,2048,768]", 2*qv.numel()*es, lambda: ops.cast_chain(qv, st, -1, out=qy))
+    del qkv, qv, qy
     # cols: [96, 2048, 64*...] along dim -2
     v = torch.randn(96*8, 2048, 64, device=dev).to(dt)
     vy = torch.empty_like(v)
