@@ -391,6 +391,8 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         p.rows = rows;
         p.rks = c.k.rs;
         p.chain = chain;
+        p.vpr_div = make_fastdiv(p.vpr);
+        for (int i = 0; i < p.nouter; ++i) p.odim_div[i] = make_fastdiv((uint32_t)std::min<int64_t>(std::max<int64_t>(p.odim[i], 1), 0x7FFFFFFF));
         bool flat = c.outer.size() <= 1 && p.K % tile == 0;
         if (flat && c.outer.size() == 1) {
             const Dim &d = c.outer[0];

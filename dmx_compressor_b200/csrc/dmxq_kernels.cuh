@@ -44,6 +44,28 @@ struct ChainDev {
 
 // Row-tiled kernel: the blocked dim is contiguous (stride 1).  A "row" is one index tuple of
 // the remaining (outer) dims.
+// n / d for n < 2^31 as one multiply-high and a shift (Granlund-Montgomery round-up method): the hardware has no
+// integer divider, `n / d` with a run-time d is a ~20-instruction sequence per use.
+struct FastDiv {
+    uint32_t mul, shr, d;
+#ifdef __CUDACC__
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1u ? n : __umulhi(n, mul) >> shr; }
+#endif
+};
+inline FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    f.d = d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        uint32_t lg = 0;
+        while ((1ull << lg) < d) ++lg;                 // ceil(log2 d)
+        const unsigned p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+        f.shr = p - 32;
+    }
+    return f;
+}
+
 struct RowsParams {
     const void *x;
     void *y;
@@ -60,6 +82,7 @@ struct RowsParams {
     int64_t odim[kMaxOuter];
     int64_t xs[kMaxOuter], ys[kMaxOuter], ss[kMaxOuter], ms[kMaxOuter], rs[kMaxOuter];
     int64_t rks;         // rand stride along K
+    FastDiv vpr_div, odim_div[kMaxOuter];  // valid while n_vec < 2^31
     ChainDev chain;
 };
 

@@ -156,7 +156,8 @@ __device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, 
 // vectorised variant 1: one 16-byte vector never straddles two qparam groups (inner % V == 0, or the channel runs
 // along the contiguous dim in groups that are multiples of V).  256 threads x 4 vectors, all loads before first use.
 template <typename Tin, typename Tout>
-__global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p, int64_t cvec, int64_t gvec)
+__global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p, int64_t cvec, int64_t gvec, FastDiv dcvec,
+                                                                  FastDiv dC, FastDiv dgvec)
 {
     // qparam index of vector g: ((g / cvec) % C') / gvec with the caller's (cvec, C', gvec) -- see launch_fixed_chan_t
     constexpr int V = VecIO<Tin>::V;
@@ -180,9 +181,9 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
         const int64_t g = g0 + (int64_t)u * kThreads;
         if (g >= nvec) continue;
         int64_t q;
-        if (nvec <= 0xFFFFFFFFll) {
-            const uint32_t t = (uint32_t)g / (uint32_t)cvec;
-            q = (t % (uint32_t)p.C) / (uint32_t)gvec;
+        if (nvec <= 0x7FFFFFFFll) {  // multiply-high divisions
+            const uint32_t t = dcvec.div((uint32_t)g);
+            q = dgvec.div(t - dC.div(t) * dC.d);
         } else {
             q = ((g / cvec) % p.C) / gvec;
         }
@@ -250,6 +251,8 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
     }
 }
 
+static FastDiv fd(int64_t d) { return make_fastdiv((uint32_t)std::min<int64_t>(std::max<int64_t>(d, 1), 0x7FFFFFFF)); }
+
 template <typename Tin, typename Tout> static void launch_fixed_chan_t(const FixedChanParams &p, cudaStream_t s)
 {
     constexpr int V = VecIO<Tin>::V;
@@ -260,13 +263,13 @@ template <typename Tin, typename Tout> static void launch_fixed_chan_t(const Fix
         // channel constant inside a vector: qparam = ((g / inner_vec) % C) / group
         FixedChanParams q = p;
         int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
-        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, p.inner / V, p.group);
+        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, p.inner / V, p.group, fd(p.inner / V), fd(q.C), fd(p.group));
     } else if (aligned && p.inner == 1 && p.C % V == 0 && p.group % V == 0) {
         // channel along the contiguous dim, groups are whole vectors: qparam = (g % (C / V)) / (group / V)
         FixedChanParams q = p;
         q.C = p.C / V;
         int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
-        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, 1, p.group / V);
+        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, 1, p.group / V, fd(1), fd(q.C), fd(p.group / V));
     } else if (aligned && fast && !p.rnd && p.inner == 1 && p.C % V == 0) {
         const int64_t R = p.n / p.C, gx = (p.C + 32 * V - 1) / (32 * V);
         int64_t gy = std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, std::max<int64_t>(1, (148 * 8) / gx)));

@@ -43,11 +43,11 @@ __device__ __forceinline__ RowAddr row_addr(const RowsParams &p, int64_t row)
         return a;
     }
     a.xo = a.yo = a.so = a.mo = a.ro = 0;
-    if (p.n_vec <= 0xFFFFFFFFll) {  // row < 2^32: 32-bit div / mod (the 64-bit forms cost ~100 instructions each)
+    if (p.n_vec <= 0x7FFFFFFFll) {  // row < 2^31: multiply-high divisions (the 64-bit forms cost ~100 instructions each)
         uint32_t r32 = (uint32_t)row;
         for (int d = p.nouter - 1; d >= 0; --d) {
             const uint32_t od = (uint32_t)p.odim[d];
-            const uint32_t q = (d == 0) ? 0u : r32 / od;
+            const uint32_t q = (d == 0) ? 0u : p.odim_div[d].div(r32);
             const int64_t i = (d == 0) ? r32 : r32 - q * od;
             r32 = q;
             a.xo += i * p.xs[d]; a.yo += i * p.ys[d]; a.so += i * p.ss[d]; a.mo += i * p.ms[d]; a.ro += i * p.rs[d];
@@ -142,9 +142,9 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
         } else {
             int64_t row;
             uint32_t kv;
-            if (p.n_vec <= 0xFFFFFFFFll) {
+            if (p.n_vec <= 0x7FFFFFFFll) {
                 uint32_t g32 = (uint32_t)g;
-                uint32_t r32 = g32 / p.vpr;
+                uint32_t r32 = p.vpr_div.div(g32);
                 kv = g32 - r32 * p.vpr;
                 row = r32;
             } else {
