@@ -104,6 +104,26 @@ def cast_shards(shards: Sequence[Shard], materialise: Callable[[Shard], torch.Te
     return nbytes, out
 
 
+def replicate_shards(plan: List[List[Shard]], local: Dict[Tuple[str, int], torch.Tensor], shapes: Dict[str, Sequence[int]], dtype, device,
+                     group=None) -> Dict[str, torch.Tensor]:
+    """Give every rank every cast tensor ("no gather unless the caller wants a replicated result").
+    ``local`` = the ``{(name, row0): tensor}`` this rank got from ``cast_shards(..., keep=True)``.  Each shard is
+    broadcast by its owner straight into its rows of the preallocated full tensor -- no staging copy, no padding for
+    the uneven row splits; on the box this is NCCL over NVLink and is reported separately from the cast throughput."""
+    import torch.distributed as dist
+
+    rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    full = {name: torch.empty(tuple(shape), dtype=dtype, device=device) for name, shape in shapes.items()}
+    for owner, shards in enumerate(plan):
+        for sh in shards:
+            rows = full[sh.name][sh.row0:sh.row1]
+            if owner == rank:
+                rows.copy_(local[(sh.name, sh.row0)])
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.broadcast(rows, src=dist.get_global_rank(group, owner) if group is not None else owner, group=group)
+    return full
+
+
 # ------------------------------------------------------------------------------------------------
 # batched statistics all-reduce
 def local_minmax(t: torch.Tensor, ch_axis: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:

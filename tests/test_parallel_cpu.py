@@ -135,3 +135,39 @@ def test_shard_stats_mixed_whole_and_split_tensors():
             assert mn == float(full[name].min()) and mx == float(full[name].max()), name
             seen.add(name)
     assert seen == set(shapes)
+
+
+def _worker_replicate(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {"big": (65, 16), "a": (8, 16), "b": (6, 16), "c": (4, 16)}  # 65 rows: uneven split
+    plan = P.plan_shards(shapes, world, split_threshold=0.5)
+    g = torch.Generator().manual_seed(13)
+    full = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+    # (the cast itself is a GPU kernel; what is exercised here is the exchange: every rank contributes "its" rows doubled)
+    local = {(sh.name, sh.row0): 2 * full[sh.name][sh.row0:sh.row1] for sh in plan[rank]}
+    out = P.replicate_shards(plan, local, shapes, torch.float32, "cpu")
+    q.put((rank, {n: t.numpy().copy() for n, t in out.items()}))
+    dist.destroy_process_group()
+
+
+def test_replicate_shards_over_gloo():
+    """every rank ends up with every tensor, rows in place, uneven row splits included"""
+    world, port = 2, 33500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_replicate, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    shapes = {"big": (65, 16), "a": (8, 16), "b": (6, 16), "c": (4, 16)}
+    g = torch.Generator().manual_seed(13)
+    full = {n: torch.randn(s, generator=g) for n, s in shapes.items()}
+    for rank in range(world):
+        assert set(res[rank]) == set(shapes)
+        for n in shapes:
+            assert np.array_equal(res[rank][n], (2 * full[n]).numpy()), (rank, n)
