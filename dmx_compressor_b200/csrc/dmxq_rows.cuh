@@ -129,10 +129,16 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
     int64_t aux_s[kUnroll], aux_m[kUnroll], aux_r[kUnroll];
     bool valid[kUnroll];
 
+    // SBFP on a flat 16-bit tensor whose block is two vectors (block 16): a thread takes both vectors of a block (still
+    // whole 32-byte sectors per lane), so the block constants -- max / 7, its scaler cast, its reciprocal -- are derived once
+    // per block instead of once per lane, and no shuffle is needed
+    const bool pair = KIND == K_SBFP && SRC16 && FLAT && p.chain.st[0].block == 2 * V;
+
     // ---- phase 1: addresses + all loads (nothing here consumes loaded data)
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         int64_t g = g0 + (int64_t)u * kThreads;
+        if (pair) g = (int64_t)blockIdx.x * (kThreads * kUnroll) + (u >> 1) * (2 * kThreads) + 2 * threadIdx.x + (u & 1);
         int64_t xoff;
         if (FLAT) {
             valid[u] = g < p.n_vec;
@@ -346,6 +352,18 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
         } else if (KIND == K_MXFP) {
             const StageDev &st = p.chain.st[0];
             mxfp_apply<V>(v, lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V), st);
+        } else if (KIND == K_SBFP && pair) {
+            if ((u & 1) == 0) {
+                const StageDev &st = p.chain.st[0];
+                float w[V];
+                const uint32_t m = max(unpack_absmax<Tin>(raw[u], v), unpack_absmax<Tin>(raw[(u + 1) % kUnroll], w));
+                const SbfpBlock b = sbfp_block_ol(m, st.sb);
+                sbfp_apply<V>(v, b, st.sb);
+                sbfp_apply<V>(w, b, st.sb);
+                if (valid[u]) VecIO<Tout>::template store<V>(y + yoff[u], v);
+                if (valid[(u + 1) % kUnroll]) VecIO<Tout>::template store<V>(y + yoff[(u + 1) % kUnroll], w);
+            }
+            continue;
         } else if (KIND == K_SBFP) {
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);

@@ -175,8 +175,8 @@ __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, con
 }
 // The same on a register vector of one block, division free for ordinary blocks.  Works on magnitudes (|x| is a free
 // operand modifier): the quotient |x| / cmax is in [0, 7.0000005] (cmax = RN(max|x| / man_scaling)), so
-//   * round-to-nearest-even is (q + 2^23) - 2^23, and half-away differs from it only on exact ties, where the
-//     remainder q - r is exactly +0.5 after rounding down: one compare and a predicated add;
+//   * round half away is trunc(q + 0.5) with the addition rounded toward zero (what roundf itself does, minus the sign
+//     handling): two instructions;
 //   * the clamp to [t_min, t_max] cannot trigger when |t_min|, t_max >= man_scaling (every SBFP format), so it is skipped;
 //   * the result carries x's sign (cmax, fs >= 0).
 template <int V> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const SbfpBlock &b, const SbfpFmt &f)
@@ -188,8 +188,7 @@ template <int V> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const
         for (int j = 0; j < V; ++j) {
             const float a = fabsf(v[j]);
             const float q = div_by_recip(a, b.cmax, b.rc);
-            float r = __fsub_rn(__fadd_rn(q, 8388608.0f), 8388608.0f);
-            if (__fsub_rn(q, r) == 0.5f) r = __fadd_rn(r, 1.0f);
+            const float r = truncf(__fadd_rz(q, 0.5f));  // round half away of q >= 0: the toward-zero add cannot round up into the next integer
             v[j] = copysignf(__fmul_rn(r, b.fs), v[j]);
         }
     } else {
