@@ -275,6 +275,14 @@ template <int V> __device__ __forceinline__ void bfp_stage(float (&v)[V], const 
         BfpBlock b = bfp_block(m, st.wl);
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = bfp_elem<R_STOCHASTIC>(v[j], b, st.sh, st.mask, r[j]);
+    } else if (st.mode == R_UP && !st.asym) {  // directed rounding: inlined too (the out-of-line call per element cost 2x)
+        BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem<R_UP>(v[j], b, st.sh, st.mask, 0u);
+    } else if (st.mode == R_DOWN && !st.asym) {
+        BfpBlock b = bfp_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem<R_DOWN>(v[j], b, st.sh, st.mask, 0u);
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) v[j] = bfp_elem_slow(v[j], m, st.wl, st.sh, st.mask, st.mode, st.asym, r[j]);
