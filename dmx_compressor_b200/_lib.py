@@ -62,6 +62,8 @@ def _load():
         "dmxq_add_cast": ([TP, TP, TP, SP, SP, SP, VP], I),
         "dmxq_bfp_pack": ([TP, VP, VP, I, I, VP], I),
         "dmxq_bfp_unpack": ([VP, VP, TP, I, I, VP], I),
+        "dmxq_sbfp_pack": ([TP, VP, VP, SP, VP, VP], I),
+        "dmxq_sbfp_unpack": ([VP, VP, TP, SP, VP], I),
         "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
         "dmxq_minmax": ([TP, I, VP, VP, VP], I),
         "dmxq_histc": ([TP, I, C.c_float, C.c_float, VP, VP, VP, VP], I),

@@ -741,6 +741,55 @@ int dmxq_bfp_unpack(const void *mantissas, const uint8_t *exponents, const dmxq_
     return DMXQ_OK;
 }
 
+static int sbfp_packed_args(const dmxq_tensor *t, const void *mant, const void *scalers, const dmxq_stage *fmt, StageDev &d, int64_t *n)
+{
+    if (!t || !mant || !scalers || !fmt) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (t->dtype < 0 || t->dtype > 2) return fail(DMXQ_ERR_BAD_ARG, "bad dtype");
+    if (fmt->kind != DMXQ_STAGE_SBFP) return fail(DMXQ_ERR_BAD_ARG, "packed SBFP needs a DMXQ_STAGE_SBFP format description");
+    int rc = decode_stage(*fmt, d);
+    if (rc) return rc;
+    if (fmt->precision < 2 || fmt->precision > 8) return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP supports block precision 2..8, got %d", fmt->precision);
+    if (d.sb.xp.mode != R_NEAREST || d.sb.xp.tie != TIE_AWAY || !d.sb.xp.clamp)
+        return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP needs a clamped nearest (half away) block format");
+    if (!d.sb.sc.flush || fmt->sc_man + fmt->sc_exp > 8 || fmt->sc_man < 0 || fmt->sc_exp < 1)
+        return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP needs a subnormal-flushing scaler format of at most 8 bits (got E%dM%d)", fmt->sc_exp, fmt->sc_man);
+    const int B = fmt->block;
+    if (B < 8 || B > 128 || !pow2(B)) return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP needs a power-of-two block size in 8..128, got %d", B);
+    int64_t total = 1, expect = 1;
+    for (int i = t->ndim - 1; i >= 0; --i) {
+        if (t->shape[i] != 1 && t->stride[i] != expect) return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP needs a contiguous tensor");
+        expect *= t->shape[i];
+        total *= t->shape[i];
+    }
+    if (t->ndim < 1 || t->shape[t->ndim - 1] % B != 0) return fail(DMXQ_ERR_BAD_ARG, "last dim must be a multiple of the block size");
+    if (total && !aligned(t->data, 16)) return fail(DMXQ_ERR_UNSUPPORTED, "packed SBFP needs 16-byte aligned data");
+    *n = total;
+    return DMXQ_OK;
+}
+
+int dmxq_sbfp_pack(const dmxq_tensor *x, void *mantissas, uint8_t *scalers, const dmxq_stage *fmt, unsigned int *n_inexact, void *stream)
+{
+    int64_t n = 0;
+    StageDev d;
+    int rc = sbfp_packed_args(x, mantissas, scalers, fmt, d, &n);
+    if (rc || n == 0) return rc;
+    cudaError_t e = launch_sbfp_pack(x->dtype, x->data, mantissas, scalers, n_inexact, n, fmt->block, d.sb, fmt->sc_man, fmt->sc_exp,
+                                     static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "sbfp_pack_kernel");
+    return DMXQ_OK;
+}
+
+int dmxq_sbfp_unpack(const void *mantissas, const uint8_t *scalers, const dmxq_tensor *y, const dmxq_stage *fmt, void *stream)
+{
+    int64_t n = 0;
+    StageDev d;
+    int rc = sbfp_packed_args(y, mantissas, scalers, fmt, d, &n);
+    if (rc || n == 0) return rc;
+    cudaError_t e = launch_sbfp_unpack(y->dtype, mantissas, scalers, y->data, n, fmt->block, d.sb, fmt->sc_man, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "sbfp_unpack_kernel");
+    return DMXQ_OK;
+}
+
 int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream)
 {
     if (!x || !out_min || !out_max) return fail(DMXQ_ERR_BAD_ARG, "null argument");

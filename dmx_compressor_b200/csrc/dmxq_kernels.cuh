@@ -174,6 +174,9 @@ cudaError_t launch_histc(int dt, const void *x, int64_t n, float lo, float hi, i
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
 cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s);
+cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers, unsigned int *n_inexact, int64_t n, int B, const SbfpFmt &f, int sc_man,
+                             int sc_exp, cudaStream_t s);
+cudaError_t launch_sbfp_unpack(int dt, const void *mant, const uint8_t *scalers, void *y, int64_t n, int B, const SbfpFmt &f, int sc_man, cudaStream_t s);
 cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s);
 int64_t launch_count();
 

@@ -1174,6 +1174,161 @@ cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, voi
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// packed SBFP storage (see dmxq_sbfp_pack in include/dmxq.h): per block one scaler byte (the low-bit float scaler's
+// exponent and mantissa fields, 0 = zero scaler) and sign-magnitude integer mantissas -- sign-magnitude because the
+// simulated cast keeps the sign of x on a zero result (roundf(-0.3) * fs = -0), which two's complement cannot hold.
+// The quotient / rounding sequence is sbfp_apply's, on magnitudes.
+struct SbfpPackFmt {
+    SbfpFmt f;
+    uint32_t base_code;  // (bits of the smallest normal scaler >> sh) - (1 << man): code = (bits(fs) >> sh) - base_code
+    uint32_t code_max;   // 2^(exp + man) - 1
+    int nibble;          // mantissas in 4 bits (precision <= 4) or 8
+};
+
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) sbfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ scalers, unsigned int *__restrict__ n_inexact, int64_t n_vec, int lanes, int lshift, const __grid_constant__ SbfpPackFmt pf)
+{
+    constexpr int V = VecIO<T>::V;
+    constexpr int U = 4;
+    constexpr uint32_t SIGN = NIBBLE ? 0x8u : 0x80u;
+    const SbfpFmt &f = pf.f;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        int64_t g = g0 + (int64_t)u * kThreads;
+        raw[u] = g < n_vec ? ldg_stream(x + g * V) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        float v[V];
+        const uint32_t m = lanes_max(unpack_absmax<T>(raw[u], v), lanes);
+        const SbfpBlock b = sbfp_block_ol(m, f);
+        const bool finite = m < 0x7F800000u;
+        // not representable: non-finite blocks, blocks so small that max / man_scaling underflows to zero (the cast passes
+        // their denormals through), scalers beyond the byte's exponent field (the reference's simulated formats saturate at
+        // 2^(2^(exp-1)) whatever the bias).  The first two are stored as zeros, the last saturates the byte.
+        bool exact = finite && (b.on || m == 0u);
+        uint32_t code = 0u;
+        if (finite && b.on && b.fs != 0.0f) {
+            code = (f2u(b.fs) >> f.sc.sh) - pf.base_code;
+            if (code > pf.code_max) { code = pf.code_max; exact = false; }
+        }
+        uint32_t k[V];
+        if (finite && b.on) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float a = fabsf(v[j]);
+                const float q = b.rok ? div_by_recip(a, b.cmax, b.rc) : __fdiv_rn(a, b.cmax);
+                const float r = fminf(truncf(__fadd_rz(q, 0.5f)), f.man_scaling);
+                k[j] = (uint32_t)(int)r | ((f2u(v[j]) >> 31) ? SIGN : 0u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) k[j] = (finite && (f2u(v[j]) >> 31)) ? SIGN : 0u;  // a zero block keeps its signs
+        }
+        if (g >= n_vec) continue;
+        if ((threadIdx.x & (lanes - 1)) == 0) {
+            scalers[g >> lshift] = (uint8_t)code;
+            if (!exact && n_inexact) atomicAdd(n_inexact, 1u);
+        }
+        if (NIBBLE) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc |= k[j] << (4 * j);
+            if (V == 8) reinterpret_cast<uint32_t *>(mant)[g] = acc;
+            else reinterpret_cast<uint16_t *>(mant)[g] = (uint16_t)acc;
+        } else {
+            uint32_t w[2] = {0u, 0u};
+#pragma unroll
+            for (int j = 0; j < V; ++j) w[j / 4] |= k[j] << (8 * (j & 3));
+            if (V == 8) reinterpret_cast<uint2 *>(mant)[g] = make_uint2(w[0], w[1]);
+            else reinterpret_cast<uint32_t *>(mant)[g] = w[0];
+        }
+    }
+}
+
+template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) sbfp_unpack_kernel(const uint8_t *__restrict__ mant, const uint8_t *__restrict__ scalers, T *__restrict__ y, int64_t n_vec, int lshift, int sh, uint32_t base_code)
+{
+    constexpr int V = VecIO<T>::V;
+    constexpr int U = 4;
+    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    uint32_t w[U][2];
+    uint32_t code[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {  // all loads first
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        w[u][0] = w[u][1] = 0u;
+        code[u] = 0u;
+        if (g < n_vec) {
+            code[u] = __ldg(scalers + (g >> lshift));
+            if (NIBBLE) {
+                w[u][0] = V == 8 ? __ldg(reinterpret_cast<const uint32_t *>(mant) + g) : (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(mant) + g);
+            } else if (V == 8) {
+                const uint2 t = __ldg(reinterpret_cast<const uint2 *>(mant) + g);
+                w[u][0] = t.x; w[u][1] = t.y;
+            } else {
+                w[u][0] = __ldg(reinterpret_cast<const uint32_t *>(mant) + g);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        if (g >= n_vec) continue;
+        const float fs = code[u] ? u2f((code[u] + base_code) << sh) : 0.0f;
+        float v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const uint32_t t = NIBBLE ? (w[u][0] >> (4 * j)) & 0xFu : (w[u][j / 4] >> (8 * (j & 3))) & 0xFFu;
+            const uint32_t mag = NIBBLE ? t & 0x7u : t & 0x7Fu;
+            const uint32_t sg = NIBBLE ? t >> 3 : t >> 7;
+            v[j] = u2f(f2u(__fmul_rn((float)mag, fs)) | (sg << 31));  // the cast's own last step: magnitude * scaler, sign of x
+        }
+        VecIO<T>::template store<V>(y + g * V, v);
+    }
+}
+
+cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers, unsigned int *n_inexact, int64_t n, int B, const SbfpFmt &f, int sc_man, int sc_exp, cudaStream_t s)
+{
+    const int V = dt == 0 ? 4 : 8;
+    int64_t n_vec = n / V;
+    int64_t grid = (n_vec + kThreads * 4 - 1) / (kThreads * 4);
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    SbfpPackFmt pf;
+    pf.f = f;
+    pf.base_code = (f.sc.shift_exp >> f.sc.sh) - (1u << sc_man);
+    pf.code_max = (1u << (sc_exp + sc_man)) - 1u;
+    pf.nibble = f.man_scaling <= 7.0f;
+    uint8_t *m8 = static_cast<uint8_t *>(mant);
+#define DMXQ_PACK(T) do { if (pf.nibble) sbfp_pack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, scalers, n_inexact, n_vec, B / V, log2_pow2(B / V), pf); \
+                          else sbfp_pack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, scalers, n_inexact, n_vec, B / V, log2_pow2(B / V), pf); } while (0)
+    if (dt == 0) DMXQ_PACK(float); else if (dt == 1) DMXQ_PACK(__nv_bfloat16); else DMXQ_PACK(__half);
+#undef DMXQ_PACK
+    count_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sbfp_unpack(int dt, const void *mant, const uint8_t *scalers, void *y, int64_t n, int B, const SbfpFmt &f, int sc_man, cudaStream_t s)
+{
+    const int V = dt == 0 ? 4 : 8;
+    int64_t n_vec = n / V;
+    int64_t grid = (n_vec + kThreads * 4 - 1) / (kThreads * 4);
+    if (grid <= 0) return cudaSuccess;
+    if (grid > 0x7FFFFFFFll) return cudaErrorInvalidConfiguration;
+    const bool nib = f.man_scaling <= 7.0f;
+    const uint32_t base_code = (f.sc.shift_exp >> f.sc.sh) - (1u << sc_man);
+    const uint8_t *m8 = static_cast<const uint8_t *>(mant);
+#define DMXQ_UNPACK(T) do { if (nib) sbfp_unpack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(m8, scalers, static_cast<T *>(y), n_vec, log2_pow2(B / V), f.sc.sh, base_code); \
+                            else sbfp_unpack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(m8, scalers, static_cast<T *>(y), n_vec, log2_pow2(B / V), f.sc.sh, base_code); } while (0)
+    if (dt == 0) DMXQ_UNPACK(float); else if (dt == 1) DMXQ_UNPACK(__nv_bfloat16); else DMXQ_UNPACK(__half);
+#undef DMXQ_UNPACK
+    count_launch();
+    return cudaGetLastError();
+}
+
 __global__ void fold_absmax_kernel(const float *mn, const float *mx, uint32_t *out, int64_t C)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -327,6 +327,16 @@ class ScaledBlockFloatingPoint(Format):
                                                             s.exponent, s.bias, s.flush_subnormal, s.unsigned,
                                                             repr(s) == "FP[1|5|10,15](FN)", s.rounding))
 
+    # packed storage: the real format whose size `bytes_per_elem` reports (reference format.py:481-486)
+    def pack(self, x: torch.Tensor, return_inexact=False):
+        """-> (mantissas, scalers[, n_inexact]); blocks along the last dim.  Sign-magnitude mantissas (nibbles for
+        precision <= 4) and one scaler byte per block; ``n_inexact`` counts blocks the bytes cannot hold."""
+        return ops.sbfp_pack(x, self.stage(), return_inexact)
+
+    def unpack(self, mantissas: torch.Tensor, scalers: torch.Tensor, dtype=torch.float32):
+        """dequantise packed storage; equals ``cast`` of the original tensor bit for bit"""
+        return ops.sbfp_unpack(mantissas, scalers, self.stage(), dtype)
+
     @property
     def bytes_per_elem(self) -> float:
         return self.block_format.bytes_per_elem + self.scaler_format.bytes_per_elem / self.block_size

@@ -247,6 +247,39 @@ def bfp_unpack(mant, exps, block_size=64, precision=8, dtype=torch.float32):
     return y
 
 
+def sbfp_pack(x, stage, return_inexact=False):
+    """-> (mantissas, scalers[, n_inexact]): packed SBFP storage of a contiguous [..., K] tensor (dmxq_sbfp_pack).
+    `stage`: the SBFP stage struct (``ScaledBlockFloatingPoint.stage()`` / ``sbfp_stage``).
+    mantissas: uint8, sign-magnitude, [..., K/2] (block precision <= 4, two nibbles per byte) or [..., K];
+    scalers: uint8 [..., K / block], the scaler's exponent | mantissa fields (0 = zero scaler).
+    n_inexact (device int32 scalar, on request): blocks the bytes cannot hold (see include/dmxq.h); 0 = exact."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    K, nib = x.shape[-1], stage.precision <= 4
+    mant = torch.empty(x.shape[:-1] + ((K // 2,) if nib else (K,)), dtype=torch.uint8, device=x.device)
+    scal = torch.empty(x.shape[:-1] + (K // max(stage.block, 1),), dtype=torch.uint8, device=x.device)
+    bad = torch.zeros((), dtype=torch.int32, device=x.device) if return_inexact else None
+    vx = L.view(x)
+    with _guard(x.device):
+        rc = L.lib.dmxq_sbfp_pack(C.byref(vx), mant.data_ptr(), scal.data_ptr(), C.byref(stage), bad.data_ptr() if return_inexact else None,
+                                  L.stream_ptr(x.device))
+    L.check(rc, "dmxq_sbfp_pack")
+    return (mant, scal, bad) if return_inexact else (mant, scal)
+
+
+def sbfp_unpack(mant, scal, stage, dtype=torch.float32):
+    """dequantise packed SBFP storage (dmxq_sbfp_unpack): bit-identical to the SBFP cast of the original tensor."""
+    L.require_cuda(mant, "mantissas")
+    L.require_cuda(scal, "scalers")
+    K = mant.shape[-1] * (2 if stage.precision <= 4 else 1)
+    y = torch.empty(mant.shape[:-1] + (K,), dtype=dtype, device=mant.device)
+    vy = L.view(y)
+    with _guard(mant.device):
+        rc = L.lib.dmxq_sbfp_unpack(mant.data_ptr(), scal.data_ptr(), C.byref(vy), C.byref(stage), L.stream_ptr(mant.device))
+    L.check(rc, "dmxq_sbfp_unpack")
+    return y
+
+
 def minmax(x, ch_axis: Optional[int] = None):
     """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax."""
     L.require_cuda(x)

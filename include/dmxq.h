@@ -24,6 +24,7 @@
  *                          back-to-back CastTo pair (output cast -> next input cast)
  *   dmxq_add_cast          ResAdd.forward (casts + add fused)  S/modeling/nn/torch_modules.py:15-37
  *   dmxq_bfp_pack/unpack   packed BFP storage (QuantizeBFP/DequantizeBFP of the ONNX export, S/numerical/cast.py:34-55)
+ *   dmxq_sbfp_pack/unpack  packed SBFP storage (bytes_per_elem S/numerical/format.py:481-486, ids S/numerical/onnx.py:53-67)
  *   dmxq_block_quantize    L1 block_quantize(x, wl, dim,...) Q/quant_cuda/quant.cu:14-112
  *   dmxq_minmax            MinMaxObserver.forward statistics S/numerical/observer.py:173-193
  *   dmxq_histc             HistogramObserver.forward: torch.histc (+ aminmax) S/numerical/observer.py:454-499
@@ -184,6 +185,25 @@ int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor 
 int dmxq_bfp_pack(const dmxq_tensor *x, void *mantissas, uint8_t *exponents, int block_size, int precision, void *stream);
 int dmxq_bfp_unpack(const void *mantissas, const uint8_t *exponents, const dmxq_tensor *y, int block_size, int precision,
                     void *stream);
+
+/* ---- packed SBFP storage (ScaledBlockFloatingPoint.bytes_per_elem, S/numerical/format.py:481-486;
+ * ids DMX_SBFP_12_16_<bias>, S/numerical/onnx.py:53-67).  `fmt`: a DMXQ_STAGE_SBFP stage (the same description
+ * dmxq_cast_chain takes).  Per block of fmt->block consecutive elements:
+ *   one scaler byte    0 = zero scaler; otherwise (E << sc_man) | M with the scaler FloatingPoint value
+ *                      (1 + M / 2^sc_man) * 2^(E - sc_bias), E >= 1 -- the byte of a real E<sc_exp>M<sc_man> number;
+ *   fmt->block mantissas, sign-magnitude (top bit = sign of x, kept on zero results exactly as the simulated cast keeps
+ *                      it), 4 bits each for precision <= 4 (two per byte, low nibble first), else 8 bits.
+ * SBFP12_16: 4.5 bits per element + the byte = 0.5625 B/elem, the reference's bytes_per_elem.
+ *   x / y: contiguous [rows, K], K % block == 0, block a power of two in 8..128; block format XP[p,0] clamped, nearest
+ *   (half away: the reference's CUDA rule), p in 2..8; scaler format flushing subnormals, sc_exp + sc_man <= 8.
+ *   dmxq_sbfp_unpack(dmxq_sbfp_pack(x)) == dmxq_sbfp_qdq(x) bit for bit for every block the byte can hold.  It cannot hold:
+ *   non-finite blocks and blocks whose max / man_scaling underflows to zero (stored as zeros), and scalers above the
+ *   exponent field's range -- the reference's simulated scaler saturates at 2^(2^(sc_exp-1)) whatever the bias, which for
+ *   sc_bias > 2^(sc_exp-1) - 1 exceeds what the real byte reaches (stored saturated).  `n_inexact` (nullable, device
+ *   counter, ACCUMULATED into) receives the number of such blocks: 0 means the round trip is exact. */
+int dmxq_sbfp_pack(const dmxq_tensor *x, void *mantissas, uint8_t *scalers, const dmxq_stage *fmt, unsigned int *n_inexact,
+                   void *stream);
+int dmxq_sbfp_unpack(const void *mantissas, const uint8_t *scalers, const dmxq_tensor *y, const dmxq_stage *fmt, void *stream);
 
 /* ---- L1 mirror: block_quantize(x, wl, dim, symmetric, rounding) of quant_cuda --------------
  * dim == -1: one exponent for the whole tensor; dim == 0: per row of view(size0,-1);

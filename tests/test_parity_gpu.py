@@ -889,6 +889,78 @@ def test_packed_bfp_storage_round_trip(dt, wl, bs):
         check(got, bits(O.cast(x.numpy(), f"BFP[{wl}|8]{{{bs}}}(SN)", -1)), "packed vs oracle")
 
 
+def _sbfp_decode_numpy(mant, scal, bs, prec, sc_man, sc_bias):
+    """independent CPU decode of the packed SBFP bytes (the format of include/dmxq.h, restated in numpy)"""
+    mant, scal = mant.cpu().numpy(), scal.cpu().numpy().astype(np.int64)
+    if prec <= 4:
+        t = np.stack([mant & 0xF, mant >> 4], -1).reshape(mant.shape[:-1] + (-1,))
+        mag, sg = (t & 7).astype(np.float32), t >> 3
+    else:
+        mag, sg = (mant & 0x7F).astype(np.float32), mant >> 7
+    E, M = scal >> sc_man, scal & ((1 << sc_man) - 1)
+    fs = np.where(scal == 0, 0.0, np.ldexp(1.0 + M / float(1 << sc_man), E - sc_bias)).astype(np.float32)
+    y = (mag.reshape(mag.shape[:-1] + (-1, bs)) * fs[..., None]).astype(np.float32).reshape(mag.shape)
+    return np.where(sg.astype(bool), -y, y).astype(np.float32)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("prec,bias,bs", [(4, 7, 16), (4, 4, 16), (4, 10, 16), (8, 7, 16), (4, 7, 64), (6, 7, 8), (4, 7, 128), (2, 7, 32)])
+def test_packed_sbfp_storage_round_trip(dt, prec, bias, bs):
+    """dmxq_sbfp_unpack(dmxq_sbfp_pack(x)) == the SBFP QDQ cast bit for bit (signs of zeros included); the bytes decode
+    to the oracle's SBFP cast with plain numpy; packed size == Format.bytes_per_elem (SBFP12_16: 0.5625 B/elem)"""
+    sh = f"SBFP<XP[{prec},0](CSN)><FP[0|4|4,{bias}](FN)>{{{bs}}}"
+    f = fmt_from(sh)
+    # magnitudes inside the byte's scaler range for every bias here (bias 10: max scaler exponent 15 - 10 = 5)
+    x = _rand((96, 1024), 300 + prec + bias + bs, spread=3).to(dt)
+    x.view(-1)[::5] = torch.round(x.view(-1)[::5].float() * 16).to(dt) / 16
+    x[5] = 0
+    x[6, ::2] = -0.0
+    x[7] = x[7] * 2.0**-12  # scalers below the smallest normal of the scaler format: flushed to zero, signs survive
+    xd = x.to(DEV)
+    want = ops.cast_chain(xd, [f.stage()], -1)
+    mant, scal, bad = f.pack(xd, return_inexact=True)
+    assert int(bad) == 0
+    nbytes = mant.numel() + scal.numel()
+    assert nbytes == x.numel() * (4 if prec <= 4 else 8) // 8 + x.numel() // bs
+    if prec in (4, 8):
+        assert nbytes == int(f.bytes_per_elem * x.numel())
+    got = f.unpack(mant, scal, dtype=dt)
+    v = torch.int32 if dt == torch.float32 else torch.int16
+    assert torch.equal(got.view(v), want.view(v))
+    dec = _sbfp_decode_numpy(mant, scal, bs, prec, 4, bias)
+    assert_bits_equal(bits(dec), bits(O.cast(x.float().numpy(), sh, -1, tie=O.TIE_AWAY)), "packed bytes vs oracle")
+    if prec <= 4:  # mantissa magnitudes really are (prec-1)-bit integers
+        m = mant.cpu()
+        assert int(torch.maximum(m & 7, (m >> 4) & 7).max()) <= 2 ** (prec - 1) - 1
+
+
+def test_packed_sbfp_reports_blocks_the_bytes_cannot_hold():
+    """non-finite blocks, denormal blocks whose max / 7 underflows, and scalers above the byte's exponent range (bias > 7:
+    the simulated scaler saturates at 2^8, the real E4M4 byte at 2^(15 - bias)) are counted, everything else is exact"""
+    f = fmt_from("SBFP<XP[4,0](CSN)><FP[0|4|4,12](FN)>{16}")
+    x = _rand((8, 256), 77, spread=0) * 2.0**-6
+    x[1, 16:32] *= 2.0**14      # scaler exponent >= 4 > 15 - 12
+    x[2, 3] = float("nan")
+    x[3, 40] = float("inf")
+    x[4, 64:80] = 0
+    x[4, 70] = 1e-45            # max / 7 == 0: the cast passes the denormal through
+    xd = x.to(DEV)
+    mant, scal, bad = f.pack(xd, return_inexact=True)
+    assert int(bad) == 4
+    got = f.unpack(mant, scal).cpu()
+    want = ops.cast_chain(xd, [f.stage()], -1).cpu()
+    ok = torch.ones(8, 16, dtype=torch.bool)
+    ok[1, 1] = ok[2, 0] = ok[3, 2] = ok[4, 4] = False
+    ok = ok.repeat_interleave(16, 1)
+    assert torch.equal(got.view(torch.int32)[ok], want.view(torch.int32)[ok])
+    assert torch.equal(got[2, :16], torch.zeros(16)) and torch.equal(got[4, 64:80], torch.zeros(16))
+    assert int(scal[1, 1]) == 255 and torch.isfinite(got).all()
+    with pytest.raises(RuntimeError, match="unsupported"):
+        fmt_from("SBFP<XP[4,0](CSN)><FP[0|4|4,7](_N)>{16}").pack(xd)       # subnormal-keeping scaler
+    with pytest.raises(RuntimeError, match="unsupported"):
+        fmt_from("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", tie="even").pack(xd)
+
+
 def test_golden_mxfp():
     """MXFP: the reference's own MXFP.cast on CPU vs the CUDA path"""
     z = np.load(os.path.join(ROOT, "tests", "golden", "mxfp_reference.npz"))
