@@ -216,11 +216,12 @@ def llama_shapes(name, layers=None):
     return shapes
 
 
-def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_stats, dtype):
+def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_stats, dtype, packed=False):
     """Whole-model weight cast sharded by parameter / row range: every rank
     materialises its shards (random, shard-local), optionally reduces per-tensor amax with ONE
     batched all-reduce, and casts each shard with one fused kernel.  Timed on the device, max
-    over ranks; value = algorithmic bytes of all ranks / time."""
+    over ranks; value = algorithmic bytes of all ranks / time.  `packed`: write the packed SBFP storage
+    (nibble mantissas + one scaler byte per block, dmxq_sbfp_pack) instead of the dequantised tensor."""
     import torch
 
     from dmx_compressor_b200 import parallel as P
@@ -233,8 +234,14 @@ def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_sta
     for sh in mine:
         cols = shapes[sh.name][1]
         ws.append(torch.randn(sh.row1 - sh.row0, cols, device=dev, dtype=torch.float32, generator=g).mul_(0.02).to(dtype))
-    outs = [torch.empty_like(w) for w in ws]
     from dmx_compressor_b200 import ops
+
+    if packed:
+        outs = [(torch.empty(w.shape[0], w.shape[1] // 2, device=dev, dtype=torch.uint8),
+                 torch.empty(w.shape[0], w.shape[1] // 16, device=dev, dtype=torch.uint8)) for w in ws]
+        inexact = torch.zeros((), device=dev, dtype=torch.int32)
+    else:
+        outs = [torch.empty_like(w) for w in ws]
 
     def run():
         if with_stats:
@@ -242,7 +249,10 @@ def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_sta
             stats = P.shard_stats(plan, rank, ws)
             amax = torch.cat([torch.maximum(-mn, mx).reshape(-1) for mn, mx in stats]).cpu().tolist()  # one host sync
             for w, y, a in zip(ws, outs, amax):
-                ops.cast_chain(w, stages_fn(a), -1, out=y)
+                if packed:
+                    ops.sbfp_pack(w, stages_fn(a)[0], out=y, inexact=inexact)
+                else:
+                    ops.cast_chain(w, stages_fn(a), -1, out=y)
         else:
             st = stages_fn(None)
             for w, y in zip(ws, outs):
@@ -258,19 +268,27 @@ def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_sta
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b)
-    nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
-    t = torch.tensor([ms, float(nbytes)], device=dev, dtype=torch.float64)
+    if packed:
+        nbytes = sum(w.numel() * w.element_size() + m.numel() + sc.numel() for w, (m, sc) in zip(ws, outs))
+    else:
+        nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
+    nelem = sum(w.numel() for w in ws)
+    n_inexact = int(inexact) // 2 if packed else None  # (two runs accumulated)
+    t = torch.tensor([ms, float(nbytes), float(nelem)], device=dev, dtype=torch.float64)
     if dist is not None:
         tm = t.clone()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_max, total = float(tm[0]), float(t[1])
+        ms_max, total, nelem = float(tm[0]), float(t[1]), float(t[2])
         ms_mean = float(t[0]) / world
     else:
         ms_max, total, ms_mean = ms, float(nbytes), ms
     del ws, outs
     torch.cuda.empty_cache()
-    return {"GB/s": round(total / (ms_max * 1e-3) / 1e9, 1), "ms": round(ms_max, 3), "bytes": int(total), "tensors": len(shapes),
+    res = {"Gelem/s": round(nelem / (ms_max * 1e-3) / 1e9, 1)}
+    if packed:
+        res["blocks_not_representable"] = n_inexact
+    return {**res, "GB/s": round(total / (ms_max * 1e-3) / 1e9, 1), "ms": round(ms_max, 3), "bytes": int(total), "tensors": len(shapes),
             "imbalance_max_over_mean_time": round(ms_max / ms_mean, 3), "plan_imbalance": round(P.plan_imbalance(plan, shapes), 3),
             "dtype": str(dtype).split(".")[-1], "layers": layers if layers is not None else LLAMA[model]["layers"]}
 
@@ -532,6 +550,10 @@ def run_ours(args):
         extras["llama3_70b_sbfp12_weight_cast"] = extra_weight_cast(
             dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16)
         extras["llama3_70b_sbfp12_weight_cast"]["note"] = "10 layers per GPU (weak scaling; 80 layers at 8 GPUs), one batched amax all-reduce"
+        # the same, written as packed storage (0.5625 B per element instead of a dequantised bf16 tensor)
+        extras["llama3_70b_sbfp12_packed_storage"] = extra_weight_cast(
+            dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16, packed=True)
+        extras["llama3_70b_sbfp12_packed_storage"]["note"] = "dmxq_sbfp_pack: bf16 in, nibble mantissas + E4M4 scaler byte out (2.5625 B/elem algorithmic)"
         if rank == 0:
             try:
                 extras["cast_sweep"] = extra_sweep(dev)

@@ -247,18 +247,33 @@ def bfp_unpack(mant, exps, block_size=64, precision=8, dtype=torch.float32):
     return y
 
 
-def sbfp_pack(x, stage, return_inexact=False):
+def sbfp_pack(x, stage, return_inexact=False, out=None, inexact=None):
     """-> (mantissas, scalers[, n_inexact]): packed SBFP storage of a contiguous [..., K] tensor (dmxq_sbfp_pack).
     `stage`: the SBFP stage struct (``ScaledBlockFloatingPoint.stage()`` / ``sbfp_stage``).
     mantissas: uint8, sign-magnitude, [..., K/2] (block precision <= 4, two nibbles per byte) or [..., K];
     scalers: uint8 [..., K / block], the scaler's exponent | mantissa fields (0 = zero scaler).
-    n_inexact (device int32 scalar, on request): blocks the bytes cannot hold (see include/dmxq.h); 0 = exact."""
+    n_inexact (device int32 scalar, on request): blocks the bytes cannot hold (see include/dmxq.h); 0 = exact.
+    `out`: optional preallocated (mantissas, scalers) pair of those shapes.  `inexact`: optional existing int32 device
+    counter to ACCUMULATE into (implies return_inexact)."""
     L.require_cuda(x)
     x = x.contiguous()
     K, nib = x.shape[-1], stage.precision <= 4
-    mant = torch.empty(x.shape[:-1] + ((K // 2,) if nib else (K,)), dtype=torch.uint8, device=x.device)
-    scal = torch.empty(x.shape[:-1] + (K // max(stage.block, 1),), dtype=torch.uint8, device=x.device)
-    bad = torch.zeros((), dtype=torch.int32, device=x.device) if return_inexact else None
+    mshape, sshape = x.shape[:-1] + ((K // 2,) if nib else (K,)), x.shape[:-1] + (K // max(stage.block, 1),)
+    if out is not None:
+        mant, scal = out
+        for t, shp, nm in ((mant, mshape, "mantissas"), (scal, sshape, "scalers")):
+            L.require_cuda(t, nm)
+            if t.dtype != torch.uint8 or tuple(t.shape) != tuple(shp) or not t.is_contiguous():
+                raise RuntimeError(f"sbfp_pack: out {nm} must be a contiguous uint8 tensor of shape {tuple(shp)}")
+    else:
+        mant = torch.empty(mshape, dtype=torch.uint8, device=x.device)
+        scal = torch.empty(sshape, dtype=torch.uint8, device=x.device)
+    if inexact is not None:
+        L.require_cuda(inexact, "inexact")
+        if inexact.dtype != torch.int32 or inexact.numel() != 1:
+            raise RuntimeError("sbfp_pack: inexact must be a one-element int32 tensor")
+        return_inexact = True
+    bad = inexact if inexact is not None else (torch.zeros((), dtype=torch.int32, device=x.device) if return_inexact else None)
     vx = L.view(x)
     with _guard(x.device):
         rc = L.lib.dmxq_sbfp_pack(C.byref(vx), mant.data_ptr(), scal.data_ptr(), C.byref(stage), bad.data_ptr() if return_inexact else None,

@@ -210,6 +210,55 @@ def sbfp_cast(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_
     return y
 
 
+def sbfp_pack(x, block_size=16, xp_precision=4, tie=TIE_AWAY, sc_mantissa=4, sc_exponent=4, sc_bias=7):
+    """Packed SBFP storage of a [..., K] fp32 array, blocks along the last dim (the format of include/dmxq.h
+    ``dmxq_sbfp_pack``), restated from the pieces of ScaledBlockFloatingPoint.cast (S/numerical/format.py:453-479):
+    per block ``cmax = max|x| / man_scaling`` (:462-464), mantissa = ``block_format.cast(chunk / cmax)`` (:468), scaler =
+    ``scaler_format.cast(cmax)`` (:469).  Stored: the mantissa as sign-magnitude (sign of x), the scaler as the exponent |
+    mantissa fields of its E<sc_exponent>M<sc_mantissa> value (0 = zero scaler).
+    -> (mantissas uint8, scalers uint8, n_inexact): n_inexact counts blocks the bytes cannot hold."""
+    x = _f32(x)
+    K = x.shape[-1]
+    assert K % block_size == 0
+    man_scaling = np.float32(2 ** (xp_precision - 1) - 1)
+    blk = x.reshape(x.shape[:-1] + (K // block_size, block_size))
+    with np.errstate(all="ignore"):
+        m = np.abs(blk).max(-1, keepdims=True)
+        finite = np.isfinite(blk).all(-1, keepdims=True)
+        cmax = (m / man_scaling).astype(np.float32)
+        on = finite & (cmax > 0)
+        fs = float_cast(np.where(on, cmax, np.float32(0)), sc_mantissa, sc_exponent, sc_bias, True, True, "nearest")
+        q = fixed_cast((blk / np.where(on, cmax, np.float32(1))).astype(np.float32), xp_precision, 0, True, True, "nearest", tie=tie)
+    mag = np.where(on, np.abs(q), 0).astype(np.uint8)
+    sign = (np.signbit(blk) & finite).astype(np.uint8)
+    sh = 23 - sc_mantissa
+    base = (((127 - (sc_bias - 1)) << 23) >> sh) - (1 << sc_mantissa)
+    code = np.where(fs == 0, 0, (fs.view(np.uint32).astype(np.int64) >> sh) - base)
+    code_max = (1 << (sc_exponent + sc_mantissa)) - 1
+    inexact = ~finite | ((m > 0) & ~(cmax > 0)) | (code > code_max)
+    code = np.minimum(code, code_max).astype(np.uint8)
+    if xp_precision <= 4:
+        t = (mag | (sign << 3)).reshape(x.shape[:-1] + (K // 2, 2))
+        mant = (t[..., 0] | (t[..., 1] << 4)).astype(np.uint8)
+    else:
+        mant = (mag | (sign << 7)).reshape(x.shape).astype(np.uint8)
+    return mant, code.reshape(x.shape[:-1] + (K // block_size,)), int(inexact.sum())
+
+
+def sbfp_unpack(mant, scal, block_size=16, xp_precision=4, sc_mantissa=4, sc_bias=7):
+    """dequantise :func:`sbfp_pack` bytes: sign * (magnitude * scaler), the last step of format.py:468-469"""
+    mant, scal = np.asarray(mant, np.uint8), np.asarray(scal, np.uint8).astype(np.int64)
+    if xp_precision <= 4:
+        t = np.stack([mant & 0xF, mant >> 4], -1).reshape(mant.shape[:-1] + (-1,))
+        mag, sg = (t & 7).astype(np.float32), (t >> 3).astype(bool)
+    else:
+        mag, sg = (mant & 0x7F).astype(np.float32), (mant >> 7).astype(bool)
+    E, M = scal >> sc_mantissa, scal & ((1 << sc_mantissa) - 1)
+    fs = np.where(scal == 0, 0.0, np.ldexp(1.0 + M / float(1 << sc_mantissa), E - sc_bias)).astype(np.float32)
+    y = (mag.reshape(mag.shape[:-1] + (-1, block_size)) * fs[..., None]).astype(np.float32).reshape(mag.shape)
+    return np.where(sg, -y, y).astype(np.float32)
+
+
 def mxfp_cast(x, block_dim=-1, block_size=32, mantissa=3, exponent=4):
     """MXFP.cast (S/numerical/format.py:545-564) on an fp32 array."""
     x = _f32(x)

@@ -889,20 +889,6 @@ def test_packed_bfp_storage_round_trip(dt, wl, bs):
         check(got, bits(O.cast(x.numpy(), f"BFP[{wl}|8]{{{bs}}}(SN)", -1)), "packed vs oracle")
 
 
-def _sbfp_decode_numpy(mant, scal, bs, prec, sc_man, sc_bias):
-    """independent CPU decode of the packed SBFP bytes (the format of include/dmxq.h, restated in numpy)"""
-    mant, scal = mant.cpu().numpy(), scal.cpu().numpy().astype(np.int64)
-    if prec <= 4:
-        t = np.stack([mant & 0xF, mant >> 4], -1).reshape(mant.shape[:-1] + (-1,))
-        mag, sg = (t & 7).astype(np.float32), t >> 3
-    else:
-        mag, sg = (mant & 0x7F).astype(np.float32), mant >> 7
-    E, M = scal >> sc_man, scal & ((1 << sc_man) - 1)
-    fs = np.where(scal == 0, 0.0, np.ldexp(1.0 + M / float(1 << sc_man), E - sc_bias)).astype(np.float32)
-    y = (mag.reshape(mag.shape[:-1] + (-1, bs)) * fs[..., None]).astype(np.float32).reshape(mag.shape)
-    return np.where(sg.astype(bool), -y, y).astype(np.float32)
-
-
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("prec,bias,bs", [(4, 7, 16), (4, 4, 16), (4, 10, 16), (8, 7, 16), (4, 7, 64), (6, 7, 8), (4, 7, 128), (2, 7, 32)])
 def test_packed_sbfp_storage_round_trip(dt, prec, bias, bs):
@@ -927,7 +913,11 @@ def test_packed_sbfp_storage_round_trip(dt, prec, bias, bs):
     got = f.unpack(mant, scal, dtype=dt)
     v = torch.int32 if dt == torch.float32 else torch.int16
     assert torch.equal(got.view(v), want.view(v))
-    dec = _sbfp_decode_numpy(mant, scal, bs, prec, 4, bias)
+    # the bytes themselves are the oracle's, and they decode (plain numpy) to the oracle's SBFP cast
+    om, os_, obad = O.sbfp_pack(x.float().numpy(), bs, prec, O.TIE_AWAY, 4, 4, bias)
+    assert obad == 0
+    assert np.array_equal(mant.cpu().numpy(), om) and np.array_equal(scal.cpu().numpy(), os_)
+    dec = O.sbfp_unpack(mant.cpu().numpy(), scal.cpu().numpy(), bs, prec, 4, bias)
     assert_bits_equal(bits(dec), bits(O.cast(x.float().numpy(), sh, -1, tie=O.TIE_AWAY)), "packed bytes vs oracle")
     if prec <= 4:  # mantissa magnitudes really are (prec-1)-bit integers
         m = mant.cpu()
@@ -947,6 +937,8 @@ def test_packed_sbfp_reports_blocks_the_bytes_cannot_hold():
     xd = x.to(DEV)
     mant, scal, bad = f.pack(xd, return_inexact=True)
     assert int(bad) == 4
+    om, os_, obad = O.sbfp_pack(x.numpy(), 16, 4, O.TIE_AWAY, 4, 4, 12)
+    assert obad == 4 and np.array_equal(scal.cpu().numpy(), os_)
     got = f.unpack(mant, scal).cpu()
     want = ops.cast_chain(xd, [f.stage()], -1).cpu()
     ok = torch.ones(8, 16, dtype=torch.bool)
