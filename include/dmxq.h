@@ -193,7 +193,8 @@ int dmxq_bfp_unpack(const void *mantissas, const uint8_t *exponents, const dmxq_
  *                      (1 + M / 2^sc_man) * 2^(E - sc_bias), E >= 1 -- the byte of a real E<sc_exp>M<sc_man> number;
  *   fmt->block mantissas, sign-magnitude (top bit = sign of x, kept on zero results exactly as the simulated cast keeps
  *                      it), 4 bits each for precision <= 4 (two per byte, low nibble first), else 8 bits.
- * SBFP12_16: 4.5 bits per element + the byte = 0.5625 B/elem, the reference's bytes_per_elem.
+ * SBFP12_16: 4 bits per element + one byte per 16 = 0.5625 B/elem (the reference's bytes_per_elem reports 0.5703: it counts
+ * a sign bit for the unsigned scaler, S/numerical/format.py:240-241).
  *   x / y: contiguous [rows, K], K % block == 0, block a power of two in 8..128; block format XP[p,0] clamped, nearest
  *   (half away: the reference's CUDA rule), p in 2..8; scaler format flushing subnormals, sc_exp + sc_man <= 8.
  *   dmxq_sbfp_unpack(dmxq_sbfp_pack(x)) == dmxq_sbfp_qdq(x) bit for bit for every block the byte can hold.  It cannot hold:
