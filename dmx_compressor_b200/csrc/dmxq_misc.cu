@@ -1220,7 +1220,7 @@ template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) s
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 const float a = fabsf(v[j]);
-                const float q = b.rok ? div_by_recip(a, b.cmax, b.rc) : __fdiv_rn(a, b.cmax);
+                const float q = b.rok ? div_by_recip2(a, b.cmax, b.rc, b.rl) : __fdiv_rn(a, b.cmax);
                 const float r = fminf(truncf(__fadd_rz(q, 0.5f)), f.man_scaling);
                 k[j] = (uint32_t)(int)r | ((f2u(v[j]) >> 31) ? SIGN : 0u);
             }

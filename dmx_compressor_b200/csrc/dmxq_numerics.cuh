@@ -324,6 +324,7 @@ struct SbfpBlock {
     float cmax;  // max|x| / man_scaling   (NaN when the block holds a NaN)
     float fs;    // FP_cast(cmax)
     float rc;    // RN(1 / cmax), for the division-free quotient (dmxq_stages.cuh sbfp_elem_fast)
+    float rl;    // ~ 1 / cmax - rc: low part of the reciprocal (div_by_recip2)
     bool on;     // cmax > 0 (false => pass the block through, format.py:467-472)
     bool rok;    // rc usable: cmax well inside the normal range and its significand not all ones
 };
@@ -335,6 +336,7 @@ __device__ __forceinline__ SbfpBlock sbfp_block(uint32_t maxabs_bits, const Sbfp
     b.fs = float_elem_rt(b.cmax, f.sc, 0u);
     b.on = b.cmax > 0.0f;
     b.rc = 0.0f;
+    b.rl = 0.0f;
     b.rok = false;
     return b;
 }

@@ -322,10 +322,11 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                 // (finite data and parameters: no NaN can reach the clamp, so min/max instructions do)
                 const bool div_free = recip_safe(sc) && fabsf(zp) < 0x1p60f && vec_absmax<V>(v) < 0x5D800000u;
                 const float rsc = __frcp_rn(sc);
+                const float rsl = recip_lo(sc, rsc);
                 if (div_free) {
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const float a = roundf(__fadd_rn(div_by_recip(v[j], sc, rsc), zp));
+                        const float a = roundf(__fadd_rn(div_by_recip2(v[j], sc, rsc, rsl), zp));
                         v[j] = __fmul_rn(__fsub_rn(fminf(fmaxf(a, t_min), t_max), zp), sc);
                     }
                 } else {

@@ -1,0 +1,58 @@
+/* CPU restatement of the kernels' division-free quotients (dmx_compressor_b200/csrc/dmxq_stages.cuh div_by_recip /
+ * div_by_recip2), checked against IEEE division.  Test code only: fmaf is the correctly rounded C99 fused multiply-add,
+ * exactly what __fmaf_rn is on the device, so the identity proven here is the one the kernels rely on.
+ *   div_by_recip :  q = a*rb;  two Newton corrections q += (a - q*b)*rb
+ *   div_by_recip2:  q = fma(a, rh, a*rl) with (rh, rl) the high / low parts of 1/b;  one correction
+ * Preconditions (the kernels check them per block / vector): b in (2^-60, 2^60) with a significand that is not all
+ * ones; the comparison is on the full quotient for a >= 2^-100 and on trunc(q + 0.5) -- what the casts consume -- below
+ * (there the residual a - q*b leaves the normal range and the last bit of a quotient < 2^-40 is immaterial).
+ * usage: div_by_recip_check <cases>   -> prints "cases N bad_two_step X bad_hilo Y", exit status 0 iff X == Y == 0 */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static uint64_t s = 88172645463325252ull;
+static inline uint64_t rnd(void) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static inline float div_hilo(float a, float b, float rh, float rl)
+{
+    float q = fmaf(a, rh, a * rl);
+    return fmaf(fmaf(-q, b, a), rh, q);
+}
+static inline float div_two_step(float a, float b, float rb)
+{
+    float q = a * rb;
+    q = fmaf(fmaf(-q, b, a), rb, q);
+    return fmaf(fmaf(-q, b, a), rb, q);
+}
+int main(int argc, char **argv)
+{
+    long n = argc > 1 ? atol(argv[1]) : 20000000L, bad1 = 0, bad2 = 0, cnt = 0;
+    for (long i = 0; i < n; ++i) {
+        uint32_t bm = (uint32_t)rnd() & 0x7FFFFF;
+        if (bm == 0x7FFFFF) continue;
+        float b = u2f(((uint32_t)(67 + (int)(rnd() % 120)) << 23) | bm); /* 2^-60 .. 2^60 */
+        float rh = 1.0f / b, rl = fmaf(-b, rh, 1.0f) * rh;
+        float a;
+        switch (i & 3) {
+        case 0: a = b * (float)((rnd() % 7000001) / 1000000.0); break;                       /* anywhere in [0, 7b]      */
+        case 1: a = u2f(f2u(b * ((float)(rnd() % 8) + 0.5f)) + (uint32_t)((int)(rnd() % 9) - 4)); break; /* around the ties */
+        case 2: a = u2f(f2u(b * (float)((rnd() % 7000001) / 1000000.0)) & 0xFFFF0000u); break; /* bf16 significands        */
+        default: a = u2f((uint32_t)rnd() & 0x7FFFFFFF); if (!(a < 7.1f * b)) a = b * 0.3f; break; /* any exponent below    */
+        }
+        if (!(a >= 0) || isinf(a)) continue;
+        const float want = a / b, g2 = div_hilo(a, b, rh, rl), g1 = div_two_step(a, b, rh);
+        ++cnt;
+        if (a < 0x1p-100f) {
+            if (truncf(g1 + 0.5f) != truncf(want + 0.5f)) ++bad1;
+            if (truncf(g2 + 0.5f) != truncf(want + 0.5f)) ++bad2;
+            continue;
+        }
+        if (f2u(g1) != f2u(want)) ++bad1;
+        if (f2u(g2) != f2u(want)) ++bad2;
+    }
+    printf("cases %ld bad_two_step %ld bad_hilo %ld\n", cnt, bad1, bad2);
+    return (bad1 || bad2) ? 1 : 0;
+}
