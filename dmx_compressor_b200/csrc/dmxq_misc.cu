@@ -136,11 +136,12 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_const
 }
 
 // The affine wrap on one value: x / sc + zp -> round half away -> clamp -> (q - zp) * sc, every step a separately
-// rounded fp32 operation (S/numerical/cast.py:279-296 around fixed_point_quantize_nearest_cuda).  `rsc` = RN(1 / sc);
+// rounded fp32 operation (S/numerical/cast.py:279-296 around fixed_point_quantize_nearest_cuda).  `rsc`, `rsl` = RN(1 / sc)
+// and its low part (div_by_recip2);
 // div_free: the exact reciprocal-based quotient may be used (scale and data well inside the normal range).
-__device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, float rsc, bool div_free, const FixedFmt &xf, bool scaled)
+__device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, float rsc, float rsl, bool div_free, const FixedFmt &xf, bool scaled)
 {
-    float a = __fadd_rn(div_free ? div_by_recip(x, sc, rsc) : __fdiv_rn(x, sc), zp);
+    float a = __fadd_rn(div_free ? div_by_recip2(x, sc, rsc, rsl) : __fdiv_rn(x, sc), zp);
     if (scaled) a = __fmul_rn(a, xf.up);
     a = roundf(a);
     if (scaled) a = __fmul_rn(a, xf.down);
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
         raw[u] = g < nvec ? ldg_stream(x + g * V) : make_uint4(0u, 0u, 0u, 0u);
     }
     int64_t q_cur = -1;
-    float sc = 1.0f, zp = 0.0f, rsc = 1.0f;
+    float sc = 1.0f, zp = 0.0f, rsc = 1.0f, rsl = 0.0f;
     bool sc_ok = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
             sc = __ldg(p.scale + q);
             zp = __ldg(p.zp + q);
             rsc = __frcp_rn(sc);
+            rsl = recip_lo(sc, rsc);
             sc_ok = recip_safe(sc) && fabsf(zp) < 0x1p60f;
         }
         float v[V];
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
         if (fast) {
             const bool div_free = sc_ok && m_in < 0x5D800000u;
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc, zp, rsc, div_free, p.xf, scaled);
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc, zp, rsc, rsl, div_free, p.xf, scaled);
         } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
     const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * V;
     if (c0 >= p.C) return;
     const bool scaled = p.xf.up != 1.0f;
-    float sc[V], zp[V], rsc[V];
+    float sc[V], zp[V], rsc[V], rsl[V];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
         sc[j] = __ldg(p.scale + q);
         zp[j] = __ldg(p.zp + q);
         rsc[j] = __frcp_rn(sc[j]);
+        rsl[j] = recip_lo(sc[j], rsc[j]);
         ok = ok && recip_safe(sc[j]) && fabsf(zp[j]) < 0x1p60f;
     }
     const int64_t step = (int64_t)gridDim.y * W;
@@ -245,7 +248,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
             const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (also fills v: keep it out of the && chain)
             const bool div_free = ok && m_in < 0x5D800000u;
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc[j], zp[j], rsc[j], div_free, p.xf, scaled);
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc[j], zp[j], rsc[j], rsl[j], div_free, p.xf, scaled);
             VecIO<Tout>::template store<V>(y + (r0 + u * step) * p.C + c0, v);
         }
     }
