@@ -417,6 +417,9 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         else if (chain.n == 1 && chain.st[0].kind == ST_NM) kind = 8;  // K_NM
         else if (chain.n == 1 && chain.st[0].kind == ST_MXFP) kind = 9;  // K_MXFP
         else if (chain.n == 1 && chain.st[0].kind == ST_BFP && chain.st[0].mode == R_NEAREST && chain.st[0].asym) kind = 10;  // K_BFP_ASYM
+        // 2:4 -> BFP on a bf16 / fp16 tensor (whole-model weight casts): the straight-line specialisation
+        if (kind == 5 && x->dtype == y->dtype && x->dtype != DMXQ_F32 && chain.st[0].block == 4 && chain.st[0].n_prune == 2 &&
+            chain.st[1].fast && chain.st[1].fast16) kind = 12;  // K_NM24_BFP
         if (qscale) {
             if (kind != 7) return kNeedFallback;
             p.qscale = qscale; p.qzp = qzp;

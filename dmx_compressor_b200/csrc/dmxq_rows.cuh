@@ -24,12 +24,13 @@
 //   K_MXFP       [MXFP]                                       OCP-MX style power-of-two block scale + low-bit float elements
 //   K_BFP_ASYM   [BFP nearest, asymmetric mantissa]            BFP16A / BFP12A (kept apart from K_BFP: it needs a copy of the inputs)
 //   K_BFP_STOCH  [BFP stochastic, external random tensor, FLAT]  the reference's default rounding; random words loaded with the data
+//   K_NM24_BFP   [2:4 with score |x| -> BFP n.s.] on a bf16 / fp16 tensor: the whole-model weight cast of config #4, straight-line
 #pragma once
 #include "dmxq_stages.cuh"
 
 namespace dmxq {
 
-enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_BFP_ASYM = 10, K_BFP_STOCH = 11, K_COUNT = 12 };
+enum : int { K_AUX = 0, K_CHAIN = 1, K_BFP = 2, K_FLOAT = 3, K_FLOAT_BFP = 4, K_NM_BFP = 5, K_SBFP = 6, K_FIXED = 7, K_NM = 8, K_MXFP = 9, K_BFP_ASYM = 10, K_BFP_STOCH = 11, K_NM24_BFP = 12, K_COUNT = 13 };
 
 struct RowAddr {
     int64_t xo, yo, so, mo, ro;
@@ -102,6 +103,13 @@ template <int V> __device__ __forceinline__ void float_fast_apply(float (&v)[V],
     }
 #pragma unroll
     for (int j = 0; j < V; ++j) v[j] = q[j];
+}
+
+// fp32 bit pattern of a non-negative 16-bit magnitude pattern
+template <typename T> __device__ __forceinline__ uint32_t widen16(uint32_t m16)
+{
+    if constexpr (std::is_same<T, __nv_bfloat16>::value) return m16 << 16;
+    else return f2u(__half2float(__ushort_as_half((unsigned short)m16)));
 }
 
 template <typename Tin, typename Tout, bool FLAT, int KIND>
@@ -275,6 +283,56 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             if (!pruned) nm_stage<V>(v, sn, lane, nullptr, nullptr, valid[u]);  // (pairwise ranks measured faster here than the packed-key network)
             const uint32_t m_thr = m_in > 0x7F800000u ? vec_absmax<V>(v) : m_in;  // NaN: whatever the pruning left
             bfp_ns_apply<V, SRC16>(v, lanes_max(m_thr, st.block / V), st);
+        } else if (KIND == K_NM24_BFP) {
+            // 2:4 (score |x|) -> symmetric nearest BFP on a 16-bit tensor, everything the general K_NM_BFP path decides at run
+            // time fixed by the dispatcher (M = 4, two pruned, BFP fast16 form).  One sorting network per group serves both
+            // stages: the threshold key selects the survivors AND the largest key is the group's max|x| (it always survives),
+            // so no separate abs-max pass exists.  The BFP rounding runs on the unpruned values and the pruned ones are
+            // zeroed afterwards: BFP of a pruned +-0 is (+-0 + C) - C = +0 in the reference too.
+            if constexpr (SAME16) {
+                const StageDev &st = p.chain.st[1];
+                constexpr uint32_t kInf16 = std::is_same<Tin, __nv_bfloat16>::value ? 0x7F80u : 0x7C00u;
+                const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+                uint32_t k[8], thr[2], gmax[2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {  // keys as in nm4_keep_raw16: magnitude pattern << 17 | index
+                    k[4 * g + 0] = imad(w[2 * g], 0x20000u, 0u);
+                    k[4 * g + 1] = imad(w[2 * g] & 0x7FFF0000u, 2u, 1u);
+                    k[4 * g + 2] = imad(w[2 * g + 1], 0x20000u, 2u);
+                    k[4 * g + 3] = imad(w[2 * g + 1] & 0x7FFF0000u, 2u, 3u);
+                    const uint32_t lo1 = min(k[4 * g], k[4 * g + 1]), hi1 = max(k[4 * g], k[4 * g + 1]);
+                    const uint32_t lo2 = min(k[4 * g + 2], k[4 * g + 3]), hi2 = max(k[4 * g + 2], k[4 * g + 3]);
+                    thr[g] = __vimax3_u32(min(hi1, hi2), lo1, lo2);  // third smallest key: it and everything above survive
+                    gmax[g] = max(hi1, hi2);
+                }
+                const int lanes = st.block / V;
+                const uint32_t mv16 = max(gmax[0], gmax[1]) >> 17;  // 15-bit magnitude pattern of this vector's max|x|
+                const uint32_t m16 = lanes == 8 ? lanes_max_n<8>(mv16) : lanes_max(mv16, lanes);  // ... of the block's
+                VecIO<Tin>::unpack(raw[u], v);
+                if (__all_sync(0xFFFFFFFFu, m16 < kInf16 && bfp_fast_ok(widen16<Tin>(m16)))) {
+                    const BfpFast b = bfp_fast_block(widen16<Tin>(m16), st.wl);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
+                    if (b.clamp) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+                    }
+#pragma unroll
+                    for (int j = 0; j < V; ++j) v[j] = k[j] >= thr[j >> 2] ? v[j] : 0.0f;
+                } else {
+                    // some block of this warp is denormal / huge / non-finite: the whole warp (the branch is warp-uniform, so the
+                    // shuffles below stay convergent) runs K_NM_BFP's general sequence, which is bit-identical for ordinary blocks
+                    const StageDev &sn = p.chain.st[0];
+                    if (mv16 < kInf16) {
+#pragma unroll
+                        for (int j = 0; j < V; ++j) v[j] = k[j] >= thr[j >> 2] ? v[j] : __fmul_rn(v[j], 0.0f);  // x * mask (finite x)
+                    } else {
+                        nm_stage<V>(v, sn, lane, nullptr, nullptr, valid[u]);
+                    }
+                    const uint32_t m_thr = mv16 > kInf16 ? vec_absmax<V>(v) : widen16<Tin>(mv16);  // NaN: whatever the pruning left
+                    bfp_ns_apply<V, true>(v, lanes_max(m_thr, lanes), st);
+                }
+            }
         } else if (KIND == K_NM) {
             const StageDev &sn = p.chain.st[0];
             bool pruned = false;
