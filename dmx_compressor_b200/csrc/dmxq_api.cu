@@ -142,6 +142,8 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         if (d.sb.sc.mode == R_STOCHASTIC) return fail(DMXQ_ERR_UNSUPPORTED, "stochastic SBFP scaler format is not supported");
         d.sb.man_scaling = (float)((1 << (s.precision - 1)) - 1);
         d.sb.inv_man = 1.0f / d.sb.man_scaling;
+        d.sb.no_clamp = !d.sb.xp.clamp || (d.sb.xp.t_max >= d.sb.man_scaling && d.sb.xp.t_min <= -d.sb.man_scaling);
+        d.sb.sc_fast = d.sb.sc.mode == R_NEAREST && d.sb.sc.flush && (!d.sb.sc.fp16_flush || d.sb.sc.min_exp >= -14);
         return DMXQ_OK;
     }
     case DMXQ_STAGE_FLOAT:

@@ -318,6 +318,8 @@ struct SbfpFmt {
     FloatFmt sc;        // scaler FloatingPoint format
     float man_scaling;  // 2^(p-1) - 1
     float inv_man;      // RN(1 / man_scaling)
+    int no_clamp;       // the XP clamp cannot trigger on |x| <= block max (host-decided: !clamp || range covers +-man_scaling)
+    int sc_fast;        // scaler cast = float_elem_flush_nearest (nearest, flushing; host-decided)
 };
 
 struct SbfpBlock {

@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                     const BfpFast b = bfp_fast_block(widen16<Tin>(m16), st.wl);
 #pragma unroll
                     for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
-                    if (b.clamp) {
+                    if (b.clamp) {  // (an unconditional clamp for small wl, where most warps hold such a block, measured slower)
 #pragma unroll
                         for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
                     }
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             const float zp = p.qzp ? __ldg(p.qzp) : st.zp;
             const bool unit = sc == 1.0f, scaled = st.xf.up != 1.0f;
             const float t_min = st.xf.t_min, t_max = st.xf.t_max;
-            VecIO<Tin>::unpack(raw[u], v);
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (packed on 16-bit sources; unused -- and dropped -- outside the calibrated branch)
             // straight-line variants for the shapes that occur (the flags are kernel-uniform)
             if (!wrap && !scaled && st.xf.clamp) {  // INT8 / INT4 with unit scale
 #pragma unroll
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
                 // x / sc, correctly rounded: reciprocal + two FMA refinements when scale and data are well inside the
                 // normal range (a -0 quotient comes out as +0, which the "+ zp" produces anyway)
                 // (finite data and parameters: no NaN can reach the clamp, so min/max instructions do)
-                const bool div_free = recip_safe(sc) && fabsf(zp) < 0x1p60f && vec_absmax<V>(v) < 0x5D800000u;
+                const bool div_free = recip_safe(sc) && fabsf(zp) < 0x1p60f && m_in < 0x5D800000u;
                 const float rsc = __frcp_rn(sc);
                 const float rsl = recip_lo(sc, rsc);
                 if (div_free) {

@@ -169,7 +169,7 @@ __device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const S
     b.cmax = (m > 0x1p-60f && m < 0x1p60f) ? div_by_recip(m, f.man_scaling, f.inv_man) : __fdiv_rn(m, f.man_scaling);
     // scaler cast: cmax >= 0 (or NaN, in which case the block passes through and fs is unused), so the
     // unsigned scaler formats of the SBFP aliases reduce to the signed nearest+flush fast path
-    if (f.sc.mode == R_NEAREST && f.sc.flush && (!f.sc.fp16_flush || f.sc.min_exp >= -14)) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
+    if (f.sc_fast) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
     else b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
     b.on = b.cmax > 0.0f;
     b.rok = recip_safe(b.cmax);
@@ -194,8 +194,7 @@ __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, con
 template <int V> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const SbfpBlock &b, const SbfpFmt &f)
 {
     if (!b.on) return;  // all-zero (or NaN) block: passes through
-    const bool no_clamp = !f.xp.clamp || (f.xp.t_max >= f.man_scaling && f.xp.t_min <= -f.man_scaling);
-    if (b.rok && no_clamp) {
+    if (b.rok && f.no_clamp) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float a = fabsf(v[j]);

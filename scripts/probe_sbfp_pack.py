@@ -19,4 +19,12 @@ for dt in (torch.float32, torch.bfloat16):
     report(f"SBFP12_16 pack -> nibbles + scaler byte {dt}", n * es + packed, lambda: ops.sbfp_pack(x, st))
     m, s = ops.sbfp_pack(x, st)
     report(f"SBFP12_16 unpack {dt}", n * es + packed, lambda: ops.sbfp_unpack(m, s, st, dtype=dt))
+    sc, zp = torch.full((1,), 0.037, device=dev), torch.full((1,), 3.0, device=dev)
+    report(f"INT8 calibrated (device scale, zero-point) {dt}", 2 * n * es, lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=sc, zero_point=zp, out=y))
+    xc = x.view(-1, 4096)[:16384]
+    yc = torch.empty_like(xc)
+    scc, zpc = torch.rand(4096, device=dev) * 0.05 + 0.01, torch.zeros(4096, device=dev)
+    scr, zpr = torch.rand(16384, device=dev) * 0.05 + 0.01, torch.zeros(16384, device=dev)
+    report(f"INT8 per-column qparams [16384,4096] {dt}", 2 * xc.numel() * es, lambda: ops.fixed_qdq(xc, 8, 0, True, True, "nearest", scale=scc, zero_point=zpc, ch_axis=1, out=yc))
+    report(f"INT8 per-row qparams [16384,4096] {dt}", 2 * xc.numel() * es, lambda: ops.fixed_qdq(xc, 8, 0, True, True, "nearest", scale=scr, zero_point=zpr, ch_axis=0, out=yc))
     del x, y, m, s
