@@ -139,9 +139,10 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_const
 // rounded fp32 operation (S/numerical/cast.py:279-296 around fixed_point_quantize_nearest_cuda).  `rsc`, `rsl` = RN(1 / sc)
 // and its low part (div_by_recip2);
 // div_free: the exact reciprocal-based quotient may be used (scale and data well inside the normal range).
+template <bool HILO = true>
 __device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, float rsc, float rsl, bool div_free, const FixedFmt &xf, bool scaled)
 {
-    float a = __fadd_rn(div_free ? div_by_recip2(x, sc, rsc, rsl) : __fdiv_rn(x, sc), zp);
+    float a = __fadd_rn(div_free ? (HILO ? div_by_recip2(x, sc, rsc, rsl) : div_by_recip(x, sc, rsc)) : __fdiv_rn(x, sc), zp);
     if (scaled) a = __fmul_rn(a, xf.up);
     a = roundf(a);
     if (scaled) a = __fmul_rn(a, xf.down);
@@ -169,38 +170,43 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
     const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
     const bool fast = p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY, scaled = p.xf.up != 1.0f;
     uint4 raw[U];
+    float scv[U], zpv[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
+    for (int u = 0; u < U; ++u) {  // all loads first -- the data AND its quantisation parameters (a dependent load per channel
+                                   // change in the compute phase left the kernel latency-bound)
         const int64_t g = g0 + (int64_t)u * kThreads;
         raw[u] = g < nvec ? ldg_stream(x + g * V) : make_uint4(0u, 0u, 0u, 0u);
+        int64_t q = 0;
+        if (p.nq != 1 && g < nvec) {
+            if (nvec <= 0x7FFFFFFFll) {  // multiply-high divisions
+                const uint32_t t = dcvec.div((uint32_t)g);
+                q = dgvec.div(t - dC.div(t) * dC.d);
+            } else {
+                q = ((g / cvec) % p.C) / gvec;
+            }
+            q = min(q, p.nq - 1);
+        }
+        scv[u] = __ldg(p.scale + q);
+        zpv[u] = __ldg(p.zp + q);
     }
-    int64_t q_cur = -1;
-    float sc = 1.0f, zp = 0.0f, rsc = 1.0f, rsl = 0.0f;
-    bool sc_ok = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const int64_t g = g0 + (int64_t)u * kThreads;
         if (g >= nvec) continue;
-        int64_t q;
-        if (nvec <= 0x7FFFFFFFll) {  // multiply-high divisions
-            const uint32_t t = dcvec.div((uint32_t)g);
-            q = dgvec.div(t - dC.div(t) * dC.d);
-        } else {
-            q = ((g / cvec) % p.C) / gvec;
-        }
-        q = p.nq == 1 ? 0 : min(q, p.nq - 1);
-        if (q != q_cur) {  // (neighbouring vectors mostly share their channel: parameters are refreshed on change only)
-            q_cur = q;
-            sc = __ldg(p.scale + q);
-            zp = __ldg(p.zp + q);
-            rsc = __frcp_rn(sc);
-            rsl = recip_lo(sc, rsc);
-            sc_ok = recip_safe(sc) && fabsf(zp) < 0x1p60f;
-        }
+        const float sc = scv[u], zp = zpv[u];
+        const float rsc = __frcp_rn(sc), rsl = recip_lo(sc, rsc);
+        const bool sc_ok = recip_safe(sc) && fabsf(zp) < 0x1p60f;
         float v[V];
         const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
-        if (fast) {
-            const bool div_free = sc_ok && m_in < 0x5D800000u;
+        const bool div_free = sc_ok && m_in < 0x5D800000u;
+        if (fast && div_free && !scaled && p.xf.clamp) {  // INT8 / INT4 with calibrated parameters: the straight-line form
+            const float t_min = p.xf.t_min, t_max = p.xf.t_max;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float a = roundf(__fadd_rn(div_by_recip2(v[j], sc, rsc, rsl), zp));
+                v[j] = __fmul_rn(__fsub_rn(fminf(fmaxf(a, t_min), t_max), zp), sc);
+            }
+        } else if (fast) {
 #pragma unroll
             for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc, zp, rsc, rsl, div_free, p.xf, scaled);
         } else {
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
     const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * V;
     if (c0 >= p.C) return;
     const bool scaled = p.xf.up != 1.0f;
-    float sc[V], zp[V], rsc[V], rsl[V];
+    float sc[V], zp[V], rsc[V];  // (no low reciprocal parts here: V more registers cost the fp32 kernel a resident CTA, 4.8 -> 4.1 TB/s)
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -233,7 +239,6 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
         sc[j] = __ldg(p.scale + q);
         zp[j] = __ldg(p.zp + q);
         rsc[j] = __frcp_rn(sc[j]);
-        rsl[j] = recip_lo(sc[j], rsc[j]);
         ok = ok && recip_safe(sc[j]) && fabsf(zp[j]) < 0x1p60f;
     }
     const int64_t step = (int64_t)gridDim.y * W;
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
             const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (also fills v: keep it out of the && chain)
             const bool div_free = ok && m_in < 0x5D800000u;
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc[j], zp[j], rsc[j], rsl[j], div_free, p.xf, scaled);
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away<false>(v[j], sc[j], zp[j], rsc[j], 0.0f, div_free, p.xf, scaled);
             VecIO<Tout>::template store<V>(y + (r0 + u * step) * p.C + c0, v);
         }
     }
