@@ -36,4 +36,9 @@ ops.bfp_unpack(_m, _e, 64, 8, dtype=torch.float32)                      # 19 unp
 sc = torch.rand(4096, device=dev) * 0.05 + 0.01
 ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=sc, zero_point=torch.zeros(4096, device=dev), ch_axis=1, out=y)   # 20 INT8 per column
 ops.minmax(x, 1)                                                        # 21 per-column amin / amax
+_st = Format.from_shorthand("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}").stage()
+_pm, _ps = ops.sbfp_pack(xb, _st)                                       # 22 packed SBFP12_16 storage of a bf16 tensor
+ops.sbfp_unpack(_pm, _ps, _st, dtype=torch.bfloat16)                    # 23 unpack
+scr = torch.rand(n // 4096, device=dev) * 0.05 + 0.01
+ops.fixed_qdq(xb, 8, 0, True, True, "nearest", scale=scr, zero_point=torch.zeros(n // 4096, device=dev), ch_axis=0, out=yb)  # 24 INT8 per row, bf16
 torch.cuda.synchronize()
