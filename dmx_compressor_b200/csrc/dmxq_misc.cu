@@ -1194,24 +1194,31 @@ struct SbfpPackFmt {
     int nibble;          // mantissas in 4 bits (precision <= 4) or 8
 };
 
-template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) sbfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ scalers, unsigned int *__restrict__ n_inexact, int64_t n_vec, int lanes, int lshift, const __grid_constant__ SbfpPackFmt pf)
+// VPB = 0: a block spans `lanes` neighbouring lanes (shuffle reduction).  VPB = 2 / 4: a block is VPB consecutive 16-byte
+// vectors and ONE thread owns it (still whole 32- / 64-byte runs per lane), so the block header -- max / man_scaling, its
+// scaler cast, the reciprocal pair -- is derived once per block instead of once per lane, and no shuffle is needed.
+template <typename T, bool NIBBLE, int VPB> __global__ void __launch_bounds__(kThreads) sbfp_pack_kernel(const T *__restrict__ x, uint8_t *__restrict__ mant, uint8_t *__restrict__ scalers, unsigned int *__restrict__ n_inexact, int64_t n_vec, int lanes, int lshift, const __grid_constant__ SbfpPackFmt pf)
 {
     constexpr int V = VecIO<T>::V;
     constexpr int U = 4;
+    constexpr int W = VPB ? VPB : 1;  // vectors per header
     constexpr uint32_t SIGN = NIBBLE ? 0x8u : 0x80u;
     const SbfpFmt &f = pf.f;
-    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const int64_t cta0 = (int64_t)blockIdx.x * (kThreads * U);
+    int64_t gi[U];
     uint4 raw[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        int64_t g = g0 + (int64_t)u * kThreads;
-        raw[u] = g < n_vec ? ldg_stream(x + g * V) : make_uint4(0, 0, 0, 0);
+        gi[u] = VPB ? cta0 + (int64_t)(u / W) * (kThreads * W) + (int64_t)threadIdx.x * W + (u % W) : cta0 + (int64_t)u * kThreads + threadIdx.x;
+        raw[u] = gi[u] < n_vec ? ldg_stream(x + gi[u] * V) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int64_t g = g0 + (int64_t)u * kThreads;
-        float v[V];
-        const uint32_t m = lanes_max(unpack_absmax<T>(raw[u], v), lanes);
+    for (int b0 = 0; b0 < U; b0 += W) {
+        float v[W][V];
+        uint32_t m = 0u;
+#pragma unroll
+        for (int t = 0; t < W; ++t) m = max(m, unpack_absmax<T>(raw[b0 + t], v[t]));
+        if (!VPB) m = lanes_max(m, lanes);
         const SbfpBlock b = sbfp_block_ol(m, f);
         const bool finite = m < 0x7F800000u;
         // not representable: non-finite blocks, blocks so small that max / man_scaling underflows to zero (the cast passes
@@ -1223,36 +1230,40 @@ template <typename T, bool NIBBLE> __global__ void __launch_bounds__(kThreads) s
             code = (f2u(b.fs) >> f.sc.sh) - pf.base_code;
             if (code > pf.code_max) { code = pf.code_max; exact = false; }
         }
-        uint32_t k[V];
-        if (finite && b.on) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const float a = fabsf(v[j]);
-                const float q = b.rok ? div_by_recip2(a, b.cmax, b.rc, b.rl) : __fdiv_rn(a, b.cmax);
-                const float r = fminf(truncf(__fadd_rz(q, 0.5f)), f.man_scaling);
-                k[j] = (uint32_t)(int)r | ((f2u(v[j]) >> 31) ? SIGN : 0u);
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) k[j] = (finite && (f2u(v[j]) >> 31)) ? SIGN : 0u;  // a zero block keeps its signs
-        }
-        if (g >= n_vec) continue;
-        if ((threadIdx.x & (lanes - 1)) == 0) {
-            scalers[g >> lshift] = (uint8_t)code;
+        if (gi[b0] < n_vec && (VPB || (threadIdx.x & (lanes - 1)) == 0)) {  // (lanes is a power of two)
+            scalers[gi[b0] >> lshift] = (uint8_t)code;
             if (!exact && n_inexact) atomicAdd(n_inexact, 1u);
         }
-        if (NIBBLE) {
-            uint32_t acc = 0;
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc |= k[j] << (4 * j);
-            if (V == 8) reinterpret_cast<uint32_t *>(mant)[g] = acc;
-            else reinterpret_cast<uint16_t *>(mant)[g] = (uint16_t)acc;
-        } else {
-            uint32_t w[2] = {0u, 0u};
+        for (int t = 0; t < W; ++t) {
+            const int64_t g = gi[b0 + t];
+            uint32_t k[V];
+            if (finite && b.on) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) w[j / 4] |= k[j] << (8 * (j & 3));
-            if (V == 8) reinterpret_cast<uint2 *>(mant)[g] = make_uint2(w[0], w[1]);
-            else reinterpret_cast<uint32_t *>(mant)[g] = w[0];
+                for (int j = 0; j < V; ++j) {
+                    const float a = fabsf(v[t][j]);
+                    const float q = b.rok ? div_by_recip2(a, b.cmax, b.rc, b.rl) : __fdiv_rn(a, b.cmax);
+                    const float r = fminf(truncf(__fadd_rz(q, 0.5f)), f.man_scaling);
+                    k[j] = (uint32_t)(int)r | ((f2u(v[t][j]) >> 31) ? SIGN : 0u);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) k[j] = (finite && (f2u(v[t][j]) >> 31)) ? SIGN : 0u;  // a zero block keeps its signs
+            }
+            if (g >= n_vec) continue;
+            if (NIBBLE) {
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc |= k[j] << (4 * j);
+                if (V == 8) reinterpret_cast<uint32_t *>(mant)[g] = acc;
+                else reinterpret_cast<uint16_t *>(mant)[g] = (uint16_t)acc;
+            } else {
+                uint32_t w[2] = {0u, 0u};
+#pragma unroll
+                for (int j = 0; j < V; ++j) w[j / 4] |= k[j] << (8 * (j & 3));
+                if (V == 8) reinterpret_cast<uint2 *>(mant)[g] = make_uint2(w[0], w[1]);
+                else reinterpret_cast<uint32_t *>(mant)[g] = w[0];
+            }
         }
     }
 }
@@ -1311,10 +1322,14 @@ cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers
     pf.code_max = (1u << (sc_exp + sc_man)) - 1u;
     pf.nibble = f.man_scaling <= 7.0f;
     uint8_t *m8 = static_cast<uint8_t *>(mant);
-#define DMXQ_PACK(T) do { if (pf.nibble) sbfp_pack_kernel<T, true><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, scalers, n_inexact, n_vec, B / V, log2_pow2(B / V), pf); \
-                          else sbfp_pack_kernel<T, false><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, scalers, n_inexact, n_vec, B / V, log2_pow2(B / V), pf); } while (0)
+    const int vpb = (B / V == 2 || B / V == 4) ? B / V : 0;  // a thread owns whole blocks (SBFP12_16: 4 fp32 / 2 sixteen-bit vectors)
+#define DMXQ_PACK_V(T, NIB, VPB) sbfp_pack_kernel<T, NIB, VPB><<<(unsigned)grid, kThreads, 0, s>>>(static_cast<const T *>(x), m8, scalers, n_inexact, n_vec, B / V, log2_pow2(B / V), pf)
+#define DMXQ_PACK_N(T, NIB) do { if (vpb == 2) DMXQ_PACK_V(T, NIB, 2); else if (vpb == 4) DMXQ_PACK_V(T, NIB, 4); else DMXQ_PACK_V(T, NIB, 0); } while (0)
+#define DMXQ_PACK(T) do { if (pf.nibble) DMXQ_PACK_N(T, true); else DMXQ_PACK_N(T, false); } while (0)
     if (dt == 0) DMXQ_PACK(float); else if (dt == 1) DMXQ_PACK(__nv_bfloat16); else DMXQ_PACK(__half);
 #undef DMXQ_PACK
+#undef DMXQ_PACK_N
+#undef DMXQ_PACK_V
     count_launch();
     return cudaGetLastError();
 }
