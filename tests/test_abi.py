@@ -73,6 +73,34 @@ def test_no_cpu_fallback():
                  lambda: quant.fixed_point_quantize(x, 8, 0, rounding="nearest")):
         with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
             call()
+    # packed storage too: no host encoder hides behind the CUDA one
+    bfp, sbfp = Format.from_shorthand("BFP[8|8]{64}(SN)"), Format.from_shorthand("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}")
+    for call in (lambda: bfp.pack(x), lambda: sbfp.pack(x), lambda: sbfp.unpack(torch.zeros(4, 32, dtype=torch.uint8), torch.zeros(4, 4, dtype=torch.uint8))):
+        with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+            call()
+
+
+def test_packed_sbfp_argument_checks_without_a_gpu():
+    """dmxq_sbfp_pack validates the format description before anything touches the device"""
+    from dmx_compressor_b200 import _lib as L
+    from dmx_compressor_b200 import ops
+    import ctypes as C
+
+    v = L.view(torch.zeros(4, 64))
+    buf = (C.c_uint8 * 512)()
+    ok = ops.sbfp_stage(16, 4, True, "nearest", L.TIE_AWAY, 4, 4, 7, True, True, False, "nearest")
+    assert L.lib.dmxq_sbfp_pack(C.byref(v), buf, buf, None, None, None) == -1                      # null format
+    bad = [ops.sbfp_stage(16, 4, True, "nearest", L.TIE_EVEN, 4, 4, 7, True, True, False, "nearest"),  # CPU tie rule
+           ops.sbfp_stage(16, 4, True, "nearest", L.TIE_AWAY, 4, 4, 7, False, True, False, "nearest"),  # subnormal-keeping scaler
+           ops.sbfp_stage(16, 4, True, "nearest", L.TIE_AWAY, 7, 4, 7, True, True, False, "nearest"),   # 11-bit scaler
+           ops.sbfp_stage(12, 4, True, "nearest", L.TIE_AWAY, 4, 4, 7, True, True, False, "nearest"),   # block not a power of two
+           ops.sbfp_stage(16, 4, False, "nearest", L.TIE_AWAY, 4, 4, 7, True, True, False, "nearest")]  # unclamped block format
+    for st in bad:
+        assert L.lib.dmxq_sbfp_pack(C.byref(v), buf, buf, C.byref(st), None, None) == -2, L.lib.dmxq_last_error()
+    vr = L.view(torch.zeros(4, 72))
+    assert L.lib.dmxq_sbfp_pack(C.byref(vr), buf, buf, C.byref(ok), None, None) == -1              # K % block != 0
+    ve = L.view(torch.zeros(0, 64))
+    assert L.lib.dmxq_sbfp_pack(C.byref(ve), buf, buf, C.byref(ok), None, None) == 0               # empty: nothing to do
 
 
 SHORTHANDS = ["SAME", "XP[8,0](CSN)", "XP[4,0](CSN)", "XP[8,+4](C_U)", "XP[8,-2](_SD)", "FP[1|5|10,15](FN)", "FP[1|8|7,127](FN)",
