@@ -4,7 +4,7 @@
  *   div_by_recip :  q = a*rb;  two Newton corrections q += (a - q*b)*rb
  *   div_by_recip2:  q = fma(a, rh, a*rl) with (rh, rl) the high / low parts of 1/b;  one correction
  * Preconditions (the kernels check them per block / vector): b in (2^-60, 2^60) with a significand that is not all
- * ones; the comparison is on the full quotient for a >= 2^-100 and on trunc(q + 0.5) -- what the casts consume -- below
+ * ones; the comparison is on the full quotient for |a| >= 2^-100 and on round-half-away(q) -- what the casts consume -- below
  * (there the residual a - q*b leaves the normal range and the last bit of a quotient < 2^-40 is immaterial).
  * usage: div_by_recip_check <cases>   -> prints "cases N bad_two_step X bad_hilo Y", exit status 0 iff X == Y == 0 */
 #include <math.h>
@@ -43,11 +43,12 @@ int main(int argc, char **argv)
         default: a = u2f((uint32_t)rnd() & 0x7FFFFFFF); if (!(a < 7.1f * b)) a = b * 0.3f; break; /* any exponent below    */
         }
         if (!(a >= 0) || isinf(a)) continue;
+        if (i & 4) a = -a; /* calibrated INT8 divides signed data: every step is odd-symmetric, checked all the same */
         const float want = a / b, g2 = div_hilo(a, b, rh, rl), g1 = div_two_step(a, b, rh);
         ++cnt;
-        if (a < 0x1p-100f) {
-            if (truncf(g1 + 0.5f) != truncf(want + 0.5f)) ++bad1;
-            if (truncf(g2 + 0.5f) != truncf(want + 0.5f)) ++bad2;
+        if (fabsf(a) < 0x1p-100f) {
+            if (roundf(g1) != roundf(want)) ++bad1;
+            if (roundf(g2) != roundf(want)) ++bad2;
             continue;
         }
         if (f2u(g1) != f2u(want)) ++bad1;
