@@ -15,6 +15,7 @@ What gets patched -- exactly the plugin points of SURVEY.md section 8b, nothing 
   dmx.compressor.numerical.format.MXINT.cast                      -> (inherits BlockFloatingPoint)
   dmx.compressor.sparse.Sparsify.forward (BlockTopK patterns)     -> dmxq_nm_prune
   dmx.compressor.quant.{fixed_point,block,float}_quantize         -> L1 mirrors (dmx_compressor_b200.quant)
+  {BlockFloatingPoint,ScaledBlockFloatingPoint}.pack / .unpack     -> NEW methods: packed storage (dmxq_bfp_pack / dmxq_sbfp_pack)
 
 Only CUDA tensors are redirected; a CPU tensor still runs the reference's own CPU extension
 (this package contains no CPU implementation).  ``uninstall()`` restores the originals.
@@ -32,10 +33,13 @@ from . import ops, quant
 _saved: Dict[Tuple[object, str], object] = {}
 
 
+_MISSING = object()  # the attribute did not exist before install(): uninstall() deletes it again
+
+
 def _patch(obj, name, new):
     key = (obj, name)
     if key not in _saved:
-        _saved[key] = getattr(obj, name)
+        _saved[key] = obj.__dict__.get(name, _MISSING) if isinstance(obj, type) else getattr(obj, name, _MISSING)
     setattr(obj, name, new)
 
 
@@ -83,6 +87,38 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
     _patch(fmt.ScaledBlockFloatingPoint, "cast", sbfp_cast)
     _patch(fmt.FloatingPoint, "cast", fp_cast)
     _patch(fmt.FixedPoint, "cast", xp_cast)
+
+    # packed storage -- the real formats whose size the reference's `bytes_per_elem` reports (format.py:345-347, 481-486):
+    # NEW methods on the reference's classes (nothing is overridden), CUDA tensors only
+    def sbfp_stage_of(f):
+        b, s = f.block_format, f.scaler_format
+        return ops.sbfp_stage(f.block_size, b.precision, b.clamp, b.rounding, L.TIE_AWAY, s.mantissa, s.exponent, s.bias,
+                              s.flush_subnormal, s.unsigned, repr(s) == "FP[1|5|10,15](FN)", s.rounding)
+
+    def bfp_pack(self, x):
+        """-> (mantissas, exponents): dmxq_bfp_pack; blocks along the last dim"""
+        assert self.symmetric and self.rounding == "nearest" and self.precision <= 8, "packed storage: symmetric nearest, <= 8 bits"
+        return ops.bfp_pack(x, self.block_size, self.precision)
+
+    def bfp_unpack(self, mantissas, exponents, dtype=torch.float32):
+        """dequantise packed storage (dmxq_bfp_unpack): equals ``cast`` of the original tensor bit for bit"""
+        return ops.bfp_unpack(mantissas, exponents, self.block_size, self.precision, dtype)
+
+    def sbfp_pack(self, x, return_inexact=False):
+        """-> (mantissas, scalers[, n_inexact]): dmxq_sbfp_pack; blocks along the last dim"""
+        if not self.scaler_format_exponent_bias_determined:
+            self.determine_scaler_exponent_bias_from(x)
+            self.scaler_format_exponent_bias_determined = True
+        return ops.sbfp_pack(x, sbfp_stage_of(self), return_inexact)
+
+    def sbfp_unpack(self, mantissas, scalers, dtype=torch.float32):
+        """dequantise packed storage (dmxq_sbfp_unpack): equals ``cast`` of the original tensor bit for bit"""
+        return ops.sbfp_unpack(mantissas, scalers, sbfp_stage_of(self), dtype)
+
+    _patch(fmt.BlockFloatingPoint, "pack", bfp_pack)
+    _patch(fmt.BlockFloatingPoint, "unpack", bfp_unpack)
+    _patch(fmt.ScaledBlockFloatingPoint, "pack", sbfp_pack)
+    _patch(fmt.ScaledBlockFloatingPoint, "unpack", sbfp_unpack)
 
     # Sparsify.forward: BlockTopK mask + apply in one kernel (other patterns: reference code)
     o_fwd = sparse.Sparsify.forward
@@ -150,9 +186,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
 
         def stage_of(f):
             if isinstance(f, fmt.ScaledBlockFloatingPoint):
-                b, s = f.block_format, f.scaler_format
-                return ops.sbfp_stage(f.block_size, b.precision, b.clamp, b.rounding, L.TIE_AWAY, s.mantissa, s.exponent, s.bias,
-                                      s.flush_subnormal, s.unsigned, repr(s) == "FP[1|5|10,15](FN)", s.rounding)
+                return sbfp_stage_of(f)
             if isinstance(f, fmt.BlockFloatingPoint):
                 return ops.bfp_stage(f.block_size, f.precision, f.symmetric, f.rounding)
             if isinstance(f, fmt.FloatingPoint):
@@ -180,7 +214,10 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
 
 def uninstall() -> None:
     for (obj, name), orig in list(_saved.items()):
-        setattr(obj, name, orig)
+        if orig is _MISSING:
+            delattr(obj, name)
+        else:
+            setattr(obj, name, orig)
     _saved.clear()
 
 

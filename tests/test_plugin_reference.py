@@ -41,9 +41,16 @@ def test_install_patches_plugin_points_and_keeps_cpu_path():
             assert torch.equal(got.view(torch.int32), want.view(torch.int32)), sh
         assert torch.equal(s(x), s_before)
         assert torch.equal(q.float_quantize(x, 5, 10, rounding="nearest"), fmt.float_quantize(x, 5, 10, rounding="nearest"))
+        # packed storage arrives as NEW methods on the reference's format classes (CUDA only: no host encoder)
+        for sh in ("BFP[8|8]{64}(SN)", "MXINT8{64}", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"):
+            f = num.Format.from_shorthand(sh)
+            assert callable(f.pack) and callable(f.unpack)
+            with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+                f.pack(x)
     finally:
         plugin.uninstall()
     assert fmt.BlockFloatingPoint.cast is orig[0] and sp.Sparsify.forward is orig[4] and not plugin.installed()
+    assert not hasattr(fmt.BlockFloatingPoint, "pack") and not hasattr(fmt.ScaledBlockFloatingPoint, "unpack")
 
 
 def test_histogram_step_drives_the_reference_observer_class():
