@@ -414,6 +414,62 @@ def test_fused_chain_matches_sequential():
     check(y, t.view(torch.int16).numpy().view(np.uint16), "bf16 chain", dtype="bfloat16")
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("sh", ["BFP[4|8]{64}(SN)", "BFP[8|8]{64}(SN)", "BFP[4|8]{128}(SN)", "BFP[8|8]{16}(SN)", "BFP[6|8]{8}(SN)"])
+def test_nm24_bfp_specialisation_on_16bit_tensors(dt, sh):
+    """2:4 -> BFP on a bf16 / fp16 tensor runs the straight-line K_NM24_BFP kernel (one sorting network for the mask and
+    the block max, BFP before the zeroing).  Checked (a) against the oracle applied stage by stage on finite data with
+    ties in |x|, signed zeros, equal groups, blocks whose max sits in the clip quantum, denormal and near-maximal
+    blocks; (b) against the general K_NM_BFP kernel -- the same chain with an fp32 output -- on rows that also hold
+    Inf / NaN blocks, which must come out identical once rounded to the tensor dtype; (c) on a row-strided view."""
+    g = torch.Generator().manual_seed(sum(map(ord, sh)) * 2 + (dt == torch.bfloat16))
+    R, K = 96, 1024
+    x = torch.randn(R, K, generator=g) * torch.pow(2.0, torch.randint(-6, 5, (R, 1), generator=g).float())
+    x = x.to(dt)
+    x[1] = x[1, :4].repeat(K // 4)                      # every group the same four values
+    x[2] = x[2].abs()[0]                                # all magnitudes equal: the stable order decides
+    x[2, 1::2] *= -1
+    x[3] = 0.0
+    x[3, ::3] = -0.0
+    x[4, :64] = torch.tensor(1.9375 if dt == torch.bfloat16 else 1.9990234375).to(dt)   # block max in the top quantum
+    x[4, 1:64:2] *= -0.5
+    tiny = 2.0**-130 if dt == torch.bfloat16 else 2.0**-22
+    x[5] = (torch.randn(K, generator=g) * tiny).to(dt)  # denormal blocks
+    big = 2.0**126 if dt == torch.bfloat16 else 30000.0
+    x[6] = (torch.sign(torch.randn(K, generator=g)) * big * (1 + torch.rand(K, generator=g))).to(dt)  # near the dtype's maximum
+    x.view(-1)[11::97] = x.view(-1)[10::97][: x.view(-1)[11::97].numel()]   # exact ties between neighbours
+    assert torch.isfinite(x).all()
+    stages = [ops.nm_stage(2, 4), fmt_from(sh).stage()]
+    v = torch.int16
+    xd = x.to(DEV)
+    got = ops.cast_chain(xd, stages, -1)
+    assert got.dtype == dt
+    want = O.cast(O.nm_prune(x.float().numpy(), 2, 4), sh)
+    hugemask = np.zeros((R, K), bool)
+    hugemask[6] = dt == torch.bfloat16      # blocks with max >= 2^126: hardware NaN sign differs between x86 and the GPU (see special_block_masks)
+    w16 = torch.from_numpy(want).to(dt)
+    ok = torch.from_numpy(~hugemask)
+    assert torch.equal(got.cpu().view(v)[ok], w16.view(v)[ok])
+    # (b) the general kernel on the same GPU, special values included
+    xs = x.clone()
+    xs[7, 5] = float("inf")
+    xs[7, 300] = float("-inf")
+    xs[8, 70] = float("nan")
+    xs[9, :8] = float("inf")                # three Infs in a group: a pruned Inf times zero
+    xsd = xs.to(DEV)
+    a = ops.cast_chain(xsd, stages, -1)                                   # K_NM24_BFP
+    b = ops.cast_chain(xsd, stages, -1, out_dtype=torch.float32).to(dt)   # K_NM_BFP (16-bit in, fp32 out)
+    an, bn = torch.isnan(a), torch.isnan(b)
+    assert torch.equal(an, bn)
+    assert torch.equal(a.view(v)[~an], b.view(v)[~bn])
+    # (c) rows of a wider matrix (not FLAT)
+    wide = torch.zeros(R, K + 64, dtype=dt, device=DEV)
+    wide[:, :K] = xd
+    outw = torch.empty_like(wide)
+    ops.cast_chain(wide[:, :K], stages, -1, out=outw[:, :K])
+    assert torch.equal(outw[:, :K].contiguous().view(v), got.view(v))
+
+
 @pytest.mark.parametrize("seed", range(int(os.environ.get("DMXQ_FUZZ_SEEDS", "12")) // 2))
 def test_fuzz_fused_chains(seed):
     """seeded fuzzing of the fused kernels (N:M -> BFP, N:M alone, FLOAT -> BFP and three-stage chains) on fp32 / bf16 /
