@@ -235,10 +235,26 @@ def bfp_pack(x, block_size=64, precision=8):
     return mant, exps
 
 
+def _check_packed(mant, side, block_size, precision, side_name):
+    """shape / layout contract of a packed (mantissas, per-block bytes) pair -> K; the C entry points take raw pointers, so
+    a mismatched pair would read out of bounds on the device"""
+    K = mant.shape[-1] * (2 if precision <= 4 else 1)
+    if block_size <= 0 or K % block_size != 0:
+        raise RuntimeError(f"packed storage: last dim {K} is not a multiple of the block size {block_size}")
+    want = tuple(mant.shape[:-1]) + (K // block_size,)
+    if tuple(side.shape) != want or side.dtype != torch.uint8 or mant.dtype not in (torch.uint8, torch.int8):
+        raise RuntimeError(f"packed storage: {side_name} must be uint8 of shape {want} for mantissas of shape {tuple(mant.shape)}, "
+                           f"got {side.dtype} {tuple(side.shape)}")
+    if not (mant.is_contiguous() and side.is_contiguous()) or side.device != mant.device:
+        raise RuntimeError(f"packed storage: mantissas and {side_name} must be contiguous tensors on one device")
+    return K
+
+
 def bfp_unpack(mant, exps, block_size=64, precision=8, dtype=torch.float32):
     """dequantise packed BFP storage (dmxq_bfp_unpack): bit-identical to bfp_qdq of the original tensor."""
     L.require_cuda(mant, "mantissas")
-    K = mant.shape[-1] * (2 if precision <= 4 else 1)
+    L.require_cuda(exps, "exponents")
+    K = _check_packed(mant, exps, block_size, precision, "exponents")
     y = torch.empty(mant.shape[:-1] + (K,), dtype=dtype, device=mant.device)
     vy = L.view(y)
     with _guard(mant.device):
@@ -286,7 +302,7 @@ def sbfp_unpack(mant, scal, stage, dtype=torch.float32):
     """dequantise packed SBFP storage (dmxq_sbfp_unpack): bit-identical to the SBFP cast of the original tensor."""
     L.require_cuda(mant, "mantissas")
     L.require_cuda(scal, "scalers")
-    K = mant.shape[-1] * (2 if stage.precision <= 4 else 1)
+    K = _check_packed(mant, scal, stage.block, stage.precision, "scalers")
     y = torch.empty(mant.shape[:-1] + (K,), dtype=dtype, device=mant.device)
     vy = L.view(y)
     with _guard(mant.device):

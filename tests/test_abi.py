@@ -159,3 +159,21 @@ def test_castto_state_and_config_surface():
     x = torch.randn(3)
     y = CastTo("SAME")(x)
     assert torch.equal(x, y) and y.data_ptr() != x.data_ptr()  # SAME clones (reference format.py:89-90)
+
+
+def test_packed_pair_contract_is_checked_on_the_host():
+    """the unpack entry points take raw pointers: the python binding refuses (mantissas, per-block bytes) pairs whose shapes
+    do not belong together before anything reaches the device"""
+    from dmx_compressor_b200 import ops
+
+    u8 = lambda *shape: torch.zeros(*shape, dtype=torch.uint8)
+    assert ops._check_packed(u8(4, 32), u8(4, 4), 16, 4, "scalers") == 64            # nibbles: K = 2 * 32
+    assert ops._check_packed(torch.zeros(4, 64, dtype=torch.int8), u8(4, 1), 64, 8, "exponents") == 64
+    assert ops._check_packed(u8(2, 3, 128), u8(2, 3, 8), 16, 8, "scalers") == 128
+    for mant, side, bs, prec in ((u8(4, 32), u8(4, 8), 16, 4),                        # too many scaler bytes
+                                 (u8(4, 32), u8(3, 4), 16, 4),                        # other leading shape
+                                 (u8(4, 32), torch.zeros(4, 4), 16, 4),               # not bytes
+                                 (u8(4, 36), u8(4, 4), 16, 4),                        # K = 72 is not a whole number of blocks
+                                 (u8(4, 64)[:, ::2], u8(4, 4), 16, 4)):               # strided mantissas
+        with pytest.raises(RuntimeError, match="packed storage"):
+            ops._check_packed(mant, side, bs, prec, "scalers")
