@@ -177,3 +177,36 @@ def test_packed_pair_contract_is_checked_on_the_host():
                                  (u8(4, 64)[:, ::2], u8(4, 4), 16, 4)):               # strided mantissas
         with pytest.raises(RuntimeError, match="packed storage"):
             ops._check_packed(mant, side, bs, prec, "scalers")
+
+
+def test_binding_signatures_match_header_prototypes():
+    """every prototype in include/dmxq.h, parameter by parameter, against the ctypes argtypes / restype the
+    binding installs: a width or arity mismatch here is silent stack corruption on the device path"""
+    from dmx_compressor_b200 import _lib as L
+
+    hdr = open(os.path.join(ROOT, "include", "dmxq.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    hdr = re.sub(r"//[^\n]*", "", hdr)
+
+    def classify(decl):
+        decl = " ".join(decl.replace("const", " ").split())
+        if decl in ("void", ""):
+            return None
+        if "*" in decl:
+            base = decl.split("*")[0].strip()
+            return {"dmxq_tensor": C.POINTER(L.Tensor), "dmxq_stage": C.POINTER(L.Stage),
+                    "char": C.c_char_p}.get(base, C.c_void_p)
+        base = decl.rsplit(" ", 1)[0] if " " in decl else decl
+        return {"int": C.c_int, "int32_t": C.c_int, "int64_t": C.c_int64, "float": C.c_float,
+                "size_t": C.c_size_t}[base]
+
+    protos = re.findall(r"([A-Za-z_][\w\s\*]*?)\b(dmxq_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(L.EXPORTS)
+    for ret, name, params in protos:
+        fn = getattr(L.lib, name)
+        want = [classify(p) for p in params.split(",")]
+        want = [w for w in want if w is not None]
+        assert list(fn.argtypes) == want, f"{name}: binding {fn.argtypes} vs header {want}"
+        ret = " ".join(ret.replace("const", " ").replace("DMXQ_API", " ").replace("extern", " ").split())
+        want_ret = None if ret == "void" else classify(ret + " r")
+        assert fn.restype == want_ret, f"{name}: restype {fn.restype} vs header {ret!r}"
