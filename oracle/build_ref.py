@@ -119,6 +119,39 @@ def build_cuda(force=False):
     return out
 
 
+def stage_python(force=False):
+    """Stage the reference's python package verbatim into ``oracle/_ref/pysrc/dmx`` (git-ignored, like the binaries
+    above: made by this committed recipe from /root/reference, never part of the history, but it travels to the GPU
+    box, where /root/reference does not exist).  It is what lets the plugin parity tests run the reference's OWN
+    ``CastTo`` / ``Sparsify`` / ``DmxModule`` code on a B200, unpatched (its CUDA path) and patched (libdmxq), and what
+    bench.py's reference arms call.  Only ``*.py`` files are staged; the native sources stay where they are (the
+    prebuilt ``ref_quant_{cpu,cuda}.so`` answer the import-time JIT, see oracle/refshim/load_reference.py)."""
+    import shutil
+
+    src = os.path.join(REF_ROOT, "src", "dmx")
+    dst = os.path.join(OUT, "pysrc", "dmx")
+    if not os.path.isdir(src):
+        return dst if os.path.isdir(dst) else None
+    stamp = os.path.join(OUT, "pysrc", ".staged")
+    newest = max(os.path.getmtime(os.path.join(d, f)) for d, _, fs in os.walk(src) for f in fs if f.endswith(".py"))
+    if not force and os.path.exists(stamp) and os.path.getmtime(stamp) >= newest:
+        return dst
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    n = 0
+    for d, _, fs in os.walk(src):
+        for f in fs:
+            if not f.endswith(".py"):
+                continue
+            rel = os.path.relpath(os.path.join(d, f), src)
+            os.makedirs(os.path.dirname(os.path.join(dst, rel)), exist_ok=True)
+            shutil.copy2(os.path.join(d, f), os.path.join(dst, rel))
+            n += 1
+    with open(stamp, "w") as fh:
+        fh.write(f"{n} python files staged verbatim from {src}\n")
+    return dst
+
+
 def load(name):
     """Import oracle/_ref/<name>.so as a python module (None if it was never built)."""
     import importlib.util
@@ -142,6 +175,7 @@ def main():
     print("cpu :", build_cpu(force))
     if "--no-cuda" not in sys.argv:
         print("cuda:", build_cuda(force))
+    print("python:", stage_python(force))
     return 0
 
 
