@@ -18,12 +18,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdmxq.so")
 MAX_DIMS = 8
 MAX_STAGES = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # enums of include/dmxq.h
 F32, BF16, F16 = 0, 1, 2
 ROUND = {"nearest": 0, "stochastic": 1, "up": 2, "down": 3}
 TIE_AWAY, TIE_EVEN = 0, 1
+SCALE_DIV, SCALE_RECIP = 0, 1  # SBFP block scale: max / man_scaling (reference on CPU tensors) | max * fp32(1 / man_scaling) (on CUDA tensors)
+NM_STABLE, NM_TORCH_CUDA = 0, 1  # N:M tie order: stable argsort (reference on CPU tensors) | torch's CUDA bitonic order
 ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED, ST_MXFP = 0, 1, 2, 3, 4, 5, 6
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
@@ -38,7 +40,8 @@ class Stage(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "kind", "block", "precision", "fraction", "man", "exp", "bias", "flush", "is_unsigned", "fp16_flush",
         "symmetric", "clamp", "rounding", "tie", "n_keep", "sc_man", "sc_exp", "sc_bias", "sc_flush", "sc_unsigned",
-        "sc_fp16_flush", "sc_rounding")] + [("scale", C.c_float), ("zero_point", C.c_float)]
+        "sc_fp16_flush", "sc_rounding")] + [("scale", C.c_float), ("zero_point", C.c_float),
+                                            ("scale_mode", C.c_int32), ("nm_order", C.c_int32)]
 
 
 def _load():
@@ -55,10 +58,10 @@ def _load():
         "dmxq_launch_count": ([], I64),
         "dmxq_cast_chain": ([TP, TP, I, SP, I, TP, TP, VP, VP], I),
         "dmxq_bfp_qdq": ([TP, TP, I, I, I, I, I, VP, VP], I),
-        "dmxq_sbfp_qdq": ([TP, TP] + [I] * 13 + [VP], I),
+        "dmxq_sbfp_qdq": ([TP, TP] + [I] * 14 + [VP], I),
         "dmxq_float_qdq": ([TP, TP] + [I] * 7 + [VP, VP], I),
         "dmxq_fixed_qdq": ([TP, TP] + [I] * 6 + [VP, VP, I64, I, I64, VP, VP], I),
-        "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, VP], I),
+        "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, I, VP], I),
         "dmxq_add_cast": ([TP, TP, TP, SP, SP, SP, VP], I),
         "dmxq_bfp_pack": ([TP, VP, VP, I, I, VP], I),
         "dmxq_bfp_unpack": ([VP, VP, TP, I, I, VP], I),

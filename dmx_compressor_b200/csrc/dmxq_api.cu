@@ -114,6 +114,9 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
             return fail(DMXQ_ERR_BAD_ARG, "N and M must be positive and N no greater than M (got %d:%d)", s.n_keep, s.block);
         if (s.block > 64) return fail(DMXQ_ERR_UNSUPPORTED, "N:M group size %d > 64", s.block);
         d.n_prune = s.block - s.n_keep;
+        if (s.nm_order != DMXQ_NM_ORDER_STABLE && s.nm_order != DMXQ_NM_ORDER_TORCH_CUDA) return fail(DMXQ_ERR_BAD_ARG, "invalid nm_order %d", s.nm_order);
+        // torch sorts rows of more than 32 keys with a stable sort on CUDA as well (Sort.cu: bitonic only for <= 32)
+        d.nm_order = (s.nm_order == DMXQ_NM_ORDER_TORCH_CUDA && s.block <= 32 && s.block >= 2) ? 1 : 0;
         return DMXQ_OK;
     case DMXQ_STAGE_BFP:
         // BlockFloatingPoint.__init__ asserts, S/numerical/format.py:289-292
@@ -142,6 +145,10 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         if (d.sb.sc.mode == R_STOCHASTIC) return fail(DMXQ_ERR_UNSUPPORTED, "stochastic SBFP scaler format is not supported");
         d.sb.man_scaling = (float)((1 << (s.precision - 1)) - 1);
         d.sb.inv_man = 1.0f / d.sb.man_scaling;
+        if (s.scale_mode != DMXQ_SCALE_DIV && s.scale_mode != DMXQ_SCALE_RECIP) return fail(DMXQ_ERR_BAD_ARG, "invalid scale_mode %d", s.scale_mode);
+        d.sb_exp_bits = s.sc_exp;
+        d.sb.recip = s.scale_mode == DMXQ_SCALE_RECIP;
+        d.sb.inv_man_t = (float)(1.0 / (double)d.sb.man_scaling);  // ATen div_true_kernel_cuda: inv_b computed in double, used in fp32
         d.sb.no_clamp = !d.sb.xp.clamp || (d.sb.xp.t_max >= d.sb.man_scaling && d.sb.xp.t_min <= -d.sb.man_scaling);
         d.sb.sc_fast = d.sb.sc.mode == R_NEAREST && d.sb.sc.flush && (!d.sb.sc.fp16_flush || d.sb.sc.min_exp >= -14);
         return DMXQ_OK;
@@ -368,6 +375,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
             } else if (sd.kind == ST_NM) {
                 int M = sd.block;
                 rows_ok &= pow2(M) && M >= 2 && (M <= V ? true : (M / V <= 4));
+                if (sd.nm_order) rows_ok &= M <= V && M <= 8;  // the network emulation is in-thread; other group sizes: generic kernel
                 tile = std::max<int64_t>(tile, M);
             }
         }
@@ -422,6 +430,8 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         // 2:4 -> BFP on a bf16 / fp16 tensor (whole-model weight casts): the straight-line specialisation
         if (kind == 5 && x->dtype == y->dtype && x->dtype != DMXQ_F32 && chain.st[0].block == 4 && chain.st[0].n_prune == 2 &&
             chain.st[1].fast && chain.st[1].fast16) kind = 12;  // K_NM24_BFP
+        for (int s = 0; s < chain.n; ++s)
+            if (chain.st[s].kind == ST_NM && chain.st[s].nm_order && kind != 0) kind = 1;  // torch tie order: runtime chain (nm_stage)
         if (qscale) {
             if (kind != 7) return kNeedFallback;
             p.qscale = qscale; p.qzp = qzp;
@@ -549,13 +559,13 @@ int dmxq_bfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int 
 
 int dmxq_sbfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size, int xp_precision, int xp_clamp,
                   int xp_rounding, int xp_tie, int sc_man, int sc_exp, int sc_bias, int sc_flush, int sc_unsigned,
-                  int sc_fp16_flush, int sc_rounding, void *stream)
+                  int sc_fp16_flush, int sc_rounding, int scale_mode, void *stream)
 {
     dmxq_stage s;
     memset(&s, 0, sizeof(s));
     s.kind = DMXQ_STAGE_SBFP; s.block = block_size; s.precision = xp_precision; s.clamp = xp_clamp; s.rounding = xp_rounding;
     s.tie = xp_tie; s.sc_man = sc_man; s.sc_exp = sc_exp; s.sc_bias = sc_bias; s.sc_flush = sc_flush; s.sc_unsigned = sc_unsigned;
-    s.sc_fp16_flush = sc_fp16_flush; s.sc_rounding = sc_rounding;
+    s.sc_fp16_flush = sc_fp16_flush; s.sc_rounding = sc_rounding; s.scale_mode = scale_mode;
     return chain_impl(x, y, block_dim, &s, 1, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
 }
 
@@ -627,11 +637,11 @@ int dmxq_fixed_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int fl, i
 }
 
 int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_tensor *y, const dmxq_tensor *mask, int block_dim,
-                  int n_keep, int m, void *stream)
+                  int n_keep, int m, int nm_order, void *stream)
 {
     dmxq_stage s;
     memset(&s, 0, sizeof(s));
-    s.kind = DMXQ_STAGE_NM; s.block = m; s.n_keep = n_keep;
+    s.kind = DMXQ_STAGE_NM; s.block = m; s.n_keep = n_keep; s.nm_order = nm_order;
     return chain_impl(x, y, block_dim, &s, 1, score, mask, nullptr, static_cast<cudaStream_t>(stream));
 }
 

@@ -25,6 +25,7 @@ struct StageDev {
     uint32_t mask;
     // NM
     int n_prune;
+    int nm_order;    // DMXQ_NM_ORDER_*: tie order of the group sort (stable, or torch's CUDA bitonic network)
     // FLOAT
     FloatFmt ff;
     // FIXED (+ per-tensor affine)
@@ -33,6 +34,7 @@ struct StageDev {
     float sc, zp;
     // SBFP
     SbfpFmt sb;
+    int sb_exp_bits;  // exponent bits of the scaler format (needed when the bias is derived on the device from an amax)
     // MXFP (element format in ff)
     float mx_largest;  // 2^(2^(exp_bits-1))
 };
@@ -84,6 +86,19 @@ struct RowsParams {
     int64_t rks;         // rand stride along K
     FastDiv vpr_div, odim_div[kMaxOuter];  // valid while n_vec < 2^31
     ChainDev chain;
+};
+
+// Many flat tensors in one launch of the rows kernel (dmxq_cast_chain_multi).  The table rides in the kernel parameters:
+// CTAs [cta0[i], cta0[i+1]) work on tensor i.
+constexpr int kMultiMax = 64;
+struct MultiTable {
+    int n;
+    uint32_t cta0[kMultiMax + 1];
+    const void *x[kMultiMax];
+    void *y[kMultiMax];
+    int64_t n_vec[kMultiMax];
+    const float *amax;    // nullable: device array of per-tensor amax (SBFP scaler bias derived in the kernel)
+    int slot[kMultiMax];  // index of tensor i in `amax`
 };
 
 // Column-tiled kernel: the blocked dim is strided, another dim ("inner") is contiguous.
@@ -162,6 +177,8 @@ struct MinMaxParams {
 
 // launchers (dmxq_kernels.cu)
 cudaError_t launch_rows(int in_dt, int out_dt, bool flat, int kind, const RowsParams &p, cudaStream_t s);  // kind: K_* of dmxq_rows.cuh
+cudaError_t launch_rows_multi(int dt, int kind, const RowsParams &p, const MultiTable &t, cudaStream_t s);  // same-dtype flat tensors
+bool rows_multi_supported(int kind);
 cudaError_t launch_cols(int in_dt, int out_dt, int B, const ColsParams &p, cudaStream_t s);
 bool cols_supported(int in_dt, int B);
 int cols_tile_inner(int in_dt, int B);  // LI * V of the instantiation used for block size B

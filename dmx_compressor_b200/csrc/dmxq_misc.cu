@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(kThreads) chain_generic_kernel(const __grid_co
         // all ranks are computed from the pristine input before the first write (in-place safe
         // because masks are buffered in a bit set: M <= 64).
         unsigned long long keepbits = 0ull;
+        if (st.nm_order && k1 - k0 <= 32) {  // torch's CUDA tie order: the 32-slot bitonic network on this group's keys
+            uint32_t keys[32];
+            const int M = (int)(k1 - k0);
+            for (int a = 0; a < M; ++a)
+                keys[a] = p.score ? score_key(p.score[so + (k0 + a) * p.sks]) : absx_key(Cvt<Tin>::to_f32(x[(k0 + a) * p.xks]));
+            keepbits = ~(unsigned long long)nm_pruned_torch32(keys, M, st.n_prune);
+        } else
         for (int64_t a = k0; a < k1; ++a) {
             float xa = Cvt<Tin>::to_f32(x[a * p.xks]);
             uint32_t ka = p.score ? score_key(p.score[so + a * p.sks]) : absx_key(xa);

@@ -320,6 +320,8 @@ struct SbfpFmt {
     float inv_man;      // RN(1 / man_scaling)
     int no_clamp;       // the XP clamp cannot trigger on |x| <= block max (host-decided: !clamp || range covers +-man_scaling)
     int sc_fast;        // scaler cast = float_elem_flush_nearest (nearest, flushing; host-decided)
+    int recip;          // DMXQ_SCALE_RECIP: block scale = max * inv_man_t (what torch computes for `cuda_tensor / python_scalar`)
+    float inv_man_t;    // fp32(1.0 / (double)man_scaling): ATen's inv_b (div_true_kernel_cuda)
 };
 
 struct SbfpBlock {
@@ -334,7 +336,7 @@ struct SbfpBlock {
 __device__ __forceinline__ SbfpBlock sbfp_block(uint32_t maxabs_bits, const SbfpFmt &f)
 {
     SbfpBlock b;
-    b.cmax = __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
+    b.cmax = f.recip ? __fmul_rn(u2f(maxabs_bits), f.inv_man_t) : __fdiv_rn(u2f(maxabs_bits), f.man_scaling);
     b.fs = float_elem_rt(b.cmax, f.sc, 0u);
     b.on = b.cmax > 0.0f;
     b.rc = 0.0f;

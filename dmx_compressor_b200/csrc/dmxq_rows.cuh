@@ -112,17 +112,45 @@ template <typename T> __device__ __forceinline__ uint32_t widen16(uint32_t m16)
     else return f2u(__half2float(__ushort_as_half((unsigned short)m16)));
 }
 
+// The scaler-format fields an SBFP stage reads per block.  Normally they are the stage's own (host-decided); with a
+// device-resident tensor-wide amax (dmxq_cast_chain_multi) the exponent bias -- and with it the flush threshold -- is derived
+// here, so a calibration all-reduce can feed the cast without a host round trip:
+//     bias = (2^E - 1) - floor(log2(amax / man_scaling)), clamped to the range FloatingPoint accepts
+// (dmx_compressor_b200.parallel.sbfp_scaler_bias_from_amax is the same rule on the host; the reference delegates the choice
+// to d-Matrix's private `numerics` module, S/numerical/format.py:13-20, 438-446 -- parity unpinned by construction).
+__device__ __forceinline__ SbfpFmt sbfp_fmt_with_amax(const SbfpFmt &f, const float *amax, int sc_exp_bits)
+{
+    SbfpFmt r = f;
+    if (amax != nullptr) {
+        const float a = __ldg(amax);
+        int bias = (1 << (sc_exp_bits - 1)) - 1;  // the format's default when amax is unusable
+        if (a > 0.0f && a < __int_as_float(0x7F800000)) {
+            // top = largest t with man_scaling * 2^t <= amax (exact: no log, no division rounding)
+            int t = (int)((f2u(__fdiv_rn(a, f.man_scaling)) >> 23) & 0xFFu) - 127;
+            if (__fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 127, 254), 1) << 23)) > a) --t;
+            else if (t < 127 && __fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 128, 254), 1) << 23)) <= a) ++t;
+            bias = ((1 << sc_exp_bits) - 1) - t;
+            const int lo = sc_exp_bits == 8 ? 127 : -128 + (1 << sc_exp_bits);
+            bias = max(lo, min(127, bias));
+        }
+        r.sc.min_exp = -(bias - 1);
+        r.sc.shift_exp = (uint32_t)(127 + r.sc.min_exp) << 23;
+    }
+    return r;
+}
+
+// body of chain_rows_kernel: `cta` is the CTA's index inside the tensor (x, y) of n_vec vectors -- the whole grid for
+// the single-tensor kernel, a segment of it for the many-tensor kernel
 template <typename Tin, typename Tout, bool FLAT, int KIND>
-__global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_constant__ RowsParams p)
+__device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *__restrict__ x, Tout *__restrict__ y, const int64_t cta,
+                                                const int64_t n_vec, const float *amax)
 {
     constexpr int V = VecIO<Tin>::V;
     constexpr bool SRC16 = sizeof(Tin) == 2;
     constexpr int SRCBITS = std::is_same<Tin, __nv_bfloat16>::value ? 16 : (std::is_same<Tin, __half>::value ? 11 : 32);
-    const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
-    Tout *__restrict__ y = static_cast<Tout *>(p.y);
     constexpr bool SAME16 = SRC16 && std::is_same<Tin, Tout>::value;
     const int lane = threadIdx.x & 31;
-    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    const int64_t g0 = cta * (kThreads * kUnroll) + threadIdx.x;
     // FLOAT -> BFP pair on a 16-bit tensor: the float format's saturation value as Tout stores it
     const uint32_t fmax_rq = (KIND == K_FLOAT_BFP && SAME16) ? f2u(requant1<Tout>(u2f(p.chain.st[0].ff.max_num))) : 0u;
     // FLOAT stage on a 16-bit tensor whose significand the format keeps: a vector whose magnitudes all lie between the
@@ -141,15 +169,19 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
     // whole 32-byte sectors per lane), so the block constants -- max / 7, its scaler cast, its reciprocal -- are derived once
     // per block instead of once per lane, and no shuffle is needed
     const bool pair = KIND == K_SBFP && SRC16 && FLAT && p.chain.st[0].block == 2 * V;
+    // K_SBFP: the stage's format, with the scaler bias taken from a device-resident amax when one is given
+    const SbfpFmt &sbf0 = p.chain.st[0].sb;
+    const SbfpFmt sbfl = (KIND == K_SBFP && amax != nullptr) ? sbfp_fmt_with_amax(sbf0, amax, (int)p.chain.st[0].sb_exp_bits) : SbfpFmt{};
+    const SbfpFmt &sbf = (KIND == K_SBFP && amax != nullptr) ? sbfl : sbf0;
 
     // ---- phase 1: addresses + all loads (nothing here consumes loaded data)
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         int64_t g = g0 + (int64_t)u * kThreads;
-        if (pair) g = (int64_t)blockIdx.x * (kThreads * kUnroll) + (u >> 1) * (2 * kThreads) + 2 * threadIdx.x + (u & 1);
+        if (pair) g = cta * (kThreads * kUnroll) + (u >> 1) * (2 * kThreads) + 2 * threadIdx.x + (u & 1);
         int64_t xoff;
         if (FLAT) {
-            valid[u] = g < p.n_vec;
+            valid[u] = g < n_vec;
             xoff = g * V;
             yoff[u] = xoff;
             if (KIND == K_AUX) { aux_s[u] = xoff; aux_m[u] = xoff; aux_r[u] = xoff; }
@@ -413,12 +445,11 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
             mxfp_apply<V>(v, lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V), st);
         } else if (KIND == K_SBFP && pair) {
             if ((u & 1) == 0) {
-                const StageDev &st = p.chain.st[0];
                 float w[V];
                 const uint32_t m = max(unpack_absmax<Tin>(raw[u], v), unpack_absmax<Tin>(raw[(u + 1) % kUnroll], w));
-                const SbfpBlock b = sbfp_block_ol(m, st.sb);
-                sbfp_apply<V>(v, b, st.sb);
-                sbfp_apply<V>(w, b, st.sb);
+                const SbfpBlock b = sbfp_block_ol(m, sbf);
+                sbfp_apply<V>(v, b, sbf);
+                sbfp_apply<V>(w, b, sbf);
                 if (valid[u]) VecIO<Tout>::template store<V>(y + yoff[u], v);
                 if (valid[(u + 1) % kUnroll]) VecIO<Tout>::template store<V>(y + yoff[(u + 1) % kUnroll], w);
             }
@@ -426,8 +457,8 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
         } else if (KIND == K_SBFP) {
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
-            SbfpBlock b = sbfp_block_ol(m, st.sb);
-            sbfp_apply<V>(v, b, st.sb);
+            SbfpBlock b = sbfp_block_ol(m, sbf);
+            sbfp_apply<V>(v, b, sbf);
         } else {
             VecIO<Tin>::unpack(raw[u], v);
 #pragma unroll 1
@@ -477,6 +508,36 @@ __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_const
         }
         if (valid[u]) VecIO<Tout>::template store<V>(y + yoff[u], v);
     }
+}
+
+template <typename Tin, typename Tout, bool FLAT, int KIND>
+__global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_constant__ RowsParams p)
+{
+    chain_rows_body<Tin, Tout, FLAT, KIND>(p, static_cast<const Tin *>(p.x), static_cast<Tout *>(p.y), (int64_t)blockIdx.x, p.n_vec, nullptr);
+}
+
+// Many tensors, one launch (dmxq_cast_chain_multi): the shards a rank owns in a sharded whole-model weight cast.  Every
+// tensor is a flat run of vectors; CTAs are dealt to tensors by a prefix table that travels in the kernel parameters (no
+// device-side table to allocate or fill), found by a CTA-uniform binary search.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kThreads) chain_rows_multi_kernel(const __grid_constant__ RowsParams p, const __grid_constant__ MultiTable t)
+{
+    int lo = 0, hi = t.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blockIdx.x >= t.cta0[mid]) lo = mid; else hi = mid;
+    }
+    chain_rows_body<T, T, true, KIND>(p, static_cast<const T *>(t.x[lo]), static_cast<T *>(t.y[lo]), (int64_t)(blockIdx.x - t.cta0[lo]), t.n_vec[lo],
+                                      t.amax ? t.amax + t.slot[lo] : nullptr);
+}
+
+template <typename T, int KIND> static cudaError_t launch_rows_multi_k(const RowsParams &p, const MultiTable &t, cudaStream_t s)
+{
+    const unsigned grid = t.cta0[t.n];
+    if (grid == 0) return cudaSuccess;
+    chain_rows_multi_kernel<T, KIND><<<grid, kThreads, 0, s>>>(p, t);
+    count_launch();
+    return cudaGetLastError();
 }
 
 template <typename Tin, typename Tout, int KIND>

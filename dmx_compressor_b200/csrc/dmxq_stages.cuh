@@ -166,7 +166,8 @@ __device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const S
     SbfpBlock b;
     const float m = u2f(maxabs_bits);
     // max / man_scaling: man_scaling = 2^(p-1) - 1 never has an all-ones significand, its reciprocal comes from the host
-    b.cmax = (m > 0x1p-60f && m < 0x1p60f) ? div_by_recip(m, f.man_scaling, f.inv_man) : __fdiv_rn(m, f.man_scaling);
+    if (f.recip) b.cmax = __fmul_rn(m, f.inv_man_t);  // torch's CUDA `max / man_scaling` (a multiplication by the rounded reciprocal)
+    else b.cmax = (m > 0x1p-60f && m < 0x1p60f) ? div_by_recip(m, f.man_scaling, f.inv_man) : __fdiv_rn(m, f.man_scaling);
     // scaler cast: cmax >= 0 (or NaN, in which case the block passes through and fs is unused), so the
     // unsigned scaler formats of the SBFP aliases reduce to the signed nearest+flush fast path
     if (f.sc_fast) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
@@ -513,6 +514,85 @@ __device__ __forceinline__ uint4 nm_apply_raw16(const uint4 &r, const bool (&kee
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// N:M tie order of the reference on CUDA tensors (DMXQ_NM_ORDER_TORCH_CUDA).  BlockTopK sorts every group with
+// torch.argsort(score, dim=1) (S/sparse.py:172); for rows of <= 32 keys ATen runs bitonicSortKVInPlace
+// (ATen/native/cuda/SortUtils.cuh) with 32 slots, the M keys in slots 0..M-1 and "invalid" slots behind them:
+//     swap = (LT(kA, kB) && validA) || !validB;   if (swap == dir) exchange(A, B)
+// so an ascending comparator (dir = false) exchanges unless kA < kB -- tied keys ARE exchanged -- and a descending
+// one (dir = true) exchanges when kA < kB.  The result for tied keys is a fixed function of the tie pattern, but not
+// a tie-break by index (scripts/probe_argsort.py: this model == torch.argsort on every tie pattern, any batch / dtype).
+//
+// With M a power of two the valid slots never leave 0..M-1 (an ascending comparator never moves a valid key behind an
+// invalid one, and slots 0..M-1 only meet descending comparators among themselves), so the 32-slot network reduces to
+//   * the bitonic build on M slots (stages size = 2..M, ATen's direction flags), then
+//   * log2(32 / M) more ascending merge passes over strides M/2..1 (the size 2M..32 stages: larger strides pair a
+//     valid slot with an invalid one and do nothing) -- which re-exchange the ties of the already sorted keys.
+// Returns the bit set of the n_prune first (= pruned) elements.
+template <int M> __device__ __forceinline__ uint32_t nm_pruned_torch(const uint32_t (&key)[M], int n_prune)
+{
+    uint32_t k[M], id[M];
+#pragma unroll
+    for (int a = 0; a < M; ++a) { k[a] = key[a]; id[a] = (uint32_t)a; }
+#pragma unroll
+    for (int size = 2; size <= 32; size *= 2) {
+#pragma unroll
+        for (int stride = (size <= M ? size / 2 : M / 2); stride > 0; stride /= 2) {
+#pragma unroll
+            for (int t = 0; t < M / 2; ++t) {
+                const bool desc = size < M && (t & (size / 2)) != 0;
+                const int a = 2 * t - (t & (stride - 1)), b = a + stride;
+                const bool lt = k[a] < k[b];
+                const bool ex = desc ? lt : !lt;
+                const uint32_t ka = k[a], kb = k[b], ia = id[a], ib = id[b];
+                k[a] = ex ? kb : ka; k[b] = ex ? ka : kb;
+                id[a] = ex ? ib : ia; id[b] = ex ? ia : ib;
+            }
+        }
+    }
+    uint32_t pruned = 0u;
+#pragma unroll
+    for (int a = 0; a < M; ++a) pruned |= (a < n_prune) ? (1u << id[a]) : 0u;
+    return pruned;
+}
+
+// The full 32-slot network for any group size M <= 32 (not a power of two, or larger than a thread's vector): scalar,
+// local-memory arrays; used by the generic kernel.
+static __device__ __noinline__ uint32_t nm_pruned_torch32(const uint32_t *key, int M, int n_prune)
+{
+    uint32_t k[32];
+    unsigned char id[32];
+    for (int a = 0; a < 32; ++a) { k[a] = a < M ? key[a] : 0u; id[a] = (unsigned char)a; }
+    for (int size = 2; size <= 32; size *= 2)
+        for (int stride = size / 2; stride > 0; stride /= 2)
+            for (int t = 0; t < 16; ++t) {
+                const bool dir = size < 32 && (t & (size / 2)) != 0;
+                const int a = 2 * t - (t & (stride - 1)), b = a + stride;
+                const bool va = id[a] < M, vb = id[b] < M;
+                const bool swap = (k[a] < k[b] && va) || !vb;
+                if (swap == dir) {
+                    const uint32_t tk = k[a]; k[a] = k[b]; k[b] = tk;
+                    const unsigned char ti = id[a]; id[a] = id[b]; id[b] = ti;
+                }
+            }
+    uint32_t pruned = 0u;
+    for (int a = 0; a < n_prune; ++a) pruned |= 1u << id[a];
+    return pruned;
+}
+
+template <int V, int M> __device__ __forceinline__ void nm_local_torch(const uint32_t (&key)[V], int n_prune, bool (&keep)[V])
+{
+#pragma unroll
+    for (int g0 = 0; g0 < V; g0 += M) {
+        uint32_t kk[M];
+#pragma unroll
+        for (int a = 0; a < M; ++a) kk[a] = key[g0 + a];
+        const uint32_t pruned = nm_pruned_torch<M>(kk, n_prune);
+#pragma unroll
+        for (int a = 0; a < M; ++a) keep[g0 + a] = ((pruned >> a) & 1u) == 0u;
+    }
+}
+
 // N:M across `lanes` = M / V neighbouring lanes (M > V): partner keys arrive by shuffle.
 template <int V> __device__ __forceinline__ void nm_lanes(const uint32_t (&key)[V], int n_prune, int lanes, int lane, bool (&keep)[V])
 {
@@ -541,7 +621,7 @@ template <int V> __device__ __forceinline__ void nm_lanes(const uint32_t (&key)[
 template <int V, int SRCBITS = 32>
 __device__ __forceinline__ void nm_stage(float (&v)[V], const StageDev &st, int lane, const float *score_vec, float *mask_vec, bool valid)
 {
-    if (SRCBITS != 32 && V == 8 && score_vec == nullptr && st.block <= 8) {
+    if (SRCBITS != 32 && V == 8 && score_vec == nullptr && st.block <= 8 && !st.nm_order) {
         // 16-bit source, score |x|: unique packed keys + sorting network
         constexpr int KS = SRCBITS == 16 ? 16 : 13;  // bf16 keeps 8+7 bits, fp16 (widened) 8+10 bits
         bool keep[V];
@@ -577,7 +657,11 @@ __device__ __forceinline__ void nm_stage(float (&v)[V], const StageDev &st, int 
     }
     bool keep[V];
     const int M = st.block;
-    if (M > V) {
+    if (st.nm_order) {  // torch's CUDA tie order (the dispatcher only sends in-thread groups here: M <= V, M <= 8)
+        if (M == 2) nm_local_torch<V, 2>(key, st.n_prune, keep);
+        else if (M == 4) nm_local_torch<V, 4>(key, st.n_prune, keep);
+        else nm_local_torch<V, (V >= 8 ? 8 : V)>(key, st.n_prune, keep);
+    } else if (M > V) {
         nm_lanes<V>(key, st.n_prune, M / V, lane, keep);
     } else if (M == 2) {
         nm_local<V, 2>(key, st.n_prune, keep);

@@ -121,7 +121,7 @@ class DmxModule:
                 return None
             if not (sp.plastic and sp.score_func is abs_score):
                 return None
-            stages.append(ops.nm_stage(sp.sparseness.K, sp.sparseness.block_size))
+            stages.append(ops.nm_stage(sp.sparseness.K, sp.sparseness.block_size, sp.sparseness.nm_order))
         for c in (self.weight_storage_cast, self.weight_cast):
             if c is None or isinstance(c.format, Same) or not c._fq_on:
                 continue

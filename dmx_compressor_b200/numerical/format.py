@@ -321,11 +321,14 @@ class ScaledBlockFloatingPoint(Format):
 
     def stage(self):
         b, s = self.block_format, self.scaler_format
+        # the block-scale rule goes with the tie rule (ops._scale_mode): tie "away" = the reference on CUDA tensors
+        # (half-away XP rounding, scale = max * fp32(1/man_scaling)), tie "even" = on CPU tensors (ties-even, max / man_scaling);
+        # `scale_mode` on the format overrides it
         key = (self.block_size, b.precision, b.clamp, b.rounding, b.tie, s.mantissa, s.exponent, s.bias, s.flush_subnormal, s.unsigned,
-               s.rounding)
+               s.rounding, getattr(self, "scale_mode", None))
         return self._memo_stage(key, lambda: ops.sbfp_stage(self.block_size, b.precision, b.clamp, b.rounding, b.tie, s.mantissa,
                                                             s.exponent, s.bias, s.flush_subnormal, s.unsigned,
-                                                            repr(s) == "FP[1|5|10,15](FN)", s.rounding))
+                                                            repr(s) == "FP[1|5|10,15](FN)", s.rounding, key[-1]))
 
     # packed storage: the real format whose size `bytes_per_elem` reports (reference format.py:481-486)
     def pack(self, x: torch.Tensor, return_inexact=False):

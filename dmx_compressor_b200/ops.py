@@ -67,10 +67,16 @@ def fixed_stage(precision: int, fraction: int, clamp: bool = True, symmetric: bo
                       rounding=L.ROUND[rounding], tie=tie, scale=scale, zero_point=zero_point)
 
 
+def _scale_mode(tie: int, scale_mode: Optional[int]) -> int:
+    """SBFP block-scale rule: by default it goes with the tie rule -- both are "which of the reference's two back ends":
+    TIE_AWAY + SCALE_RECIP = the reference on CUDA tensors, TIE_EVEN + SCALE_DIV = on CPU tensors (include/dmxq.h)"""
+    return (L.SCALE_RECIP if tie == L.TIE_AWAY else L.SCALE_DIV) if scale_mode is None else scale_mode
+
+
 def sbfp_stage(block_size: int, xp_precision: int, xp_clamp: bool, xp_rounding: str, tie: int, sc_mantissa: int,
                sc_exponent: int, sc_bias: int, sc_flush: bool, sc_unsigned: bool, sc_fp16_flush: bool = False,
-               sc_rounding: str = "nearest") -> L.Stage:
-    return make_stage(kind=L.ST_SBFP, block=block_size, precision=xp_precision, clamp=int(xp_clamp),
+               sc_rounding: str = "nearest", scale_mode: Optional[int] = None) -> L.Stage:
+    return make_stage(scale_mode=_scale_mode(tie, scale_mode), kind=L.ST_SBFP, block=block_size, precision=xp_precision, clamp=int(xp_clamp),
                       rounding=L.ROUND[xp_rounding], tie=tie, sc_man=sc_mantissa, sc_exp=sc_exponent, sc_bias=sc_bias,
                       sc_flush=int(sc_flush), sc_unsigned=int(sc_unsigned), sc_fp16_flush=int(sc_fp16_flush),
                       sc_rounding=L.ROUND[sc_rounding])
@@ -80,8 +86,10 @@ def mxfp_stage(block_size: int, mantissa: int, exponent: int) -> L.Stage:
     return make_stage(kind=L.ST_MXFP, block=block_size, man=mantissa, exp=exponent)
 
 
-def nm_stage(n_keep: int, m: int) -> L.Stage:
-    return make_stage(kind=L.ST_NM, block=m, n_keep=n_keep)
+def nm_stage(n_keep: int, m: int, nm_order: int = L.NM_STABLE) -> L.Stage:
+    """N:M prune stage.  ``nm_order``: tie order inside a group -- NM_STABLE (torch.argsort(stable=True), what the reference
+    gets on CPU tensors) or NM_TORCH_CUDA (what it gets on CUDA tensors; see include/dmxq.h)."""
+    return make_stage(kind=L.ST_NM, block=m, n_keep=n_keep, nm_order=nm_order)
 
 
 def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, out: Optional[torch.Tensor] = None,
@@ -131,7 +139,7 @@ def bfp_qdq(x, block_dim=-1, block_size=64, precision=8, symmetric=True, roundin
 
 def sbfp_qdq(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_rounding="nearest", tie=L.TIE_AWAY,
              sc_mantissa=4, sc_exponent=4, sc_bias=7, sc_flush=True, sc_unsigned=True, sc_fp16_flush=False,
-             sc_rounding="nearest", out=None, out_dtype=None):
+             sc_rounding="nearest", out=None, out_dtype=None, scale_mode=None):
     """ScaledBlockFloatingPoint.cast (reference S/numerical/format.py:453-479) via dmxq_sbfp_qdq."""
     L.require_cuda(x)
     y = out if out is not None else _out_like(x, out_dtype)
@@ -139,7 +147,8 @@ def sbfp_qdq(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_r
     with _guard(x.device):
         rc = L.lib.dmxq_sbfp_qdq(C.byref(vx), C.byref(vy), block_dim, block_size, xp_precision, int(xp_clamp),
                                  L.ROUND[xp_rounding], tie, sc_mantissa, sc_exponent, sc_bias, int(sc_flush),
-                                 int(sc_unsigned), int(sc_fp16_flush), L.ROUND[sc_rounding], L.stream_ptr(x.device))
+                                 int(sc_unsigned), int(sc_fp16_flush), L.ROUND[sc_rounding], _scale_mode(tie, scale_mode),
+                                 L.stream_ptr(x.device))
     L.check(rc, "dmxq_sbfp_qdq")
     return y
 
@@ -186,7 +195,7 @@ def fixed_qdq(x, precision, fraction, clamp=True, symmetric=True, rounding="near
     return y
 
 
-def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None, out_dtype=None):
+def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None, out_dtype=None, nm_order=L.NM_STABLE):
     """Sparsify.forward with BlockTopK (reference S/sparse.py:163-180, 287-301) via dmxq_nm_prune."""
     L.require_cuda(x)
     y = out if out is not None else _out_like(x, out_dtype)
@@ -200,7 +209,7 @@ def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, out=None
     if mask is not None:
         vm = C.byref(L.view(mask))
     with _guard(x.device):
-        rc = L.lib.dmxq_nm_prune(C.byref(vx), vs, C.byref(vy), vm, block_dim, n_keep, m, L.stream_ptr(x.device))
+        rc = L.lib.dmxq_nm_prune(C.byref(vx), vs, C.byref(vy), vm, block_dim, n_keep, m, nm_order, L.stream_ptr(x.device))
     L.check(rc, "dmxq_nm_prune")
     return (y, mask) if return_mask else y
 

@@ -43,7 +43,13 @@ def _patch(obj, name, new):
     setattr(obj, name, new)
 
 
-def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
+def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order: str = "torch_cuda") -> None:
+    """``tie_order``: N:M tie order of the patched ``Sparsify.forward`` -- "torch_cuda" (default) reproduces what the
+    unpatched reference computes for CUDA tensors (torch's unstable bitonic argsort) bit for bit, "stable" is the
+    reference's CPU order (and the faster kernel).  FixedPoint ties (half away) and the SBFP block scale (multiplied by
+    the rounded reciprocal) always follow the reference's CUDA behaviour: only CUDA tensors are redirected."""
+    assert tie_order in ("torch_cuda", "stable")
+    nm_order = L.NM_TORCH_CUDA if tie_order == "torch_cuda" else L.NM_STABLE
     fmt = importlib.import_module(package + ".numerical.format")
     sparse = importlib.import_module(package + ".sparse")
     refquant = importlib.import_module(package + ".quant")
@@ -134,7 +140,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True) -> None:
             score = self.score
         out_dtype = torch.promote_types(x.dtype, score.dtype)
         y, mask = ops.nm_prune(x, sp.K, sp.block_size, sp.block_dim, score=score.detach(), return_mask=True,
-                               out_dtype=torch.float32 if out_dtype == torch.float32 else x.dtype)
+                               out_dtype=torch.float32 if out_dtype == torch.float32 else x.dtype, nm_order=nm_order)
         self.mask = mask.to(score.dtype)
         return y
 

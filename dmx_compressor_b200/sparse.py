@@ -19,6 +19,7 @@ from torch.autograd import Function
 from torch.nn.modules.lazy import LazyModuleMixin
 from torch.nn.parameter import UninitializedParameter
 
+from . import _lib as L
 from . import ops
 
 __ALL__ = ["Sparseness", "Dense", "TopK", "BlockTopK", "Bernoulli", "Sparsify", "LazySparsify", "abs_score"]
@@ -118,17 +119,31 @@ class BlockTopK(Sparseness):
     blocked = True
     _RX = re.compile(r"^BTOPK\{(?P<K>\d+):(?P<block_size>\d+),(?P<block_dim>[-+]?\d+)\}\((?P<mask_grad>[A-Za-z])\)$")
 
-    def __init__(self, K=4, block_size=8, block_dim=-1, mask_gradient=False):
+    # Tie order inside a group.  The reference sorts with torch.argsort (sparse.py:172), whose order for tied scores
+    # differs between its two back ends: stable on CPU tensors, an unstable bitonic network on CUDA tensors (groups of
+    # <= 32).  "stable" (default: deterministic, lower index pruned first) or "torch_cuda" (bit-identical to what the
+    # reference produces on a GPU; include/dmxq.h DMXQ_NM_ORDER_*).  A class-level default, overridable per instance.
+    tie_order = "stable"
+
+    def __init__(self, K=4, block_size=8, block_dim=-1, mask_gradient=False, tie_order=None):
         super().__init__(mask_gradient)
         assert 0 < K <= block_size, "N and M must be positive and N no greater than M"
         self.K = K
         self.block_size = block_size
         self.block_dim = block_dim
         self.density = self.K / self.block_size
+        if tie_order is not None:
+            assert tie_order in ("stable", "torch_cuda"), f"unknown tie order {tie_order!r}"
+            self.tie_order = tie_order
+
+    @property
+    def nm_order(self) -> int:
+        return L.NM_TORCH_CUDA if self.tie_order == "torch_cuda" else L.NM_STABLE
 
     def get_mask(self, score):
         """mask only (reference BlockTopK.forward, sparse.py:163-180)."""
-        _, mask = ops.nm_prune(score.detach(), self.K, self.block_size, self.block_dim, score=score.detach(), return_mask=True)
+        _, mask = ops.nm_prune(score.detach(), self.K, self.block_size, self.block_dim, score=score.detach(), return_mask=True,
+                               nm_order=self.nm_order)
         return mask.to(score.dtype)
 
     @classmethod
@@ -174,7 +189,7 @@ class _NMPrune(Function):
         # x * mask promotes to the mask's dtype, which is the score's (sparse.py:173-178, 300)
         out_dtype = x.dtype if score is None else torch.promote_types(x.dtype, score.dtype)
         y, mask = ops.nm_prune(x, sp.K, sp.block_size, sp.block_dim, score=score, return_mask=True,
-                               out_dtype=torch.float32 if out_dtype == torch.float32 else x.dtype)
+                               out_dtype=torch.float32 if out_dtype == torch.float32 else x.dtype, nm_order=sp.nm_order)
         ctx.save_for_backward(x, mask)
         ctx.flags = (weight_grad, mask_grad, score is not None)
         ctx.mark_non_differentiable(mask)

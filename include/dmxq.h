@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define DMXQ_ABI_VERSION 1
+#define DMXQ_ABI_VERSION 2
 #define DMXQ_MAX_DIMS 8
 #define DMXQ_MAX_STAGES 4
 
@@ -83,6 +83,27 @@ typedef enum dmxq_rounding {
  * DMXQ_TIE_AWAY is what a user of the reference gets on CUDA tensors (the default of the
  * python binding); DMXQ_TIE_EVEN reproduces the CPU extension bit for bit. */
 typedef enum dmxq_tie { DMXQ_TIE_AWAY = 0, DMXQ_TIE_EVEN = 1 } dmxq_tie;
+
+/* The reference's CPU and CUDA back ends also disagree in two places that are not kernels of its own but torch
+ * operators it calls; both are selectable per stage, the python binding defaults to what a user of the reference
+ * gets on CUDA tensors:
+ *
+ * SBFP block scale (S/numerical/format.py:461-463, `get_chunk_max(chunk) / self.man_scaling`): dividing a CUDA tensor
+ *   by a python scalar, torch multiplies by the reciprocal instead (ATen div_true_kernel_cuda: inv_b = 1.0 / b in
+ *   double, rounded to fp32, then a * inv_b); on CPU tensors it divides.  The two differ in the last bit for about one
+ *   max in ten, which moves rounding ties of x / scale and of the scaler cast.
+ *     DMXQ_SCALE_DIV    max / man_scaling          (CPU tensors)
+ *     DMXQ_SCALE_RECIP  max * fp32(1 / man_scaling) (CUDA tensors)
+ *
+ * N:M tie order (S/sparse.py:172, `torch.argsort(score, dim=1)`, default = unstable): on CPU the sort is stable (ties
+ *   keep index order, so the lower index is pruned first); on CUDA rows of <= 32 keys go through ATen's 32-slot
+ *   bitonic network (bitonicSortKVInPlace, ATen/native/cuda/SortUtils.cuh: LT comparator, tied keys ARE exchanged by
+ *   the ascending comparators), whose result for tied keys is a fixed but pattern-dependent permutation.  Rows of more
+ *   than 32 keys use a stable sort on CUDA too.
+ *     DMXQ_NM_ORDER_STABLE      torch.argsort(stable=True) == the reference on CPU tensors
+ *     DMXQ_NM_ORDER_TORCH_CUDA  the bitonic network's order, bit for bit == the reference on CUDA tensors */
+typedef enum dmxq_scale_mode { DMXQ_SCALE_DIV = 0, DMXQ_SCALE_RECIP = 1 } dmxq_scale_mode;
+typedef enum dmxq_nm_order { DMXQ_NM_ORDER_STABLE = 0, DMXQ_NM_ORDER_TORCH_CUDA = 1 } dmxq_nm_order;
 
 typedef struct dmxq_tensor {
     void *data;                    /* device pointer (host pointer for *_host entry points) */
@@ -124,6 +145,8 @@ typedef struct dmxq_stage {
     int32_t n_keep;     /* NM: K of K:M */
     int32_t sc_man, sc_exp, sc_bias, sc_flush, sc_unsigned, sc_fp16_flush, sc_rounding; /* SBFP scaler format */
     float scale, zero_point; /* FIXED per-tensor affine (cast.py:293,296); scale = 1, zp = 0 for none */
+    int32_t scale_mode; /* SBFP: dmxq_scale_mode */
+    int32_t nm_order;   /* NM: dmxq_nm_order */
 } dmxq_stage;
 
 int dmxq_abi_version(void);
@@ -149,7 +172,7 @@ int dmxq_bfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int 
 int dmxq_sbfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size,
                   int xp_precision, int xp_clamp, int xp_rounding, int xp_tie,
                   int sc_man, int sc_exp, int sc_bias, int sc_flush, int sc_unsigned,
-                  int sc_fp16_flush, int sc_rounding, void *stream);
+                  int sc_fp16_flush, int sc_rounding, int scale_mode, void *stream);
 int dmxq_float_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int man, int exp, int bias,
                    int flush_subnormal, int is_unsigned, int fp16_flush, int rounding,
                    const int32_t *rand, void *stream);
@@ -162,7 +185,7 @@ int dmxq_fixed_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int fl, i
                    const float *zero_point, int64_t n_qparams, int ch_axis, int64_t group_size,
                    const float *rand, void *stream);
 int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_tensor *y,
-                  const dmxq_tensor *mask, int block_dim, int n_keep, int m, void *stream);
+                  const dmxq_tensor *mask, int block_dim, int n_keep, int m, int nm_order, void *stream);
 
 /* ---- fused residual add: y = out( A(a) + B(b) ) in one pass (ResAdd.forward of the reference,
  * S/modeling/nn/torch_modules.py:15-37, with its two input casts and its output cast folded into the

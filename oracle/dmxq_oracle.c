@@ -259,9 +259,11 @@ void orc_fixed_cast_affine(const float *x, float *y, int64_t outer, int64_t C, i
 void orc_sbfp_cast(const float *x, float *y, int64_t outer, int64_t K, int64_t inner, int64_t bs,
                    int xp_wl, int xp_clamp, int xp_mode, int tie,
                    int sc_man, int sc_exp, int sc_bias, int sc_flush, int sc_unsigned, int sc_fp16_flush,
-                   int sc_mode)
+                   int sc_mode, int scale_recip)
 {
     float man_scaling = (float)((1 << (xp_wl - 1)) - 1);
+    /* `chunk_max / self.man_scaling` on a CUDA tensor: ATen multiplies by inv_b = fp32(1.0 / b) (div_true_kernel_cuda) */
+    float inv_b = (float)(1.0 / (double)man_scaling);
     float t_min, t_max;
     orc_fixed_min_max(xp_wl, 0, 1, &t_min, &t_max);
     for (int64_t o = 0; o < outer; o++)
@@ -273,7 +275,7 @@ void orc_sbfp_cast(const float *x, float *y, int64_t outer, int64_t K, int64_t i
                     uint32_t a = absbits(x[(o * K + k) * inner + i]);
                     if (a > m) m = a;
                 }
-                float cmax = u2f(m) / man_scaling;
+                float cmax = scale_recip ? u2f(m) * inv_b : u2f(m) / man_scaling;
                 float fs = float_elem(cmax, sc_man, sc_exp, sc_bias, sc_flush, sc_mode, 0u);
                 if (sc_fp16_flush && fabsf(fs) < 6.103515625e-05f) fs = 0.0f;
                 if (sc_unsigned) fs = fabsf(fs);
@@ -323,10 +325,65 @@ void orc_mxfp_cast(const float *x, float *y, int64_t outer, int64_t K, int64_t i
  * first M - Kkeep indices get mask 0; y = x * mask (fp32 multiply: masked negatives become
  * -0.0, masked Inf/NaN become NaN).  score == NULL means score = |x| (the documented
  * `lambda s, x: x.abs()` score function).  mask_out may be NULL. */
+/* torch.argsort's default (unstable) order on CUDA for rows of <= 32 keys: ATen's bitonicSortKVInPlace
+ * (ATen/native/cuda/SortUtils.cuh) restated literally -- 32 slots, the M keys in slots 0..M-1, "invalid" slots behind
+ * them, 16 "threads" per stage, comparator LTOp<float, handleNaN = true> (SortingCommon.cuh:55-61):
+ *     swap = (LT(kA, kB) && validA) || !validB;   if (swap == dir) exchange
+ * pinned by tests/golden/argsort_cuda_order.npz (torch.argsort run on the B200 over every tie pattern). */
+static int lt_nan_last(float a, float b) { return (isnan(b) && !isnan(a)) || a < b; }
+static void bitonic32_order(const float *key, int M, int *order)
+{
+    float k[32];
+    int id[32];
+    for (int a = 0; a < 32; a++) { k[a] = a < M ? key[a] : 0.0f; id[a] = a; }
+    for (int size = 2; size <= 32; size *= 2)
+        for (int stride = size / 2; stride > 0; stride /= 2)
+            for (int t = 0; t < 16; t++) {
+                int dir = size < 32 && (t & (size / 2)) != 0;
+                int a = 2 * t - (t & (stride - 1)), b = a + stride;
+                int va = id[a] < M, vb = id[b] < M;
+                int swap = (lt_nan_last(k[a], k[b]) && va) || !vb;
+                if (swap == dir) {
+                    float tk = k[a]; k[a] = k[b]; k[b] = tk;
+                    int ti = id[a]; id[a] = id[b]; id[b] = ti;
+                }
+            }
+    for (int a = 0; a < M; a++) order[a] = id[a];
+}
+void orc_argsort_cuda_order(const float *keys, int64_t rows, int M, int32_t *out)
+{
+    int order[32];
+    for (int64_t r = 0; r < rows; r++) {
+        bitonic32_order(keys + r * M, M, order);
+        for (int a = 0; a < M; a++) out[r * M + a] = order[a];
+    }
+}
+
+/* nm_order: 0 = stable (torch.argsort on CPU tensors / stable=True), 1 = torch's CUDA order (groups of <= 32). */
 void orc_nm_prune(const float *x, const float *score, float *y, float *mask_out,
-                  int64_t outer, int64_t K, int64_t inner, int n_keep, int M)
+                  int64_t outer, int64_t K, int64_t inner, int n_keep, int M, int nm_order)
 {
     int n_prune = M - n_keep;
+    if (nm_order == 1 && M <= 32) {
+        float key[32];
+        int order[32];
+        for (int64_t o = 0; o < outer; o++)
+            for (int64_t i = 0; i < inner; i++)
+                for (int64_t k0 = 0; k0 + M <= K; k0 += M) {
+                    for (int a = 0; a < M; a++) {
+                        int64_t ia = (o * K + k0 + a) * inner + i;
+                        key[a] = score ? score[ia] : fabsf(x[ia]);
+                    }
+                    bitonic32_order(key, M, order);
+                    for (int a = 0; a < M; a++) {
+                        int64_t ia = (o * K + k0 + order[a]) * inner + i;
+                        float mk = a < n_prune ? 0.0f : 1.0f;
+                        if (mask_out) mask_out[ia] = mk;
+                        y[ia] = x[ia] * mk;
+                    }
+                }
+        return;
+    }
     for (int64_t o = 0; o < outer; o++)
         for (int64_t i = 0; i < inner; i++)
             for (int64_t k0 = 0; k0 + M <= K; k0 += M)

@@ -52,8 +52,10 @@ def lib():
         L.orc_float_cast.argtypes = [_fp, _fp, _i64] + [_int] * 7 + [_ip]
         L.orc_fixed_quantize.argtypes = [_fp, _fp, _i64] + [_int] * 6 + [_fp]
         L.orc_fixed_cast_affine.argtypes = [_fp, _fp, _i64, _i64, _i64] + [_int] * 6 + [_fp, _fp, _i64, _i64, _fp]
-        L.orc_sbfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64] + [_int] * 11
-        L.orc_nm_prune.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, _int, _int]
+        L.orc_sbfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64] + [_int] * 12
+        L.orc_nm_prune.argtypes = [_fp, _fp, _fp, _fp, _i64, _i64, _i64, _int, _int, _int]
+        L.orc_argsort_cuda_order.argtypes = [_fp, _i64, _int, _fp]
+        L.orc_argsort_cuda_order.restype = None
         L.orc_mxfp_cast.argtypes = [_fp, _fp, _i64, _i64, _i64, _i64, _int, _int]
         L.orc_mxfp_cast.restype = None
         L.orc_minmax.argtypes = [_fp, _i64, _i64, _i64, _fp, _fp]
@@ -198,19 +200,23 @@ def fixed_cast(x, precision, fraction, clamp=True, symmetric=True, rounding="nea
 
 
 def sbfp_cast(x, block_dim=-1, block_size=16, xp_precision=4, xp_clamp=True, xp_rounding="nearest", tie=TIE_EVEN,
-              sc_mantissa=4, sc_exponent=4, sc_bias=7, sc_flush=True, sc_unsigned=True, sc_rounding="nearest"):
-    """ScaledBlockFloatingPoint.cast (S/numerical/format.py:453-479) on an fp32 array."""
+              sc_mantissa=4, sc_exponent=4, sc_bias=7, sc_flush=True, sc_unsigned=True, sc_rounding="nearest", scale_recip=None):
+    """ScaledBlockFloatingPoint.cast (S/numerical/format.py:453-479) on an fp32 array.  ``scale_recip``: the block scale
+    as torch computes it for CUDA tensors (max * fp32(1/man_scaling)) instead of max / man_scaling; default = it goes
+    with the tie rule (TIE_AWAY == "the reference on CUDA tensors", TIE_EVEN == "on CPU tensors")."""
+    if scale_recip is None:
+        scale_recip = tie == TIE_AWAY
     x = _f32(x)
     o, K, i = _okI(x.shape, block_dim)
     y = np.empty_like(x)
     fp16_flush = _fp_repr(sc_mantissa, sc_exponent, sc_bias, sc_flush, sc_unsigned, sc_rounding) == "FP[1|5|10,15](FN)"
     lib().orc_sbfp_cast(_p(x), _p(y), o, K, i, block_size, xp_precision, int(xp_clamp), ROUNDING[xp_rounding], tie,
                         sc_mantissa, sc_exponent, sc_bias, int(sc_flush), int(sc_unsigned), int(fp16_flush),
-                        ROUNDING[sc_rounding])
+                        ROUNDING[sc_rounding], int(scale_recip))
     return y
 
 
-def sbfp_pack(x, block_size=16, xp_precision=4, tie=TIE_AWAY, sc_mantissa=4, sc_exponent=4, sc_bias=7):
+def sbfp_pack(x, block_size=16, xp_precision=4, tie=TIE_AWAY, sc_mantissa=4, sc_exponent=4, sc_bias=7, scale_recip=None):
     """Packed SBFP storage of a [..., K] fp32 array, blocks along the last dim (the format of include/dmxq.h
     ``dmxq_sbfp_pack``), restated from the pieces of ScaledBlockFloatingPoint.cast (S/numerical/format.py:453-479):
     per block ``cmax = max|x| / man_scaling`` (:462-464), mantissa = ``block_format.cast(chunk / cmax)`` (:468), scaler =
@@ -225,7 +231,9 @@ def sbfp_pack(x, block_size=16, xp_precision=4, tie=TIE_AWAY, sc_mantissa=4, sc_
     with np.errstate(all="ignore"):
         m = np.abs(blk).max(-1, keepdims=True)
         finite = np.isfinite(blk).all(-1, keepdims=True)
-        cmax = (m / man_scaling).astype(np.float32)
+        if scale_recip is None:
+            scale_recip = tie == TIE_AWAY
+        cmax = (m * np.float32(1.0 / float(man_scaling))).astype(np.float32) if scale_recip else (m / man_scaling).astype(np.float32)
         on = finite & (cmax > 0)
         fs = float_cast(np.where(on, cmax, np.float32(0)), sc_mantissa, sc_exponent, sc_bias, True, True, "nearest")
         q = fixed_cast((blk / np.where(on, cmax, np.float32(1))).astype(np.float32), xp_precision, 0, True, True, "nearest", tie=tie)
@@ -268,15 +276,29 @@ def mxfp_cast(x, block_dim=-1, block_size=32, mantissa=3, exponent=4):
     return y
 
 
-def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False):
-    """Sparsify.forward with a BlockTopK sparseness (S/sparse.py:163-180, 287-301)."""
+def argsort_cuda_order(keys):
+    """torch.argsort(keys, dim=1) as torch computes it on CUDA for rows of <= 32 keys (unstable bitonic network)."""
+    keys = _f32(keys)
+    rows, m = keys.shape
+    assert m <= 32
+    out = np.empty((rows, m), np.int32)
+    lib().orc_argsort_cuda_order(_p(keys), rows, m, _p(out))
+    return out
+
+
+NM_STABLE, NM_TORCH_CUDA = 0, 1
+
+
+def nm_prune(x, n_keep, m, block_dim=-1, score=None, return_mask=False, nm_order=NM_STABLE):
+    """Sparsify.forward with a BlockTopK sparseness (S/sparse.py:163-180, 287-301).  ``nm_order``: tie order of the
+    group sort -- stable (the reference on CPU tensors) or torch's CUDA order (groups of <= 32)."""
     x = _f32(x)
     o, K, i = _okI(x.shape, block_dim)
     assert K % m == 0, f"score has size {K} at dimension {block_dim}, not a multiple of block size {m}"
     y = np.empty_like(x)
     mask = np.empty_like(x) if return_mask else None
     s = None if score is None else _f32(score)
-    lib().orc_nm_prune(_p(x), _p(s), _p(y), _p(mask), o, K, i, n_keep, m)
+    lib().orc_nm_prune(_p(x), _p(s), _p(y), _p(mask), o, K, i, n_keep, m, int(nm_order))
     return (y, mask) if return_mask else y
 
 

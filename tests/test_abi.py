@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(os.path.join(ROOT, "dmx_compressor_b200", "lib", "libdmxq.so"))
     for name in sorted(declared):
         assert hasattr(lib, name), f"libdmxq.so does not export {name}"
-    assert lib.dmxq_abi_version() == 1
+    assert lib.dmxq_abi_version() == 2
     from dmx_compressor_b200 import _lib
 
     assert set(_lib.EXPORTS) == declared, "python binding and header disagree"
@@ -30,7 +30,7 @@ def test_struct_layout_matches_header():
     from dmx_compressor_b200 import _lib as L
 
     assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 8 * 8 * 2
-    assert C.sizeof(L.Stage) == 22 * 4 + 2 * 4
+    assert C.sizeof(L.Stage) == 22 * 4 + 2 * 4 + 2 * 4
 
 
 def test_argument_validation_without_a_device():
@@ -47,10 +47,12 @@ def test_argument_validation_without_a_device():
     assert rc == -1 and b"block_dim" in L.lib.dmxq_last_error()
     rc = L.lib.dmxq_bfp_qdq(C.byref(vx), C.byref(vy), -1, 64, 8, 1, 1, None, None)
     assert rc == -1 and b"random tensor" in L.lib.dmxq_last_error()
-    rc = L.lib.dmxq_nm_prune(C.byref(vx), None, C.byref(vy), None, -1, 2, 5, None)
+    rc = L.lib.dmxq_nm_prune(C.byref(vx), None, C.byref(vy), None, -1, 2, 5, 0, None)
     assert rc == -1 and b"not a multiple of block size" in L.lib.dmxq_last_error()
     with pytest.raises(AssertionError):
         L.check(rc)
+    rc = L.lib.dmxq_nm_prune(C.byref(vx), None, C.byref(vy), None, -1, 2, 4, 7, None)
+    assert rc == -1 and b"nm_order" in L.lib.dmxq_last_error()
     rc = L.lib.dmxq_float_qdq(C.byref(vx), C.byref(vy), 24, 8, 127, 0, 0, 0, 0, None, None)
     assert rc == -1
     vz = L.view(torch.zeros(4, 32))

@@ -687,6 +687,77 @@ def test_vs_torch_cuda_argsort():
         assert torch.equal(unstable.abs().sum(1), got.abs().sum(1))
 
 
+def test_nm_torch_cuda_tie_order():
+    """nm_order = NM_TORCH_CUDA: the pruned set is exactly the first M-K entries of torch.argsort's default (unstable) CUDA
+    order -- checked against torch.argsort itself on this GPU and against the oracle's restatement of the bitonic network --
+    for in-thread groups (rows kernel), groups wider than a thread's vector / not a power of two (generic kernel), score
+    tensors, mask output, strided block dims, 16-bit sources and the fused sparsify -> BFP chain"""
+    g = torch.Generator(device=DEV).manual_seed(123)
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
+        for m, k in ((2, 1), (4, 2), (4, 1), (4, 3), (8, 4), (8, 2), (16, 8), (32, 16), (6, 3)):
+            x = (torch.randint(-4, 5, (512, 2 * 96), device=DEV, generator=g).float() / 4).to(dt)  # tie-heavy
+            score = x.abs().float()
+            idx = torch.argsort(score.reshape(-1, m), dim=1)[:, : m - k]
+            mask = torch.ones_like(score).reshape(-1, m).scatter_(dim=1, index=idx, value=0).reshape(x.shape)
+            want = x * mask.to(dt)
+            got, gmask = ops.nm_prune(x, k, m, -1, return_mask=True, nm_order=L.NM_TORCH_CUDA)
+            assert torch.equal(gmask, mask), f"{k}:{m} {dt} mask vs torch.argsort"
+            assert torch.equal(got.view(torch.int16 if dt != torch.float32 else torch.int32),
+                               want.view(torch.int16 if dt != torch.float32 else torch.int32)), f"{k}:{m} {dt}"
+            got2 = ops.nm_prune(x, k, m, -1, nm_order=L.NM_TORCH_CUDA)  # no mask output: another kernel specialisation
+            assert torch.equal(got2, got)
+            ow = O.nm_prune(x.float().cpu().numpy(), k, m, -1, nm_order=O.NM_TORCH_CUDA)
+            assert (got.float().cpu().numpy().view(np.uint32) == ow.view(np.uint32)).all(), f"{k}:{m} {dt} vs oracle"
+            if m <= 8:
+                st = ops.nm_prune(x, k, m, -1)
+                assert not torch.equal(st, got), "tie-heavy data must tell the two orders apart"
+    # explicit score tensor (the plugin's path), block dim 0 (strided groups), and the sparsify -> BFP12 chain
+    x = torch.randn(64, 256, device=DEV, generator=g)
+    sc = torch.randint(0, 3, (64, 256), device=DEV, generator=g).float()
+    for bd, m, k in ((-1, 4, 2), (0, 4, 2), (0, 8, 4), (-1, 8, 4)):
+        s2 = sc.transpose(bd, -1).reshape(-1, m)
+        idx = torch.argsort(s2, dim=1)[:, : m - k]
+        mask = torch.ones_like(s2).scatter_(dim=1, index=idx, value=0).reshape(sc.transpose(bd, -1).shape).transpose(bd, -1)
+        got, gmask = ops.nm_prune(x, k, m, bd, score=sc, return_mask=True, nm_order=L.NM_TORCH_CUDA)
+        assert torch.equal(gmask, mask) and torch.equal(got, x * mask), f"score tensor, block_dim {bd}, {k}:{m}"
+    for dt in (torch.float32, torch.bfloat16):
+        w = (torch.randint(-8, 9, (128, 512), device=DEV, generator=g).float() / 8).to(dt)
+        f12 = fmt_from("BFP[4|8]{64}(SN)").stage()
+        fused = ops.cast_chain(w, [ops.nm_stage(2, 4, L.NM_TORCH_CUDA), f12], -1)
+        two = ops.cast_chain(ops.nm_prune(w, 2, 4, -1, nm_order=L.NM_TORCH_CUDA), [f12], -1)
+        assert torch.equal(fused, two), f"fused 2:4 -> BFP12 in torch order, {dt}"
+        assert not torch.equal(fused, ops.cast_chain(w, [ops.nm_stage(2, 4), f12], -1))
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_sbfp_scale_modes(dt):
+    """the SBFP block scale as the reference computes it on CPU tensors (max / 7) and on CUDA tensors (max * fp32(1/7):
+    torch's division of a CUDA tensor by a python scalar), each with both XP tie rules, against the oracle; rows, cols and
+    generic kernels; packed storage follows the same rule"""
+    x = _rand((256, 1024), 321, spread=10).to(dt)
+    xn = x.float().numpy()
+    for sh in ("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}", "SBFP<XP[8,0](CSN)><FP[0|4|4,5](FN)>{32}"):
+        for tie in ("away", "even"):
+            for mode in (L.SCALE_DIV, L.SCALE_RECIP):
+                f = fmt_from(sh, tie)
+                f.scale_mode = mode
+                for bd in (-1, 0):
+                    got = f.cast(x.to(DEV), bd)
+                    m = O._RX_SBFP.match(sh)
+                    xp, fp = O._RX_XP.match(m[1]), O._RX_FP.match(m[2])
+                    want = O.sbfp_cast(xn, bd, int(m[3]), int(xp[1]), True, "nearest", TIE[tie], int(fp[3]), int(fp[2]), int(fp[4]),
+                                       True, True, "nearest", scale_recip=bool(mode))
+                    check(got, bits(want), f"{sh} tie={tie} scale_mode={mode} bd={bd} {dt}")
+    # default: the scale rule goes with the tie rule
+    sh = "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"
+    a = fmt_from(sh, "away").cast(x.to(DEV), -1)
+    f = fmt_from(sh, "away"); f.scale_mode = L.SCALE_RECIP
+    assert torch.equal(a, f.cast(x.to(DEV), -1))
+    f = fmt_from(sh, "away"); f.scale_mode = L.SCALE_DIV
+    if dt != torch.float32:
+        assert not torch.equal(a, f.cast(x.to(DEV), -1)), "16-bit data: the two scale rules must differ on some tie"
+
+
 # =============================================================================== (d) properties at full size
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SN)", "BFP[4|8]{64}(SN)"])

@@ -86,16 +86,22 @@ def same_bits(a, b, what=""):
 
 
 def make_x(shape, dtype, seed=0, specials=True):
+    """finite test data: per-row scales 2^-12..2^12 (2^-6..2^5 for fp16, whose range ends at 65504), zeros of both signs,
+    denormals and a few outliers.  Non-finite values are left to tests/test_parity_gpu.py (kernel against kernel): through
+    the python layers the reference's behaviour on Inf / NaN blocks depends on tensor-wide state (e.g.
+    make_mantissa_asymmetric rewrites every block of a chunk through int() once ANY block holds an edge mantissa,
+    S/numerical/format.py:349-372) and is not a per-block contract."""
     g = torch.Generator(device=DEV).manual_seed(seed)
     x = torch.randn(shape, device=DEV, generator=g)
-    x = x * torch.pow(2.0, torch.randint(-12, 13, shape[:-1] + (1,), device=DEV, generator=g).float())
+    lo, hi = (-6, 6) if dtype == torch.float16 else (-12, 13)
+    x = x * torch.pow(2.0, torch.randint(lo, hi, shape[:-1] + (1,), device=DEV, generator=g).float())
     if specials:
         f = x.view(-1)
         f[::97] = 0.0
         f[5::131] = -0.0
         f[7::211] = 1e-41  # denormals
         f[11::223] = -3e-39
-        f[13::301] *= 1024.0
+        f[13::301] *= 64.0
     return x.to(dtype)
 
 
@@ -229,7 +235,7 @@ def _distinct_scores(shape, seed):
 @pytest.mark.parametrize("sp", ["BTOPK{2:4,-1}(U)", "BTOPK{4:8,-1}(U)", "BTOPK{2:8,0}(U)", "BTOPK{1:4,1}(U)", "BTOPK{2:4,-1}(M)"])
 def test_sparsify_patched_equals_reference_cuda(ref, plugin, sp, dtype):
     """Sparsify.forward (sparse.py:287-301): plastic with score_func (first forward), then the stored score; y and .mask.
-    Scores are tie-free here (torch's CUDA argsort is unstable: tie order is covered by test_nm_tie_order_*)."""
+    The |w| scores of 16-bit weights are full of ties: the plugin's default tie order is torch's CUDA argsort order."""
     S = ref.sparse
     shape = (64, 32, 16)
     x = make_x(shape, dtype, seed=9, specials=False)
@@ -238,7 +244,7 @@ def test_sparsify_patched_equals_reference_cuda(ref, plugin, sp, dtype):
         s = S.Sparsify(shape, sp).to(DEV).eval()
         with torch.no_grad():
             s.score.copy_(_distinct_scores(shape, 10))
-        s.configure(score_func=lambda score, w: w.abs().float() + score * 1e-9)
+        s.configure(score_func=lambda score, w: w.abs().float())
         assert s.plastic
         y1 = s(x)
         m1 = s.mask.clone()
@@ -249,6 +255,36 @@ def test_sparsify_patched_equals_reference_cuda(ref, plugin, sp, dtype):
     a, b = both(plugin, run)
     for u, v, what in zip(a, b, ("y plastic", "mask plastic", "y score", "mask score")):
         same_bits(u, v, f"{sp} {dtype} {what}")
+
+
+def test_sparsify_tie_heavy_and_stable_option(ref, plugin):
+    """scores drawn from a handful of values (most groups tied): default install == the unpatched reference on CUDA;
+    install(tie_order="stable") == the reference's CPU result for the same tensors"""
+    S = ref.sparse
+    for sp, shape in (("BTOPK{2:4,-1}(U)", (128, 64)), ("BTOPK{4:8,-1}(U)", (128, 64)), ("BTOPK{2:8,0}(U)", (64, 48)),
+                      ("BTOPK{8:16,-1}(U)", (32, 64)), ("BTOPK{16:32,-1}(U)", (32, 64)), ("BTOPK{3:6,-1}(U)", (32, 36))):
+        g = torch.Generator(device=DEV).manual_seed(31)
+        x = (torch.randint(-3, 4, shape, device=DEV, generator=g).float() / 2)
+        sc = (torch.randint(0, 3, shape, device=DEV, generator=g).float())
+
+        def run(dev=DEV):
+            s = S.Sparsify(shape, sp).to(dev).eval()
+            with torch.no_grad():
+                s.score.copy_(sc.to(dev))
+            s.configure(score_func=lambda score, w: w.abs())
+            y1 = s(x.to(dev))
+            y2 = s(x.to(dev))
+            return y1, s.mask.clone(), y2
+
+        a, b = both(plugin, run)
+        for u, v, what in zip(a, b, ("y plastic", "mask", "y score")):
+            same_bits(u, v, f"{sp} {what}")
+        if sp.startswith("BTOPK{16:32"):
+            continue  # torch's CPU sort of 32-key rows is not the stable order either (unspecified; stable is what we document)
+        cpu = run("cpu")
+        _, c = both(plugin, run, tie_order="stable")
+        for u, v, what in zip(cpu, c, ("y plastic", "mask", "y score")):
+            same_bits(u.to(DEV), v, f"{sp} stable == reference on CPU: {what}")
 
 
 def test_sparsify_training_mode_keeps_reference_autograd(ref, plugin):
