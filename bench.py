@@ -1,7 +1,8 @@
 #!/usr/bin/env python
-"""bench.py -- BFP cast throughput on B200 (BASELINE.json metric: "BFP cast GB/s & % of HBM peak").
+"""bench.py -- BFP cast throughput on B200 (BASELINE.json metric: "BFP cast GB/s & % of HBM peak;
+OPT-125m BASIC-mode forward tokens/s").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda]
 
 Workload (BASELINE.json configs[1], the configuration the metric is quoted on): the standalone
 block-size-64 cast sweep point  n = 2^28 elements as [65536, 4096]:
@@ -11,20 +12,35 @@ One "step" = those four casts over the batch.  Algorithmic bytes per cast = read
 cast touches 1-2 GiB, far above the 126 MB L2, so every step streams from HBM (no L2 flush
 needed; stated in config.l2).
 
-value     whole-job GB/s with inputs resident in HBM (device timed with CUDA events around the
-          K steps, barrier + synchronize on both sides, max over ranks).
-e2e       the same metric through the C ABI host entry (dmxq_cast_chain_host): pinned HOST
-          buffers in, host buffers out, H2D + kernel + D2H inside the timed region.
-roofline  the dominant kernel (chain_rows_kernel<float,float,flat,bfp>; the two fp32 casts are
-          2/3 of the step's bytes): algorithmic bytes per launch / its mean duration measured
-          with CUDA events around every launch of it inside the timed region.
-cpu_baseline  the reference's own CPU path on a bounded sample, on the host cores of this box.
---impl reference  times that CPU path alone (rank 0 only), same metric / unit / config.
+The LAST stdout line is the result (kept compact so a tail capture holds all of it); longer tables
+(the configs[1] size sweep, per-size OPT numbers) are printed BEFORE it as {"detail": ...} lines.
 
-N > 1 (torchrun): every rank runs the same workload on its own GPU (independent tensors, no
+value      whole-job GB/s with inputs resident in HBM (CUDA events around the K steps, barrier +
+           synchronize on both sides, max over ranks).
+e2e        the same metric through the C ABI host entry (dmxq_cast_chain_host): pinned HOST buffers in,
+           host buffers out, H2D + kernel + D2H inside the timed region.
+roofline   the dominant kernel (chain_rows_kernel<float,float,flat,K_BFP>; the two fp32 casts are 2/3 of
+           the step's bytes): algorithmic bytes per launch / its mean duration, CUDA events around
+           every launch of it inside the timed region.
+roofline_by_format   the same figure for every format the north star names (INT8, FLOAT16, 2:4,
+           2:4 -> BFP12, SBFP, MXFP8 ...) on fp32 and bf16 tensors of 2^28 elements.
+sharded    BASELINE configs #4 / #5, the north star's multi-GPU path: Llama-3-8B-shaped weights,
+           2:4 -> BFP12, sharded by parameter / row range over the N ranks (STRONG scaling: the whole
+           model at every N), and Llama-3-70B-shaped weights, SBFP12_16 with the scaler bias taken
+           from ONE batched amax all-reduce, 10 layers per GPU.  Every tensor is generated from a seed
+           of its NAME, so the cast bytes do not depend on N: `checksum` (64-bit sums of the output
+           bit patterns, all-reduced) must be identical at N = 1 / 2 / 4 / 8.
+reference_cuda   the reference's OWN CUDA path (its CastTo.forward -> python split/cat loop ->
+           quant_cuda kernels, oracle/_ref) on the same 2^28 tensors, CUDA-event timed: what a user of
+           the reference gets on this GPU.
+cpu_baseline / --impl reference   the reference's CPU path (its CastTo.forward on CPU tensors) on
+           a bounded sample, on the host cores of this box.
+
+N > 1 (torchrun): every rank runs the configs[1] step on its own GPU (independent tensors, no
 data-path collective) -> weak scaling; value = bytes of all ranks / max-over-ranks time.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -38,18 +54,18 @@ sys.path.insert(0, ROOT)
 N_ELEMS = 1 << 28
 COLS = 4096
 FORMATS = [("BFP16_64", "BFP[8|8]{64}(SN)", 8), ("BFP12_64", "BFP[4|8]{64}(SN)", 4)]
-CPU_SAMPLE_ELEMS = 1 << 22
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the model-level extras (OPT-125m forward, sharded weight casts)")
+    ap.add_argument("--no-extras", action="store_true", help="only the timed step, e2e and cpu_baseline")
+    ap.add_argument("--no-details", action="store_true", help="skip the long detail tables (size sweep)")
     return ap.parse_args()
 
 
@@ -58,7 +74,8 @@ def config_dict(n_gpus):
         "workload": "configs[1]: standalone BFP16_64 + BFP12_64 cast of fp32 and bf16 [65536,4096] (2^28 elements), block 64 along the last dim",
         "formats": [f[1] for f in FORMATS], "dtypes": ["fp32", "bf16"], "elements_per_cast": N_ELEMS,
         "bytes_per_step": bytes_per_step(), "l2": "inputs (1-2 GiB per cast) exceed the 126 MB L2; no flush needed",
-        "parallelism": f"independent replicas x{n_gpus} (no collective on the data path)",
+        "parallelism": f"weak scaling: the configs[1] step on each of {n_gpus} GPU(s), no collective on the data path; "
+                       "configs #4/#5 (sharded weight casts) are in `sharded`",
     }
 
 
@@ -66,7 +83,19 @@ def bytes_per_step():
     return sum(2 * es * N_ELEMS for es in (4, 2)) * len(FORMATS)
 
 
-# ------------------------------------------------------------------------------------------ CPU path
+def load_peak():
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
+    return peak, src
+
+
+# ------------------------------------------------------------------------------------------ the reference itself
 def _make_rows(n, seed=0):
     import torch
 
@@ -75,19 +104,37 @@ def _make_rows(n, seed=0):
     return x * torch.pow(2.0, torch.randint(-8, 9, (n // COLS, 1), generator=g).float())
 
 
-def _reference_cpu_cast():
-    """-> (callable(x_fp32_or_bf16_tensor, precision) -> tensor, kind, cores).
+def _reference_castto():
+    """-> (dict name -> the reference's own CastTo module, how): the unmodified reference python (oracle/_ref/pysrc, staged by
+    oracle/build_ref.py) with its own compiled extensions (oracle/_ref/ref_quant_{cpu,cuda}.so).  None when it did not travel."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    try:
+        import load_reference
 
-    kind "reference": the reference's compiled quant_cpu kernels (oracle/_ref/ref_quant_cpu.so, built
-    from /root/reference by oracle/build_ref.py) driven by the restated python loop of
-    BlockFloatingPoint.cast (S/numerical/format.py:322-341) + CastTo.forward's dtype round trip
-    (S/numerical/cast.py:262,306) -- i.e. exactly what the reference executes for a CPU tensor.
-    kind "port": oracle/dmxq_oracle.c when the reference binary is not available."""
+        if not load_reference.available():
+            return None, "reference python not staged"
+        num, _, _ = load_reference.load()
+        return {name: num.CastTo(sh) for name, sh, _ in FORMATS}, "reference CastTo.forward (S/numerical/cast.py:261-306), unmodified python + its compiled quant_cpu / quant_cuda"
+    except Exception as e:  # pragma: no cover
+        return None, f"reference python failed to import: {e!r}"
+
+
+def _reference_cpu_cast():
+    """-> (callable(x, name) -> tensor, kind, cores, how).
+
+    kind "reference": the reference's own CastTo.forward on CPU tensors -- S/numerical/cast.py:261-306 ->
+    BlockFloatingPoint.cast S/numerical/format.py:304-343 -> its compiled quant_cpu (oracle/_ref/ref_quant_cpu.so).  If the
+    staged python is missing, the same compiled kernels under a restated split / cat loop.  kind "port":
+    oracle/dmxq_oracle.c when not even the reference binary is available."""
     import torch
 
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    casts, how = _reference_castto()
+    if casts is not None:
+        return (lambda x, name: casts[name](x)), "reference", cores, how
+    prec = {name: p for name, _, p in FORMATS}
     try:
         import build_ref
 
@@ -95,23 +142,22 @@ def _reference_cpu_cast():
     except Exception:
         ref = None
     if ref is not None:
-        def cast(x, precision):
+        def cast(x, name):
             dt = x.dtype
-            _x = x.float().transpose(-1, -1)
+            _x = x.float()
             shp = _x.shape
             chunks = torch.split(_x.reshape(-1, shp[-1]), 64, dim=-1)
-            out = [ref.block_quantize_nearest(c.contiguous(), precision, 0, True) for c in chunks]
+            out = [ref.block_quantize_nearest(c.contiguous(), prec[name], 0, True) for c in chunks]
             return torch.cat(out, dim=-1).reshape(shp).to(dt)
 
-        return cast, "reference", cores
+        return cast, "reference", cores, "reference quant_cpu kernels under a restated BlockFloatingPoint.cast loop (" + how + ")"
     import oracle as O
 
-    def cast(x, precision):
+    def cast(x, name):
         dt = x.dtype
-        y = O.bfp_cast(x.float().numpy(), -1, 64, precision)
-        return torch.from_numpy(y).to(dt)
+        return torch.from_numpy(O.bfp_cast(x.float().numpy(), -1, 64, prec[name])).to(dt)
 
-    return cast, "port", 1
+    return cast, "port", 1, "oracle/dmxq_oracle.c"
 
 
 def cpu_pass(cast, xs):
@@ -119,20 +165,24 @@ def cpu_pass(cast, xs):
     t0 = time.perf_counter()
     nbytes = 0
     for x in xs:
-        for _, _, prec in FORMATS:
-            cast(x, prec)
+        for name, _, _ in FORMATS:
+            cast(x, name)
             nbytes += 2 * x.element_size() * x.numel()
     return time.perf_counter() - t0, nbytes
 
 
 def run_reference_arm(args):
+    """the reference's CPU implementation of the path on the host cores (rank 0 only)"""
     import torch
 
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    cast, kind, cores = _reference_cpu_cast()
-    x32 = _make_rows(CPU_SAMPLE_ELEMS)
+    cast, kind, cores, how = _reference_cpu_cast()
+    # bounded sample: the same [rows, 4096] layout, n = 2^26 per tensor when the run is short enough, else 2^24 / 2^22
+    total = args.steps + args.warmup
+    log2n = 26 if total <= 30 else (24 if total <= 120 else 22)
+    n = 1 << log2n
+    x32 = _make_rows(n)
     xs = [x32, x32.to(torch.bfloat16)]
     for _ in range(args.warmup):
         cpu_pass(cast, xs)
@@ -143,7 +193,8 @@ def run_reference_arm(args):
         t += dt
         nbytes += nb
     gbs = nbytes / t / 1e9
-    sample = f"each step = the 4 casts on a bounded sample of n=2^{CPU_SAMPLE_ELEMS.bit_length() - 1} elements per tensor ([{CPU_SAMPLE_ELEMS // COLS},{COLS}])"
+    sample = (f"each step = the 4 casts on a bounded sample of n=2^{log2n} elements per tensor ([{n // COLS},{COLS}]) of the 2^28 workload; "
+              f"GB/s is size-normalised (the CPU path is compute-bound); mean over the {args.steps} timed steps; {how}")
     line = {
         "impl": "reference", "metric": "BFP cast GB/s", "value": round(gbs, 4), "unit": "GB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * t / args.steps, 3), "higher_is_better": True,
@@ -152,6 +203,67 @@ def run_reference_arm(args):
         "e2e": {"value": round(gbs, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def time_reference_cuda(dev, xs, steps=2):
+    """the reference's own CUDA path on the bench tensors: its CastTo.forward, unpatched (python split / contiguous / cat loop
+    of S/numerical/format.py:322-341 + quant_cuda block_quantize_nearest + get_max_entry, Q/quant_cuda/quant.cu:14-74).
+    -> dict or {"unavailable": why}"""
+    import torch
+
+    casts, how = _reference_castto()
+    if casts is None:
+        return {"unavailable": how}
+    qf = sys.modules.get("dmx.compressor.quant.quant_function")
+    if qf is None or "quant_cuda" not in repr(getattr(qf, "quant_cuda", None)):
+        return {"unavailable": "the reference's quant_cuda extension is not loaded"}
+    try:
+        from dmx_compressor_b200 import plugin
+
+        assert not plugin.installed()
+    except ImportError:
+        pass
+    for c in casts.values():
+        c.to(dev)
+
+    def step():
+        for x in xs:
+            for name, _, _ in FORMATS:
+                casts[name](x)
+
+    with torch.no_grad():
+        step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    torch.cuda.empty_cache()
+    return {"value": round(bytes_per_step() / (ms * 1e-3) / 1e9, 1), "unit": "GB/s", "ms_per_step": round(ms, 2), "steps": steps,
+            "what": how + "; same [65536,4096] fp32 + bf16 tensors, same 4 casts, CUDA events"}
+
+
+def run_reference_cuda_arm(args):
+    import torch
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    x32 = _make_rows(N_ELEMS).to(dev)
+    xs = [x32, x32.to(torch.bfloat16)]
+    r = time_reference_cuda(dev, xs, steps=max(1, min(args.steps, 5)))
+    if "unavailable" in r:
+        print(json.dumps({"impl": "reference-cuda", "unavailable": r["unavailable"]}), flush=True)
+        return 0
+    line = {"impl": "reference-cuda", "metric": "BFP cast GB/s", "value": r["value"], "unit": "GB/s", "n_gpus": 1, "steps": r["steps"],
+            "warmup": 1, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(1), "what": r["what"]}
     print(json.dumps(line), flush=True)
     return 0
 
@@ -198,7 +310,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ extras
+# ------------------------------------------------------------------------------------------ sharded weight casts
 LLAMA = {
     "8b": dict(layers=32, d=4096, kv=1024, ffn=14336, vocab=128256),
     "70b": dict(layers=80, d=8192, kv=1024, ffn=28672, vocab=128256),
@@ -216,84 +328,178 @@ def llama_shapes(name, layers=None):
     return shapes
 
 
-def extra_weight_cast(dev, rank, world, dist, model, stages_fn, layers, with_stats, dtype, packed=False):
-    """Whole-model weight cast sharded by parameter / row range: every rank
-    materialises its shards (random, shard-local), optionally reduces per-tensor amax with ONE
-    batched all-reduce, and casts each shard with one fused kernel.  Timed on the device, max
-    over ranks; value = algorithmic bytes of all ranks / time.  `packed`: write the packed SBFP storage
-    (nibble mantissas + one scaler byte per block, dmxq_sbfp_pack) instead of the dequantised tensor."""
+def name_seed(name):
+    return int.from_bytes(hashlib.sha256(name.encode()).digest()[:6], "little")
+
+
+def make_shard(name, shape, row0, row1, dev, dtype):
+    """rows [row0, row1) of the tensor `name`: generated from a seed of (name, row block), so the values do not depend on
+    how many ranks share the tensor.  Row blocks of 1024 rows keep a shard's generation local to its rows."""
     import torch
 
+    RB = 1024
+    out = torch.empty(row1 - row0, shape[1], device=dev, dtype=dtype)
+    g = torch.Generator(device=dev)
+    b = row0 // RB
+    while b * RB < row1:
+        r0, r1 = b * RB, min((b + 1) * RB, shape[0])
+        g.manual_seed(name_seed(f"{name}#{b}"))
+        blk = torch.randn(r1 - r0, shape[1], device=dev, dtype=torch.float32, generator=g).mul_(0.02).to(dtype)
+        lo, hi = max(r0, row0), min(r1, row1)
+        out[lo - row0:hi - row0] = blk[lo - r0:hi - r0]
+        b += 1
+    return out
+
+
+def checksum_shards(mine, ys):
+    """two 64-bit sums (mod 2^64, as int64) over the output bit patterns of this rank's shards: sum(v) and sum((global row + 1) * v)
+    weighted by a per-tensor odd multiplier -- additive over row ranges, so the all-reduced value does not depend on the split"""
+    import torch
+
+    dev = ys[0].device if ys else None
+    acc = torch.zeros(2, dtype=torch.int64, device=dev)
+    for sh, y in zip(mine, ys):
+        it = torch.int16 if y.element_size() == 2 else torch.int32
+        mult = (name_seed(sh.name) | 1) & 0x7FFFFFFF
+        rs = y.view(it).sum(dim=1, dtype=torch.int64)
+        rows = torch.arange(sh.row0 + 1, sh.row1 + 1, device=dev, dtype=torch.int64)
+        acc[0] += rs.sum() * mult
+        acc[1] += (rs * rows).sum() * mult
+    return acc
+
+
+def sharded_weight_cast(dev, rank, world, dist, model, layers, dtype, mode, peak, reps=3):
+    """Whole-model weight cast sharded by parameter / row range.  Every rank materialises its shards
+    (seeded by tensor name), then per repetition: [amax: one dmxq_minmax per shard + ONE batched all-reduce(MAX)] and ONE
+    dmxq_cast_chain_multi over all its shards.  Timed on the device with CUDA events, max over ranks, best of `reps` (each
+    repetition streams > 10x the L2 from HBM).  mode: "nm24_bfp12" | "sbfp_amax"."""
+    import torch
+
+    from dmx_compressor_b200 import ops
     from dmx_compressor_b200 import parallel as P
+    from dmx_compressor_b200.numerical import Format
 
     shapes = llama_shapes(model, layers)
     plan = P.plan_shards(shapes, world, row_align=1)
     mine = plan[rank]
-    g = torch.Generator(device=dev).manual_seed(99 + rank)
-    ws = []
-    for sh in mine:
-        cols = shapes[sh.name][1]
-        ws.append(torch.randn(sh.row1 - sh.row0, cols, device=dev, dtype=torch.float32, generator=g).mul_(0.02).to(dtype))
-    from dmx_compressor_b200 import ops
-
-    if packed:
-        outs = [(torch.empty(w.shape[0], w.shape[1] // 2, device=dev, dtype=torch.uint8),
-                 torch.empty(w.shape[0], w.shape[1] // 16, device=dev, dtype=torch.uint8)) for w in ws]
-        inexact = torch.zeros((), device=dev, dtype=torch.int32)
+    ws = [make_shard(sh.name, shapes[sh.name], sh.row0, sh.row1, dev, dtype) for sh in mine]
+    outs = [torch.empty_like(w) for w in ws]
+    if mode == "nm24_bfp12":
+        stages = [ops.nm_stage(2, 4), Format.from_shorthand("BFP[4|8]{64}(SN)").stage()]
     else:
-        outs = [torch.empty_like(w) for w in ws]
+        stages = [Format.from_shorthand("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}").stage()]
+    amax_buf = torch.empty(len(ws), dtype=torch.float32, device=dev) if mode == "sbfp_amax" else None
 
     def run():
-        if with_stats:
-            # per-tensor amax: local dmxq_minmax per shard + ONE all_reduce(MAX) for the row-split tensors
-            stats = P.shard_stats(plan, rank, ws)
-            amax = torch.cat([torch.maximum(-mn, mx).reshape(-1) for mn, mx in stats]).cpu().tolist()  # one host sync
-            for w, y, a in zip(ws, outs, amax):
-                if packed:
-                    ops.sbfp_pack(w, stages_fn(a)[0], out=y, inexact=inexact)
-                else:
-                    ops.cast_chain(w, stages_fn(a), -1, out=y)
+        if mode == "sbfp_amax":
+            P.shard_amax(plan, rank, ws, out=amax_buf)  # local dmxq_minmax per shard + one all_reduce(MAX); stays on the device
+            ops.cast_chain_multi(ws, stages, -1, outs=outs, amax=amax_buf)
         else:
-            st = stages_fn(None)
-            for w, y in zip(ws, outs):
-                ops.cast_chain(w, st, -1, out=y)
+            ops.cast_chain_multi(ws, stages, -1, outs=outs)
+
+    from dmx_compressor_b200 import _lib
 
     run()
+    n0 = _lib.launch_count()
+    times = []
+    for _ in range(reps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    launches = (_lib.launch_count() - n0) // reps
+    nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
+    ck = checksum_shards(mine, outs)
+    t = torch.tensor(times + [float(nbytes)], device=dev, dtype=torch.float64)
     if dist is not None:
-        dist.barrier()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    run()
-    b.record()
-    torch.cuda.synchronize()
-    ms = a.elapsed_time(b)
-    if packed:
-        nbytes = sum(w.numel() * w.element_size() + m.numel() + sc.numel() for w, (m, sc) in zip(ws, outs))
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dist.all_reduce(ck, op=dist.ReduceOp.SUM)
+        per_rep_max = tmax[:reps].tolist()
+        best = min(range(reps), key=lambda i: per_rep_max[i])
+        ms_max, ms_mean, total = per_rep_max[best], float(tsum[best]) / world, float(tsum[reps])
     else:
-        nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
-    nelem = sum(w.numel() for w in ws)
-    n_inexact = int(inexact) // 2 if packed else None  # (two runs accumulated)
-    t = torch.tensor([ms, float(nbytes), float(nelem)], device=dev, dtype=torch.float64)
-    if dist is not None:
-        tm = t.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_max, total, nelem = float(tm[0]), float(t[1]), float(t[2])
-        ms_mean = float(t[0]) / world
-    else:
-        ms_max, total, ms_mean = ms, float(nbytes), ms
+        ms_max = min(times)
+        ms_mean, total = ms_max, float(nbytes)
     del ws, outs
     torch.cuda.empty_cache()
-    res = {"Gelem/s": round(nelem / (ms_max * 1e-3) / 1e9, 1)}
-    if packed:
-        res["blocks_not_representable"] = n_inexact
-    return {**res, "GB/s": round(total / (ms_max * 1e-3) / 1e9, 1), "ms": round(ms_max, 3), "bytes": int(total), "tensors": len(shapes),
-            "imbalance_max_over_mean_time": round(ms_max / ms_mean, 3), "plan_imbalance": round(P.plan_imbalance(plan, shapes), 3),
-            "dtype": str(dtype).split(".")[-1], "layers": layers if layers is not None else LLAMA[model]["layers"]}
+    gbs = total / (ms_max * 1e-3) / 1e9
+    res = {"GB/s": round(gbs, 1), "ms": round(ms_max, 3), "frac_of_peak_per_gpu": round(gbs / world / peak, 3), "GB_cast": round(total / 1e9, 2),
+           "tensors": len(shapes), "launches_per_rank": launches, "imbalance": round(ms_max / ms_mean, 3),
+           "checksum": "%016x%016x" % (int(ck[0]) & 0xFFFFFFFFFFFFFFFF, int(ck[1]) & 0xFFFFFFFFFFFFFFFF)}
+    if mode == "sbfp_amax":
+        # the amax pass re-reads every weight: real HBM traffic is 3 * sizeof per element, not the 2 * sizeof counted above
+        res["hbm_traffic_GB/s"] = round(gbs * 1.5, 1)
+        res["frac_of_peak_incl_amax_pass"] = round(gbs * 1.5 / world / peak, 3)
+    return res
 
 
-def extra_sweep(dev):
+# ------------------------------------------------------------------------------------------ per-format roofline
+def roofline_by_format(dev, peak):
+    """kernel time of every north-star format on 2^28-element fp32 and bf16 tensors ([65536,4096]): algorithmic bytes (read
+    once + write once) / mean of 10 launches (CUDA events; inputs 1-2 GiB >> L2).  Rows: [name, dtype, GB/s, frac of measured peak]"""
+    import torch
+
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format
+
+    F = Format.from_shorthand
+    g = torch.Generator(device=dev).manual_seed(7)
+    x32 = torch.randn(N_ELEMS // COLS, COLS, device=dev, generator=g)
+    x32 *= torch.pow(2.0, torch.randint(-8, 9, (N_ELEMS // COLS, 1), device=dev, generator=g).float())
+    rows = []
+    sc = torch.full((1,), 0.037, device=dev)
+    zp = torch.full((1,), 3.0, device=dev)
+    scr = torch.rand(N_ELEMS // COLS, device=dev) * 0.05 + 0.01
+    zpr = torch.zeros(N_ELEMS // COLS, device=dev)
+    for dt in (torch.float32, torch.bfloat16):
+        x = x32.to(dt)
+        y = torch.empty_like(x)
+        es = x.element_size()
+        cases = [
+            ("BFP16_64", lambda: ops.cast_chain(x, [F("BFP[8|8]{64}(SN)").stage()], -1, out=y)),
+            ("BFP12_64", lambda: ops.cast_chain(x, [F("BFP[4|8]{64}(SN)").stage()], -1, out=y)),
+            ("FLOAT16", lambda: ops.cast_chain(x, [F("FP[1|5|10,15](FN)").stage()], -1, out=y)),
+            ("FP8_E4M3", lambda: ops.cast_chain(x, [F("FP[1|4|3,7](_N)").stage()], -1, out=y)),
+            ("INT8", lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", out=y)),
+            ("INT8_calibrated", lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=sc, zero_point=zp, out=y)),
+            ("INT8_per_channel", lambda: ops.fixed_qdq(x, 8, 0, True, True, "nearest", scale=scr, zero_point=zpr, ch_axis=0, out=y)),
+            ("2:4", lambda: ops.nm_prune(x, 2, 4, -1, out=y)),
+            ("2:4->BFP12", lambda: ops.cast_chain(x, [ops.nm_stage(2, 4), F("BFP[4|8]{64}(SN)").stage()], -1, out=y)),
+            ("SBFP12_16", lambda: ops.cast_chain(x, [F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}").stage()], -1, out=y)),
+            ("MXFP8_E4M3_32", lambda: ops.cast_chain(x, [F("MXFP8[E4M3]{32}").stage()], -1, out=y)),
+            ("FLOAT16->BFP16", lambda: ops.cast_chain(x, [F("FP[1|5|10,15](FN)").stage(), F("BFP[8|8]{64}(SN)").stage()], -1, out=y)),
+        ]
+        for name, fn in cases:
+            try:
+                for _ in range(3):
+                    fn()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(10):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / 10
+                gbs = 2 * es * N_ELEMS / (ms * 1e-3) / 1e9
+                rows.append([name, "fp32" if es == 4 else "bf16", round(gbs), round(gbs / peak, 3)])
+            except Exception as e:  # pragma: no cover
+                rows.append([name, "fp32" if es == 4 else "bf16", None, repr(e)[:60]])
+        del x, y
+        torch.cuda.empty_cache()
+    return rows
+
+
+# ------------------------------------------------------------------------------------------ detail tables
+def detail_sweep(dev):
     """configs[1] in full: BFP16_64 / BFP12_64 on fp32 / bf16 tensors of 2^20 .. 2^30 elements ([n/4096, 4096]).
     Sizes whose input + output fit the 126 MB L2 are timed over 8 rotating buffer pairs so that every launch
     streams from HBM (labelled hbm_rotating); CUDA events around 20 back-to-back launches, median of 5."""
@@ -329,8 +535,8 @@ def extra_sweep(dev):
                 row = {"format": name, "dtype": str(dt).split(".")[-1], "log2_elements": e, "us_per_cast": round(ts[2] * 1e3, 2),
                        "GB/s": round(footprint / ts[2] / 1e6, 1), "mode": "hbm_rotating" if nbuf > 1 else "hbm"}
                 if e <= 24:
-                    # below ~2^24 elements a cast is shorter than the python + launch path (~15 us): the same 20
-                    # launches replayed from a CUDA graph show the device-side time
+                    # below ~2^24 elements a cast is shorter than the python + launch path: the same 20 launches replayed
+                    # from a CUDA graph show the device-side time
                     g = torch.cuda.CUDAGraph()
                     side = torch.cuda.Stream()
                     side.wait_stream(torch.cuda.current_stream())
@@ -360,7 +566,7 @@ def extra_sweep(dev):
     return out
 
 
-def extra_opt125m(dev):
+def opt125m(dev):
     """BASELINE config #3: OPT-125m-shaped random-init stack, batch 8 x seq 2048 forward, BASIC rule set.
     tokens/s for the unquantised torch twin, the drop-in BASIC path, and BASIC with cast elision."""
     import torch
@@ -384,45 +590,22 @@ def extra_opt125m(dev):
     for dt in (torch.float32, torch.bfloat16):
         q, p = opt.build_pair(device=dev, dtype=dt)
         ids = torch.randint(0, 50272, (B, S), device=dev)
-
         with torch.no_grad():
             t_plain = timeit(lambda: p(ids))
-            n0 = _lib.launch_count()
             y1 = q(ids)
-            n1 = _lib.launch_count()
             t_basic = timeit(lambda: q(ids))
             with elide.enabled():
                 y2 = q(ids)
-                n2 = _lib.launch_count()
                 q(ids)
-                n3 = _lib.launch_count()
                 t_el = timeit(lambda: q(ids))
         res[str(dt).split(".")[-1]] = {
-            "tokens_per_s_unquantised": round(B * S / t_plain * 1e3), "tokens_per_s_basic": round(B * S / t_basic * 1e3),
-            "tokens_per_s_basic_elided": round(B * S / t_el * 1e3), "ms_unquantised": round(t_plain, 2), "ms_basic": round(t_basic, 2),
-            "ms_basic_elided": round(t_el, 2), "cast_overhead_basic": round((t_basic - t_plain) / t_plain, 3),
-            "cast_overhead_basic_elided": round((t_el - t_plain) / t_plain, 3), "dmxq_launches_basic": n1 - n0,
-            "dmxq_launches_elided": n3 - n2, "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2))}
+            "tok/s_unquantised": round(B * S / t_plain * 1e3), "tok/s_basic": round(B * S / t_basic * 1e3),
+            "tok/s_basic_elided": round(B * S / t_el * 1e3), "ms": [round(t_plain, 2), round(t_basic, 2), round(t_el, 2)],
+            "cast_overhead_basic": round((t_basic - t_plain) / t_plain, 3), "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3),
+            "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2))}
         del q, p, y1, y2
         torch.cuda.empty_cache()
-    # small-batch latency: launch-bound eagerly, so also as a captured CUDA graph
-    try:
-        from dmx_compressor_b200 import graph
-
-        q, p = opt.build_pair(device=dev, dtype=torch.float32)
-        ids = torch.randint(0, 50272, (4, 128), device=dev)
-        with torch.no_grad():
-            want = q(ids)
-            t_eager = timeit(lambda: q(ids), 5)
-        fq, fp = graph.capture(q, ids), graph.capture(p, ids)
-        res["small_batch_4x128_fp32"] = {"ms_basic_eager": round(t_eager, 2), "ms_basic_cuda_graph": round(timeit(lambda: fq(ids), 20), 2),
-                                         "ms_unquantised_cuda_graph": round(timeit(lambda: fp(ids), 20), 2),
-                                         "graph_equals_eager_bitwise": bool(torch.equal(fq(ids), want))}
-        del q, p, fq, fp
-        torch.cuda.empty_cache()
-    except Exception as e:  # pragma: no cover
-        res["small_batch_4x128_fp32"] = {"error": repr(e)}
-    res["config"] = "OPT-125m shape (12 layers, d=768, ffn=3072, 12 heads, vocab 50272), random init, batch 8 x seq 2048, config_rules.BASIC"
+    res["config"] = "OPT-125m shape, random init, batch 8 x seq 2048, config_rules.BASIC; ms = [unquantised, BASIC drop-in, BASIC + elision]"
     return res
 
 
@@ -445,6 +628,7 @@ def run_ours(args):
     from dmx_compressor_b200 import ops
     from dmx_compressor_b200.numerical import Format
 
+    peak, peak_src = load_peak()
     stages = {name: [Format.from_shorthand(sh).stage()] for name, sh, _ in FORMATS}
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x32 = torch.randn(N_ELEMS // COLS, COLS, device=dev, generator=g)
@@ -469,7 +653,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -524,59 +709,57 @@ def run_ours(args):
             t = torch.tensor([th], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             th = float(t.item())
-        # check the host path against the device path on the last cast
-        ok = torch.equal(yh16.view(torch.int16)[:64], y16[:64].cpu().view(torch.int16))
+        # the host path against the device path: both results of the last format, every element
+        ok = bool(torch.equal(yh16.view(torch.int16), y16.cpu().view(torch.int16))) and bool(torch.equal(yh32.view(torch.int32), y32.cpu().view(torch.int32)))
         half = bytes_per_step() // 2
         e2e = {"value": round(bytes_per_step() * args.e2e_steps * world / th / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": half, "d2h_bytes_per_step": half, "steps": args.e2e_steps,
-               "api": "dmxq_cast_chain_host (pinned host in/out, 3-stream chunked pipeline)", "matches_device_path": bool(ok)}
+               "api": "dmxq_cast_chain_host (pinned host in/out, 3-stream chunked pipeline)", "matches_device_path": ok}
         del xh32, xh16, yh32, yh16
 
-    # ---------------- extras: the model-level configs of BASELINE.json (not part of `value`)
-    extras = {}
+    # ---------------- the model-level configs of BASELINE.json (not part of `value`)
+    sharded = by_format = ref_cuda = opt = None
+    details = []
     if not args.no_extras:
-        from dmx_compressor_b200 import parallel as P
-
-        f12 = Format.from_shorthand("BFP[4|8]{64}(SN)").stage()
-        # config #4: Llama-3-8B-shaped weights, 2:4 sparsity (score |w|) -> BFP12, sharded over the ranks
-        extras["llama3_8b_24sparse_bfp12_weight_cast"] = extra_weight_cast(
-            dev, rank, world, dist, "8b", lambda amax: [ops.nm_stage(2, 4), f12], None, False, torch.bfloat16)
-
-        # config #5: Llama-3-70B-shaped weights, SBFP12_16 with the scaler bias chosen from the amax all-reduce
-        def sbfp(amax):
-            b = 7 if amax is None else P.sbfp_scaler_bias_from_amax(amax)
-            return [Format.from_shorthand(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}").stage()]
-
-        extras["llama3_70b_sbfp12_weight_cast"] = extra_weight_cast(
-            dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16)
-        extras["llama3_70b_sbfp12_weight_cast"]["note"] = "10 layers per GPU (weak scaling; 80 layers at 8 GPUs), one batched amax all-reduce"
-        # the same, written as packed storage (0.5625 B per element instead of a dequantised bf16 tensor)
-        extras["llama3_70b_sbfp12_packed_storage"] = extra_weight_cast(
-            dev, rank, world, dist, "70b", sbfp, 10 * world, True, torch.bfloat16, packed=True)
-        extras["llama3_70b_sbfp12_packed_storage"]["note"] = "dmxq_sbfp_pack: bf16 in, nibble mantissas + E4M4 scaler byte out (2.5625 B/elem algorithmic)"
+        del y32, y16
+        torch.cuda.empty_cache()
+        # the reference's own CUDA path on the very tensors of the timed step (rank 0; the other ranks wait at the next barrier)
         if rank == 0:
             try:
-                extras["cast_sweep"] = extra_sweep(dev)
+                ref_cuda = time_reference_cuda(dev, [x32, x16])
             except Exception as e:  # pragma: no cover
-                extras["cast_sweep"] = {"error": repr(e)}
+                ref_cuda = {"unavailable": repr(e)[:200]}
+        del x32, x16, casts
+        torch.cuda.empty_cache()
+        sharded = {
+            # config #4: strong scaling, the whole Llama-3-8B-shaped model at every N
+            "llama3_8b_24sparse_bfp12_bf16": sharded_weight_cast(dev, rank, world, dist, "8b", None, torch.bfloat16, "nm24_bfp12", peak),
+            # config #5: 10 layers per GPU (80 layers = the whole model at N = 8), scaler bias from the amax all-reduce
+            "llama3_70b_sbfp12_amax_bf16": sharded_weight_cast(dev, rank, world, dist, "70b", 10 * world, torch.bfloat16, "sbfp_amax", peak),
+            "note": "8b: whole model at every N (strong scaling; checksum must not depend on N). 70b: 10 layers per GPU + lm_head, one NCCL all-reduce(MAX) "
+                    "of per-tensor amax feeds the SBFP scaler bias on the device; its GB/s counts 2*sizeof per element although the amax pass re-reads the weights",
+        }
+        if rank == 0:
             try:
-                extras["opt125m_basic_forward"] = extra_opt125m(dev)
+                by_format = roofline_by_format(dev, peak)
             except Exception as e:  # pragma: no cover
-                extras["opt125m_basic_forward"] = {"error": repr(e)}
+                by_format = {"error": repr(e)[:200]}
+            try:
+                opt = opt125m(dev)
+            except Exception as e:  # pragma: no cover
+                opt = {"error": repr(e)[:200]}
+            if not args.no_details:
+                try:
+                    details.append({"detail": "cast_sweep (configs[1], every size)", "rows": detail_sweep(dev)})
+                except Exception as e:  # pragma: no cover
+                    details.append({"detail": "cast_sweep", "error": repr(e)[:200]})
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     k_bytes = 8 * N_ELEMS
     achieved = k_bytes / (k_mean * 1e-3) / 1e9
     traffic = None
@@ -585,7 +768,7 @@ def run_ours(args):
             traffic = json.load(f).get("chain_rows_kernel_f32_flat_bfp", {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "chain_rows_kernel<float,float,FLAT,SPECIAL=2> (BFP16/BFP12 fp32 casts)",
+    roofline = {"bound": "hbm", "kernel": "chain_rows_kernel<float,float,FLAT,K_BFP> (BFP16/BFP12 fp32 casts)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "frac_of_8TBps_nominal": round(achieved / 8000.0, 4), "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": k_bytes, "launch_ms_mean": round(k_mean, 4), "launch_ms_median": round(kms[len(kms) // 2], 4),
@@ -593,28 +776,31 @@ def run_ours(args):
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cast, kind, cores = _reference_cpu_cast()
-        c32 = _make_rows(CPU_SAMPLE_ELEMS)
+        cast, kind, cores, how = _reference_cpu_cast()
+        c32 = _make_rows(1 << 24)
         xs = [c32, c32.to(torch.bfloat16)]
         cpu_pass(cast, xs)
-        best = None
-        tot = 0.0
+        tot, nb_tot, passes = 0.0, 0, 0
         while tot < 10.0:
             dt, nb = cpu_pass(cast, xs)
             tot += dt
-            best = dt if best is None else min(best, dt)
-        cpu_baseline = {"value": round(nb / best / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": kind,
-                        "sample": f"the step's 4 casts on n=2^{CPU_SAMPLE_ELEMS.bit_length() - 1} elements per tensor, best pass of ~10 s of CPU work"}
+            nb_tot += nb
+            passes += 1
+        cpu_baseline = {"value": round(nb_tot / tot / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": kind,
+                        "sample": f"the step's 4 casts on n=2^24 elements per tensor, mean of {passes} passes (~10 s of CPU work); {how}"}
 
+    for d in details:
+        print(json.dumps(d), flush=True)
     line = {
-        "metric": "BFP cast GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": "BFP cast GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": config_dict(world), "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "frac_of_hbm_peak": round(value / world / peak, 4), "extras": extras,
+        "data": "synthetic", "config": config_dict(world), "gpu_launches": launches, "clocks": clocks,
+        "frac_of_hbm_peak": round(value / world / peak, 4), "opt125m_basic_forward": opt, "roofline_by_format": by_format,
+        "reference_cuda": ref_cuda, "cpu_baseline": cpu_baseline, "roofline": roofline, "e2e": e2e, "sharded": sharded,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -623,6 +809,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.impl == "reference-cuda":
+        return run_reference_cuda_arm(args)
     return run_ours(args)
 
 

@@ -57,6 +57,7 @@ def _load():
         "dmxq_status_string": ([I], C.c_char_p),
         "dmxq_launch_count": ([], I64),
         "dmxq_cast_chain": ([TP, TP, I, SP, I, TP, TP, VP, VP], I),
+        "dmxq_cast_chain_multi": ([TP, TP, I, I, SP, I, VP, VP], I),
         "dmxq_bfp_qdq": ([TP, TP, I, I, I, I, I, VP, VP], I),
         "dmxq_sbfp_qdq": ([TP, TP] + [I] * 14 + [VP], I),
         "dmxq_float_qdq": ([TP, TP] + [I] * 7 + [VP, VP], I),

@@ -276,9 +276,16 @@ int run_generic(const dmxq_tensor *x, const dmxq_tensor *y, const Canon &c, cons
 // dmxq_fixed_qdq falls back to fixed_chan_kernel.
 constexpr int kNeedFallback = -100;
 
+// what chain_impl decided for a tensor that the many-tensor launch can take over (flat rows layout, same dtype in and out)
+struct RowsPlan {
+    bool planned = false;
+    int kind = -1, dt = -1;
+    RowsParams p;
+};
+
 int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const dmxq_stage *stages, int n_stages,
                const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, cudaStream_t st,
-               const float *qscale = nullptr, const float *qzp = nullptr)
+               const float *qscale = nullptr, const float *qzp = nullptr, const float *amax = nullptr, RowsPlan *plan = nullptr)
 {
     if (!x || !y || !stages) return fail(DMXQ_ERR_BAD_ARG, "null argument");
     if (n_stages < 1 || n_stages > DMXQ_MAX_STAGES) return fail(DMXQ_ERR_BAD_ARG, "n_stages must be 1..%d, got %d", DMXQ_MAX_STAGES, n_stages);
@@ -437,6 +444,17 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
             p.qscale = qscale; p.qzp = qzp;
         }
         const int special = kind;
+        if (amax) {
+            bool has_sbfp = false;
+            for (int s = 0; s < chain.n; ++s) has_sbfp |= chain.st[s].kind == ST_SBFP;
+            if (has_sbfp && kind != 6)
+                return fail(DMXQ_ERR_UNSUPPORTED, "a device-resident amax drives the SBFP scaler bias only for a single nearest / half-away SBFP stage");
+            if (has_sbfp) p.amax = amax;
+        }
+        if (rows_ok && plan && flat && x->dtype == y->dtype && rows_multi_supported(special)) {
+            plan->planned = true; plan->kind = special; plan->dt = x->dtype; plan->p = p;
+            return DMXQ_OK;
+        }
         if (rows_ok) {
             cudaError_t e = launch_rows(x->dtype, y->dtype, flat, special, p, st);
             if (e != cudaSuccess) return cuda_fail(e, "chain_rows_kernel");
@@ -445,6 +463,10 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     }
 
     if (qscale) return kNeedFallback;
+    if (amax)
+        for (int s = 0; s < chain.n; ++s)
+            if (chain.st[s].kind == ST_SBFP)
+                return fail(DMXQ_ERR_UNSUPPORTED, "a device-resident amax needs the rows layout (blocked dim contiguous, 16-byte aligned, whole blocks)");
 
     // ---------------------------------------------------------------- cols path
     if (blocked && !score_p && !mask_p && c.k.n > 1) {
@@ -546,6 +568,46 @@ int dmxq_cast_chain(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, c
                     const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, void *stream)
 {
     return chain_impl(x, y, block_dim, stages, n_stages, score, mask, rand, static_cast<cudaStream_t>(stream));
+}
+
+int dmxq_cast_chain_multi(const dmxq_tensor *xs, const dmxq_tensor *ys, int n_tensors, int block_dim, const dmxq_stage *stages,
+                          int n_stages, const float *amax, void *stream)
+{
+    if (n_tensors < 0 || (n_tensors > 0 && (!xs || !ys))) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    MultiTable t;
+    RowsParams p0;
+    int kind0 = -1, dt0 = -1;
+    t.n = 0; t.cta0[0] = 0; t.amax = amax;
+    auto flush = [&]() -> int {
+        if (t.n == 0) return DMXQ_OK;
+        cudaError_t e = launch_rows_multi(dt0, kind0, p0, t, st);
+        t.n = 0; t.cta0[0] = 0;
+        return e == cudaSuccess ? DMXQ_OK : cuda_fail(e, "chain_rows_multi_kernel");
+    };
+    for (int i = 0; i < n_tensors; ++i) {
+        RowsPlan pl;
+        int rc = chain_impl(&xs[i], &ys[i], block_dim, stages, n_stages, nullptr, nullptr, nullptr, st, nullptr, nullptr,
+                            amax ? amax + i : nullptr, &pl);
+        if (rc) { flush(); return rc; }
+        if (!pl.planned) continue;  // empty tensor, or a layout the rows kernel does not take: already launched on its own
+        const int64_t per_cta = (int64_t)256 * 4;  // kThreads * kUnroll of dmxq_stages.cuh
+        const int64_t ctas = (pl.p.n_vec + per_cta - 1) / per_cta;
+        if (ctas > 0x3FFFFFFFll) {  // a tensor this large gets its own launch
+            cudaError_t e = launch_rows(pl.dt, pl.dt, true, pl.kind, pl.p, st);
+            if (e != cudaSuccess) { flush(); return cuda_fail(e, "chain_rows_kernel"); }
+            continue;
+        }
+        if (t.n > 0 && (pl.kind != kind0 || pl.dt != dt0 || t.n == kMultiMax || (int64_t)t.cta0[t.n] + ctas > 0x7FFFFFFFll)) {
+            rc = flush();
+            if (rc) return rc;
+        }
+        if (t.n == 0) { p0 = pl.p; p0.amax = nullptr; kind0 = pl.kind; dt0 = pl.dt; }
+        t.x[t.n] = pl.p.x; t.y[t.n] = pl.p.y; t.n_vec[t.n] = pl.p.n_vec; t.slot[t.n] = i;
+        t.cta0[t.n + 1] = t.cta0[t.n] + (uint32_t)ctas;
+        ++t.n;
+    }
+    return flush();
 }
 
 int dmxq_bfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size, int precision, int symmetric,
@@ -922,6 +984,11 @@ int dmxq_cast_chain_host(const void *x_host, void *y_host, int in_dtype, int out
     if (rows < 0 || K <= 0) return fail(DMXQ_ERR_BAD_ARG, "bad shape");
     if (rows == 0) return DMXQ_OK;
     std::lock_guard<std::mutex> lock(g_host_mu);
+    struct DeviceGuard {  // the caller's current device is restored on every exit path
+        int prev = -1;
+        DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     HostCtx &h = g_host;

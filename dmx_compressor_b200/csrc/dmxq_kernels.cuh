@@ -75,6 +75,7 @@ struct RowsParams {
     float *mask;         // nullable, NM stage
     const void *rnd;     // nullable, stochastic stage (int32 or fp32)
     const float *qscale, *qzp;  // nullable: per-tensor FixedPoint affine parameters in device memory (K_FIXED)
+    const float *amax;          // nullable: tensor-wide amax in device memory; the SBFP scaler bias is derived from it (K_SBFP)
     int64_t n_vec;       // total (padded) vectors = rows * vpr
     int64_t rows;
     int64_t K;

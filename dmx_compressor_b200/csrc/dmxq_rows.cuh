@@ -513,7 +513,7 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
 template <typename Tin, typename Tout, bool FLAT, int KIND>
 __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_constant__ RowsParams p)
 {
-    chain_rows_body<Tin, Tout, FLAT, KIND>(p, static_cast<const Tin *>(p.x), static_cast<Tout *>(p.y), (int64_t)blockIdx.x, p.n_vec, nullptr);
+    chain_rows_body<Tin, Tout, FLAT, KIND>(p, static_cast<const Tin *>(p.x), static_cast<Tout *>(p.y), (int64_t)blockIdx.x, p.n_vec, p.amax);
 }
 
 // Many tensors, one launch (dmxq_cast_chain_multi): the shards a rank owns in a sharded whole-model weight cast.  Every

@@ -122,6 +122,40 @@ def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, 
     return y
 
 
+def cast_chain_multi(xs: Sequence[torch.Tensor], stages: Sequence[L.Stage], block_dim: int = -1,
+                     outs: Optional[Sequence[torch.Tensor]] = None, amax: Optional[torch.Tensor] = None):
+    """ys[i] = chain(xs[i]) for many tensors in as few launches as possible (dmxq_cast_chain_multi): the shards one rank
+    owns in a sharded whole-model weight cast.  ``amax``: optional fp32 CUDA vector, one tensor-wide amax per entry of
+    ``xs`` (e.g. straight out of an all-reduce); an SBFP stage then takes its scaler exponent bias from it on the device."""
+    n = len(xs)
+    if n == 0:
+        return []
+    for x in xs:
+        L.require_cuda(x)
+    ns = len(stages)
+    if not 1 <= ns <= L.MAX_STAGES:
+        raise RuntimeError(f"dmxq: a chain holds 1..{L.MAX_STAGES} stages, got {ns}")
+    ys = list(outs) if outs is not None else [_out_like(x, None) for x in xs]
+    if len(ys) != n:
+        raise RuntimeError("dmxq: outs must have one tensor per input")
+    dev = xs[0].device
+    if any(t.device != dev for t in list(xs) + ys):
+        raise RuntimeError("dmxq: all tensors of one call must live on one device")
+    ap = None
+    if amax is not None:
+        L.require_cuda(amax, "amax")
+        if amax.dtype != torch.float32 or amax.numel() != n or not amax.is_contiguous() or amax.device != dev:
+            raise RuntimeError("dmxq: amax must be a contiguous fp32 CUDA vector with one entry per tensor")
+        ap = amax.data_ptr()
+    vx = (L.Tensor * n)(*[L.view(x) for x in xs])
+    vy = (L.Tensor * n)(*[L.view(y) for y in ys])
+    arr = (L.Stage * ns)(*stages)
+    with _guard(dev):
+        rc = L.lib.dmxq_cast_chain_multi(vx, vy, n, block_dim, arr, ns, ap, L.stream_ptr(dev))
+    L.check(rc, "dmxq_cast_chain_multi")
+    return ys
+
+
 def bfp_qdq(x, block_dim=-1, block_size=64, precision=8, symmetric=True, rounding="nearest", rand=None, out=None,
             out_dtype=None):
     """BlockFloatingPoint.cast (reference S/numerical/format.py:304-372) via dmxq_bfp_qdq."""
@@ -320,13 +354,20 @@ def sbfp_unpack(mant, scal, stage, dtype=torch.float32):
     return y
 
 
-def minmax(x, ch_axis: Optional[int] = None):
-    """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax."""
+def minmax(x, ch_axis: Optional[int] = None, out=None):
+    """amin / amax per tensor or per channel (MinMaxObserver statistics) via dmxq_minmax.  ``out``: optional (min, max) pair of
+    contiguous fp32 CUDA vectors (or slices of larger ones) to write into."""
     L.require_cuda(x)
     x = x.contiguous()
     c = 1 if ch_axis is None else x.shape[ch_axis]
-    mn = torch.empty(c, dtype=torch.float32, device=x.device)
-    mx = torch.empty(c, dtype=torch.float32, device=x.device)
+    if out is not None:
+        mn, mx = out
+        for t in (mn, mx):
+            if t.dtype != torch.float32 or t.numel() != c or not t.is_contiguous() or t.device != x.device:
+                raise RuntimeError(f"dmxq: minmax out tensors must be contiguous fp32 vectors of {c} elements on the input's device")
+    else:
+        mn = torch.empty(c, dtype=torch.float32, device=x.device)
+        mx = torch.empty(c, dtype=torch.float32, device=x.device)
     vx = L.view(x)
     with _guard(x.device):
         rc = L.lib.dmxq_minmax(C.byref(vx), -1 if ch_axis is None else ch_axis % x.dim(), mn.data_ptr(), mx.data_ptr(),

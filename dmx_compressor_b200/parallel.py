@@ -135,25 +135,26 @@ def local_minmax(t: torch.Tensor, ch_axis: Optional[int] = None) -> Tuple[torch.
 
 
 def allreduce_minmax(stats: Sequence[Tuple[torch.Tensor, torch.Tensor]], group=None):
-    """One collective for all tensors: pack [max_0.., -min_0..] and all_reduce(MAX).
+    """One collective for all tensors: pack [max_0.., -min_0.., isnan_0..] and all_reduce(MAX).
     ``stats``: per tensor (min, max) fp32 vectors (length 1 or #channels), identical lengths on
-    every rank.  Returns the reduced list in the same order.  NaN propagates (max of NaN)."""
+    every rank.  Returns the reduced list in the same order.  NaN propagates (as in torch.aminmax): it travels as an
+    explicit 0/1 flag segment of the same buffer -- +-inf stay what they are, so a channel that really holds both
+    +inf and -inf reduces to (-inf, +inf) exactly as on a single GPU."""
     import torch.distributed as dist
 
     if not stats:
         return []
     dev = stats[0][0].device
     sizes = [mn.numel() for mn, _ in stats]
-    buf = torch.cat([mx.reshape(-1).float() for _, mx in stats] + [(-mn.reshape(-1).float()) for mn, _ in stats]).to(dev)
-    nan = torch.isnan(buf)
-    buf = torch.where(nan, torch.full_like(buf, float("inf")), buf)  # NaN must win a MAX reduction
+    mx0 = torch.cat([mx.reshape(-1).float() for _, mx in stats]).to(dev)
+    mn0 = torch.cat([mn.reshape(-1).float() for mn, _ in stats]).to(dev)
+    nan = torch.isnan(mx0) | torch.isnan(mn0)
+    ninf = torch.full_like(mx0, float("-inf"))
+    buf = torch.cat([torch.where(nan, ninf, mx0), torch.where(nan, ninf, -mn0), nan.float()])  # a NaN entry is neutral in the value slots
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
     n = sum(sizes)
-    mx_all, mn_all = buf[:n], -buf[n:]
-    # +inf on the max side / -inf on the min side can only come from a NaN marker or a real inf;
-    # a NaN marker always sets BOTH sides of an entry to inf
-    was_nan = torch.isinf(mx_all) & torch.isinf(mn_all) & (mx_all > 0) & (mn_all < 0)
+    mx_all, mn_all, was_nan = buf[:n], -buf[n:2 * n], buf[2 * n:] > 0
     mx_all = torch.where(was_nan, torch.full_like(mx_all, float("nan")), mx_all)
     mn_all = torch.where(was_nan, torch.full_like(mn_all, float("nan")), mn_all)
     out, o = [], 0
@@ -190,6 +191,56 @@ def shard_stats(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tens
         local = [(rmn[pos[sh.name]].reshape(1), rmx[pos[sh.name]].reshape(1)) if not sh.whole else st
                  for sh, st in zip(mine, local)]
     return local
+
+
+_AMAX_PLANS: dict = {}
+
+
+def shard_amax(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None, group=None,
+               local: Callable = None) -> torch.Tensor:
+    """Tensor-wide max|x| for every shard `plan[rank]` lists (as if each tensor were whole), as ONE fp32 device vector --
+    the form ``ops.cast_chain_multi(..., amax=...)`` consumes, so calibration statistics go from the reduction into the cast
+    kernel without ever visiting the host.  Per shard one ``dmxq_minmax`` writing straight into its slot; the row-split tensors
+    (the same set, in the same order, on every rank) share ONE ``all_reduce(MAX)``.  A NaN anywhere in a tensor makes its
+    amax +inf (the cast then keeps the format's default scaler bias)."""
+    import torch.distributed as dist
+
+    from . import ops
+
+    mine = plan[rank]
+    n = len(mine)
+    dev = tensors[0].device if n else torch.device("cpu")
+    key = (id(plan), rank, str(dev))
+    ent = _AMAX_PLANS.get(key)
+    if ent is None or ent[0] is not plan:
+        split_names = sorted({sh.name for shards in plan for sh in shards if not sh.whole})
+        pos = {nm: i for i, nm in enumerate(split_names)}
+        src = [i for i, sh in enumerate(mine) if not sh.whole]
+        ent = (plan, len(split_names), torch.tensor(src, dtype=torch.long, device=dev),
+               torch.tensor([pos[mine[i].name] for i in src], dtype=torch.long, device=dev),
+               torch.empty(2, max(n, 1), dtype=torch.float32, device=dev))
+        if len(_AMAX_PLANS) > 64:
+            _AMAX_PLANS.clear()
+        _AMAX_PLANS[key] = ent
+    _, n_split, src_idx, dst_idx, mnmx = ent
+    amax = out if out is not None else torch.empty(n, dtype=torch.float32, device=dev)
+    if n:
+        for i, t in enumerate(tensors):
+            if local is None:
+                ops.minmax(t, None, out=(mnmx[0, i:i + 1], mnmx[1, i:i + 1]))
+            else:  # the gloo unit tests inject a CPU statistic
+                a, b = local(t, None)
+                mnmx[0, i], mnmx[1, i] = a.reshape(()), b.reshape(())
+        torch.maximum(-mnmx[0, :n], mnmx[1, :n], out=amax)
+        torch.nan_to_num_(amax, nan=float("inf"))
+    if n_split and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        buf = torch.zeros(n_split, dtype=torch.float32, device=dev)
+        if src_idx.numel():
+            buf[dst_idx] = amax[src_idx]
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=group)
+        if src_idx.numel():
+            amax[src_idx] = buf[dst_idx]
+    return amax
 
 
 def qparams_from_minmax(mn: torch.Tensor, mx: torch.Tensor, fmt, symmetric: bool = True, eps: float = torch.finfo(torch.float32).eps):

@@ -166,6 +166,20 @@ int dmxq_cast_chain(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim,
                     const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand,
                     void *stream);
 
+/* ---- many tensors, one launch: the shards a rank owns in a sharded whole-model weight cast (SURVEY.md section 8e;
+ * replaces the per-module python loop of DmxModel.fold_weights_and_biases, S/modeling/model.py:145-150, over
+ * DmxModule.weight_hypernet, S/modeling/nn/core.py:178-198).  ys[i] = chain(xs[i]) for i < n_tensors, the same stages and
+ * block_dim for all.  Tensors whose layout the row-tiled kernel takes flat (contiguous, blocked along the last dim, same
+ * dtype in and out) share launches -- up to 64 tensors each, CTAs dealt to tensors by a prefix table inside the kernel
+ * parameters, so nothing is allocated or copied -- every other tensor is launched exactly as dmxq_cast_chain would.
+ * `amax` (nullable): device array of n_tensors floats, amax[i] = max|x| over the WHOLE tensor xs[i] is a shard of (the
+ * result of a calibration all-reduce).  When given, an SBFP stage takes its scaler exponent bias from it on the device,
+ *     bias = (2^sc_exp - 1) - floor(log2(amax[i] / man_scaling)),  clamped to what FloatingPoint accepts,
+ * instead of stage.sc_bias: the statistics never visit the host between the all-reduce and the cast.  (The reference
+ * delegates this choice to the private `numerics` module, S/numerical/format.py:13-20, 438-446: parity unpinned.) */
+int dmxq_cast_chain_multi(const dmxq_tensor *xs, const dmxq_tensor *ys, int n_tensors, int block_dim,
+                          const dmxq_stage *stages, int n_stages, const float *amax, void *stream);
+
 /* ---- single-format conveniences (thin wrappers over dmxq_cast_chain) ---------------------- */
 int dmxq_bfp_qdq(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, int block_size,
                  int precision, int symmetric, int rounding, const int32_t *rand, void *stream);

@@ -171,3 +171,56 @@ def test_replicate_shards_over_gloo():
         assert set(res[rank]) == set(shapes)
         for n in shapes:
             assert np.array_equal(res[rank][n], (2 * full[n]).numpy()), (rank, n)
+
+
+def _worker_amax(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    shapes = {"big": (64, 32), "big2": (48, 32), "a": (8, 32), "b": (6, 32), "c": (4, 32), "nan": (5, 32)}
+    plan = P.plan_shards(shapes, world, split_threshold=0.4)
+    g = torch.Generator().manual_seed(17)
+    full = {n: torch.randn(s, generator=g) * (i + 1) for i, (n, s) in enumerate(shapes.items())}
+    full["nan"][2, 3] = float("nan")
+    full["big"][60, 1] = -1e6  # the tensor-wide amax lives in the LAST rank's rows, and is a negative value
+    mine = [full[sh.name][sh.row0:sh.row1] for sh in plan[rank]]
+    for _ in range(2):  # second call: the cached index plan
+        amax = P.shard_amax(plan, rank, mine, local=_cpu_minmax)
+    q.put((rank, [(sh.name, float(a)) for sh, a in zip(plan[rank], amax)]))
+    dist.destroy_process_group()
+
+
+def test_shard_amax_one_vector_one_allreduce():
+    """shard_amax: per-shard statistic -> one device vector in plan order, the row-split tensors reduced over the ranks"""
+    world, port = 2, 35500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_amax, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    shapes = {"big": (64, 32), "big2": (48, 32), "a": (8, 32), "b": (6, 32), "c": (4, 32), "nan": (5, 32)}
+    g = torch.Generator().manual_seed(17)
+    full = {n: torch.randn(s, generator=g) * (i + 1) for i, (n, s) in enumerate(shapes.items())}
+    full["big"][60, 1] = -1e6
+    seen = {}
+    for rank in range(world):
+        for name, a in res[rank]:
+            want = float("inf") if name == "nan" else float(full[name].abs().max())
+            assert a == want, (name, a, want)
+            seen[name] = seen.get(name, 0) + 1
+    assert set(seen) == set(shapes) and seen["big"] == world and seen["a"] == 1
+
+
+def test_allreduce_minmax_keeps_real_infinities():
+    """a channel that really holds +inf and -inf is (-inf, +inf), not NaN; a NaN channel is NaN (single process: no group)"""
+    mn = torch.tensor([-float("inf"), -1.0, float("nan"), 2.0])
+    mx = torch.tensor([float("inf"), 3.0, float("nan"), float("inf")])
+    (rmn, rmx), = P.allreduce_minmax([(mn, mx)])
+    assert rmn[0] == -float("inf") and rmx[0] == float("inf")
+    assert rmn[1] == -1.0 and rmx[1] == 3.0
+    assert torch.isnan(rmn[2]) and torch.isnan(rmx[2])
+    assert rmn[3] == 2.0 and rmx[3] == float("inf")

@@ -1213,3 +1213,68 @@ def test_histc_division_free_bins_are_exact():
     for lo, hi in [(0.0, float(np.float32(2.0) - np.float32(2.0**-23))), (-1e30, 1e30), (0.0, 1e-20)]:
         x = (torch.rand(1 << 18, generator=g) * (hi - lo) + lo).to(DEV)
         assert torch.equal(ops.histc(x, 100, min=lo, max=hi), torch.histc(x, 100, min=lo, max=hi))
+
+
+# =============================================================================== many tensors, one launch
+def test_cast_chain_multi_equals_per_tensor():
+    """dmxq_cast_chain_multi == dmxq_cast_chain tensor by tensor, in far fewer launches: the whole-model weight-cast kinds,
+    fp32 / bf16 / fp16, more tensors than one table holds, ragged sizes, an empty tensor, a layout the batched kernel does
+    not take (row-strided view) mixed in"""
+    g = torch.Generator(device=DEV).manual_seed(2024)
+    F = lambda sh: fmt_from(sh).stage()
+    chains = {
+        "bfp16": [F("BFP[8|8]{64}(SN)")], "bfp12": [F("BFP[4|8]{64}(SN)")], "sbfp": [F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}")],
+        "24_bfp12": [ops.nm_stage(2, 4), F("BFP[4|8]{64}(SN)")], "24": [ops.nm_stage(2, 4)], "float16": [F("FP[1|5|10,15](FN)")],
+        "sbfp_bfp": [F("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"), F("BFP[8|8]{64}(SN)")],  # runtime chain
+        "24_torch_order": [ops.nm_stage(2, 4, L.NM_TORCH_CUDA), F("BFP[4|8]{64}(SN)")],
+    }
+    shapes = [(37, 256), (1, 64), (128, 1024), (5, 4096), (0, 64), (1000, 64), (3, 7, 128), (64, 64)] + [(2 + i, 128) for i in range(70)]
+    for dt in (torch.float32, torch.bfloat16, torch.float16):
+        xs = [(torch.randn(s, device=DEV, generator=g) * 3).to(dt) for s in shapes]
+        big = (torch.randn(40, 512, device=DEV, generator=g)).to(dt)
+        xs.insert(3, big[:, :256])  # row-strided view: launched on its own inside the same call
+        for name, st in chains.items():
+            want = [ops.cast_chain(x, st, -1) for x in xs]
+            n0 = L.launch_count()
+            got = ops.cast_chain_multi(xs, st, -1)
+            used = L.launch_count() - n0
+            assert used <= 4, f"{name} {dt}: {used} launches for {len(xs)} tensors"
+            for i, (a, b) in enumerate(zip(got, want)):
+                assert a.shape == b.shape and torch.equal(a.view(torch.int16 if dt != torch.float32 else torch.int32),
+                                                          b.view(torch.int16 if dt != torch.float32 else torch.int32)), f"{name} {dt} tensor {i}"
+        # preallocated outputs
+        outs = [torch.empty_like(x) for x in xs]
+        r = ops.cast_chain_multi(xs, chains["bfp12"], -1, outs=outs)
+        assert all(a is b for a, b in zip(r, outs))
+
+
+def test_cast_chain_multi_amax_drives_sbfp_bias_on_device():
+    """amax= : the SBFP scaler bias is derived inside the kernel from a device-resident tensor-wide amax and equals the host
+    rule (parallel.sbfp_scaler_bias_from_amax) for every tensor -- amax at exact power-of-two boundaries of amax / 7, one ulp
+    either side, tiny, huge, zero, inf"""
+    from dmx_compressor_b200 import parallel as P
+
+    g = torch.Generator(device=DEV).manual_seed(77)
+    amaxs = [1.0, 0.02, 7.0, 7.0 * 2.0**-5, float(np.nextafter(np.float32(7.0 * 2.0**-5), np.float32(0))), float(np.nextafter(np.float32(7.0 * 2.0**3), np.float32(1e9))),
+             3.5, 1e-30, 1e30, 0.0, float("inf"), 0.4375, 14.0 - 2.0**-20, 6.9999995]
+    for dt in (torch.bfloat16, torch.float32):
+        xs = [(torch.randn(16 + i, 256, device=DEV, generator=g) * (a if 0 < a < 1e20 else 1.0) / 4).to(dt) for i, a in enumerate(amaxs)]
+        amax = torch.tensor(amaxs, dtype=torch.float32, device=DEV)
+        sh0 = fmt_from("SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}").stage()
+        got = ops.cast_chain_multi(xs, [sh0], -1, amax=amax)
+        for i, (x, a) in enumerate(zip(xs, amaxs)):
+            b = P.sbfp_scaler_bias_from_amax(float(np.float32(a)))
+            want = ops.cast_chain(x, [fmt_from(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}").stage()], -1)
+            assert torch.equal(got[i].view(torch.int16 if dt != torch.float32 else torch.int32),
+                               want.view(torch.int16 if dt != torch.float32 else torch.int32)), f"tensor {i}: amax {a} -> bias {b}, {dt}"
+    # shard_amax feeds it: whole tensors on one GPU
+    shapes = {f"t{i}": (32 + 8 * i, 512) for i in range(6)}
+    plan = P.plan_shards(shapes, 1)
+    ws = [torch.randn(shapes[sh.name], device=DEV, generator=g).mul_(0.02 * (1 + i)).to(torch.bfloat16) for i, sh in enumerate(plan[0])]
+    amax = P.shard_amax(plan, 0, ws)
+    assert torch.equal(amax, torch.stack([w.float().abs().max() for w in ws]))
+    got = ops.cast_chain_multi(ws, [sh0], -1, amax=amax)
+    for w, y, a in zip(ws, got, amax.tolist()):
+        b = P.sbfp_scaler_bias_from_amax(a)
+        want = ops.cast_chain(w, [fmt_from(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}").stage()], -1)
+        assert torch.equal(y.view(torch.int16), want.view(torch.int16))
