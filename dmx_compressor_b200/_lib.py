@@ -70,6 +70,7 @@ def _load():
         "dmxq_sbfp_unpack": ([VP, VP, TP, SP, VP], I),
         "dmxq_block_quantize": ([TP, TP, I, I, I, I, VP, VP, VP], I),
         "dmxq_minmax": ([TP, I, VP, VP, VP], I),
+        "dmxq_amax_multi": ([TP, I, VP, VP], I),
         "dmxq_histc": ([TP, I, C.c_float, C.c_float, VP, VP, VP, VP], I),
         "dmxq_cast_chain_host": ([VP, VP, I, I, I64, I64, SP, I, I], I),
         "dmxq_host_alloc": ([I64], VP),

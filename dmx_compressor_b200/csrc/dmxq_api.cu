@@ -444,12 +444,12 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
             p.qscale = qscale; p.qzp = qzp;
         }
         const int special = kind;
+        bool amax_sbfp = false;
         if (amax) {
-            bool has_sbfp = false;
-            for (int s = 0; s < chain.n; ++s) has_sbfp |= chain.st[s].kind == ST_SBFP;
-            if (has_sbfp && kind != 6)
-                return fail(DMXQ_ERR_UNSUPPORTED, "a device-resident amax drives the SBFP scaler bias only for a single nearest / half-away SBFP stage");
-            if (has_sbfp) p.amax = amax;
+            for (int s = 0; s < chain.n; ++s) amax_sbfp |= chain.st[s].kind == ST_SBFP;
+            if (amax_sbfp && !(kind == 6 && chain.st[0].sb.sc_fast && plan && flat && x->dtype == y->dtype))
+                return fail(DMXQ_ERR_UNSUPPORTED, "a device-resident amax drives the SBFP scaler bias only for a single SBFP stage (nearest, half away, "
+                                                  "flushing scaler format) on a contiguous tensor with whole blocks and the same dtype in and out");
         }
         if (rows_ok && plan && flat && x->dtype == y->dtype && rows_multi_supported(special)) {
             plan->planned = true; plan->kind = special; plan->dt = x->dtype; plan->p = p;
@@ -602,8 +602,49 @@ int dmxq_cast_chain_multi(const dmxq_tensor *xs, const dmxq_tensor *ys, int n_te
             rc = flush();
             if (rc) return rc;
         }
-        if (t.n == 0) { p0 = pl.p; p0.amax = nullptr; kind0 = pl.kind; dt0 = pl.dt; }
+        if (t.n == 0) { p0 = pl.p; kind0 = pl.kind; dt0 = pl.dt; }
         t.x[t.n] = pl.p.x; t.y[t.n] = pl.p.y; t.n_vec[t.n] = pl.p.n_vec; t.slot[t.n] = i;
+        t.cta0[t.n + 1] = t.cta0[t.n] + (uint32_t)ctas;
+        ++t.n;
+    }
+    return flush();
+}
+
+int dmxq_amax_multi(const dmxq_tensor *xs, int n_tensors, float *out_amax, void *stream)
+{
+    if (n_tensors < 0 || (n_tensors > 0 && (!xs || !out_amax))) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (n_tensors == 0) return DMXQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(out_amax, 0, sizeof(float) * (size_t)n_tensors, st);  // max over |x| bit patterns starts at +0
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    MultiTable t;
+    t.n = 0; t.cta0[0] = 0; t.amax = nullptr;
+    int dt0 = -1;
+    auto flush = [&]() -> int {
+        if (t.n == 0) return DMXQ_OK;
+        cudaError_t e2 = launch_amax_multi(dt0, t, out_amax, st);
+        t.n = 0; t.cta0[0] = 0;
+        return e2 == cudaSuccess ? DMXQ_OK : cuda_fail(e2, "amax_multi_kernel");
+    };
+    for (int i = 0; i < n_tensors; ++i) {
+        const dmxq_tensor &x = xs[i];
+        if (x.dtype < 0 || x.dtype > 2) { flush(); return fail(DMXQ_ERR_BAD_ARG, "bad dtype"); }
+        int64_t n = 1, expect = 1;
+        for (int d = x.ndim - 1; d >= 0; --d) {
+            if (x.shape[d] != 1 && x.stride[d] != expect) { flush(); return fail(DMXQ_ERR_UNSUPPORTED, "dmxq_amax_multi needs contiguous tensors"); }
+            expect *= x.shape[d];
+            n *= x.shape[d];
+        }
+        if (n == 0) continue;
+        if (!x.data || !aligned(x.data, 16)) { flush(); return fail(DMXQ_ERR_UNSUPPORTED, "dmxq_amax_multi needs 16-byte aligned data"); }
+        const int64_t ctas = amax_multi_ctas(x.dtype, n);
+        if (t.n > 0 && (x.dtype != dt0 || t.n == kMultiMax || (int64_t)t.cta0[t.n] + ctas > 0x7FFFFFFFll)) {
+            int rc = flush();
+            if (rc) return rc;
+        }
+        if (ctas > 0x7FFFFFFFll) return fail(DMXQ_ERR_UNSUPPORTED, "tensor too large");
+        dt0 = x.dtype;
+        t.x[t.n] = x.data; t.y[t.n] = nullptr; t.n_vec[t.n] = n /* elements */; t.slot[t.n] = i;
         t.cta0[t.n + 1] = t.cta0[t.n] + (uint32_t)ctas;
         ++t.n;
     }

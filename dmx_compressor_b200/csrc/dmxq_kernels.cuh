@@ -75,7 +75,6 @@ struct RowsParams {
     float *mask;         // nullable, NM stage
     const void *rnd;     // nullable, stochastic stage (int32 or fp32)
     const float *qscale, *qzp;  // nullable: per-tensor FixedPoint affine parameters in device memory (K_FIXED)
-    const float *amax;          // nullable: tensor-wide amax in device memory; the SBFP scaler bias is derived from it (K_SBFP)
     int64_t n_vec;       // total (padded) vectors = rows * vpr
     int64_t rows;
     int64_t K;
@@ -195,6 +194,8 @@ cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, voi
 cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers, unsigned int *n_inexact, int64_t n, int B, const SbfpFmt &f, int sc_man,
                              int sc_exp, cudaStream_t s);
 cudaError_t launch_sbfp_unpack(int dt, const void *mant, const uint8_t *scalers, void *y, int64_t n, int B, const SbfpFmt &f, int sc_man, cudaStream_t s);
+cudaError_t launch_amax_multi(int dt, const MultiTable &t, float *out, cudaStream_t s);  // t.n_vec holds ELEMENT counts here
+int64_t amax_multi_ctas(int dt, int64_t n_elems);
 cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, int64_t C, cudaStream_t s);
 int64_t launch_count();
 

@@ -146,10 +146,14 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_kernel(const __grid_const
 // rounded fp32 operation (S/numerical/cast.py:279-296 around fixed_point_quantize_nearest_cuda).  `rsc`, `rsl` = RN(1 / sc)
 // and its low part (div_by_recip2);
 // div_free: the exact reciprocal-based quotient may be used (scale and data well inside the normal range).
-template <bool HILO = true>
+// HILO: 0 = two-step quotient from rsc alone, 1 = high / low reciprocal pair, 2 = the pair on a 16-bit-significand dividend
+template <int HILO = 1>
 __device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, float rsc, float rsl, bool div_free, const FixedFmt &xf, bool scaled)
 {
-    float a = __fadd_rn(div_free ? (HILO ? div_by_recip2(x, sc, rsc, rsl) : div_by_recip(x, sc, rsc)) : __fdiv_rn(x, sc), zp);
+    float a = __fadd_rn(div_free ? (HILO == 2 ? div_by_recip16(x, rsc, rsl) : HILO == 1 ? div_by_recip2(x, sc, rsc, rsl) : div_by_recip(x, sc, rsc))
+                                 : __fdiv_rn(x, sc), zp);
+    if (div_free && !scaled && xf.clamp && xf.t_max <= 0x1p21f && xf.t_min >= -0x1p21f)  // (t +- 0.25 must be exact)
+        return __fmul_rn(__fsub_rn(round_away_clamped(a, xf.t_min - 0.25f, xf.t_max + 0.25f), zp), sc);
     if (scaled) a = __fmul_rn(a, xf.up);
     a = roundf(a);
     if (scaled) a = __fmul_rn(a, xf.down);
@@ -164,63 +168,76 @@ __device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, 
 
 // vectorised variant 1: one 16-byte vector never straddles two qparam groups (inner % V == 0, or the channel runs
 // along the contiguous dim in groups that are multiples of V).  256 threads x 4 vectors, all loads before first use.
-template <typename Tin, typename Tout>
+// PAIR (host-decided): two neighbouring vectors always share their parameters (an even number of vectors per channel /
+// group), so a thread takes vector PAIRS -- still whole 32-byte sectors per lane -- and derives the parameter set (index
+// arithmetic, two loads, reciprocal pair, range checks: ~40 instructions) once per pair instead of once per vector.
+template <typename Tin, typename Tout, bool PAIR>
 __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_constant__ FixedChanParams p, int64_t cvec, int64_t gvec, FastDiv dcvec,
                                                                   FastDiv dC, FastDiv dgvec)
 {
     // qparam index of vector g: ((g / cvec) % C') / gvec with the caller's (cvec, C', gvec) -- see launch_fixed_chan_t
     constexpr int V = VecIO<Tin>::V;
     constexpr int U = 4;
+    constexpr int S = PAIR ? 2 : 1;  // vectors per parameter set
+    constexpr bool SRC16 = sizeof(Tin) == 2;
     const Tin *__restrict__ x = static_cast<const Tin *>(p.x);
     Tout *__restrict__ y = static_cast<Tout *>(p.y);
     const int64_t nvec = p.n / V;
-    const int64_t g0 = (int64_t)blockIdx.x * (kThreads * U) + threadIdx.x;
+    const int64_t cta0 = (int64_t)blockIdx.x * (kThreads * U);
     const bool fast = p.xf.mode == R_NEAREST && p.xf.tie == TIE_AWAY, scaled = p.xf.up != 1.0f;
+    const bool straight = fast && !scaled && p.xf.clamp && p.xf.t_max <= 0x1p21f && p.xf.t_min >= -0x1p21f;  // INT8 / INT4 with calibrated parameters
+    const float lo = p.xf.t_min - 0.25f, hi = p.xf.t_max + 0.25f;
     uint4 raw[U];
-    float scv[U], zpv[U];
+    int64_t gi[U];
+    float scv[U / S], zpv[U / S];
 #pragma unroll
     for (int u = 0; u < U; ++u) {  // all loads first -- the data AND its quantisation parameters (a dependent load per channel
                                    // change in the compute phase left the kernel latency-bound)
-        const int64_t g = g0 + (int64_t)u * kThreads;
+        const int64_t g = PAIR ? cta0 + (int64_t)(u >> 1) * (2 * kThreads) + 2 * threadIdx.x + (u & 1) : cta0 + (int64_t)u * kThreads + threadIdx.x;
+        gi[u] = g;
         raw[u] = g < nvec ? ldg_stream(x + g * V) : make_uint4(0u, 0u, 0u, 0u);
-        int64_t q = 0;
-        if (p.nq != 1 && g < nvec) {
-            if (nvec <= 0x7FFFFFFFll) {  // multiply-high divisions
-                const uint32_t t = dcvec.div((uint32_t)g);
-                q = dgvec.div(t - dC.div(t) * dC.d);
-            } else {
-                q = ((g / cvec) % p.C) / gvec;
+        if (u % S == 0) {
+            int64_t q = 0;
+            if (p.nq != 1 && g < nvec) {
+                if (nvec <= 0x7FFFFFFFll) {  // multiply-high divisions
+                    const uint32_t t = dcvec.div((uint32_t)g);
+                    q = dgvec.div(t - dC.div(t) * dC.d);
+                } else {
+                    q = ((g / cvec) % p.C) / gvec;
+                }
+                q = min(q, p.nq - 1);
             }
-            q = min(q, p.nq - 1);
+            scv[u / S] = __ldg(p.scale + q);
+            zpv[u / S] = __ldg(p.zp + q);
         }
-        scv[u] = __ldg(p.scale + q);
-        zpv[u] = __ldg(p.zp + q);
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const int64_t g = g0 + (int64_t)u * kThreads;
-        if (g >= nvec) continue;
-        const float sc = scv[u], zp = zpv[u];
+    for (int s0 = 0; s0 < U; s0 += S) {
+        const float sc = scv[s0 / S], zp = zpv[s0 / S];
         const float rsc = __frcp_rn(sc), rsl = recip_lo(sc, rsc);
         const bool sc_ok = recip_safe(sc) && fabsf(zp) < 0x1p60f;
-        float v[V];
-        const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
-        const bool div_free = sc_ok && m_in < 0x5D800000u;
-        if (fast && div_free && !scaled && p.xf.clamp) {  // INT8 / INT4 with calibrated parameters: the straight-line form
-            const float t_min = p.xf.t_min, t_max = p.xf.t_max;
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const float a = roundf(__fadd_rn(div_by_recip2(v[j], sc, rsc, rsl), zp));
-                v[j] = __fmul_rn(__fsub_rn(fminf(fmaxf(a, t_min), t_max), zp), sc);
+        for (int u = s0; u < s0 + S; ++u) {
+            const int64_t g = gi[u];
+            if (g >= nvec) continue;
+            float v[V];
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
+            const bool div_free = sc_ok && m_in < 0x5D800000u;
+            if (straight && div_free) {  // the straight-line form
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float q = SRC16 ? div_by_recip16(v[j], rsc, rsl) : div_by_recip2(v[j], sc, rsc, rsl);
+                    v[j] = __fmul_rn(__fsub_rn(round_away_clamped(__fadd_rn(q, zp), lo, hi), zp), sc);
+                }
+            } else if (fast) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = fixed_affine_away<(SRC16 ? 2 : 1)>(v[j], sc, zp, rsc, rsl, div_free, p.xf, scaled);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
             }
-        } else if (fast) {
-#pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away(v[j], sc, zp, rsc, rsl, div_free, p.xf, scaled);
-        } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
+            VecIO<Tout>::template store<V>(y + g * V, v);
         }
-        VecIO<Tout>::template store<V>(y + g * V, v);
     }
 }
 
@@ -238,7 +255,10 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
     const int64_t c0 = ((int64_t)blockIdx.x * 32 + lane) * V;
     if (c0 >= p.C) return;
     const bool scaled = p.xf.up != 1.0f;
-    float sc[V], zp[V], rsc[V];  // (no low reciprocal parts here: V more registers cost the fp32 kernel a resident CTA, 4.8 -> 4.1 TB/s)
+    // fp32 data: no low reciprocal parts (V more registers cost the kernel a resident CTA, 4.8 -> 4.1 TB/s), the two-step quotient
+    // instead; 16-bit data: the pair, because with it the quotient is two operations (div_by_recip16)
+    constexpr bool PAIR = sizeof(Tin) == 2;
+    float sc[V], zp[V], rsc[V], rsl[PAIR ? V : 1];
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
@@ -246,6 +266,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
         sc[j] = __ldg(p.scale + q);
         zp[j] = __ldg(p.zp + q);
         rsc[j] = __frcp_rn(sc[j]);
+        if (PAIR) rsl[j] = recip_lo(sc[j], rsc[j]);
         ok = ok && recip_safe(sc[j]) && fabsf(zp[j]) < 0x1p60f;
     }
     const int64_t step = (int64_t)gridDim.y * W;
@@ -260,7 +281,7 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_cols_kernel(const __grid_
             const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (also fills v: keep it out of the && chain)
             const bool div_free = ok && m_in < 0x5D800000u;
 #pragma unroll
-            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away<false>(v[j], sc[j], zp[j], rsc[j], 0.0f, div_free, p.xf, scaled);
+            for (int j = 0; j < V; ++j) v[j] = fixed_affine_away<(PAIR ? 2 : 0)>(v[j], sc[j], zp[j], rsc[j], PAIR ? rsl[PAIR ? j : 0] : 0.0f, div_free, p.xf, scaled);
             VecIO<Tout>::template store<V>(y + (r0 + u * step) * p.C + c0, v);
         }
     }
@@ -278,13 +299,17 @@ template <typename Tin, typename Tout> static void launch_fixed_chan_t(const Fix
         // channel constant inside a vector: qparam = ((g / inner_vec) % C) / group
         FixedChanParams q = p;
         int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
-        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, p.inner / V, p.group, fd(p.inner / V), fd(q.C), fd(p.group));
+        const unsigned gr = (unsigned)std::max<int64_t>(grid, 1);
+        if ((p.inner / V) % 2 == 0) fixed_chan_vec_kernel<Tin, Tout, true><<<gr, kThreads, 0, s>>>(q, p.inner / V, p.group, fd(p.inner / V), fd(q.C), fd(p.group));
+        else fixed_chan_vec_kernel<Tin, Tout, false><<<gr, kThreads, 0, s>>>(q, p.inner / V, p.group, fd(p.inner / V), fd(q.C), fd(p.group));
     } else if (aligned && p.inner == 1 && p.C % V == 0 && p.group % V == 0) {
         // channel along the contiguous dim, groups are whole vectors: qparam = (g % (C / V)) / (group / V)
         FixedChanParams q = p;
         q.C = p.C / V;
         int64_t grid = (p.n / V + kThreads * 4 - 1) / (kThreads * 4);
-        fixed_chan_vec_kernel<Tin, Tout><<<(unsigned)std::max<int64_t>(grid, 1), kThreads, 0, s>>>(q, 1, p.group / V, fd(1), fd(q.C), fd(p.group / V));
+        const unsigned gr = (unsigned)std::max<int64_t>(grid, 1);
+        if ((p.group / V) % 2 == 0 && q.C % 2 == 0) fixed_chan_vec_kernel<Tin, Tout, true><<<gr, kThreads, 0, s>>>(q, 1, p.group / V, fd(1), fd(q.C), fd(p.group / V));
+        else fixed_chan_vec_kernel<Tin, Tout, false><<<gr, kThreads, 0, s>>>(q, 1, p.group / V, fd(1), fd(q.C), fd(p.group / V));
     } else if (aligned && fast && !p.rnd && p.inner == 1 && p.C % V == 0) {
         const int64_t R = p.n / p.C, gx = (p.C + 32 * V - 1) / (32 * V);
         int64_t gy = std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, std::max<int64_t>(1, (148 * 8) / gx)));
@@ -1249,7 +1274,7 @@ template <typename T, bool NIBBLE, int VPB> __global__ void __launch_bounds__(kT
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const float a = fabsf(v[t][j]);
-                    const float q = b.rok ? div_by_recip2(a, b.cmax, b.rc, b.rl) : __fdiv_rn(a, b.cmax);
+                    const float q = b.rok ? (sizeof(T) == 2 ? div_by_recip16(a, b.rc, b.rl) : div_by_recip2(a, b.cmax, b.rc, b.rl)) : __fdiv_rn(a, b.cmax);
                     const float r = fminf(truncf(__fadd_rz(q, 0.5f)), f.man_scaling);
                     k[j] = (uint32_t)(int)r | ((f2u(v[t][j]) >> 31) ? SIGN : 0u);
                 }
@@ -1369,6 +1394,88 @@ cudaError_t launch_fold_absmax(const float *mn, const float *mx, uint32_t *out, 
 {
     if (C <= 0) return cudaSuccess;
     fold_absmax_kernel<<<(unsigned)((C + 255) / 256), 256, 0, s>>>(mn, mx, out, C);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace dmxq
+
+namespace dmxq {
+
+// ------------------------------------------------------------------------------------------------
+// max|x| of many contiguous tensors in one launch (dmxq_amax_multi): the per-shard statistic of a sharded calibration
+// pass.  A pure streaming read: 8 independent 16-byte loads per thread (32 KiB in flight per CTA), max over the magnitude
+// bit patterns (packed two-per-instruction on 16-bit data; a NaN pattern is larger than Inf's, so NaN wins and sticks),
+// shuffle + shared-memory reduction, ONE atomicMax per CTA on the tensor's slot (unsigned order == order of |x|).
+constexpr int kAmaxUnroll = 8;
+
+template <typename T> __global__ void __launch_bounds__(kThreads) amax_multi_kernel(const __grid_constant__ MultiTable t, uint32_t *__restrict__ out)
+{
+    constexpr int V = VecIO<T>::V;
+    int lo = 0, hi = t.n;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (blockIdx.x >= t.cta0[mid]) lo = mid; else hi = mid;
+    }
+    const T *__restrict__ x = static_cast<const T *>(t.x[lo]);
+    const int64_t n = t.n_vec[lo], n_vec = n / V;
+    const int64_t g0 = (int64_t)(blockIdx.x - t.cta0[lo]) * (kThreads * kAmaxUnroll) + threadIdx.x;
+    uint4 raw[kAmaxUnroll];
+#pragma unroll
+    for (int u = 0; u < kAmaxUnroll; ++u) {
+        const int64_t g = g0 + (int64_t)u * kThreads;
+        raw[u] = g < n_vec ? ldg_stream(x + g * V) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    uint32_t m = 0u;
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int u = 0; u < kAmaxUnroll; ++u)
+            m = max(max(m, raw[u].x & 0x7FFFFFFFu), max(max(raw[u].y & 0x7FFFFFFFu, raw[u].z & 0x7FFFFFFFu), raw[u].w & 0x7FFFFFFFu));
+    } else {
+        uint32_t m2 = 0u;
+#pragma unroll
+        for (int u = 0; u < kAmaxUnroll; ++u)
+            m2 = __vmaxu2(m2, __vmaxu2(__vmaxu2(raw[u].x & 0x7FFF7FFFu, raw[u].y & 0x7FFF7FFFu), __vmaxu2(raw[u].z & 0x7FFF7FFFu, raw[u].w & 0x7FFF7FFFu)));
+        m = max(m2 & 0xFFFFu, m2 >> 16);
+    }
+    if (g0 == 0) {  // the (< V) elements behind the last whole vector
+        for (int64_t i = n_vec * V; i < n; ++i) {
+            if constexpr (sizeof(T) == 4) m = max(m, f2u(Cvt<T>::to_f32(x[i])) & 0x7FFFFFFFu);
+            else m = max(m, (uint32_t)(*reinterpret_cast<const unsigned short *>(x + i) & 0x7FFFu));
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, d));
+    __shared__ uint32_t sm[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < kThreads / 32; ++w) m = max(m, sm[w]);
+        if constexpr (sizeof(T) == 2) {  // widen the 15-bit magnitude pattern to the fp32 pattern of the same value
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) m <<= 16;
+            else m = f2u(__half2float(__ushort_as_half((unsigned short)m)));
+        }
+        if (m != 0u) atomicMax(out + t.slot[lo], m);
+    }
+}
+
+int64_t amax_multi_ctas(int dt, int64_t n_elems)
+{
+    const int V = dt == 0 ? 4 : 8;
+    const int64_t per = (int64_t)kThreads * kAmaxUnroll * V;
+    return std::max<int64_t>(1, (n_elems + per - 1) / per);
+}
+
+cudaError_t launch_amax_multi(int dt, const MultiTable &t, float *out, cudaStream_t s)
+{
+    const unsigned grid = t.cta0[t.n];
+    if (grid == 0) return cudaSuccess;
+    uint32_t *o = reinterpret_cast<uint32_t *>(out);
+    if (dt == 0) amax_multi_kernel<float><<<grid, kThreads, 0, s>>>(t, o);
+    else if (dt == 1) amax_multi_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(t, o);
+    else if (dt == 2) amax_multi_kernel<__half><<<grid, kThreads, 0, s>>>(t, o);
+    else return cudaErrorInvalidValue;
     count_launch();
     return cudaGetLastError();
 }

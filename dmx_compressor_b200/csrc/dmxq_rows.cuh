@@ -112,38 +112,32 @@ template <typename T> __device__ __forceinline__ uint32_t widen16(uint32_t m16)
     else return f2u(__half2float(__ushort_as_half((unsigned short)m16)));
 }
 
-// The scaler-format fields an SBFP stage reads per block.  Normally they are the stage's own (host-decided); with a
-// device-resident tensor-wide amax (dmxq_cast_chain_multi) the exponent bias -- and with it the flush threshold -- is derived
-// here, so a calibration all-reduce can feed the cast without a host round trip:
-//     bias = (2^E - 1) - floor(log2(amax / man_scaling)), clamped to the range FloatingPoint accepts
+// Flush threshold (FloatFmt.shift_exp) of an SBFP scaler format whose exponent bias is derived on the device from a
+// tensor-wide amax (dmxq_cast_chain_multi), so a calibration all-reduce can feed the cast without a host round trip:
+//     bias = (2^E - 1) - floor(log2(amax / man_scaling)), clamped to the range FloatingPoint accepts;  threshold = 2^(1 - bias)
 // (dmx_compressor_b200.parallel.sbfp_scaler_bias_from_amax is the same rule on the host; the reference delegates the choice
 // to d-Matrix's private `numerics` module, S/numerical/format.py:13-20, 438-446 -- parity unpinned by construction).
-__device__ __forceinline__ SbfpFmt sbfp_fmt_with_amax(const SbfpFmt &f, const float *amax, int sc_exp_bits)
+__device__ __forceinline__ uint32_t sbfp_thr_from_amax(const SbfpFmt &f, const float *amax, int sc_exp_bits)
 {
-    SbfpFmt r = f;
-    if (amax != nullptr) {
-        const float a = __ldg(amax);
-        int bias = (1 << (sc_exp_bits - 1)) - 1;  // the format's default when amax is unusable
-        if (a > 0.0f && a < __int_as_float(0x7F800000)) {
-            // top = largest t with man_scaling * 2^t <= amax (exact: no log, no division rounding)
-            int t = (int)((f2u(__fdiv_rn(a, f.man_scaling)) >> 23) & 0xFFu) - 127;
-            if (__fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 127, 254), 1) << 23)) > a) --t;
-            else if (t < 127 && __fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 128, 254), 1) << 23)) <= a) ++t;
-            bias = ((1 << sc_exp_bits) - 1) - t;
-            const int lo = sc_exp_bits == 8 ? 127 : -128 + (1 << sc_exp_bits);
-            bias = max(lo, min(127, bias));
-        }
-        r.sc.min_exp = -(bias - 1);
-        r.sc.shift_exp = (uint32_t)(127 + r.sc.min_exp) << 23;
+    const float a = __ldg(amax);
+    int bias = (1 << (sc_exp_bits - 1)) - 1;  // the format's default when amax is unusable (zero, Inf, NaN)
+    if (a > 0.0f && a < __int_as_float(0x7F800000)) {
+        // top = largest t with man_scaling * 2^t <= amax (exact: no log, and the quotient's rounding is corrected)
+        int t = (int)((f2u(__fdiv_rn(a, f.man_scaling)) >> 23) & 0xFFu) - 127;
+        if (__fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 127, 254), 1) << 23)) > a) --t;
+        else if (t < 127 && __fmul_rn(f.man_scaling, u2f((uint32_t)max(min(t + 128, 254), 1) << 23)) <= a) ++t;
+        bias = ((1 << sc_exp_bits) - 1) - t;
+        const int lo = sc_exp_bits == 8 ? 127 : -128 + (1 << sc_exp_bits);
+        bias = max(lo, min(127, bias));
     }
-    return r;
+    return (uint32_t)(127 - (bias - 1)) << 23;
 }
 
 // body of chain_rows_kernel: `cta` is the CTA's index inside the tensor (x, y) of n_vec vectors -- the whole grid for
 // the single-tensor kernel, a segment of it for the many-tensor kernel
-template <typename Tin, typename Tout, bool FLAT, int KIND>
+template <typename Tin, typename Tout, bool FLAT, int KIND, bool AMAX = false>
 __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *__restrict__ x, Tout *__restrict__ y, const int64_t cta,
-                                                const int64_t n_vec, const float *amax)
+                                                const int64_t n_vec, const float *amax = nullptr)
 {
     constexpr int V = VecIO<Tin>::V;
     constexpr bool SRC16 = sizeof(Tin) == 2;
@@ -159,6 +153,26 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
     const uint32_t f16_lo = f16_same ? pattern16_ru<Tin>(u2f(p.chain.st[0].ff.shift_exp)) : 0u;
     const uint32_t f16_hi = f16_same ? min(pattern16_rn<Tin>(u2f(p.chain.st[0].ff.max_num)), (uint32_t)(std::is_same<Tin, __half>::value ? 0x7BFFu : 0x7F7Fu)) : 0u;
 
+    // K_FIXED: the per-tensor parameters (device-resident after calibration, or the stage's immediates), everything derived from
+    // them and the choice of variant, ONCE per thread -- the parameter loads go out ahead of the data loads.  (Left inside the
+    // per-vector code they were re-loaded and re-derived for every vector: ~80 of 174 instructions per vector.)
+    float fx_sc = 1.0f, fx_zp = 0.0f, fx_rsc = 0.0f, fx_rsl = 0.0f, fx_lo = 0.0f, fx_hi = 0.0f;
+    int fx_mode = 0;  // 0 general, 1 unit scale + clamp, 2 calibrated + clamp (reciprocal usable), 3 calibrated + clamp (divide)
+    if (KIND == K_FIXED) {
+        const StageDev &st = p.chain.st[0];
+        fx_sc = p.qscale ? __ldg(p.qscale) : st.sc;
+        fx_zp = p.qzp ? __ldg(p.qzp) : st.zp;
+        const bool wrap = st.affine || p.qscale != nullptr, scaled = st.xf.up != 1.0f;
+        const bool small = st.xf.t_max <= 0x1p21f && st.xf.t_min >= -0x1p21f;  // t +- 0.25 exact
+        fx_lo = st.xf.t_min - 0.25f; fx_hi = st.xf.t_max + 0.25f;
+        if (!wrap && !scaled && st.xf.clamp && small) fx_mode = 1;
+        else if (wrap && fx_sc != 1.0f && !scaled && st.xf.clamp && small) {
+            fx_rsc = __frcp_rn(fx_sc);
+            fx_rsl = recip_lo(fx_sc, fx_rsc);
+            fx_mode = (recip_safe(fx_sc) && fabsf(fx_zp) < 0x1p60f) ? 2 : 3;
+        }
+    }
+
     uint4 raw[kUnroll];
     uint4 rraw[kUnroll][V / 4];  // K_BFP_STOCH only
     int64_t yoff[kUnroll];
@@ -169,10 +183,10 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
     // whole 32-byte sectors per lane), so the block constants -- max / 7, its scaler cast, its reciprocal -- are derived once
     // per block instead of once per lane, and no shuffle is needed
     const bool pair = KIND == K_SBFP && SRC16 && FLAT && p.chain.st[0].block == 2 * V;
-    // K_SBFP: the stage's format, with the scaler bias taken from a device-resident amax when one is given
-    const SbfpFmt &sbf0 = p.chain.st[0].sb;
-    const SbfpFmt sbfl = (KIND == K_SBFP && amax != nullptr) ? sbfp_fmt_with_amax(sbf0, amax, (int)p.chain.st[0].sb_exp_bits) : SbfpFmt{};
-    const SbfpFmt &sbf = (KIND == K_SBFP && amax != nullptr) ? sbfl : sbf0;
+    // K_SBFP: the scaler format's flush threshold -- the stage's own, or derived from a device-resident amax (AMAX)
+    const SbfpFmt &sbf = p.chain.st[0].sb;
+    uint32_t sc_thr = 0u;
+    if (KIND == K_SBFP) sc_thr = AMAX ? sbfp_thr_from_amax(sbf, amax, p.chain.st[0].sb_exp_bits) : sbf.sc.shift_exp;
 
     // ---- phase 1: addresses + all loads (nothing here consumes loaded data)
 #pragma unroll
@@ -392,51 +406,45 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
             // CastTo.forward for FixedPoint (S/numerical/cast.py:279-296): x/sc + zp -> round -> clamp -> (q - zp)*sc,
             // every step a separately rounded fp32 op.  sc == 1 makes the division and the final multiply exact
             // identities, zp == 0 the final subtraction; the leading "+ zp" is kept (it turns -0 into +0).
+            // The per-tensor parameters and the variant (fx_mode) were fixed once per thread above the load phase.
             const StageDev &st = p.chain.st[0];
-            const bool wrap = st.affine || p.qscale != nullptr;
-            const float sc = p.qscale ? __ldg(p.qscale) : st.sc;
-            const float zp = p.qzp ? __ldg(p.qzp) : st.zp;
-            const bool unit = sc == 1.0f, scaled = st.xf.up != 1.0f;
             const float t_min = st.xf.t_min, t_max = st.xf.t_max;
-            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (packed on 16-bit sources; unused -- and dropped -- outside the calibrated branch)
-            // straight-line variants for the shapes that occur (the flags are kernel-uniform)
-            if (!wrap && !scaled && st.xf.clamp) {  // INT8 / INT4 with unit scale
+            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);  // (packed on 16-bit sources)
+            if (fx_mode == 1 && m_in <= 0x7F800000u) {  // INT8 / INT4 with unit scale, no NaN in this vector: clamp first, then round
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = round_away_clamped(v[j], fx_lo, fx_hi);
+            } else if (fx_mode == 1) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const float a = roundf(v[j]);
                     v[j] = a > t_max ? t_max : (a < t_min ? t_min : a);
                 }
-            } else if (wrap && !unit && !scaled && st.xf.clamp) {  // calibrated INT8 / INT4: scale and zero-point
-                // x / sc, correctly rounded: reciprocal + two FMA refinements when scale and data are well inside the
-                // normal range (a -0 quotient comes out as +0, which the "+ zp" produces anyway)
-                // (finite data and parameters: no NaN can reach the clamp, so min/max instructions do)
-                const bool div_free = recip_safe(sc) && fabsf(zp) < 0x1p60f && m_in < 0x5D800000u;
-                const float rsc = __frcp_rn(sc);
-                const float rsl = recip_lo(sc, rsc);
-                if (div_free) {
+            } else if (fx_mode == 2 && m_in < 0x5D800000u) {  // calibrated INT8 / INT4, data well inside the normal range
+                // x / sc correctly rounded without the division sequence (div_by_recip16 / div_by_recip2; a -0 quotient comes out
+                // as +0, which the "+ zp" produces anyway); finite data and parameters: no NaN can reach the clamp
 #pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const float a = roundf(__fadd_rn(div_by_recip2(v[j], sc, rsc, rsl), zp));
-                        v[j] = __fmul_rn(__fsub_rn(fminf(fmaxf(a, t_min), t_max), zp), sc);
-                    }
-                } else {
+                for (int j = 0; j < V; ++j) {
+                    const float q = SRC16 ? div_by_recip16(v[j], fx_rsc, fx_rsl) : div_by_recip2(v[j], fx_sc, fx_rsc, fx_rsl);
+                    v[j] = __fmul_rn(__fsub_rn(round_away_clamped(__fadd_rn(q, fx_zp), fx_lo, fx_hi), fx_zp), fx_sc);
+                }
+            } else if (fx_mode == 2 || fx_mode == 3) {  // calibrated, literal operation sequence
 #pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        float a = roundf(__fadd_rn(__fdiv_rn(v[j], sc), zp));
-                        a = a > t_max ? t_max : (a < t_min ? t_min : a);
-                        v[j] = __fmul_rn(__fsub_rn(a, zp), sc);
-                    }
+                for (int j = 0; j < V; ++j) {
+                    float a = roundf(__fadd_rn(__fdiv_rn(v[j], fx_sc), fx_zp));
+                    a = a > t_max ? t_max : (a < t_min ? t_min : a);
+                    v[j] = __fmul_rn(__fsub_rn(a, fx_zp), fx_sc);
                 }
             } else {
+                const bool wrap = st.affine || p.qscale != nullptr, unit = fx_sc == 1.0f, scaled = st.xf.up != 1.0f;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     float a = v[j];
-                    if (wrap) a = __fadd_rn(unit ? a : __fdiv_rn(a, sc), zp);
+                    if (wrap) a = __fadd_rn(unit ? a : __fdiv_rn(a, fx_sc), fx_zp);
                     if (scaled) a = __fmul_rn(a, st.xf.up);
                     a = roundf(a);
                     if (scaled) a = __fmul_rn(a, st.xf.down);
                     if (st.xf.clamp) a = a > t_max ? t_max : (a < t_min ? t_min : a);
-                    if (wrap && !(unit && zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, zp), sc);
+                    if (wrap && !(unit && fx_zp == 0.0f)) a = __fmul_rn(__fsub_rn(a, fx_zp), fx_sc);
                     v[j] = a;
                 }
             }
@@ -447,9 +455,9 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
             if ((u & 1) == 0) {
                 float w[V];
                 const uint32_t m = max(unpack_absmax<Tin>(raw[u], v), unpack_absmax<Tin>(raw[(u + 1) % kUnroll], w));
-                const SbfpBlock b = sbfp_block_ol(m, sbf);
-                sbfp_apply<V>(v, b, sbf);
-                sbfp_apply<V>(w, b, sbf);
+                const SbfpBlock b = sbfp_block_ol(m, sbf, sc_thr);
+                sbfp_apply<V, SRC16>(v, b, sbf);
+                sbfp_apply<V, SRC16>(w, b, sbf);
                 if (valid[u]) VecIO<Tout>::template store<V>(y + yoff[u], v);
                 if (valid[(u + 1) % kUnroll]) VecIO<Tout>::template store<V>(y + yoff[(u + 1) % kUnroll], w);
             }
@@ -457,8 +465,8 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
         } else if (KIND == K_SBFP) {
             const StageDev &st = p.chain.st[0];
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
-            SbfpBlock b = sbfp_block_ol(m, sbf);
-            sbfp_apply<V>(v, b, sbf);
+            SbfpBlock b = sbfp_block_ol(m, sbf, sc_thr);
+            sbfp_apply<V, SRC16>(v, b, sbf);
         } else {
             VecIO<Tin>::unpack(raw[u], v);
 #pragma unroll 1
@@ -513,13 +521,13 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
 template <typename Tin, typename Tout, bool FLAT, int KIND>
 __global__ void __launch_bounds__(kThreads) chain_rows_kernel(const __grid_constant__ RowsParams p)
 {
-    chain_rows_body<Tin, Tout, FLAT, KIND>(p, static_cast<const Tin *>(p.x), static_cast<Tout *>(p.y), (int64_t)blockIdx.x, p.n_vec, p.amax);
+    chain_rows_body<Tin, Tout, FLAT, KIND>(p, static_cast<const Tin *>(p.x), static_cast<Tout *>(p.y), (int64_t)blockIdx.x, p.n_vec);
 }
 
 // Many tensors, one launch (dmxq_cast_chain_multi): the shards a rank owns in a sharded whole-model weight cast.  Every
 // tensor is a flat run of vectors; CTAs are dealt to tensors by a prefix table that travels in the kernel parameters (no
 // device-side table to allocate or fill), found by a CTA-uniform binary search.
-template <typename T, int KIND>
+template <typename T, int KIND, bool AMAX>
 __global__ void __launch_bounds__(kThreads) chain_rows_multi_kernel(const __grid_constant__ RowsParams p, const __grid_constant__ MultiTable t)
 {
     int lo = 0, hi = t.n;
@@ -527,15 +535,20 @@ __global__ void __launch_bounds__(kThreads) chain_rows_multi_kernel(const __grid
         const int mid = (lo + hi) >> 1;
         if (blockIdx.x >= t.cta0[mid]) lo = mid; else hi = mid;
     }
-    chain_rows_body<T, T, true, KIND>(p, static_cast<const T *>(t.x[lo]), static_cast<T *>(t.y[lo]), (int64_t)(blockIdx.x - t.cta0[lo]), t.n_vec[lo],
-                                      t.amax ? t.amax + t.slot[lo] : nullptr);
+    chain_rows_body<T, T, true, KIND, AMAX>(p, static_cast<const T *>(t.x[lo]), static_cast<T *>(t.y[lo]), (int64_t)(blockIdx.x - t.cta0[lo]), t.n_vec[lo],
+                                            AMAX ? t.amax + t.slot[lo] : nullptr);
 }
 
 template <typename T, int KIND> static cudaError_t launch_rows_multi_k(const RowsParams &p, const MultiTable &t, cudaStream_t s)
 {
     const unsigned grid = t.cta0[t.n];
     if (grid == 0) return cudaSuccess;
-    chain_rows_multi_kernel<T, KIND><<<grid, kThreads, 0, s>>>(p, t);
+    if constexpr (KIND == K_SBFP) {
+        if (t.amax != nullptr) chain_rows_multi_kernel<T, KIND, true><<<grid, kThreads, 0, s>>>(p, t);
+        else chain_rows_multi_kernel<T, KIND, false><<<grid, kThreads, 0, s>>>(p, t);
+    } else {
+        chain_rows_multi_kernel<T, KIND, false><<<grid, kThreads, 0, s>>>(p, t);
+    }
     count_launch();
     return cudaGetLastError();
 }

@@ -154,6 +154,23 @@ __device__ __forceinline__ float div_by_recip(float a, float b, float rb)
 // IEEE division on 4e8 random, tie-adjacent and 16-bit-significand operand pairs on the CPU; the SBFP tie tests hammer
 // it on the GPU.)
 __device__ __forceinline__ float recip_lo(float b, float rh) { return __fmul_rn(__fmaf_rn(-b, rh, 1.0f), rh); }
+// ... and in TWO operations when the dividend has at most 16 significant bits (a widened bf16 / fp16 value: 8 / 11 bits).
+// rh + rl equals 1/b to ~2^-47 and RN(a*rl) adds ~2^-48, so q0 = RN(a*rh + RN(a*rl)) is the correct rounding of a value
+// within 2^-46 (relative) of a/b -- and a/b itself cannot come closer than 2^-(s+25) to a rounding boundary of fp32: with
+// a = A*2^i (A < 2^s), b = B*2^j (B < 2^24) and a boundary (2Q+1)*2^k, |A/B - (2Q+1)*2^k'| = |A*2^m - (2Q+1)*B| / (B*2^m) is a
+// non-zero integer over B*2^m.  For s <= 16 that is >= 2^-41 >> 2^-46: q0 is already a/b correctly rounded, no correction step.
+// (tests/native/div_by_recip_check.c: 2*10^8 quotients with 8- / 11- / 16-bit dividends incl. tie neighbourhoods, 0 mismatches;
+// with 24-bit dividends the same form does fail, rarely.)  Same preconditions as div_by_recip.
+__device__ __forceinline__ float div_by_recip16(float a, float rh, float rl) { return __fmaf_rn(a, rh, __fmul_rn(a, rl)); }
+// round half away from zero, then clamp to the integers [t_min, t_max] (|t| <= 2^22), for finite a: clamping FIRST -- to
+// [t_min - 0.25, t_max + 0.25], which rounds to the same integers -- bounds the magnitude, so the rounding is
+// trunc(|c| + 0.5) with the addition rounded toward zero (it cannot round up into the next integer) and the sign put back:
+// five instructions instead of roundf's sequence plus two.  lo = t_min - 0.25, hi = t_max + 0.25.
+__device__ __forceinline__ float round_away_clamped(float a, float lo, float hi)
+{
+    const float c = fminf(fmaxf(a, lo), hi);
+    return copysignf(truncf(__fadd_rz(fabsf(c), 0.5f)), c);
+}
 __device__ __forceinline__ float div_by_recip2(float a, float b, float rh, float rl)
 {
     const float q = __fmaf_rn(a, rh, __fmul_rn(a, rl));
@@ -161,7 +178,10 @@ __device__ __forceinline__ float div_by_recip2(float a, float b, float rh, float
 }
 __device__ __forceinline__ bool recip_safe(float b) { return b > 0x1p-60f && b < 0x1p60f && (f2u(b) & 0x7FFFFFu) != 0x7FFFFFu; }
 
-__device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const SbfpFmt &f)
+// `sc_thr`: the scaler format's flush threshold (FloatFmt.shift_exp) -- the one quantity of the fast scaler cast that depends
+// on the exponent bias; passed separately so a bias derived on the device (from an all-reduced amax) can replace the
+// host-decided one while every other format constant keeps coming from the kernel parameters
+__device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const SbfpFmt &f, uint32_t sc_thr)
 {
     SbfpBlock b;
     const float m = u2f(maxabs_bits);
@@ -170,14 +190,20 @@ __device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const S
     else b.cmax = (m > 0x1p-60f && m < 0x1p60f) ? div_by_recip(m, f.man_scaling, f.inv_man) : __fdiv_rn(m, f.man_scaling);
     // scaler cast: cmax >= 0 (or NaN, in which case the block passes through and fs is unused), so the
     // unsigned scaler formats of the SBFP aliases reduce to the signed nearest+flush fast path
-    if (f.sc_fast) b.fs = float_elem_flush_nearest<false>(b.cmax, f.sc);
-    else b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
+    if (f.sc_fast) {  // float_elem_flush_nearest<false> with the threshold made explicit
+        const uint32_t ab = f2u(b.cmax) & 0x7FFFFFFFu;
+        const uint32_t mag = min(round_bits<R_NEAREST>(ab, f.sc.sh, f.sc.mask, 0u), f.sc.max_num);
+        b.fs = ab < sc_thr ? 0.0f : u2f(mag | (f2u(b.cmax) & 0x80000000u));
+    } else {
+        b.fs = float_elem_slow(b.cmax, &f.sc, 0u);
+    }
     b.on = b.cmax > 0.0f;
     b.rok = recip_safe(b.cmax);
     b.rc = __frcp_rn(b.cmax);
     b.rl = recip_lo(b.cmax, b.rc);
     return b;
 }
+__device__ __forceinline__ SbfpBlock sbfp_block_ol(uint32_t maxabs_bits, const SbfpFmt &f) { return sbfp_block_ol(maxabs_bits, f, f.sc.shift_exp); }
 __device__ __forceinline__ bool sbfp_fast(const SbfpFmt &f) { return f.xp.mode == R_NEAREST && f.xp.tie == TIE_AWAY; }
 // XP[p,0] nearest, half away (the reference's CUDA rule) of the IEEE quotient; fl = 0 => no scaling multiplies.
 __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, const SbfpFmt &f)
@@ -192,14 +218,14 @@ __device__ __forceinline__ float sbfp_elem_fast(float x, const SbfpBlock &b, con
 //     handling): two instructions;
 //   * the clamp to [t_min, t_max] cannot trigger when |t_min|, t_max >= man_scaling (every SBFP format), so it is skipped;
 //   * the result carries x's sign (cmax, fs >= 0).
-template <int V> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const SbfpBlock &b, const SbfpFmt &f)
+template <int V, bool SRC16 = false> __device__ __forceinline__ void sbfp_apply(float (&v)[V], const SbfpBlock &b, const SbfpFmt &f)
 {
     if (!b.on) return;  // all-zero (or NaN) block: passes through
     if (b.rok && f.no_clamp) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const float a = fabsf(v[j]);
-            const float q = div_by_recip2(a, b.cmax, b.rc, b.rl);
+            const float q = SRC16 ? div_by_recip16(a, b.rc, b.rl) : div_by_recip2(a, b.cmax, b.rc, b.rl);
             const float r = truncf(__fadd_rz(q, 0.5f));  // round half away of q >= 0: the toward-zero add cannot round up into the next integer
             v[j] = copysignf(__fmul_rn(r, b.fs), v[j]);
         }

@@ -13,10 +13,26 @@ from __future__ import annotations
 import torch
 
 
+def _drop_weight_caches(model) -> None:
+    for m in model.modules():
+        if getattr(m, "_wcache", None) is not None:
+            m._wcache = None
+
+
 class Captured:
+    """A captured forward.  What the graph reads besides ``static_in`` is FROZEN at capture time: the parameters and buffers
+    of ``model`` (kept alive by the reference held here) and -- with ``elide_casts`` -- the cast weights computed during the
+    capture; after a weight update, ``configure()`` or ``fold_weight_and_bias()``, capture again.
+
+    With ``elide_casts`` the cast memo and the weight caches are cleared right before the capture: a memo hit on a tensor
+    computed during warm-up would otherwise leave that cast OUT of the graph (the graph would keep reading the warm-up
+    result, freed when the elision context ends), so every cast the forward needs is recorded; and they are cleared again
+    afterwards, so nothing outside the graph keeps pointing into the graph's private memory pool."""
+
     def __init__(self, model, *example, warmup: int = 3, elide_casts: bool = False):
         from . import elide
 
+        self.model = model
         self.static_in = [e.clone() for e in example]
         self.elide = elide_casts
         ctx = elide.enabled if elide_casts else _null
@@ -27,9 +43,15 @@ class Captured:
                 for _ in range(warmup):
                     model(*self.static_in)
             torch.cuda.current_stream().wait_stream(s)
+            if elide_casts:
+                elide.reset()
+                _drop_weight_caches(model)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_out = model(*self.static_in)
+            if elide_casts:
+                elide.reset()
+                _drop_weight_caches(model)
 
     def __call__(self, *inputs):
         for dst, src in zip(self.static_in, inputs):

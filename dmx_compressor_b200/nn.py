@@ -154,9 +154,18 @@ class DmxModule:
             if stages is not None:
                 if not stages:
                     return _w
-                if self.weight_sparsifier is not None and not isinstance(self.weight_sparsifier.sparseness, Dense):
-                    self.weight_sparsifier.plastic = False  # the reference rewires once, on this forward
-                return ops.cast_chain(_w, stages, -1)  # ONE kernel: prune -> storage cast -> weight cast
+                sp = self.weight_sparsifier
+                if sp is not None and not isinstance(sp.sparseness, Dense):
+                    # everything the sparsifier's own forward would leave behind: the lazily created score parameter (same
+                    # RNG draw), the mask (Sparsify.mask / density / mask_str consumers) and the one-shot `plastic` flag
+                    if isinstance(sp, LazySparsify) and sp.has_uninitialized_params():
+                        sp._infer_parameters(sp, (_w,), {})
+                    mask = torch.empty(_w.shape, dtype=torch.float32, device=_w.device)
+                    out = ops.cast_chain(_w, stages, -1, mask=mask)  # ONE kernel: prune (+ mask) -> storage cast -> weight cast
+                    sp.mask = mask
+                    sp.plastic = False  # the reference rewires once, on this forward
+                    return out
+                return ops.cast_chain(_w, stages, -1)  # ONE kernel: storage cast -> weight cast
         if self.weight_sparsifier is not None:
             _w = self.weight_sparsifier(_w)
         if self.weight_storage_cast is not None:
@@ -169,9 +178,16 @@ class DmxModule:
     def _weight(self):
         if elide.active() and not torch.is_grad_enabled() and not self._smoothing_weight():
             w = self.weight
-            key = (w.data_ptr(), w._version, tuple(w.shape), repr(self.weight_format),
-                   repr(self.weight_storage_cast.format) if self.weight_storage_cast is not None else None,
-                   repr(self.weight_sparseness))
+            casts = (self.weight_storage_cast, self.weight_cast)
+            if any(c is not None and c._obs_on for c in casts):
+                return self.weight_hypernet(w)  # calibrating: the observers must see every forward
+            sp = self.weight_sparsifier
+            # everything the result depends on: the weight (storage + in-place version), each weight-path cast (format,
+            # fake-quant switch, block dim, pre-transform, FixedPoint qparams) and the sparsifier (pattern, tie order, the
+            # one-shot `plastic` flag and its score function, the score parameter's version)
+            key = (w.data_ptr(), w._version, tuple(w.shape)) + tuple(_cast_state(c) for c in casts) + (
+                None if sp is None else (repr(sp.sparseness), getattr(sp.sparseness, "tie_order", None), sp.plastic,
+                                         id(getattr(sp, "score_func", None)) if sp.plastic else None, _param_state(getattr(sp, "score", None))),)
             if self._wcache is not None and self._wcache[0] == key:
                 return self._wcache[1]
             out = self.weight_hypernet(w)

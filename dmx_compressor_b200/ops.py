@@ -376,6 +376,26 @@ def minmax(x, ch_axis: Optional[int] = None, out=None):
     return mn, mx
 
 
+def amax_multi(xs: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """max|x| of every tensor of ``xs`` as one fp32 CUDA vector, in one launch per 64 tensors (dmxq_amax_multi)."""
+    n = len(xs)
+    dev = xs[0].device if n else (out.device if out is not None else torch.device("cuda"))
+    res = out if out is not None else torch.empty(n, dtype=torch.float32, device=dev)
+    if n == 0:
+        return res
+    for x in xs:
+        L.require_cuda(x)
+        if not x.is_contiguous() or x.device != dev:
+            raise RuntimeError("dmxq: amax_multi needs contiguous tensors on one device")
+    if res.dtype != torch.float32 or res.numel() != n or not res.is_contiguous() or res.device != dev:
+        raise RuntimeError("dmxq: amax_multi out must be a contiguous fp32 vector with one entry per tensor")
+    vx = (L.Tensor * n)(*[L.view(x) for x in xs])
+    with _guard(dev):
+        rc = L.lib.dmxq_amax_multi(vx, n, res.data_ptr(), L.stream_ptr(dev))
+    L.check(rc, "dmxq_amax_multi")
+    return res
+
+
 def _f32(v) -> float:
     """a python number rounded to fp32 (what a torch Scalar becomes inside an fp32 kernel)"""
     return struct.unpack("f", struct.pack("f", float(v)))[0]

@@ -200,7 +200,7 @@ def shard_amax(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tenso
                local: Callable = None) -> torch.Tensor:
     """Tensor-wide max|x| for every shard `plan[rank]` lists (as if each tensor were whole), as ONE fp32 device vector --
     the form ``ops.cast_chain_multi(..., amax=...)`` consumes, so calibration statistics go from the reduction into the cast
-    kernel without ever visiting the host.  Per shard one ``dmxq_minmax`` writing straight into its slot; the row-split tensors
+    kernel without ever visiting the host.  One ``dmxq_amax_multi`` launch per 64 shards; the row-split tensors
     (the same set, in the same order, on every rank) share ONE ``all_reduce(MAX)``.  A NaN anywhere in a tensor makes its
     amax +inf (the cast then keeps the format's default scaler bias)."""
     import torch.distributed as dist
@@ -224,13 +224,13 @@ def shard_amax(plan: List[List[Shard]], rank: int, tensors: Sequence[torch.Tenso
         _AMAX_PLANS[key] = ent
     _, n_split, src_idx, dst_idx, mnmx = ent
     amax = out if out is not None else torch.empty(n, dtype=torch.float32, device=dev)
-    if n:
+    if n and local is None:
+        ops.amax_multi(tensors, out=amax)  # one launch per 64 shards
+        torch.nan_to_num_(amax, nan=float("inf"))
+    elif n:  # the gloo unit tests inject a CPU statistic
         for i, t in enumerate(tensors):
-            if local is None:
-                ops.minmax(t, None, out=(mnmx[0, i:i + 1], mnmx[1, i:i + 1]))
-            else:  # the gloo unit tests inject a CPU statistic
-                a, b = local(t, None)
-                mnmx[0, i], mnmx[1, i] = a.reshape(()), b.reshape(())
+            a, b = local(t, None)
+            mnmx[0, i], mnmx[1, i] = a.reshape(()), b.reshape(())
         torch.maximum(-mnmx[0, :n], mnmx[1, :n], out=amax)
         torch.nan_to_num_(amax, nan=float("inf"))
     if n_split and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:

@@ -257,6 +257,14 @@ int dmxq_block_quantize(const dmxq_tensor *x, const dmxq_tensor *y, int wl, int 
  * bit-identical to the single-device result. */
 int dmxq_minmax(const dmxq_tensor *x, int ch_axis, float *out_min, float *out_max, void *stream);
 
+/* ---- max|x| of many tensors in one launch: out_amax[i] = max over xs[i] of |x| (fp32; NaN propagates), the per-shard
+ * statistic of a sharded calibration pass (a tensor-wide amax for the SBFP scaler range; the symmetric
+ * half of MinMaxObserver's statistic, S/numerical/observer.py:181-186).  Exact and order independent, so the per-shard
+ * results followed by an all-reduce(MAX) equal the single-device value bit for bit.  xs: contiguous, 16-byte aligned,
+ * any shapes, one dtype per launch group (mixed dtypes just cost extra launches).  out_amax: device array of n_tensors
+ * floats, overwritten.  Feeds dmxq_cast_chain_multi(amax=...) without leaving the device. */
+int dmxq_amax_multi(const dmxq_tensor *xs, int n_tensors, float *out_amax, void *stream);
+
 /* ---- calibration histogram: the torch.histc call of HistogramObserver.forward (S/numerical/observer.py:470-491)
  * counts[b] += #{ v in x : lo <= v <= hi, b == min((int)((v - lo) * bins / (hi - lo)), bins - 1) }, the bin expression
  * evaluated in fp32 exactly as torch does; NaN and out-of-range values are dropped.  `counts`: device array of `bins`

@@ -6,7 +6,11 @@
  * Preconditions (the kernels check them per block / vector): b in (2^-60, 2^60) with a significand that is not all
  * ones; the comparison is on the full quotient for |a| >= 2^-100 and on round-half-away(q) -- what the casts consume -- below
  * (there the residual a - q*b leaves the normal range and the last bit of a quotient < 2^-40 is immaterial).
- * usage: div_by_recip_check <cases>   -> prints "cases N bad_two_step X bad_hilo Y", exit status 0 iff X == Y == 0 */
+ *   div_by_recip16:  q = fma(a, rh, a*rl) alone, for dividends of at most 16 significant bits (widened bf16 / fp16 values):
+ *                   a/b then stays >= 2^-41 (relative) away from every fp32 rounding boundary, further than the error of the
+ *                   estimate, so no correction step is needed.  Checked with 8-, 11- and 16-bit dividends, half of them in the
+ *                   neighbourhood of quotient ties (k + 0.5) * b.
+ * usage: div_by_recip_check <cases>   -> prints "cases N bad_two_step X bad_hilo Y bad_16bit Z", exit status 0 iff all are 0 */
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,6 +58,26 @@ int main(int argc, char **argv)
         if (f2u(g1) != f2u(want)) ++bad1;
         if (f2u(g2) != f2u(want)) ++bad2;
     }
-    printf("cases %ld bad_two_step %ld bad_hilo %ld\n", cnt, bad1, bad2);
-    return (bad1 || bad2) ? 1 : 0;
+    long bad3 = 0, cnt3 = 0;
+    for (long i = 0; i < n; ++i) {
+        const int bits = (i % 3 == 0) ? 8 : (i % 3 == 1) ? 11 : 16;
+        const uint32_t keep = ~((1u << (24 - bits)) - 1u);
+        uint32_t bm = (uint32_t)rnd() & 0x7FFFFF;
+        if (bm == 0x7FFFFF) continue;
+        float b = u2f(((uint32_t)(67 + (int)(rnd() % 120)) << 23) | bm);
+        float rh = 1.0f / b, rl = fmaf(-b, rh, 1.0f) * rh;
+        int ae = (int)((f2u(b) >> 23) & 0xFF) + (int)(rnd() % 40) - 30; /* quotient in 2^-30 .. 2^9 */
+        if (ae < 1 || ae > 254) continue;
+        float a = u2f(((uint32_t)ae << 23) | (((uint32_t)rnd() & 0x7FFFFF) & keep));
+        if (i & 8) { /* around the ties of the quotient, on the dividend's own grid */
+            a = u2f(f2u(b * ((float)(rnd() % 300) + 0.5f)) & keep);
+            if (rnd() & 1) a = u2f(f2u(a) + (1u << (24 - bits)));
+        }
+        if (i & 4) a = -a;
+        if (!(fabsf(a) < 0x1p60f) || fabsf(a) < 0x1p-100f) continue;
+        ++cnt3;
+        if (f2u(a / b) != f2u(fmaf(a, rh, a * rl))) ++bad3;
+    }
+    printf("cases %ld bad_two_step %ld bad_hilo %ld bad_16bit %ld (of %ld)\n", cnt, bad1, bad2, bad3, cnt3);
+    return (bad1 || bad2 || bad3) ? 1 : 0;
 }

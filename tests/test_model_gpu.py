@@ -320,3 +320,94 @@ def test_linear_with_smoothquant():
     assert sq.fused_to_weight.item() == 1
     assert torch.equal(lin.weight, w)
     assert torch.equal(lin(x), want)
+
+
+class _FloatMLP(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.fc1, self.act, self.fc2 = dmxnn.Linear(64, 128), dmxnn.ReLU(), dmxnn.Linear(128, 32)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+def test_graph_capture_with_elision_records_every_cast_of_a_float_input_model():
+    """a small float-input model makes fewer cast-memo entries than the memo holds: the first input cast hit the warm-up's memo
+    entry during capture and was left out of the graph.  Capture now starts from an empty memo / weight cache: replay with a
+    DIFFERENT input must equal eager, and the caches hold nothing from inside the graph afterwards"""
+    from dmx_compressor_b200 import graph
+
+    torch.manual_seed(9)
+    net = _FloatMLP().to(DEV).eval()
+    for m in net.modules():
+        if isinstance(m, dmxnn.Linear):
+            m.configure(dict(input_formats=[fmt.BFP16_64], weight_format=fmt.BFP16_64, bias_format=fmt.BFP32_1, output_formats=[fmt.FLOAT16]))
+        elif isinstance(m, dmxnn.ReLU):
+            m.configure(dict(input_formats=[fmt.FLOAT16], output_formats=[fmt.FLOAT16]))
+    x1, x2 = torch.randn(8, 64, device=DEV), torch.randn(8, 64, device=DEV) * 3
+    with torch.no_grad():
+        want1, want2 = net(x1), net(x2)
+    fwd = graph.capture(net, x1, elide_casts=True)
+    assert torch.equal(fwd(x2), want2)
+    assert torch.equal(fwd(x1), want1)
+    assert all(getattr(m, "_wcache", None) is None for m in net.modules())
+    with torch.no_grad(), elide.enabled():  # eager elided forwards after the capture are unaffected
+        assert torch.equal(net(x2), want2)
+
+
+def test_weight_cache_follows_cast_state():
+    """under elision the cast weight is cached; every switch that changes what `_weight` means must miss the cache:
+    fake-quant off / on, calibration (observer must see each forward), new qparams, a re-armed sparsifier"""
+    torch.manual_seed(10)
+    lin = dmxnn.Linear(64, 32).to(DEV).eval()
+    lin.configure(dict(weight_format=fmt.INT8))
+    x = torch.randn(4, 64, device=DEV)
+    with torch.no_grad(), elide.enabled():
+        wq = lin._weight.clone()
+        assert lin._weight is lin._weight  # cached
+        lin.weight_cast.disable_fake_quant()
+        assert torch.equal(lin._weight, lin.weight)  # not the stale quantised tensor
+        lin.weight_cast.enable_fake_quant()
+        assert torch.equal(lin._weight, wq)
+        lin.weight_cast.enable_calibration(True, MinMaxObserver, qscheme_to_overload=torch.per_tensor_symmetric)
+        lin.weight_cast.to(DEV)
+        lin(x)
+        lin(x)  # observer runs on every forward while calibrating
+        lin.weight_cast.enable_calibration(False)
+        wc = lin._weight.clone()
+        assert not torch.equal(wc, wq)  # calibrated scale, not the unit scale
+        lin.weight_cast.scale.mul_(2.0)
+        assert not torch.equal(lin._weight, wc)
+    want = CastTo(fmt.INT8).to(DEV)
+    with torch.no_grad():
+        want.scale.copy_(lin.weight_cast.scale); want.zero_point.copy_(lin.weight_cast.zero_point)
+        with elide.enabled():
+            assert torch.equal(lin._weight, want(lin.weight))
+
+
+def test_fused_hypernet_leaves_the_sparsifier_state_of_the_module_path():
+    """fused sparsify -> cast under elision: mask stored, lazy score created, `plastic` consumed; the NEXT forward (no longer
+    plastic: the score parameter decides, as in the reference) equals the non-elided module path"""
+    def build():
+        torch.manual_seed(11)
+        lin = dmxnn.Linear(256, 64).to(DEV).eval()
+        lin.configure(dict(weight_sparseness="BTOPK{2:4,-1}(U)", weight_format=fmt.BFP12_128))
+        lin.weight_sparsifier.configure(score_func=abs_score)
+        return lin
+
+    a, b = build(), build()
+    with torch.no_grad():
+        torch.manual_seed(12)
+        w1 = a._weight.clone()
+        w2 = a._weight.clone()
+        with elide.enabled():
+            torch.manual_seed(12)
+            n0 = _lib.launch_count()
+            v1 = b._weight.clone()
+            assert _lib.launch_count() - n0 == 1
+            v2 = b._weight.clone()
+    assert torch.equal(w1, v1) and torch.equal(w2, v2)
+    assert not torch.equal(w1, w2)  # the second forward prunes with the (random) score parameter
+    assert torch.equal(a.weight_sparsifier.mask, b.weight_sparsifier.mask) and not b.weight_sparsifier.plastic
+    assert torch.equal(a.weight_sparsifier.score, b.weight_sparsifier.score)
+    assert float(b.weight_sparsifier.mask.mean()) == 0.5

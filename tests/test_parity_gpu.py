@@ -1278,3 +1278,43 @@ def test_cast_chain_multi_amax_drives_sbfp_bias_on_device():
         b = P.sbfp_scaler_bias_from_amax(a)
         want = ops.cast_chain(w, [fmt_from(f"SBFP<XP[4,0](CSN)><FP[0|4|4,{b}](FN)>{{16}}").stage()], -1)
         assert torch.equal(y.view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16, torch.float32])
+def test_int8_affine_quotient_ties(dt):
+    """calibrated INT8: x / scale + zp lands on (and one grid step either side of) the rounding ties k + 0.5, the clamp edges
+    +-127.5 and beyond, for many scales -- per tensor (K_FIXED rows kernel), per row and per column (fixed_chan kernels).  On
+    16-bit tensors the quotient is the two-operation form (div_by_recip16) and the rounding is clamp-first: both must equal
+    the oracle's divide / roundf / clamp sequence bit for bit"""
+    g = torch.Generator().manual_seed(4242)
+    R, Cn = 256, 512
+    sc_row = (torch.rand(R, generator=g) * 0.2 + 0.003) * torch.pow(2.0, torch.randint(-6, 7, (R,), generator=g).float())
+    zp_row = torch.randint(-5, 6, (R,), generator=g).float()
+    k = torch.randint(-140, 141, (R, Cn), generator=g).float() + 0.5
+    x = (k - zp_row[:, None]) * sc_row[:, None]
+    x = x.to(dt)  # onto the dtype's grid ...
+    it = torch.int32 if dt == torch.float32 else torch.int16
+    x = (x.view(it) + torch.randint(-1, 2, (R, Cn), generator=g, dtype=torch.int32).to(it)).view(dt)  # ... and its neighbours
+    x[0, :8] = torch.tensor([0.0, -0.0, 1e-30, -1e-30, 3e4, -3e4, 1.0, -1.0]).to(dt)
+    xn = x.float().numpy()
+
+    def cmp(got, want, what):
+        want = torch.from_numpy(want).to(dt)
+        assert torch.equal(got.cpu().view(it), want.view(it)), what
+
+    for fmt in ("XP[8,0](CSN)", "XP[4,0](CSN)", "XP[8,0](C_N)"):
+        f = fmt_from(fmt)
+        args = (f.precision, f.fraction, f.clamp, f.symmetric, "nearest")
+        for r in (0, 7, 100):  # per tensor
+            sc, zp = sc_row[r:r + 1], zp_row[r:r + 1]
+            want = O.fixed_cast(xn, *args, tie=O.TIE_AWAY, scale=sc.numpy(), zero_point=zp.numpy())
+            cmp(ops.fixed_qdq(x.to(DEV), *args, scale=sc.to(DEV), zero_point=zp.to(DEV)), want, f"{fmt} per tensor {dt} row-scale {r}")
+        want = O.fixed_cast(xn, *args, tie=O.TIE_AWAY, scale=sc_row.numpy(), zero_point=zp_row.numpy(), ch_axis=0)
+        cmp(ops.fixed_qdq(x.to(DEV), *args, scale=sc_row.to(DEV), zero_point=zp_row.to(DEV), ch_axis=0), want, f"{fmt} per row {dt}")
+        xt = x.t().contiguous()
+        want = O.fixed_cast(xt.float().numpy(), *args, tie=O.TIE_AWAY, scale=sc_row.numpy(), zero_point=zp_row.numpy(), ch_axis=1)
+        cmp(ops.fixed_qdq(xt.to(DEV), *args, scale=sc_row.to(DEV), zero_point=zp_row.to(DEV), ch_axis=1), want, f"{fmt} per column {dt}")
+        # group quantisation along the contiguous dim (groups of 16 columns)
+        scg, zpg = sc_row[: Cn // 16], zp_row[: Cn // 16]
+        want = O.fixed_cast(xn, *args, tie=O.TIE_AWAY, scale=scg.numpy(), zero_point=zpg.numpy(), ch_axis=1, group_size=16)
+        cmp(ops.fixed_qdq(x.to(DEV), *args, scale=scg.to(DEV), zero_point=zpg.to(DEV), ch_axis=1, group_size=16), want, f"{fmt} groups {dt}")
