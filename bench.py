@@ -402,6 +402,8 @@ def sharded_weight_cast(dev, rank, world, dist, model, layers, dtype, mode, peak
     run()
     n0 = _lib.launch_count()
     times = []
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    tc0 = time.perf_counter()
     for _ in range(reps):
         if dist is not None:
             dist.barrier()
@@ -412,6 +414,7 @@ def sharded_weight_cast(dev, rank, world, dist, model, layers, dtype, mode, peak
         b.record()
         torch.cuda.synchronize()
         times.append(a.elapsed_time(b))
+    clk = sampler.stop(tc0, time.perf_counter()) if sampler else None
     launches = (_lib.launch_count() - n0) // reps
     nbytes = sum(2 * w.numel() * w.element_size() for w in ws)
     ck = checksum_shards(mine, outs)
@@ -433,7 +436,8 @@ def sharded_weight_cast(dev, rank, world, dist, model, layers, dtype, mode, peak
     gbs = total / (ms_max * 1e-3) / 1e9
     res = {"GB/s": round(gbs, 1), "ms": round(ms_max, 3), "frac_of_peak_per_gpu": round(gbs / world / peak, 3), "GB_cast": round(total / 1e9, 2),
            "tensors": len(shapes), "launches_per_rank": launches, "imbalance": round(ms_max / ms_mean, 3),
-           "checksum": "%016x%016x" % (int(ck[0]) & 0xFFFFFFFFFFFFFFFF, int(ck[1]) & 0xFFFFFFFFFFFFFFFF)}
+           "checksum": "%016x%016x" % (int(ck[0]) & 0xFFFFFFFFFFFFFFFF, int(ck[1]) & 0xFFFFFFFFFFFFFFFF),
+           "sm_mhz": clk["sm_mhz"] if clk else None}
     if mode == "sbfp_amax":
         # the amax pass re-reads every weight: real HBM traffic is 3 * sizeof per element, not the 2 * sizeof counted above
         res["hbm_traffic_GB/s"] = round(gbs * 1.5, 1)

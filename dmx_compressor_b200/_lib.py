@@ -140,6 +140,32 @@ def view(t: torch.Tensor) -> Tensor:
     return v
 
 
+def views(ts):
+    """dmxq_tensor descriptors of many tensors at once -> (pointer usable as ``const dmxq_tensor *``, keep-alive object).
+    One numpy fill instead of one ctypes struct per tensor (~2 us each through ``view``): struct dmxq_tensor is 18 int64 words --
+    data | dtype + (ndim << 32) | shape[8] | stride[8]."""
+    import numpy as np
+
+    n = len(ts)
+    a = np.zeros((n, 18), dtype=np.int64)
+    a[:, 0] = [t.data_ptr() for t in ts]
+    nd = ts[0].dim() if n else 0
+    if all(t.dim() == nd for t in ts) and nd <= MAX_DIMS:
+        a[:, 1] = [dtype_code(t.dtype) | (nd << 32) for t in ts]
+        if nd:
+            a[:, 2:2 + nd] = [t.shape for t in ts]
+            a[:, 10:10 + nd] = [t.stride() for t in ts]
+    else:
+        for i, t in enumerate(ts):
+            d = t.dim()
+            if d > MAX_DIMS:
+                raise RuntimeError(f"dmxq: tensors of more than {MAX_DIMS} dims are not supported")
+            a[i, 1] = dtype_code(t.dtype) | (d << 32)
+            a[i, 2:2 + d] = t.shape
+            a[i, 10:10 + d] = t.stride()
+    return a.ctypes.data_as(C.POINTER(Tensor)), a
+
+
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 

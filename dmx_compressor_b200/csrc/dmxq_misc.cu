@@ -166,6 +166,13 @@ __device__ __forceinline__ float fixed_affine_away(float x, float sc, float zp, 
     return __fmul_rn(__fsub_rn(a, zp), sc);
 }
 
+static __device__ __noinline__ float fixed_chan_cold(float x, const FixedFmt *xf, float sc, float zp, float rsc, float rsl, bool div_free, bool fast,
+                                                     bool scaled, float rnd)
+{
+    if (fast) return fixed_affine_away<1>(x, sc, zp, rsc, rsl, div_free, *xf, scaled);
+    return fixed_elem_slow(x, xf, 1, sc, zp, rnd);
+}
+
 // vectorised variant 1: one 16-byte vector never straddles two qparam groups (inner % V == 0, or the channel runs
 // along the contiguous dim in groups that are multiples of V).  256 threads x 4 vectors, all loads before first use.
 // PAIR (host-decided): two neighbouring vectors always share their parameters (an even number of vectors per channel /
@@ -229,12 +236,10 @@ __global__ void __launch_bounds__(kThreads) fixed_chan_vec_kernel(const __grid_c
                     const float q = SRC16 ? div_by_recip16(v[j], rsc, rsl) : div_by_recip2(v[j], sc, rsc, rsl);
                     v[j] = __fmul_rn(__fsub_rn(round_away_clamped(__fadd_rn(q, zp), lo, hi), zp), sc);
                 }
-            } else if (fast) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = fixed_affine_away<(SRC16 ? 2 : 1)>(v[j], sc, zp, rsc, rsl, div_free, p.xf, scaled);
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = fixed_elem_slow(v[j], &p.xf, 1, sc, zp, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
+            } else {  // every other mode / range: ONE out-of-line copy (inlined per element it cost ~45 predicate-shuffling
+                      // instructions per vector on the hot path as well)
+#pragma unroll  // (unrolled: a run-time index would move v[] into local memory for the hot path too)
+                for (int j = 0; j < V; ++j) v[j] = fixed_chan_cold(v[j], &p.xf, sc, zp, rsc, rsl, div_free, fast, scaled, p.rnd ? __ldg(p.rnd + g * V + j) : 0.5f);
             }
             VecIO<Tout>::template store<V>(y + g * V, v);
         }

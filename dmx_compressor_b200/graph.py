@@ -48,7 +48,9 @@ class Captured:
                 _drop_weight_caches(model)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self.static_out = model(*self.static_in)
+                # (a deferred output cast -- elide.Lazy -- must run INSIDE the graph: materialised later, eagerly, it would be
+                # computed once from the first replay's data and then returned for every input)
+                self.static_out = elide.materialise(model(*self.static_in))
             if elide_casts:
                 elide.reset()
                 _drop_weight_caches(model)

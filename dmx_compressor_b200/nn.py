@@ -32,6 +32,22 @@ from .numerical.smoothquant import ActivationWeightSmoothQuant
 from .sparse import BlockTopK, Dense, LazySparsify, Sparsify
 
 
+def _param_state(t):
+    if t is None or isinstance(t, torch.nn.parameter.UninitializedParameter):
+        return None
+    return (t.data_ptr(), t._version)
+
+
+def _cast_state(c):
+    """what a CastTo's result depends on besides its input (key material of the weight cache)"""
+    if c is None:
+        return None
+    pt = c.pre_transform
+    return (repr(c.format), bool(c._fq_on), int(c.block_dim), tuple(sorted((k, repr(v)) for k, v in pt.items())) if pt else None,
+            _param_state(getattr(c, "scale", None)), _param_state(getattr(c, "zero_point", None)), getattr(c, "group_size", None),
+            getattr(getattr(c, "format", None), "tie", None))
+
+
 class DmxModule:
     r"""Mixin that adds the boundary casts and the weight hypernet to a torch.nn.Module
     (reference NumericalCastMixin cast.py:401-467 + WeightSparseMixin sparse.py:366-421 +
@@ -123,9 +139,11 @@ class DmxModule:
                 return None
             stages.append(ops.nm_stage(sp.sparseness.K, sp.sparseness.block_size, sp.sparseness.nm_order))
         for c in (self.weight_storage_cast, self.weight_cast):
+            if c is not None and c._obs_on and not isinstance(c.format, Same):
+                return None  # calibrating: the observer must see the weight (even with fake-quant off)
             if c is None or isinstance(c.format, Same) or not c._fq_on:
                 continue
-            if c.pre_transform or c._obs_on or not isinstance(c.format, Format):
+            if c.pre_transform or not isinstance(c.format, Format):
                 return None
             st = c.format.stage() if not hasattr(c.format, "tie") else None  # FixedPoint carries affine state
             if st is None or (c.format.blocked and c.block_dim not in (-1, self.weight.dim() - 1)):

@@ -122,6 +122,20 @@ def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, 
     return y
 
 
+def _groups(n: int):
+    """(start, size) of the per-call tensor groups of the many-tensor entry points: 8, 24, then 64 each"""
+    i = 0
+    for g in (8, 24):
+        if i < n:
+            g = min(g, n - i)
+            yield i, g
+            i += g
+    while i < n:
+        g = min(64, n - i)
+        yield i, g
+        i += g
+
+
 def cast_chain_multi(xs: Sequence[torch.Tensor], stages: Sequence[L.Stage], block_dim: int = -1,
                      outs: Optional[Sequence[torch.Tensor]] = None, amax: Optional[torch.Tensor] = None):
     """ys[i] = chain(xs[i]) for many tensors in as few launches as possible (dmxq_cast_chain_multi): the shards one rank
@@ -147,11 +161,18 @@ def cast_chain_multi(xs: Sequence[torch.Tensor], stages: Sequence[L.Stage], bloc
         if amax.dtype != torch.float32 or amax.numel() != n or not amax.is_contiguous() or amax.device != dev:
             raise RuntimeError("dmxq: amax must be a contiguous fp32 CUDA vector with one entry per tensor")
         ap = amax.data_ptr()
-    vx = (L.Tensor * n)(*[L.view(x) for x in xs])
-    vy = (L.Tensor * n)(*[L.view(y) for y in ys])
     arr = (L.Stage * ns)(*stages)
+    stream = L.stream_ptr(dev)
+    # one C call per group of up to 64 tensors (= one launch for flat tensors), a small first group: the GPU starts almost at
+    # once and works on group k while the host is still describing group k + 1 (~3 us per tensor in python)
+    rc = 0
     with _guard(dev):
-        rc = L.lib.dmxq_cast_chain_multi(vx, vy, n, block_dim, arr, ns, ap, L.stream_ptr(dev))
+        for i, g in _groups(n):
+            vx, kx = L.views(xs[i:i + g])
+            vy, ky = L.views(ys[i:i + g])
+            rc = L.lib.dmxq_cast_chain_multi(vx, vy, g, block_dim, arr, ns, None if ap is None else ap + 4 * i, stream)
+            if rc:
+                break
     L.check(rc, "dmxq_cast_chain_multi")
     return ys
 
@@ -389,9 +410,14 @@ def amax_multi(xs: Sequence[torch.Tensor], out: Optional[torch.Tensor] = None) -
             raise RuntimeError("dmxq: amax_multi needs contiguous tensors on one device")
     if res.dtype != torch.float32 or res.numel() != n or not res.is_contiguous() or res.device != dev:
         raise RuntimeError("dmxq: amax_multi out must be a contiguous fp32 vector with one entry per tensor")
-    vx = (L.Tensor * n)(*[L.view(x) for x in xs])
+    stream = L.stream_ptr(dev)
+    rc = 0
     with _guard(dev):
-        rc = L.lib.dmxq_amax_multi(vx, n, res.data_ptr(), L.stream_ptr(dev))
+        for i, g in _groups(n):
+            vx, keep = L.views(xs[i:i + g])
+            rc = L.lib.dmxq_amax_multi(vx, g, res.data_ptr() + 4 * i, stream)
+            if rc:
+                break
     L.check(rc, "dmxq_amax_multi")
     return res
 

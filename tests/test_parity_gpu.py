@@ -1238,7 +1238,7 @@ def test_cast_chain_multi_equals_per_tensor():
             n0 = L.launch_count()
             got = ops.cast_chain_multi(xs, st, -1)
             used = L.launch_count() - n0
-            assert used <= 4, f"{name} {dt}: {used} launches for {len(xs)} tensors"
+            assert used <= 6, f"{name} {dt}: {used} launches for {len(xs)} tensors"
             for i, (a, b) in enumerate(zip(got, want)):
                 assert a.shape == b.shape and torch.equal(a.view(torch.int16 if dt != torch.float32 else torch.int32),
                                                           b.view(torch.int16 if dt != torch.float32 else torch.int32)), f"{name} {dt} tensor {i}"
