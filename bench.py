@@ -613,6 +613,81 @@ def opt125m(dev):
     return res
 
 
+def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
+    """The north-star claim through the REFERENCE's API: an OPT-125m-shaped stack assembled from the reference's own
+    dmx.compressor.nn modules (oracle/_ref/pysrc, unmodified), configured by its own config_rules.BASIC, batch 8 x seq 2048:
+    plain-torch twin / plugin drop-in (plugin.install()) / plugin with elision (install(elide=True) + elide.enabled()).
+    `with_unpatched` also times the reference's own CUDA path (seconds per forward)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "refshim"))
+    import load_reference
+
+    if not load_reference.available():
+        return {"unavailable": "reference python not staged"}
+    ref = load_reference.load_full()
+    from dmx_compressor_b200 import elide, opt, plugin
+
+    B, S = 8, 2048
+    res = {}
+
+    def timeit(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / n
+
+    for dt in (dtypes or (torch.float32, torch.bfloat16)):
+        torch.manual_seed(0)
+        q = opt.OPTStack(None, mods=ref.nn)
+        p = opt.OPTStack(None, mods=opt.plain)
+        p.load_state_dict({k: v for k, v in q.state_dict().items() if k in p.state_dict()}, strict=True)
+        q, p = q.to(device=dev, dtype=dt).eval(), p.to(device=dev, dtype=dt).eval()
+        for m in q.modules():
+            if isinstance(m, ref.nn.DmxModule):
+                for rule in ref.config_rules.BASIC:
+                    if isinstance(m, rule.module_types):
+                        m.configure(rule.module_config)
+                        break
+        ids = torch.randint(0, 50272, (B, S), device=dev)
+        row = {}
+        with torch.no_grad():
+            t_plain = timeit(lambda: p(ids))
+            if with_unpatched:
+                plugin.uninstall()
+                y_ref = q(ids)
+                row["ms_reference_unpatched"] = round(timeit(lambda: q(ids), 1), 1)
+            plugin.install("dmx.compressor")
+            try:
+                y0 = q(ids)
+                t_drop = timeit(lambda: q(ids))
+            finally:
+                plugin.uninstall()
+            plugin.install("dmx.compressor", elide=True)
+            try:
+                with elide.enabled():
+                    y1 = elide.materialise(q(ids))
+                    t_el = timeit(lambda: elide.materialise(q(ids)))
+            finally:
+                plugin.uninstall()
+        row.update({"ms": [round(t_plain, 2), round(t_drop, 2), round(t_el, 2)], "tok/s_plugin_dropin": round(B * S / t_drop * 1e3),
+                    "tok/s_plugin_elided": round(B * S / t_el * 1e3), "cast_overhead_dropin": round((t_drop - t_plain) / t_plain, 3),
+                    "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3), "elided_equals_dropin_bitwise": bool(torch.equal(y0, y1))})
+        if with_unpatched:
+            row["dropin_equals_reference_bitwise"] = bool(torch.equal(y_ref, y0))
+        res[str(dt).split(".")[-1]] = row
+        del q, p
+        torch.cuda.empty_cache()
+    res["config"] = ("OPT-125m shape built from the reference's own dmx.compressor.nn modules + its config_rules.BASIC, batch 8 x seq 2048; "
+                     "ms = [plain torch, plugin drop-in, plugin + elision]")
+    return res
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -719,10 +794,37 @@ def run_ours(args):
         e2e = {"value": round(bytes_per_step() * args.e2e_steps * world / th / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": half, "d2h_bytes_per_step": half, "steps": args.e2e_steps,
                "api": "dmxq_cast_chain_host (pinned host in/out, 3-stream chunked pipeline)", "matches_device_path": ok}
+        # the host-link ceiling for the same traffic: the step's H2D and D2H bytes as bare pinned copies on two streams, no kernels.
+        # e2e / this = how much of the link the pipeline uses; when it stops scaling with N the limiter is the host (shared PCIe
+        # root / host DRAM of the VM: every GPU reports the same CPU and NUMA affinity), not the cast path.
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        def copies():
+            with torch.cuda.stream(s_in):
+                x32.copy_(xh32, non_blocking=True); x16.copy_(xh16, non_blocking=True)
+                x32.copy_(xh32, non_blocking=True); x16.copy_(xh16, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh32.copy_(y32, non_blocking=True); yh16.copy_(y16, non_blocking=True)
+                yh32.copy_(y32, non_blocking=True); yh16.copy_(y16, non_blocking=True)
+
+        x32c, x16c = x32.clone(), x16.clone()  # (the copies overwrite the device inputs: restore them afterwards)
+        copies()
+        barrier()
+        tc0 = time.perf_counter()
+        copies()
+        torch.cuda.synchronize()
+        tc = time.perf_counter() - tc0
+        if dist is not None:
+            t = torch.tensor([tc], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tc = float(t.item())
+        x32.copy_(x32c); x16.copy_(x16c)
+        del x32c, x16c
+        e2e["host_link_copy_only"] = round(bytes_per_step() * world / tc / 1e9, 1)
+        e2e["fraction_of_copy_only"] = round(e2e["value"] / e2e["host_link_copy_only"], 3)
         del xh32, xh16, yh32, yh16
 
     # ---------------- the model-level configs of BASELINE.json (not part of `value`)
-    sharded = by_format = ref_cuda = opt = None
+    sharded = by_format = ref_cuda = opt = popt = None
     details = []
     if not args.no_extras:
         del y32, y16
@@ -752,6 +854,10 @@ def run_ours(args):
                 opt = opt125m(dev)
             except Exception as e:  # pragma: no cover
                 opt = {"error": repr(e)[:200]}
+            try:
+                popt = plugin_opt125m(dev, with_unpatched=True)
+            except Exception as e:  # pragma: no cover
+                popt = {"error": repr(e)[:200]}
             if not args.no_details:
                 try:
                     details.append({"detail": "cast_sweep (configs[1], every size)", "rows": detail_sweep(dev)})
@@ -779,7 +885,7 @@ def run_ours(args):
                 "launches_timed": len(kms)}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only: torchrun pins OMP_NUM_THREADS to 1)
         cast, kind, cores, how = _reference_cpu_cast()
         c32 = _make_rows(1 << 24)
         xs = [c32, c32.to(torch.bfloat16)]
@@ -799,7 +905,7 @@ def run_ours(args):
         "metric": "BFP cast GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": config_dict(world), "gpu_launches": launches, "clocks": clocks,
-        "frac_of_hbm_peak": round(value / world / peak, 4), "opt125m_basic_forward": opt, "roofline_by_format": by_format,
+        "frac_of_hbm_peak": round(value / world / peak, 4), "opt125m_basic_forward": opt, "opt125m_reference_modules_plus_plugin": popt, "roofline_by_format": by_format,
         "reference_cuda": ref_cuda, "cpu_baseline": cpu_baseline, "roofline": roofline, "e2e": e2e, "sharded": sharded,
     }
     print(json.dumps(line), flush=True)

@@ -152,6 +152,8 @@ class Lazy(torch.Tensor):
         if func in _passthrough():
             with torch._C.DisableTorchFunctionSubclass():
                 return func(*args, **kwargs)
+        if func is torch.Tensor.to and len(args) == 2 and not kwargs and isinstance(args[0], Lazy) and args[1] == args[0].dtype:
+            return args[0]  # `.to(own dtype)` (DmxModule.forward's boundary alignment, core.py:258-263) returns the tensor itself
         stats["lazy_materialised_by_torch_op"] = stats.get("lazy_materialised_by_torch_op", 0) + 1
         return func(*_unlazy(args), **_unlazy(kwargs))
 

@@ -36,6 +36,22 @@ _saved: Dict[Tuple[object, str], object] = {}
 _MISSING = object()  # the attribute did not exist before install(): uninstall() deletes it again
 
 
+def _flag(m, name: str) -> int:
+    """``int(m.<name>[0])`` for FakeQuantize's uint8 switch buffers (``fake_quant_enabled`` / ``observer_enabled``) without a
+    device read per call: the reference tests them with ``self.fake_quant_enabled[0] == 1`` (numerical/cast.py:276,281) -- on a
+    CUDA module that is an ``eq`` kernel plus a blocking 1-byte device-to-host copy, twice per ``CastTo.forward``, ~2000 times
+    per OPT-125m forward, which leaves the whole forward host-bound.  The value is re-read only when the buffer object or its
+    in-place version counter changes (``enable_fake_quant()``, ``load_state_dict``, ``.to(device)`` all do one or the other)."""
+    t = getattr(m, name)
+    c = m.__dict__.get("_dmxq_" + name)
+    v = t._version
+    if c is not None and c[0] is t and c[1] == v:
+        return c[2]
+    val = int(t[0])
+    m.__dict__["_dmxq_" + name] = (t, v, val)
+    return val
+
+
 def _patch(obj, name, new):
     key = (obj, name)
     if key not in _saved:
@@ -43,8 +59,16 @@ def _patch(obj, name, new):
     setattr(obj, name, new)
 
 
-def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order: str = "torch_cuda") -> None:
-    """``tie_order``: N:M tie order of the patched ``Sparsify.forward`` -- "torch_cuda" (default) reproduces what the
+def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order: str = "torch_cuda", elide: bool = False) -> None:
+    """``elide``: also wrap the reference's own callers of the path -- ``CastTo.forward`` (numerical/cast.py:261-306),
+    ``CastToDict.forward`` (:59-86), ``DmxModule._weight`` / ``.forward`` (modeling/nn/core.py:200-264) and ``ResAdd.forward``
+    (modeling/nn/torch_modules.py:15-37) -- with the cast-elision machinery of ``dmx_compressor_b200.elide``: inside
+    ``with torch.no_grad(), dmx_compressor_b200.elide.enabled():`` SAME clones and idempotent repeats are skipped, shared casts are
+    memoised, weights are cast once while unchanged, FLOAT output casts are deferred to (and fused with) their consumer, and a
+    residual add runs as ONE kernel with its three casts.  Values are identical to the non-elided run (results may alias
+    their inputs: that is the one observable difference, hence opt-in twice -- here and the context manager).  Implies fuse_castto.
+
+    ``tie_order``: N:M tie order of the patched ``Sparsify.forward`` -- "torch_cuda" (default) reproduces what the
     unpatched reference computes for CUDA tensors (torch's unstable bitonic argsort) bit for bit, "stable" is the
     reference's CPU order (and the faster kernel).  FixedPoint ties (half away) and the SBFP block scale (multiplied by
     the rounded reciprocal) always follow the reference's CUDA behaviour: only CUDA tensors are redirected."""
@@ -174,7 +198,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
 
     _patch(obs.HistogramObserver, "forward", histogram_forward)
 
-    if fuse_castto:
+    if fuse_castto or elide:
         # CastTo.forward's x.float() ... .to(dtype) round trip fused into the kernel for the plain
         # (no pre-transform, no observer, non-FixedPoint) case; everything else: reference code.
         cast = importlib.import_module(package + ".numerical.cast")
@@ -200,12 +224,78 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                                        repr(f) == "FP[1|5|10,15](FN)", f.rounding)
             return None
 
+        from . import elide as E
+
+        def ref_key(f, block_dim):
+            """hashable identity of an idempotent cast of the reference's format classes (elide.format_key's rule)"""
+            if isinstance(f, fmt.FloatingPoint) and f.rounding == "nearest":
+                return ("FP", repr(f))
+            if isinstance(f, fmt.BlockFloatingPoint) and not isinstance(f, fmt.ScaledBlockFloatingPoint) and f.symmetric \
+                    and f.rounding == "nearest" and f.block_size > 1:
+                return ("BFP", repr(f), block_dim)
+            return None
+
+        def fp_identity(f, dtype):
+            return isinstance(f, fmt.FloatingPoint) and not f.unsigned and (
+                (dtype == torch.float32 and repr(f) == "FP[1|8|23,127](_N)") or (dtype == torch.float16 and repr(f) == "FP[1|5|10,15](_N)"))
+
+        def castto_elided(self, x, lazy_ok):
+            """CastTo._forward_elided of the mirror (numerical/cast.py) on the reference's objects: value-identical fast path"""
+            f = self.format
+            if _flag(self, "fake_quant_enabled") != 1 or isinstance(f, fmt.Same):
+                E.stats["elided"] += 1
+                return x
+            pend = x if isinstance(x, E.Lazy) else None
+            key = ref_key(f, self.block_dim if isinstance(f, fmt.BlockFloatingPoint) else None)
+            if key is None:
+                return None
+            if pend is not None:
+                if pend._key == key:
+                    E.stats["elided"] += 1
+                    return pend.materialise()
+                ckey = ("chain", pend._key, key)
+                y = E.memo_get(pend._raw, ckey)
+                if y is None:  # the producer's output cast fused with this input cast: ONE pass over the tensor
+                    y = ops.cast_chain(pend._raw, [stage_of(pend._fmt), stage_of(f)], self.block_dim)
+                    E.stats["casts"] += 1
+                    E.stats["elided"] += 1
+                    E.memo_put(pend._raw, ckey, y)
+                    E.tag(y, key)
+                return y
+            if E.is_tagged(x, key) or fp_identity(f, x.dtype):
+                E.stats["elided"] += 1
+                return x
+            if lazy_ok and key[0] == "FP" and f.flush_subnormal and not f.unsigned and type(x) is torch.Tensor:
+                st, bd = stage_of(f), self.block_dim
+                return E.Lazy(x, f, bd, key, materialise=lambda raw: ops.cast_chain(raw, [st], bd))
+            y = E.memo_get(x, key)
+            if y is None:
+                y = ops.cast_chain(x, [stage_of(f)], self.block_dim)
+                E.stats["casts"] += 1
+                E.memo_put(x, key, y)
+                E.tag(y, key)
+            return y
+
+        _out_depth = [0]  # > 0 while CastToDict.forward(output=True) runs: its CastTo may defer
+
         def castto_forward(self, x):
             f = self.format
+            if elide and E.active() and not torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point() \
+                    and not self.pre_transform and _flag(self, "observer_enabled") != 1 and isinstance(f, fmt.Format):
+                self.physical_dtype = x.dtype
+                y = castto_elided(self, x, _out_depth[0] > 0 and E.defer_output_casts)
+                if y is not None:
+                    return y
+            if isinstance(x, E.Lazy):
+                x = x.materialise()
             plain = (isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point() and not self.pre_transform
                      and isinstance(f, (fmt.BlockFloatingPoint, fmt.ScaledBlockFloatingPoint, fmt.FloatingPoint))
                      and getattr(f, "rounding", "nearest") != "stochastic")
-            if not plain or self.observer_enabled[0] == 1 or self.fake_quant_enabled[0] != 1:
+            if isinstance(f, fmt.Same) and isinstance(x, torch.Tensor) and x.is_cuda and not self.pre_transform:
+                # the default format of every CastTo: the reference's own two steps (cast.py:281-296, 306) minus its device reads
+                self.physical_dtype = x.dtype
+                return cast.CastToFormat.apply(x, f, self.block_dim) if _flag(self, "fake_quant_enabled") == 1 else x
+            if not plain or _flag(self, "observer_enabled") == 1 or _flag(self, "fake_quant_enabled") != 1:
                 return o_cfwd(self, x)
             if isinstance(f, fmt.ScaledBlockFloatingPoint) and not f.scaler_format_exponent_bias_determined:
                 return o_cfwd(self, x)
@@ -216,6 +306,168 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
             return _Fused.apply(x, stage_of(f), self.block_dim)
 
         _patch(cast.CastTo, "forward", castto_forward)
+
+        if True:  # (kept as a block: the wrappers below close over the names above)
+            o_dict_fwd = cast.CastToDict.forward
+
+            def castdict_forward(self, x, *args, output=False, **kwargs):
+                if not output:
+                    return o_dict_fwd(self, x, *args, output=False, **kwargs)
+                _out_depth[0] += 1
+                try:
+                    return o_dict_fwd(self, x, *args, output=True, **kwargs)
+                finally:
+                    _out_depth[0] -= 1
+
+            if elide:
+                _patch(cast.CastToDict, "forward", castdict_forward)
+
+            def patch_modules():
+                core = importlib.import_module(package + ".modeling.nn.core")
+                tmods = importlib.import_module(package + ".modeling.nn.torch_modules")
+                o_weight = core.DmxModule.__dict__["_weight"]
+
+                def _pstate(t):
+                    return None if t is None or isinstance(t, torch.nn.parameter.UninitializedParameter) else (t.data_ptr(), t._version)
+
+                def _cstate(c):
+                    if c is None:
+                        return None
+                    return (repr(c.format), _flag(c, "fake_quant_enabled"), c.block_dim, repr(c.pre_transform) if c.pre_transform else None,
+                            _pstate(getattr(c, "scale", None)), _pstate(getattr(c, "zero_point", None)), getattr(c, "group_size", None))
+
+                def hypernet(self):
+                    """DmxModule.weight_hypernet applied to the weight (core.py:178-205): sparsify -> SmoothQuant scale -> storage cast ->
+                    weight cast, with the SmoothQuant switches read through the host-side cache (scale_weight is the identity while
+                    SmoothQuant is disabled, numerical/smoothquant.py:280-283)"""
+                    w = self.weight
+                    if self.weight_sparsifier is not None:
+                        w = self.weight_sparsifier(w)
+                    sq = self.smoothquant
+                    if sq is not None and _flag(sq, "fused_to_weight") == 0 and _flag(sq, "enabled") == 1:
+                        w = sq.scale_weight(w)
+                    if self.weight_storage_cast is not None:
+                        w = self.weight_storage_cast(w)
+                    if self.weight_cast is not None:
+                        w = self.weight_cast(w)
+                    return w
+
+                def weight_cached(self):
+                    """DmxModule._weight (core.py:200-205); under elision the result is kept while nothing it depends on changes"""
+                    if not (elide and E.active() and not torch.is_grad_enabled()):
+                        return hypernet(self)
+                    casts = (self.weight_storage_cast, self.weight_cast)
+                    sq = getattr(self, "smoothquant", None)
+                    if any(c is not None and _flag(c, "observer_enabled") == 1 for c in casts) or (
+                            sq is not None and _flag(sq, "enabled") == 1 and _flag(sq, "fused_to_weight") == 0):  # SmoothQuant scaling the weight
+                        return hypernet(self)
+                    w, sp = self.weight, self.weight_sparsifier
+                    key = (w.data_ptr(), w._version, tuple(w.shape)) + tuple(_cstate(c) for c in casts) + (
+                        None if sp is None else (repr(sp.sparseness), sp.plastic, id(getattr(sp, "score_func", None)) if sp.plastic else None,
+                                                 _pstate(getattr(sp, "score", None))),)
+                    ent = self.__dict__.get("_dmxq_wcache")
+                    if ent is not None and ent[0] == key:
+                        return ent[1]
+                    out = hypernet(self)
+                    self.__dict__["_dmxq_wcache"] = (key, out)
+                    return out
+
+                _patch(core.DmxModule, "_weight", property(weight_cached))
+
+                o_mod_fwd = core.DmxModule.forward
+
+                def module_forward(self, input, *args, **kwargs):
+                    """DmxModule.forward (core.py:215-264) for the common inference case -- no SmoothQuant in effect, no OBC / AFT / plugins
+                    / FLOP counting: input casts -> _forward -> output casts -> boundary dtype, with the SmoothQuant switches read through
+                    the host-side cache instead of one blocking device read each.  Everything else: the reference's own forward."""
+                    if core.DmxModule.plugins or self.flop_counter_enabled or self.obc is not None or self.aft is not None \
+                            or not isinstance(input, torch.Tensor):
+                        return o_mod_fwd(self, input, *args, **kwargs)
+                    sq = self.smoothquant
+                    if sq is not None and (sq.calibrating or _flag(sq, "dynamic") == 1 or _flag(sq, "enabled") == 1):
+                        return o_mod_fwd(self, E.materialise(input), *args, **kwargs)
+                    _dtype, _device = input.dtype, input.device
+                    if hasattr(self, "weight") and self.weight is not None:
+                        _device = self.weight.device
+                    _input, args, kwargs = self.input_casts(input, *args, **kwargs)
+                    if _input.device != _device or any(isinstance(a, torch.Tensor) and a.device != _device for a in args):
+                        _input, args, kwargs = self.align_device(_input, args, kwargs, _device)
+                    _output = self._forward(_input, *args, **kwargs)
+                    output = self.output_casts(_output, output=True)
+                    if self.align_boundary_dtype:
+                        if isinstance(output, (tuple, list)):
+                            output = type(output)(a if a.dtype == _dtype else a.to(_dtype) for a in output)
+                        elif output.dtype != _dtype:
+                            output = output.to(_dtype)
+                    return output
+
+                _patch(core.DmxModule, "forward", module_forward)
+
+                def resadd_forward(self, input, residual):
+                    """ResAdd.forward: input casts + add + output cast as ONE kernel (dmxq_add_cast) for plain nearest + flush FLOAT casts"""
+                    if E.active() and not torch.is_grad_enabled() and not DmxModule_plugins(core) and not getattr(self, "flop_counter_enabled", False):
+                        plan = _resadd_plan(self, input, residual)
+                        if plan is not None:
+                            try:
+                                y = ops.add_cast(plan[4], plan[5], plan[0], plan[1], plan[2])
+                            except RuntimeError:
+                                y = None
+                            if y is not None:
+                                E.stats["elided"] += 2
+                                E.tag(y, plan[3])
+                                return y
+                    return module_forward(self, E.materialise(input), E.materialise(residual))
+
+                def DmxModule_plugins(core_mod):
+                    return bool(core_mod.DmxModule.plugins)
+
+                def _resadd_plan(self, a, b):
+                    if not (isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor) and a.is_cuda and b.is_cuda and a.dtype == b.dtype
+                            and a.is_floating_point() and a.is_contiguous() and a.dim() >= b.dim()):
+                        return None
+                    if self.smoothquant is not None or getattr(self, "obc", None) is not None or getattr(self, "aft", None) is not None:
+                        return None
+                    casts = (self.input_casts.input_cast, self.input_casts.residual_cast, self.output_casts.output_cast)
+                    stages, raws = [], []
+                    for c, t in zip(casts, (a, b, None)):
+                        f = c.format
+                        if c.pre_transform or _flag(c, "observer_enabled") == 1:
+                            return None
+                        on = _flag(c, "fake_quant_enabled") == 1
+                        fast = isinstance(f, fmt.FloatingPoint) and f.rounding == "nearest" and f.flush_subnormal and not f.unsigned
+                        key = ref_key(f, None) if fast else None
+                        if isinstance(t, E.Lazy):
+                            if fast and t._key == key and on:  # F(F(x)) == F(x): the deferred producer cast folds into the add
+                                stages.append(stage_of(f))
+                                raws.append(t._raw)
+                                continue
+                            t = t.materialise()
+                        if t is not None:
+                            raws.append(t)
+                        if isinstance(f, fmt.Same) or not on:
+                            stages.append(None)
+                        elif fast:
+                            if t is not None and not E.is_tagged(t, key) and 0 in t.stride() and t.numel() > 0:
+                                tc = E.memo_get(t, key)  # broadcast operand (the attention mask): cast its un-expanded base once
+                                if tc is None:
+                                    base = t[tuple(slice(0, 1) if (st == 0 and n > 1) else slice(None) for n, st in zip(t.shape, t.stride()))]
+                                    tc = ops.cast_chain(base, [stage_of(f)], -1).expand(t.shape)
+                                    E.stats["casts"] += 1
+                                    E.memo_put(t, key, tc, pinned=True)
+                                    E.tag(tc, key)
+                                raws[-1] = t = tc
+                            stages.append(None if (t is not None and E.is_tagged(t, key)) else stage_of(f))
+                        else:
+                            return None
+                    return stages[0], stages[1], stages[2], (None if stages[2] is None else ref_key(casts[2].format, None)), raws[0], raws[1]
+
+                if elide:
+                    _patch(tmods.ResAdd, "forward", resadd_forward)
+
+            try:
+                patch_modules()
+            except ImportError:
+                pass  # a numerics-only import of the reference (numerical / sparse / quant without modeling): nothing above CastTo to patch
 
 
 def uninstall() -> None:

@@ -443,3 +443,49 @@ def test_histogram_observer_on_gpu(ref, plugin):
     a, b = both(plugin, run)
     for u, v, what in zip(a, b, ("histogram", "min", "max", "scale", "zero_point")):
         same_bits(u, v, what)
+
+
+def _ref_opt_stack(ref, cfg, dtype):
+    """an OPT-shaped decoder assembled from the REFERENCE's own dmx.compressor.nn modules (the graph DmxModel.from_torch would
+    produce for OPTForCausalLM), every module configured by the reference's config_rules.BASIC"""
+    from dmx_compressor_b200 import opt
+
+    torch.manual_seed(0)
+    net = opt.OPTStack(cfg, mods=ref.nn).to(DEV).to(dtype).eval()
+    for m in net.modules():
+        if isinstance(m, ref.nn.DmxModule):
+            for rule in ref.config_rules.BASIC:
+                if isinstance(m, rule.module_types):
+                    m.configure(rule.module_config)
+                    break
+    return net
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
+def test_reference_opt_stack_dropin_and_elided(ref, plugin, dtype):
+    """the reference's own module stack in BASIC mode: unpatched (its CUDA path) == plugin drop-in == plugin with elision
+    (install(elide=True) + elide.enabled()), logits bit for bit; the elided run launches far fewer kernels"""
+    from dmx_compressor_b200 import elide
+
+    cfg = dict(vocab_size=512, max_position_embeddings=128, hidden_size=128, num_hidden_layers=2, ffn_dim=256, num_attention_heads=2, dropout=0.0)
+    net = _ref_opt_stack(ref, cfg, dtype)
+    ids = torch.randint(0, 512, (2, 64), device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    with torch.no_grad():
+        a, b = both(plugin, lambda: net(ids))
+        same_bits(a, b, f"drop-in {dtype}")
+        plugin.install("dmx.compressor", elide=True)
+        try:
+            n0 = launches()
+            c0 = net(ids)  # installed with elide=True but outside the context: plain drop-in
+            n1 = launches()
+            with elide.enabled():
+                c1 = elide.materialise(net(ids))
+                n2 = launches()
+                c2 = elide.materialise(net(ids))  # second forward: weights come from the cache
+                n3 = launches()
+        finally:
+            plugin.uninstall()
+    same_bits(a, c0, f"elide installed, context off {dtype}")
+    same_bits(a, c1, f"elided {dtype}")
+    same_bits(a, c2, f"elided, cached weights {dtype}")
+    assert (n3 - n2) <= (n2 - n1) < (n1 - n0), (n1 - n0, n2 - n1, n3 - n2)
