@@ -287,6 +287,12 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.rows.append((time.perf_counter(), ln.strip()))
 
+    def wait_first(self, timeout=5.0):
+        """block until nvidia-smi delivered its first sample (its start-up takes longer than a short timed region)"""
+        t_end = time.perf_counter() + timeout
+        while self.proc is not None and not self.rows and time.perf_counter() < t_end:
+            time.sleep(0.01)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return None
@@ -399,10 +405,12 @@ def sharded_weight_cast(dev, rank, world, dist, model, layers, dtype, mode, peak
 
     from dmx_compressor_b200 import _lib
 
+    sampler = ClockSampler(dev.index) if rank == 0 else None
     run()
+    if sampler is not None:
+        sampler.wait_first()
     n0 = _lib.launch_count()
     times = []
-    sampler = ClockSampler(dev.index) if rank == 0 else None
     tc0 = time.perf_counter()
     for _ in range(reps):
         if dist is not None:
@@ -733,10 +741,12 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     warmup = max(args.warmup, 3)
+    sampler = ClockSampler(local) if rank == 0 else None  # started ahead of the warm-up: nvidia-smi needs a moment to come up
     for _ in range(warmup):
         step()
+    if sampler is not None:
+        sampler.wait_first()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = dmx._lib.launch_count()
     kern_events = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -3,7 +3,7 @@
 # scripts/ncu_summarise.py; copy gpurun_out/<r>_*.csv into profiles/ afterwards.
 # usage: bash scripts/capture_profiles.sh r01
 set -x
-R=${1:-r01}
+R=${1:-r02}
 mkdir -p gpurun_out
 B="python bench.py --warmup 3 --no-extras --e2e-steps 1 --no-cpu-baseline"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_bench.csv $B --steps 2 > /dev/null 2>&1
