@@ -225,6 +225,7 @@ template <bool EXACT> __device__ __forceinline__ float float_elem_flush_nearest(
 // place.  Both are "round val to a multiple of 2^(exponent(val) - man), ties to even", which one more fp32 add of
 // C = 1.5 * 2^(exponent(val) + 23 - man) performs: (val + C) - C.  With shift = +-0 for ordinary values the two cases
 // share one instruction sequence; the saturation is an unsigned min on the magnitude, as in float_elem_flush_nearest.
+// Precondition: |x| < 2^(128 - sh) (C must stay finite); larger and non-finite values take the literal path.
 __device__ __forceinline__ float float_elem_nearest_sub(float x, const FloatFmt &f)
 {
     const uint32_t t = f2u(x), ab = t & 0x7FFFFFFFu;

@@ -173,6 +173,14 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
         }
     }
 
+    // K_FLOAT (subnormals kept) / K_MXFP on a 16-bit tensor: the packed form (sub16_pair) -- per-format constants
+    Sub16Fmt s16f{};
+    Sub16 s16{};
+    if constexpr (SAME16 && (KIND == K_FLOAT || KIND == K_MXFP)) {
+        s16f = sub16_fmt<Tin>(p.chain.st[0].ff);
+        if (KIND == K_FLOAT) s16 = sub16_consts<Tin>(s16f, 0);
+    }
+
     uint4 raw[kUnroll];
     uint4 rraw[kUnroll][V / 4];  // K_BFP_STOCH only
     int64_t yoff[kUnroll];
@@ -264,7 +272,14 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
         } else if (KIND == K_FLOAT && p.chain.st[0].ff.nsub) {
             // nearest with subnormals kept (FP8 E4M3 / E5M2 ...): the branch-free form; Inf / NaN vectors take the literal path
             const StageDev &st = p.chain.st[0];
-            if (unpack_absmax<Tin>(raw[u], v) < 0x7F800000u) {
+            if constexpr (SAME16) {
+                if (s16.ok && raw16_absmax(raw[u]) < s16.limit) {  // finite, room for the rounding constant: two elements per instruction
+                    if (valid[u]) stg_stream(y + yoff[u], sub16_vec<Tin>(raw[u], s16));
+                    continue;
+                }
+            }
+            // (finite, and the rounding constant 1.5 * 2^(e + sh) must itself be finite: exponent field below 255 - sh)
+            if (unpack_absmax<Tin>(raw[u], v) < ((255u - (uint32_t)st.ff.sh) << 23)) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[j] = float_elem_nearest_sub(v[j], st.ff);
             } else {
@@ -450,7 +465,26 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
             }
         } else if (KIND == K_MXFP) {
             const StageDev &st = p.chain.st[0];
-            mxfp_apply<V>(v, lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V), st);
+            if constexpr (SAME16) {
+                // the block maximum as a 16-bit pattern; an ordinary block (mxfp_apply's conditions: normal maximum that is not
+                // a power of two, normal scale) folds its power-of-two scale into the packed rounding constants
+                constexpr int P = Arith16<Tin>::kMan;
+                constexpr int BIAS = std::is_same<Tin, __nv_bfloat16>::value ? 127 : 15;
+                const uint32_t m16 = lanes_max(raw16_absmax(raw[u]), st.block / V);
+                const int ef = (int)(m16 >> P) - BIAS + 127;  // fp32 exponent field of the maximum
+                const int se = ef - (int)((f2u(st.mx_largest) >> 23) - 127u);  // ... of the scale
+                if (s16f.ok && (m16 & ((1u << P) - 1u)) != 0u && (m16 >> P) >= 1u && m16 < s16f.limit && se >= 2 && se <= 252) {
+                    const Sub16 c = sub16_consts<Tin>(s16f, se - 127);
+                    if (c.ok) {
+                        if (valid[u]) stg_stream(y + yoff[u], sub16_vec<Tin>(raw[u], c));
+                        continue;
+                    }
+                }
+                VecIO<Tin>::unpack(raw[u], v);
+                mxfp_apply<V>(v, widen16<Tin>(m16), st);
+            } else {
+                mxfp_apply<V>(v, lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V), st);
+            }
         } else if (KIND == K_SBFP && pair) {
             if ((u & 1) == 0) {
                 float w[V];

@@ -339,6 +339,111 @@ template <int V> __device__ __forceinline__ void sbfp_stage(float (&v)[V], const
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Low-bit float with subnormals kept (float_elem_nearest_sub), on PACKED 16-bit values: a bf16 / fp16 tensor cast to a
+// format of man <= 5 mantissa bits (FP8 E4M3 / E5M2, the MX element formats) never needs fp32.  For a 16-bit source the
+// reference's sequence (x + shift is exact: 8 / 11 significant bits) is ONE rounding of x, ties to even, to a multiple of
+//     Q = 2^(max(e(x), min_exp) - man)
+// followed by the saturation of the magnitude.  In the source's own arithmetic that rounding is (x + C) - C with
+// C = 1.5 * 2^(max(e, min_exp) + P - man), P = 7 (bf16) / 10 (fp16) significand bits: |x| < 2^(max(e,min_exp)+1) <= C / 3 for
+// man <= 5, so the sum stays in C's binade, whose ulp is Q; C / Q is even, so ties land on the same neighbour as the
+// reference's magnitude arithmetic for either sign; the subtraction is exact; a zero result is +0 as in the reference
+// (-0 and negative values that round to zero included).  C's exponent field is a packed max + add on the raw words: two
+// elements per instruction throughout -- 8 instructions per PAIR instead of ~12 per element plus widening / narrowing.
+// The caller guarantees finite inputs whose exponent leaves room for C (pattern below Sub16.limit); the MX
+// variant passes per-block constants (the block scale folded into min_exp and the saturation value).
+template <typename T> struct Arith16;
+template <> struct Arith16<__nv_bfloat16> {
+    static constexpr uint32_t kExp2 = 0x7F807F80u;
+    static constexpr int kMan = 7;
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b)
+    {
+        uint32_t d;
+        asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t sub2(uint32_t a, uint32_t b)
+    {
+        uint32_t d;
+        asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+};
+template <> struct Arith16<__half> {
+    static constexpr uint32_t kExp2 = 0x7C007C00u;
+    static constexpr int kMan = 10;
+    static __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b)
+    {
+        uint32_t d;
+        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t sub2(uint32_t a, uint32_t b)
+    {
+        uint32_t d;
+        asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+};
+struct Sub16 {
+    uint32_t minexp2;  // exponent field of 2^min_exp, in both halves
+    uint32_t magic2;   // ((P - man) << P) | (1 << (P - 1)), in both halves: exponent offset + mantissa 1.5 of C
+    uint32_t maxnum2;  // saturation magnitude pattern, in both halves
+    uint32_t limit;    // fast path only for vectors whose largest magnitude pattern is below this (finite, room for C)
+    bool ok;           // the format (and, for MX, the block scale) qualifies
+};
+struct Sub16Fmt {      // the per-format part, derived once per thread
+    int me0, xe0;      // exponent fields (in T) of 2^min_exp and of the saturation value, before any block scale
+    int room;          // P - man
+    uint32_t manbits;  // mantissa field of the saturation value in T
+    uint32_t magic2, limit;
+    bool ok;
+};
+template <typename T> __device__ __forceinline__ Sub16Fmt sub16_fmt(const FloatFmt &f)
+{
+    constexpr int P = Arith16<T>::kMan;
+    constexpr int BIAS = std::is_same<T, __nv_bfloat16>::value ? 127 : 15;
+    constexpr int EMAX = std::is_same<T, __nv_bfloat16>::value ? 254 : 30;
+    Sub16Fmt c;
+    const int man = 23 - f.sh;
+    c.room = P - man;
+    c.me0 = f.min_exp + BIAS;
+    c.xe0 = (int)f.max_store - 127 + BIAS;
+    c.manbits = (f.max_num & 0x007FFFFFu) >> (23 - P);
+    // (fp16: x + 2^min_exp must be exact in the reference's fp32 add: min_exp + 25 bits at most 24)
+    c.ok = f.nsub && man <= 5 && (std::is_same<T, __nv_bfloat16>::value || f.min_exp <= -1);
+    const uint32_t mg = ((uint32_t)c.room << P) | (1u << (P - 1));
+    c.magic2 = mg * 0x10001u;
+    c.limit = (uint32_t)(EMAX + 1 - c.room) << P;
+    return c;
+}
+// e_off = extra exponent (the MX block scale); 0 for a plain FLOAT stage
+template <typename T> __device__ __forceinline__ Sub16 sub16_consts(const Sub16Fmt &b, int e_off)
+{
+    constexpr int P = Arith16<T>::kMan;
+    constexpr int EMAX = std::is_same<T, __nv_bfloat16>::value ? 254 : 30;
+    Sub16 c;
+    const int me = b.me0 + e_off, xe = b.xe0 + e_off;
+    c.ok = b.ok && me >= 1 && me <= EMAX - b.room && xe >= 1;
+    // a saturation value beyond T's range cannot trigger: the largest finite pattern stands in for it
+    const uint32_t mx = xe > EMAX ? (std::is_same<T, __nv_bfloat16>::value ? 0x7F7Fu : 0x7BFFu) : (((uint32_t)max(xe, 0) << P) | b.manbits);
+    c.minexp2 = ((uint32_t)max(me, 0) << P) * 0x10001u;
+    c.maxnum2 = mx * 0x10001u;
+    c.magic2 = b.magic2;
+    c.limit = b.limit;
+    return c;
+}
+template <typename T> __device__ __forceinline__ uint32_t sub16_pair(uint32_t w, const Sub16 &c)
+{
+    const uint32_t C = __vmaxu2(w & Arith16<T>::kExp2, c.minexp2) + c.magic2;
+    const uint32_t q = Arith16<T>::sub2(Arith16<T>::add2(w, C), C);
+    return __vminu2(q & 0x7FFF7FFFu, c.maxnum2) | (q & 0x80008000u);
+}
+template <typename T> __device__ __forceinline__ uint4 sub16_vec(const uint4 &r, const Sub16 &c)
+{
+    return make_uint4(sub16_pair<T>(r.x, c), sub16_pair<T>(r.y, c), sub16_pair<T>(r.z, c), sub16_pair<T>(r.w, c));
+}
+
 static __device__ __noinline__ float mx_elem_ol(float x, float scale, const FloatFmt *f)
 {
     MxBlock b{scale};

@@ -1117,6 +1117,67 @@ def test_mxfp_vs_oracle_at_scale(sh):
     check(gpu_cast(xc, sh, 0), bits(O.cast(x[:256].contiguous().numpy(), sh, 0)), sh + " cols")
 
 
+@pytest.mark.parametrize("dt", ["bfloat16", "float16"])
+@pytest.mark.parametrize("sh", ["FP[1|4|3,7](_N)", "FP[1|5|2,15](_N)", "FP[1|2|3,1](_N)", "FP[1|3|2,3](_N)", "FP[1|2|1,1](_N)", "FP[1|4|5,7](_N)",
+                                "FP[1|5|6,15](_N)", "FP[1|8|3,127](_N)", "MXFP8[E4M3]{32}", "MXFP8[E5M2]{32}", "MXFP6[E2M3]{32}", "MXFP6[E3M2]{64}",
+                                "MXFP4[E2M1]{32}", "MXFP8[E4M3]{128}"])
+def test_packed16_low_bit_float(dt, sh):
+    """K_FLOAT (subnormals kept) / K_MXFP on a 16-bit tensor, same dtype out: the packed form (two elements per instruction,
+    rounding in the source's own arithmetic, dmxq_stages.cuh sub16_pair) against the oracle -- values deep in the element
+    format's subnormals, every rounding tie of the format, +-0, results that round to zero from either side, saturation, rows
+    whose magnitudes leave no room for the rounding constant / Inf / NaN (literal path), power-of-two and zero block maxima"""
+    tdt = getattr(torch, dt)
+    g = torch.Generator().manual_seed(123)
+    x = torch.randn(384, 2048, generator=g) * torch.pow(2.0, torch.randint(-14, 3, (384, 2048), generator=g).float())
+    x = x * torch.pow(2.0, torch.randint(-10, 10, (384, 1), generator=g).float())
+    flat = x.view(-1)
+    flat[::5] = torch.round(flat[::5] * 64) / 64          # coarse values: exact ties of 2..5-bit mantissas
+    flat[1::11] = torch.round(flat[1::11] * 4) / 4
+    flat[3::17] = 0.0
+    flat[4::17] = -0.0
+    flat[6::17] *= -1
+    x[7] = 0.0                                              # all-zero blocks
+    x[9, ::3] = 0.5                                         # power-of-two block maxima
+    x[9, 1::3] = 0.25
+    x[9, 2::3] = -0.5
+    x[11] = x[11] * 2.0**9                                  # saturation
+    if dt == "bfloat16":
+        x[13] = x[13] * 2.0**105                            # exponent fields above the packed path's limit, still finite
+        x[14] = x[14] * 2.0**-120                           # bf16 denormals
+    else:
+        x[13] = (x[13] * 2.0**12).clamp(-60000.0, 60000.0)
+        x[14] = x[14] * 2.0**-14                            # fp16 denormals
+    xh = x.to(tdt)
+    assert bool(torch.isfinite(xh).all())
+    xh[15, 5] = float("inf"); xh[15, 77] = float("-inf"); xh[16, 9] = float("nan")
+    finite_rows = np.ones(384, dtype=bool)
+    finite_rows[15:17] = False
+    want32 = O.cast(xh.float().numpy(), sh, -1)
+    y = ops.cast_chain(xh.to(DEV), [fmt_from(sh).stage()], -1)
+    assert y.dtype == tdt
+    got = y.cpu().view(torch.int16).numpy().view(np.uint16)
+    want = torch.from_numpy(want32).to(tdt).view(torch.int16).numpy().view(np.uint16)
+    # rows of finite values: the oracle, bit for bit (MX all-zero blocks are NaN = 0 / 0 on both sides)
+    nan_w = np.isnan(want32)
+    nan_g = torch.isnan(y.float()).cpu().numpy()
+    assert np.array_equal(nan_w[finite_rows], nan_g[finite_rows]), f"{sh} {dt}: NaN positions differ"
+    bad = (got != want) & ~nan_w
+    bad[~finite_rows] = False
+    assert not bad.any(), f"{sh} {dt}: {int(bad.sum())} mismatches, first at {np.argwhere(bad)[0]}: x={xh.float().numpy()[tuple(np.argwhere(bad)[0])]!r} got={got[bad][0]:#06x} want={want[bad][0]:#06x}"
+    # every row, Inf / NaN included (where x86 and the GPU legitimately produce different NaNs, see special_block_masks): the
+    # fp32-out kernels -- the unpacked path, pinned to the reference's own CUDA kernels elsewhere -- narrowed like CastTo does
+    y32 = gpu_cast(xh.to(DEV), sh, -1)
+    assert torch.equal(y32.to(tdt).view(torch.int16), y.view(torch.int16)), f"{sh} {dt}: packed path != unpacked path"
+    b32 = (y32.cpu().numpy().view(np.uint32) != bits(want32)) & ~nan_w
+    b32[~finite_rows] = False
+    assert not b32.any()
+    if dt == "bfloat16":  # the fp32 kernel on the unrounded values (incl. magnitudes whose rounding constant would overflow)
+        w = O.cast(x.numpy(), sh, -1)
+        yf = gpu_cast(x.to(DEV), sh, -1).cpu().numpy()
+        assert np.array_equal(np.isnan(w), np.isnan(yf))
+        assert not ((yf.view(np.uint32) != bits(w)) & ~np.isnan(w)).any(), f"{sh} fp32"
+
+
 # ---- (f3) calibration histogram: dmxq_histc / HistogramObserver ---------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("bins,lo,hi", [(2048, -3, 4), (1000, -7, 10), (7, -1, 1), (2048, 0, 0), (12288, -40, 41), (1, -2, 2)])
