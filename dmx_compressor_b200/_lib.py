@@ -64,6 +64,7 @@ def _load():
         "dmxq_fixed_qdq": ([TP, TP] + [I] * 6 + [VP, VP, I64, I, I64, VP, VP], I),
         "dmxq_nm_prune": ([TP, TP, TP, TP, I, I, I, I, VP], I),
         "dmxq_add_cast": ([TP, TP, TP, SP, SP, SP, VP], I),
+        "dmxq_softmax_cast": ([TP, TP, TP, SP, SP, SP, SP, I, VP], I),
         "dmxq_bfp_pack": ([TP, VP, VP, I, I, VP], I),
         "dmxq_bfp_unpack": ([VP, VP, TP, I, I, VP], I),
         "dmxq_sbfp_pack": ([TP, VP, VP, SP, VP, VP], I),

@@ -271,6 +271,40 @@ int run_generic(const dmxq_tensor *x, const dmxq_tensor *y, const Canon &c, cons
     return DMXQ_OK;
 }
 
+// the stages of one fused chain as the kernels consume them: decoded formats plus what depends on the position in the chain
+// (significant bits of the values a stage sees, rounding to the tensor dtype between consecutive CastTo.forward calls)
+int decode_chain(int x_dtype, int y_dtype, const dmxq_stage *stages, int n_stages, ChainDev &chain, bool *blocked_out, int *n_stoch_out)
+{
+    memset(&chain, 0, sizeof(chain));
+    chain.n = n_stages;
+    bool blocked = false;
+    int n_stoch = 0;
+    for (int s = 0; s < n_stages; ++s) {
+        int rc = decode_stage(stages[s], chain.st[s]);
+        if (rc) return rc;
+        if (chain.st[s].kind == ST_BFP) {
+            // significant bits of the values this stage sees: the source dtype's for stage 0 (and
+            // after an N:M stage, which only zeroes elements), the output dtype's after a requant
+            int src = -1;
+            if (s == 0 || (s == 1 && chain.st[0].kind == ST_NM)) src = x_dtype;
+            else if (chain.st[s - 1].requant) src = y_dtype;
+            chain.st[s].fast16 = (src == DMXQ_BF16 && chain.st[s].wl <= 14) || (src == DMXQ_F16 && chain.st[s].wl <= 11);
+        }
+        if (s == 0 && chain.st[s].kind == ST_FLOAT && chain.st[s].ff.mode == R_NEAREST) {
+            // a bf16 (7 mantissa bits) / fp16 (10) source is already representable: rounding is the identity
+            int src_man = x_dtype == DMXQ_BF16 ? 7 : x_dtype == DMXQ_F16 ? 10 : 23;
+            if (23 - chain.st[s].ff.sh >= src_man) chain.st[s].ff.exact = 1;
+        }
+        blocked |= stage_blocked(chain.st[s]);
+        n_stoch += stage_mode(chain.st[s]) == R_STOCHASTIC;
+        // consecutive CastTo.forward calls round to the tensor dtype in between (cast.py:306)
+        chain.st[s].requant = (s + 1 < n_stages && y_dtype != DMXQ_F32 && chain.st[s].kind != ST_NM) ? 1 : 0;
+    }
+    if (blocked_out) *blocked_out = blocked;
+    if (n_stoch_out) *n_stoch_out = n_stoch;
+    return DMXQ_OK;
+}
+
 // qscale / qzp (nullable): device-resident per-tensor FixedPoint affine parameters; only the vectorised rows
 // kernel consumes them -- when the layout needs another path the call returns kNeedFallback (no message) and
 // dmxq_fixed_qdq falls back to fixed_chan_kernel.
@@ -296,30 +330,11 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     if (mask && (!same_shape(x, mask) || mask->dtype != DMXQ_F32)) return fail(DMXQ_ERR_BAD_ARG, "mask must be fp32 with the shape of x");
 
     ChainDev chain;
-    memset(&chain, 0, sizeof(chain));
-    chain.n = n_stages;
     bool blocked = false;
     int n_stoch = 0;
-    for (int s = 0; s < n_stages; ++s) {
-        int rc = decode_stage(stages[s], chain.st[s]);
+    {
+        int rc = decode_chain(x->dtype, y->dtype, stages, n_stages, chain, &blocked, &n_stoch);
         if (rc) return rc;
-        if (chain.st[s].kind == ST_BFP) {
-            // significant bits of the values this stage sees: the source dtype's for stage 0 (and
-            // after an N:M stage, which only zeroes elements), the output dtype's after a requant
-            int src = -1;
-            if (s == 0 || (s == 1 && chain.st[0].kind == ST_NM)) src = x->dtype;
-            else if (chain.st[s - 1].requant) src = y->dtype;
-            chain.st[s].fast16 = (src == DMXQ_BF16 && chain.st[s].wl <= 14) || (src == DMXQ_F16 && chain.st[s].wl <= 11);
-        }
-        if (s == 0 && chain.st[s].kind == ST_FLOAT && chain.st[s].ff.mode == R_NEAREST) {
-            // a bf16 (7 mantissa bits) / fp16 (10) source is already representable: rounding is the identity
-            int src_man = x->dtype == DMXQ_BF16 ? 7 : x->dtype == DMXQ_F16 ? 10 : 23;
-            if (23 - chain.st[s].ff.sh >= src_man) chain.st[s].ff.exact = 1;
-        }
-        blocked |= stage_blocked(chain.st[s]);
-        n_stoch += stage_mode(chain.st[s]) == R_STOCHASTIC;
-        // consecutive CastTo.forward calls round to the tensor dtype in between (cast.py:306)
-        chain.st[s].requant = (s + 1 < n_stages && y->dtype != DMXQ_F32 && chain.st[s].kind != ST_NM) ? 1 : 0;
     }
     if (n_stoch > 1) return fail(DMXQ_ERR_UNSUPPORTED, "at most one stochastic stage per chain");
     if (n_stoch == 1 && !rand) return fail(DMXQ_ERR_BAD_ARG, "stochastic rounding needs a random tensor");
@@ -816,6 +831,93 @@ int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor 
     if (outer.size() == 2) { p.d1 = (uint32_t)outer[1].first; p.bs1 = outer[1].second; p.bs0 = outer[0].second; }
     cudaError_t e = launch_add(a->dtype, p, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return cuda_fail(e, "add_cast_kernel");
+    return DMXQ_OK;
+}
+
+int dmxq_softmax_cast(const dmxq_tensor *x, const dmxq_tensor *addend, const dmxq_tensor *y, const dmxq_stage *stage_x,
+                      const dmxq_stage *stage_addend, const dmxq_stage *stage_sum, const dmxq_stage *post, int n_post, void *stream)
+{
+    if (!x || !y) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (!same_shape(x, y) || x->dtype != y->dtype) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: x and y must share shape and dtype");
+    if (x->dtype < 0 || x->dtype > 2 || x->ndim < 1 || x->ndim > DMXQ_MAX_DIMS) return fail(DMXQ_ERR_BAD_ARG, "softmax_cast: bad dtype / rank");
+    if (n_post < 0 || n_post > DMXQ_MAX_STAGES || (n_post > 0 && !post)) return fail(DMXQ_ERR_BAD_ARG, "softmax_cast: 0..%d output stages", DMXQ_MAX_STAGES);
+    if (!addend && (stage_x || stage_addend || stage_sum)) return fail(DMXQ_ERR_BAD_ARG, "softmax_cast: add stages without an addend");
+    const int nd = x->ndim, V = 16 / dtype_size(x->dtype);
+    const int64_t n = x->shape[nd - 1];
+    // torch's persistent-warp softmax with a full warp per row (ATen host_softmax: dim_size <= 2048 and <= 8 KiB per row)
+    if (n <= 32 || n > 2048) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: rows of 33..2048 elements (got %lld)", (long long)n);
+    if (n % V != 0) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: row length must be a multiple of %d", V);
+    SoftmaxParams p;
+    memset(&p, 0, sizeof(p));
+    int64_t rows = 1, expect = n;
+    for (int i = nd - 2; i >= 0; --i) {
+        if (x->shape[i] != 1 && (x->stride[i] != expect || y->stride[i] != expect)) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: x and y must be contiguous");
+        expect *= x->shape[i];
+        rows *= x->shape[i];
+    }
+    if (x->stride[nd - 1] != 1 && n > 1) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: the softmax dim must be contiguous");
+    if (rows == 0) return DMXQ_OK;
+    if (!x->data || !y->data || !aligned(x->data, 16) || !aligned(y->data, 16)) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: 16-byte aligned data");
+    if (rows > 0xFFFFFFFFll) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: too many rows");
+    p.x = x->data; p.y = y->data; p.rows = rows; p.n = (int)n; p.xs = n; p.ys = n;
+    p.d1 = p.d2 = 1;
+    if (addend) {
+        const dmxq_tensor *b = addend;
+        if (b->dtype != x->dtype || b->ndim > nd || b->ndim < 1) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: addend dtype / rank");
+        if (!b->data || !aligned(b->data, 16)) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: 16-byte aligned addend");
+        if (b->shape[b->ndim - 1] != n || b->stride[b->ndim - 1] != 1) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: the addend must span the softmax dim contiguously");
+        // outer dims of x (right-aligned against the addend; broadcast dims get stride 0), size-1 dims dropped, neighbours that
+        // the addend walks like one dim merged, at most three left
+        std::vector<std::pair<int64_t, int64_t>> outer;  // (size, addend stride), outermost first
+        for (int i = 0; i < nd - 1; ++i) {
+            if (x->shape[i] == 1) continue;
+            int64_t bst = 0;
+            const int bi = i - (nd - b->ndim);
+            if (bi >= 0) {
+                if (b->shape[bi] == x->shape[i]) bst = b->stride[bi];
+                else if (b->shape[bi] != 1) return fail(DMXQ_ERR_BAD_ARG, "softmax_cast: the addend is not broadcastable to x");
+            }
+            if (!outer.empty() && outer.back().second == bst * x->shape[i]) { outer.back().first *= x->shape[i]; outer.back().second = bst; }
+            else outer.emplace_back(x->shape[i], bst);
+        }
+        if (outer.size() > 3) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: addend broadcast pattern needs more than three outer dims");
+        for (auto &o : outer)
+            if ((o.second * dtype_size(x->dtype)) % 16 != 0) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: misaligned addend stride");
+        while (outer.size() < 3) outer.insert(outer.begin(), std::make_pair<int64_t, int64_t>(1, 0));
+        if (outer[1].first > 0xFFFFFFFFll || outer[2].first > 0xFFFFFFFFll) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: extent too large");
+        p.b = b->data;
+        p.d1 = (uint32_t)outer[1].first; p.d2 = (uint32_t)outer[2].first;
+        p.bs[0] = outer[0].second; p.bs[1] = outer[1].second; p.bs[2] = outer[2].second;
+        const dmxq_stage *sts[3] = {stage_x, stage_addend, stage_sum};
+        FloatFmt *fmts[3] = {&p.fa, &p.fb, &p.fo};
+        int *has[3] = {&p.has_a, &p.has_b, &p.has_o};
+        for (int i = 0; i < 3; ++i) {
+            if (!sts[i]) continue;
+            StageDev d;
+            int rc = decode_stage(*sts[i], d);
+            if (rc) return rc;
+            if (d.kind != ST_FLOAT || !d.ff.fastpath) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: only nearest+flush FLOAT stages fuse into the add");
+            const int src_man = x->dtype == DMXQ_BF16 ? 7 : x->dtype == DMXQ_F16 ? 10 : 23;
+            if (23 - d.ff.sh >= src_man) d.ff.exact = 1;
+            *fmts[i] = d.ff;
+            *has[i] = 1;
+        }
+    }
+    if (n_post > 0) {
+        bool blocked = false;
+        int n_stoch = 0;
+        int rc = decode_chain(x->dtype, y->dtype, post, n_post, p.chain, &blocked, &n_stoch);
+        if (rc) return rc;
+        if (n_stoch) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: stochastic stages are not fused");
+        for (int s = 0; s < n_post; ++s) {
+            const StageDev &d = p.chain.st[s];
+            if (d.kind == ST_NM) return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: N:M stages are not fused");
+            if (stage_blocked(d) && (d.block % V != 0 || !pow2(d.block / V) || d.block / V > 32 || n % d.block != 0))
+                return fail(DMXQ_ERR_UNSUPPORTED, "softmax_cast: block size %d needs whole blocks of whole 16-byte vectors along the row", d.block);
+        }
+    }
+    cudaError_t e = launch_softmax(x->dtype, p, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "softmax_cast_kernel");
     return DMXQ_OK;
 }
 

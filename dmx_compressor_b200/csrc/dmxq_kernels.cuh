@@ -167,6 +167,21 @@ struct AddParams {
     FloatFmt fa, fb, fo;
 };
 
+// dmxq_softmax_cast (dmxq_softmax.cu)
+struct SoftmaxParams {
+    const void *x, *b;
+    void *y;
+    int64_t rows;
+    int n;                 // row length
+    int64_t xs, ys;        // row strides of x / y (elements)
+    // addend row of row r = (i0, i1, i2) with r = (i0 * d1 + i1) * d2 + i2: b + i0 * bs[0] + i1 * bs[1] + i2 * bs[2]
+    uint32_t d1, d2;
+    int64_t bs[3];
+    int has_a, has_b, has_o;  // FLOAT casts of x, of the addend, of their sum (ResAdd's input / residual / output casts)
+    FloatFmt fa, fb, fo;
+    ChainDev chain;        // casts applied to the probabilities (chain.n may be 0)
+};
+
 struct MinMaxParams {
     const void *x;
     int dtype;
@@ -189,6 +204,7 @@ cudaError_t launch_minmax(const MinMaxParams &p, cudaStream_t s);
 cudaError_t launch_histc(int dt, const void *x, int64_t n, float lo, float hi, int bins, unsigned long long *counts, float *out_min,
                          float *out_max, cudaStream_t s);
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
+cudaError_t launch_softmax(int dt, const SoftmaxParams &p, cudaStream_t s);
 cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers, unsigned int *n_inexact, int64_t n, int B, const SbfpFmt &f, int sc_man,

@@ -133,6 +133,60 @@ __device__ __forceinline__ uint32_t sbfp_thr_from_amax(const SbfpFmt &f, const f
     return (uint32_t)(127 - (bias - 1)) << 23;
 }
 
+// K_FLOAT_BFP on one vector: [FLOAT nearest + flush + signed] -> rounding to Tout -> [BFP nearest symmetric], the output cast of
+// one module fused with the input cast of the next (also the tail of dmxq_softmax_cast).  Per-thread constants in FloatBfpCtx.
+struct FloatBfpCtx {
+    uint32_t fmax_rq;        // the float format's saturation value as Tout stores it
+    bool f16_same;           // 16-bit tensor whose significand the format keeps: vectors inside [f16_lo, f16_hi] pass unchanged
+    uint32_t f16_lo, f16_hi;
+};
+template <typename Tin, typename Tout> __device__ __forceinline__ FloatBfpCtx float_bfp_ctx(const StageDev &sf)
+{
+    constexpr bool SAME16 = sizeof(Tin) == 2 && std::is_same<Tin, Tout>::value;
+    FloatBfpCtx c;
+    c.fmax_rq = SAME16 ? f2u(requant1<Tout>(u2f(sf.ff.max_num))) : 0u;
+    c.f16_same = SAME16 && sf.ff.exact && !sf.ff.is_unsigned;
+    c.f16_lo = c.f16_same ? pattern16_ru<Tin>(u2f(sf.ff.shift_exp)) : 0u;
+    c.f16_hi = c.f16_same ? min(pattern16_rn<Tin>(u2f(sf.ff.max_num)), (uint32_t)(std::is_same<Tin, __half>::value ? 0x7BFFu : 0x7F7Fu)) : 0u;
+    return c;
+}
+template <typename Tin, typename Tout, int V>
+__device__ __forceinline__ void float_bfp_apply(const uint4 &raw, float (&v)[V], const StageDev &sf, const StageDev &st, const FloatBfpCtx &c)
+{
+    constexpr bool SAME16 = sizeof(Tin) == 2 && std::is_same<Tin, Tout>::value;
+    const uint32_t fmax_rq = c.fmax_rq, f16_lo = c.f16_lo, f16_hi = c.f16_hi;
+    const bool f16_same = c.f16_same;
+    {
+            // The float stage (nearest, flush, saturate) and the rounding to Tout are monotone in |x|, so the block
+            // maximum the BFP stage needs is the stage applied to the maximum of the inputs: one scalar evaluation
+            // instead of a second max over the vector.
+            const uint32_t m_in = unpack_absmax<Tin>(raw, v);
+            uint32_t m_thr;
+            if (m_in > 0x7F800000u) {  // a NaN in this vector: literal path
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_slow(v[j], &sf.ff, 0u));
+                m_thr = vec_absmax<V>(v);
+            } else if (SAME16 && f16_same && raw16_absmin(raw) >= f16_lo && raw16_absmax(raw) <= f16_hi) {
+                m_thr = m_in;  // every magnitude inside [flush threshold, saturation value]: the float stage is the identity
+            } else if (SAME16 && sf.ff.exact) {
+                // the values already sit on Tout's grid and the format keeps their significand: only flush and
+                // saturate act, and the saturation value is the one constant that needs Tout's rounding
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = float_elem_flush_nearest<true>(v[j], sf.ff, fmax_rq);
+                m_thr = f2u(float_elem_flush_nearest<true>(u2f(m_in), sf.ff, fmax_rq));
+            } else if (sf.ff.exact) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<true>(v[j], sf.ff));
+                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<true>(u2f(m_in), sf.ff)));
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<false>(v[j], sf.ff));
+                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<false>(u2f(m_in), sf.ff)));
+            }
+            bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, lanes_max(m_thr, st.block / V), st);  // the values now carry Tout's significand
+    }
+}
+
 // body of chain_rows_kernel: `cta` is the CTA's index inside the tensor (x, y) of n_vec vectors -- the whole grid for
 // the single-tensor kernel, a segment of it for the many-tensor kernel
 template <typename Tin, typename Tout, bool FLAT, int KIND, bool AMAX = false>
@@ -296,35 +350,7 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
             const bool any_nan = unpack_absmax<Tin>(raw[u], v) > 0x7F800000u;
             float_fast_apply<V>(v, p.chain.st[0], any_nan);
         } else if (KIND == K_FLOAT_BFP) {
-            // The float stage (nearest, flush, saturate) and the rounding to Tout are monotone in |x|, so the block
-            // maximum the BFP stage needs is the stage applied to the maximum of the inputs: one scalar evaluation
-            // instead of a second max over the vector.
-            const StageDev &sf = p.chain.st[0];
-            const StageDev &st = p.chain.st[1];
-            const uint32_t m_in = unpack_absmax<Tin>(raw[u], v);
-            uint32_t m_thr;
-            if (m_in > 0x7F800000u) {  // a NaN in this vector: literal path
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_slow(v[j], &sf.ff, 0u));
-                m_thr = vec_absmax<V>(v);
-            } else if (SAME16 && f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {
-                m_thr = m_in;  // every magnitude inside [flush threshold, saturation value]: the float stage is the identity
-            } else if (SAME16 && sf.ff.exact) {
-                // the values already sit on Tout's grid and the format keeps their significand: only flush and
-                // saturate act, and the saturation value is the one constant that needs Tout's rounding
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = float_elem_flush_nearest<true>(v[j], sf.ff, fmax_rq);
-                m_thr = f2u(float_elem_flush_nearest<true>(u2f(m_in), sf.ff, fmax_rq));
-            } else if (sf.ff.exact) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<true>(v[j], sf.ff));
-                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<true>(u2f(m_in), sf.ff)));
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) v[j] = requant1<Tout>(float_elem_flush_nearest<false>(v[j], sf.ff));
-                m_thr = f2u(requant1<Tout>(float_elem_flush_nearest<false>(u2f(m_in), sf.ff)));
-            }
-            bfp_ns_apply<V, (sizeof(Tout) == 2)>(v, lanes_max(m_thr, st.block / V), st);  // the values now carry Tout's significand
+            float_bfp_apply<Tin, Tout, V>(raw[u], v, p.chain.st[0], p.chain.st[1], FloatBfpCtx{fmax_rq, f16_same, f16_lo, f16_hi});
         } else if (KIND == K_NM_BFP) {
             // score = |x|: the largest magnitude of every group survives the pruning, so the block maximum is the
             // maximum of the inputs (packed 16-bit max on the raw words for 16-bit sources)

@@ -646,6 +646,59 @@ __device__ __forceinline__ uint4 nm_apply_raw16(const uint4 &r, const bool (&kee
 }
 
 // ------------------------------------------------------------------------------------------------
+// nearest + flush FLOAT stage on a register vector (dmxq_add_cast, dmxq_softmax_cast)
+template <int V> __device__ __forceinline__ void float_fast_vec(float (&v)[V], const FloatFmt &f)
+{
+    const bool any_nan = vec_absmax<V>(v) > 0x7F800000u;
+    float q[V];
+    if (f.exact) {  // values already fit the format's mantissa (16-bit tensor dtype): flush + saturate only
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<true>(v[j], f);
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_flush_nearest<false>(v[j], f);
+    }
+    if (any_nan) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) q[j] = float_elem_slow(v[j], &f, 0u);
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) v[j] = q[j];
+}
+
+// 16-bit helpers: pack a register vector to T (round to nearest: the tensor dtype's rounding) and the "this FLOAT stage
+// is the identity on the whole vector" test on the packed patterns (see f16_same in dmxq_rows.cuh)
+template <typename T> __device__ __forceinline__ uint4 pack16(const float (&v)[8])
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        } else {
+            __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t *>(&h);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+struct Range16 {
+    uint32_t lo, hi;
+    bool on;  // the stage exists, keeps T's significand, and is the signed nearest+flush kind
+};
+template <typename T> __device__ __forceinline__ Range16 range16(int has, const FloatFmt &f)
+{
+    Range16 r;
+    r.on = has && f.exact && !f.is_unsigned;
+    r.lo = pattern16_ru<T>(u2f(f.shift_exp));
+    r.hi = min(pattern16_rn<T>(u2f(f.max_num)), (uint32_t)(std::is_same<T, __half>::value ? 0x7BFFu : 0x7F7Fu));
+    return r;
+}
+__device__ __forceinline__ bool inside16(const uint4 &w, const Range16 &r) { return r.on && raw16_absmin(w) >= r.lo && raw16_absmax(w) <= r.hi; }
+
+
+// ------------------------------------------------------------------------------------------------
 // N:M tie order of the reference on CUDA tensors (DMXQ_NM_ORDER_TORCH_CUDA).  BlockTopK sorts every group with
 // torch.argsort(score, dim=1) (S/sparse.py:172); for rows of <= 32 keys ATen runs bitonicSortKVInPlace
 // (ATen/native/cuda/SortUtils.cuh) with 32 slots, the M keys in slots 0..M-1 and "invalid" slots behind them:

@@ -129,9 +129,14 @@ class Lazy(torch.Tensor):
     Only shape / dtype / device style metadata is answered without materialising."""
 
     @staticmethod
-    def __new__(cls, raw, fmt, block_dim, key, materialise=None):
+    def __new__(cls, raw, fmt, block_dim, key, materialise=None, kind="cast", fuse=None, add=None):
         r = torch.Tensor._make_subclass(cls, raw, False)
         r._raw, r._fmt, r._bd, r._key, r._real, r._mat = raw, fmt, block_dim, key, None, materialise
+        # kind "cast": `raw` is the uncast value, a consumer may chain [fmt, its own format] over it.  Other kinds carry an
+        # OPERATION in front of the pending cast -- "softmax" (raw = the softmax input) / "add" (raw = the first addend, `add` =
+        # (a, b, stage_a, stage_b, stage_out)): only `materialise` -- or `fuse(next_stage, block_dim)`, which returns the
+        # operation + pending cast + the consumer's cast in one kernel, or None -- may produce values from them.
+        r._kind, r._fuse, r._add = kind, fuse, add
         return r
 
     def materialise(self) -> torch.Tensor:

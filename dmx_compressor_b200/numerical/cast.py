@@ -262,6 +262,15 @@ class CastTo(FakeQuantize):
             if pend._key == key:  # producer's output format == this input format: cast once
                 elide.stats["elided"] += 1
                 return pend.materialise()
+            if pend._kind != "cast":  # an operation is pending in front of the cast (softmax / add): its own fused kernel, or run it first
+                y = pend._fuse(fmt.stage(), self.block_dim) if (pend._fuse is not None and pend._real is None) else None
+                if y is None:
+                    y = ops.cast_chain(pend.materialise(), [fmt.stage()], self.block_dim)
+                else:
+                    elide.stats["elided"] += 1
+                elide.stats["casts"] += 1
+                elide.tag(y, key)
+                return y
             ckey = ("chain", pend._key, key)
             y = elide.memo_get(pend._raw, ckey)
             if y is None:  # output cast fused with this input cast: ONE pass over the tensor

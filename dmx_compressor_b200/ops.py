@@ -283,6 +283,36 @@ def add_cast(a, b, stage_a=None, stage_b=None, stage_out=None, out=None):
     return y
 
 
+def softmax_cast(x, post=(), addend=None, stage_x=None, stage_addend=None, stage_sum=None, out=None):
+    """y = post(softmax(x [+ addend], dim=-1)) in one pass (dmxq_softmax_cast): torch's CUDA softmax bit for bit, with the
+    attention-mask add and its casts in front (``addend`` + the three FLOAT stages, as ``add_cast``) and the casts of the
+    probabilities behind (``post``: a sequence of stages applied along the last dim, each followed by the rounding to
+    x.dtype).  Rows of 33..2048 elements; raises RuntimeError('... unsupported ...') otherwise."""
+    L.require_cuda(x)
+    if addend is not None:
+        L.require_cuda(addend, "addend")
+    y = out if out is not None else torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    vx, vy = L.view(x), L.view(y)
+    vb = L.view(addend) if addend is not None else None
+    n = len(post)
+    arr = (L.Stage * n)(*post) if n else None
+    ptr = lambda s: None if s is None else C.byref(s)
+    with _guard(x.device):
+        rc = L.lib.dmxq_softmax_cast(C.byref(vx), ptr(vb), C.byref(vy), ptr(stage_x), ptr(stage_addend), ptr(stage_sum), arr, n, L.stream_ptr(x.device))
+    L.check(rc, "dmxq_softmax_cast")
+    return y
+
+
+def softmax_supported(x, dim=-1) -> bool:
+    """whether dmxq_softmax_cast takes this tensor (else: torch.softmax)"""
+    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16, torch.float16) and x.dim() >= 1):
+        return False
+    if dim not in (-1, x.dim() - 1):
+        return False
+    n = x.shape[-1]
+    return 32 < n <= 2048 and n % (16 // x.element_size()) == 0 and x.is_contiguous() and x.data_ptr() % 16 == 0 and x.numel() > 0
+
+
 def bfp_pack(x, block_size=64, precision=8):
     """-> (mantissas, exponents): packed BFP storage of a contiguous [..., K] tensor (dmxq_bfp_pack).
     mantissas: int8 [..., K] (precision 5..8) or uint8 [..., K/2] (precision <= 4, two nibbles per byte);

@@ -225,6 +225,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
             return None
 
         from . import elide as E
+        from . import fused
 
         def ref_key(f, block_dim):
             """hashable identity of an idempotent cast of the reference's format classes (elide.format_key's rule)"""
@@ -253,6 +254,15 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                 if pend._key == key:
                     E.stats["elided"] += 1
                     return pend.materialise()
+                if pend._kind != "cast":  # an operation is pending in front of the cast (softmax / add): its own fused kernel, or run it first
+                    y = pend._fuse(stage_of(f), self.block_dim) if (pend._fuse is not None and pend._real is None) else None
+                    if y is None:
+                        y = ops.cast_chain(pend.materialise(), [stage_of(f)], self.block_dim)
+                    else:
+                        E.stats["elided"] += 1
+                    E.stats["casts"] += 1
+                    E.tag(y, key)
+                    return y
                 ckey = ("chain", pend._key, key)
                 y = E.memo_get(pend._raw, ckey)
                 if y is None:  # the producer's output cast fused with this input cast: ONE pass over the tensor
@@ -407,6 +417,10 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                     """ResAdd.forward: input casts + add + output cast as ONE kernel (dmxq_add_cast) for plain nearest + flush FLOAT casts"""
                     if E.active() and not torch.is_grad_enabled() and not DmxModule_plugins(core) and not getattr(self, "flop_counter_enabled", False):
                         plan = _resadd_plan(self, input, residual)
+                        if plan is not None and plan[2] is not None and E.defer_output_casts and fused.add_supported(plan[4], plan[5]):
+                            # hand the add itself to the consumer: a Softmax folds it into its kernel, anything else runs dmxq_add_cast
+                            E.stats["elided"] += 2
+                            return fused.lazy_add(plan, self.output_casts.output_cast.format)
                         if plan is not None:
                             try:
                                 y = ops.add_cast(plan[4], plan[5], plan[0], plan[1], plan[2])
@@ -437,7 +451,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                         fast = isinstance(f, fmt.FloatingPoint) and f.rounding == "nearest" and f.flush_subnormal and not f.unsigned
                         key = ref_key(f, None) if fast else None
                         if isinstance(t, E.Lazy):
-                            if fast and t._key == key and on:  # F(F(x)) == F(x): the deferred producer cast folds into the add
+                            if fast and t._key == key and on and t._kind == "cast":  # F(F(x)) == F(x): the deferred producer cast folds into the add
                                 stages.append(stage_of(f))
                                 raws.append(t._raw)
                                 continue
@@ -463,6 +477,67 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
 
                 if elide:
                     _patch(tmods.ResAdd, "forward", resadd_forward)
+
+                # ---- Softmax (torch_modules.py:970-998): torch's CUDA softmax bit for bit, 1.2 - 3x faster (dmxq_softmax_cast); under
+                # elision the softmax -- and a pending attention-mask add in front of it -- is handed to the consumer with the output cast
+                approx = importlib.import_module(package + ".functional.approximate")
+                o_sm_fwd = tmods.Softmax.__dict__["_forward"]
+
+                def _plain_softmax(self):
+                    return self.functional_forward is None and isinstance(self.approximator.function, approx.NoApproximation)
+
+                def softmax__forward(self, _input, *args, **kwargs):
+                    if not args and not kwargs and _plain_softmax(self) and ops.softmax_supported(_input, self.dim) and not (
+                            torch.is_grad_enabled() and _input.requires_grad):
+                        return ops.softmax_cast(_input)
+                    return o_sm_fwd(self, _input, *args, **kwargs)
+
+                _patch(tmods.Softmax, "_forward", softmax__forward)
+
+                def softmax_forward(self, input, *args, **kwargs):
+                    if E.active() and not torch.is_grad_enabled() and not args and not kwargs and isinstance(input, torch.Tensor) and input.is_cuda \
+                            and not DmxModule_plugins(core) and not self.flop_counter_enabled and self.obc is None and self.aft is None \
+                            and self.smoothquant is None and _plain_softmax(self) and self.dim in (-1, input.dim() - 1):
+                        ic, oc = self.input_casts.input_cast, self.output_casts.output_cast
+                        if not (ic.pre_transform or oc.pre_transform or _flag(ic, "observer_enabled") == 1 or _flag(oc, "observer_enabled") == 1):
+                            fo = oc.format
+                            o_on = _flag(oc, "fake_quant_enabled") == 1 and not isinstance(fo, fmt.Same)
+                            o_fast = isinstance(fo, fmt.FloatingPoint) and fo.rounding == "nearest" and fo.flush_subnormal and not fo.unsigned
+                            if not o_on or o_fast:
+                                i_on = _flag(ic, "fake_quant_enabled") == 1 and not isinstance(ic.format, fmt.Same)
+                                took = fused.take_add(input, i_on, ref_key(ic.format, None) if i_on else None)
+                                if took is not None:
+                                    x, add = took
+                                else:
+                                    x, add = E.materialise(ic(input)), None
+                                y = fused.softmax(x, add, fo, stage_of(fo) if o_on else None, ref_key(fo, None) if o_on else None)
+                                if y is None and took is None:  # the input cast has run (and is tagged / memoised): finish module by module
+                                    _out_depth[0] += 1
+                                    try:
+                                        y = oc(o_sm_fwd(self, x))
+                                    finally:
+                                        _out_depth[0] -= 1
+                                if y is not None:
+                                    return y
+                    return module_forward(self, E.materialise(input), *args, **kwargs)
+
+                if elide:
+                    _patch(tmods.Softmax, "forward", softmax_forward)
+
+                def dropout_forward(self, input, *args, **kwargs):
+                    """inference-mode Dropout with SAME casts is the identity (torch's F.dropout returns its input): under elision the
+                    tensor is not even touched, which keeps a deferred producer (the attention softmax) alive for its real consumer"""
+                    if E.active() and not self.training and not torch.is_grad_enabled() and not args and not kwargs and not DmxModule_plugins(core) \
+                            and not self.flop_counter_enabled and self.obc is None and self.aft is None and self.smoothquant is None \
+                            and self.functional_forward is None and isinstance(self.approximator.function, approx.NoApproximation) \
+                            and all(isinstance(c.format, fmt.Same) or _flag(c, "fake_quant_enabled") != 1
+                                    for c in (self.input_casts.input_cast, self.output_casts.output_cast)) \
+                            and not any(_flag(c, "observer_enabled") == 1 for c in (self.input_casts.input_cast, self.output_casts.output_cast)):
+                        return input
+                    return module_forward(self, input, *args, **kwargs)
+
+                if elide and hasattr(tmods, "Dropout"):
+                    _patch(tmods.Dropout, "forward", dropout_forward)
 
             try:
                 patch_modules()

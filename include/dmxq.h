@@ -209,6 +209,21 @@ int dmxq_nm_prune(const dmxq_tensor *x, const dmxq_tensor *score, const dmxq_ten
 int dmxq_add_cast(const dmxq_tensor *a, const dmxq_tensor *b, const dmxq_tensor *y, const dmxq_stage *stage_a,
                   const dmxq_stage *stage_b, const dmxq_stage *stage_out, void *stream);
 
+/* ---- fused attention softmax: y = post( softmax( sum( A(x) + B(addend) ) ) ) along the last (contiguous) dim, ONE pass.
+ * Replaces, for one attention block of a BASIC-mode model, the reference's module sequence
+ *   ResAdd.forward (mask add with its input / residual / output casts, S/modeling/nn/torch_modules.py:15-37)
+ *   -> Softmax.forward (input cast, torch softmax, output cast; S/modeling/nn/core.py:215-264 around torch.nn.Softmax)
+ *   -> the consumer's input cast (ActActMatMul's BFP16 cast of the probabilities, S/numerical/cast.py:261-306)
+ * The softmax itself reproduces torch's CUDA kernel for rows of 33..2048 elements (ATen PersistentSoftmax.cuh
+ * softmax_warp_forward: per-lane sequential max / expf / sum over elements lane, lane + 32, ..., xor-butterfly reductions,
+ * IEEE division, result rounded to the tensor dtype) BIT FOR BIT; other row lengths return DMXQ_ERR_UNSUPPORTED (the caller
+ * keeps torch.softmax).  addend (nullable): same dtype, broadcastable to x, contiguous along the last dim (an attention
+ * mask); stage_x / stage_addend / stage_sum: nearest + flush FLOAT stages or NULL, as in dmxq_add_cast.  post[0..n_post):
+ * the casts applied to the probabilities (n_post may be 0), blocked formats along the row with whole blocks; each stage is
+ * followed by the rounding to the tensor dtype, as consecutive CastTo.forward calls do.  x, y: same shape / dtype, contiguous. */
+int dmxq_softmax_cast(const dmxq_tensor *x, const dmxq_tensor *addend, const dmxq_tensor *y, const dmxq_stage *stage_x,
+                      const dmxq_stage *stage_addend, const dmxq_stage *stage_sum, const dmxq_stage *post, int n_post, void *stream);
+
 /* ---- packed BFP storage: the real format behind the simulation ------------
  * The reference only ever materialises dequantised fp32 tensors, but it reports the packed size
  * (BlockFloatingPoint.bytes_per_elem, S/numerical/format.py:345-347) and names the packed ops in its ONNX
