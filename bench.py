@@ -622,21 +622,46 @@ def opt125m(dev):
         ids = torch.randint(0, 50272, (B, S), device=dev)
         with torch.no_grad():
             t_plain = timeit(lambda: p(ids))
+            y0 = p(ids)
+            t_plain_fs = _with_dmxq_softmax(p, lambda: timeit(lambda: p(ids)))
+            fs_same = _with_dmxq_softmax(p, lambda: bool(torch.equal(y0, p(ids))))
             y1 = q(ids)
             t_basic = timeit(lambda: q(ids))
             with elide.enabled():
-                y2 = q(ids)
+                y2 = elide.materialise(q(ids))
                 q(ids)
-                t_el = timeit(lambda: q(ids))
+                t_el = timeit(lambda: elide.materialise(q(ids)))
         res[str(dt).split(".")[-1]] = {
             "tok/s_unquantised": round(B * S / t_plain * 1e3), "tok/s_basic": round(B * S / t_basic * 1e3),
             "tok/s_basic_elided": round(B * S / t_el * 1e3), "ms": [round(t_plain, 2), round(t_basic, 2), round(t_el, 2)],
             "cast_overhead_basic": round((t_basic - t_plain) / t_plain, 3), "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3),
-            "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2))}
-        del q, p, y1, y2
+            "elided_equals_dropin_bitwise": bool(torch.equal(y1, y2)),
+            # the same comparison against an unquantised twin that already uses dmxq's (bit-identical, faster) softmax: what the casts
+            # themselves still cost once the softmax speed-up is taken out of the picture
+            "ms_unquantised_with_dmxq_softmax": round(t_plain_fs, 2), "dmxq_softmax_twin_equals_torch_twin_bitwise": fs_same,
+            "cast_overhead_elided_vs_dmxq_softmax_twin": round((t_el - t_plain_fs) / t_plain_fs, 3)}
+        del q, p, y0, y1, y2
         torch.cuda.empty_cache()
-    res["config"] = "OPT-125m shape, random init, batch 8 x seq 2048, config_rules.BASIC; ms = [unquantised, BASIC drop-in, BASIC + elision]"
+    res["config"] = ("OPT-125m shape, random init, batch 8 x seq 2048, config_rules.BASIC; ms = [unquantised (torch ops only), BASIC drop-in, "
+                     "BASIC + elision]; BASIC's Softmax modules run dmxq_softmax_cast (= torch's softmax bit for bit)")
     return res
+
+
+def _with_dmxq_softmax(model, fn):
+    """run fn() with every torch.nn.Softmax of the plain twin computing through dmxq_softmax_cast (bit-identical values)"""
+    import torch
+
+    from dmx_compressor_b200 import ops
+
+    mods = [m for m in model.modules() if type(m) is torch.nn.Softmax]
+    saved = [m.forward for m in mods]
+    for m in mods:
+        m.forward = (lambda x, _m=m: ops.softmax_cast(x) if ops.softmax_supported(x, _m.dim) else torch.softmax(x, _m.dim))
+    try:
+        return fn()
+    finally:
+        for m, f in zip(mods, saved):
+            m.forward = f
 
 
 def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
@@ -684,6 +709,7 @@ def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
         row = {}
         with torch.no_grad():
             t_plain = timeit(lambda: p(ids))
+            t_plain_fs = _with_dmxq_softmax(p, lambda: timeit(lambda: p(ids)))
             if with_unpatched:
                 plugin.uninstall()
                 y_ref = q(ids)
@@ -703,7 +729,9 @@ def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
                 plugin.uninstall()
         row.update({"ms": [round(t_plain, 2), round(t_drop, 2), round(t_el, 2)], "tok/s_plugin_dropin": round(B * S / t_drop * 1e3),
                     "tok/s_plugin_elided": round(B * S / t_el * 1e3), "cast_overhead_dropin": round((t_drop - t_plain) / t_plain, 3),
-                    "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3), "elided_equals_dropin_bitwise": bool(torch.equal(y0, y1))})
+                    "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3), "elided_equals_dropin_bitwise": bool(torch.equal(y0, y1)),
+                    "ms_unquantised_with_dmxq_softmax": round(t_plain_fs, 2),
+                    "cast_overhead_elided_vs_dmxq_softmax_twin": round((t_el - t_plain_fs) / t_plain_fs, 3)})
         if with_unpatched:
             row["dropin_equals_reference_bitwise"] = bool(torch.equal(y_ref, y0))
         res[str(dt).split(".")[-1]] = row

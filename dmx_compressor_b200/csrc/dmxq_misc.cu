@@ -970,25 +970,23 @@ template <typename T, int BCAST> __global__ void __launch_bounds__(kThreads) add
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             float va[V], vb[V];
-            VecIO<T>::unpack(ra[u], va);
-            VecIO<T>::unpack(rb[u], vb);
-            if (p.has_a && !inside16(ra[u], qa)) {
-                float_fast_vec<V>(va, p.fa);
-#pragma unroll
-                for (int j = 0; j < V; ++j) va[j] = requant1<T>(va[j]);
+            uint4 wa = ra[u], wb = rb[u];
+            if (p.has_a && !inside16(wa, qa)) {  // (stages that keep T's significand act on the packed words: flush_sat16_vec)
+                if (qa.on) wa = flush_sat16_vec<T>(wa, p.fa, qa);
+                else { VecIO<T>::unpack(wa, va); float_fast_vec<V>(va, p.fa); wa = pack16<T>(va); }
             }
-            if (p.has_b && !inside16(rb[u], qb)) {
-                float_fast_vec<V>(vb, p.fb);
-#pragma unroll
-                for (int j = 0; j < V; ++j) vb[j] = requant1<T>(vb[j]);
+            if (p.has_b && !inside16(wb, qb)) {
+                if (qb.on) wb = flush_sat16_vec<T>(wb, p.fb, qb);
+                else { VecIO<T>::unpack(wb, vb); float_fast_vec<V>(vb, p.fb); wb = pack16<T>(vb); }
             }
+            VecIO<T>::unpack(wa, va);
+            VecIO<T>::unpack(wb, vb);
 #pragma unroll
             for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);  // torch adds in fp32, rounds to T
             uint4 w = pack16<T>(va);
             if (p.has_o && !inside16(w, qo)) {
-                VecIO<T>::unpack(w, va);
-                float_fast_vec<V>(va, p.fo);
-                w = pack16<T>(va);
+                if (qo.on) w = flush_sat16_vec<T>(w, p.fo, qo);
+                else { VecIO<T>::unpack(w, va); float_fast_vec<V>(va, p.fo); w = pack16<T>(va); }
             }
             if (valid[u]) stg_stream(y + (g0 + (int64_t)u * kThreads) * V, w);
         }

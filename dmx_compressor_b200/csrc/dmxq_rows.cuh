@@ -168,9 +168,19 @@ __device__ __forceinline__ void float_bfp_apply(const uint4 &raw, float (&v)[V],
                 m_thr = vec_absmax<V>(v);
             } else if (SAME16 && f16_same && raw16_absmin(raw) >= f16_lo && raw16_absmax(raw) <= f16_hi) {
                 m_thr = m_in;  // every magnitude inside [flush threshold, saturation value]: the float stage is the identity
+            } else if (SAME16 && f16_same) {
+                // the values already sit on Tout's grid and the format keeps their significand: only flush and saturate act --
+                // on the packed words, two elements per instruction (no NaN here: m_in was checked above)
+                if constexpr (SAME16) {
+                    const Range16 rg = range16<Tin>(1, sf.ff);
+                    const uint4 w = flush_sat16_vec<Tin>(raw, sf.ff, rg);
+                    VecIO<Tin>::unpack(w, v);
+                    m_thr = widen16<Tin>(raw16_absmax(w));
+                } else {
+                    m_thr = m_in;
+                }
             } else if (SAME16 && sf.ff.exact) {
-                // the values already sit on Tout's grid and the format keeps their significand: only flush and
-                // saturate act, and the saturation value is the one constant that needs Tout's rounding
+                // (unsigned variants of such formats: element by element)
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[j] = float_elem_flush_nearest<true>(v[j], sf.ff, fmax_rq);
                 m_thr = f2u(float_elem_flush_nearest<true>(u2f(m_in), sf.ff, fmax_rq));

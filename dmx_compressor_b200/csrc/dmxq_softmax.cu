@@ -28,29 +28,30 @@ template <typename T, int V> __device__ __forceinline__ uint4 add_vec(const uint
                                                                        const Range16 &qb, const Range16 &qo)
 {
     float va[V], vb[V];
-    VecIO<T>::unpack(ra, va);
-    VecIO<T>::unpack(rb, vb);
     if constexpr (sizeof(T) == 2) {
-        if (p.has_a && !inside16(ra, qa)) {
-            float_fast_vec<V>(va, p.fa);
-#pragma unroll
-            for (int j = 0; j < V; ++j) va[j] = requant1<T>(va[j]);
+        // stages that keep T's significand (FLOAT16 on bf16 / fp16 tensors) stay on the packed words; others widen
+        uint4 wa = ra, wb = rb;
+        if (p.has_a && !inside16(wa, qa)) {
+            if (qa.on) wa = flush_sat16_vec<T>(wa, p.fa, qa);
+            else { VecIO<T>::unpack(wa, va); float_fast_vec<V>(va, p.fa); wa = pack16<T>(va); }
         }
-        if (p.has_b && !inside16(rb, qb)) {
-            float_fast_vec<V>(vb, p.fb);
-#pragma unroll
-            for (int j = 0; j < V; ++j) vb[j] = requant1<T>(vb[j]);
+        if (p.has_b && !inside16(wb, qb)) {
+            if (qb.on) wb = flush_sat16_vec<T>(wb, p.fb, qb);
+            else { VecIO<T>::unpack(wb, vb); float_fast_vec<V>(vb, p.fb); wb = pack16<T>(vb); }
         }
+        VecIO<T>::unpack(wa, va);
+        VecIO<T>::unpack(wb, vb);
 #pragma unroll
         for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);  // torch adds in fp32, rounds to T
         uint4 w = pack16<T>(va);
         if (p.has_o && !inside16(w, qo)) {
-            VecIO<T>::unpack(w, va);
-            float_fast_vec<V>(va, p.fo);
-            w = pack16<T>(va);
+            if (qo.on) w = flush_sat16_vec<T>(w, p.fo, qo);
+            else { VecIO<T>::unpack(w, va); float_fast_vec<V>(va, p.fo); w = pack16<T>(va); }
         }
         return w;
     } else {
+        VecIO<T>::unpack(ra, va);
+        VecIO<T>::unpack(rb, vb);
         if (p.has_a) float_fast_vec<V>(va, p.fa);
         if (p.has_b) float_fast_vec<V>(vb, p.fb);
 #pragma unroll

@@ -686,16 +686,47 @@ template <typename T> __device__ __forceinline__ uint4 pack16(const float (&v)[8
 struct Range16 {
     uint32_t lo, hi;
     bool on;  // the stage exists, keeps T's significand, and is the signed nearest+flush kind
+    uint32_t sat;  // the format's saturation value rounded to T (fp16: FLOAT16's 131008 becomes Inf, as CastTo's `.to(dtype)` makes it)
 };
 template <typename T> __device__ __forceinline__ Range16 range16(int has, const FloatFmt &f)
 {
     Range16 r;
     r.on = has && f.exact && !f.is_unsigned;
     r.lo = pattern16_ru<T>(u2f(f.shift_exp));
-    r.hi = min(pattern16_rn<T>(u2f(f.max_num)), (uint32_t)(std::is_same<T, __half>::value ? 0x7BFFu : 0x7F7Fu));
+    r.sat = pattern16_rn<T>(u2f(f.max_num));
+    r.hi = min(r.sat, (uint32_t)(std::is_same<T, __half>::value ? 0x7BFFu : 0x7F7Fu));
     return r;
 }
 __device__ __forceinline__ bool inside16(const uint4 &w, const Range16 &r) { return r.on && raw16_absmin(w) >= r.lo && raw16_absmax(w) <= r.hi; }
+
+// The same stage (r.on: nearest + flush + signed, T's significand kept, so only flush and saturate act) applied to a vector of
+// packed 16-bit values, two elements per instruction: magnitude patterns below r.lo become +0, above r.sat become r.sat with the
+// sign kept -- what float_elem_flush_nearest<true> followed by the rounding to T yields, element for element.  The flush mask
+// comes from bit 15 of (magnitude + 0x8000 - lo), replicated over its half by a sign-extending byte permute.  A NaN anywhere in
+// the vector (the one input class whose reference result depends on the payload) takes the per-element literal path.
+template <typename T> __device__ __forceinline__ uint4 flush_sat16_vec(const uint4 &w, const FloatFmt &f, const Range16 &r)
+{
+    constexpr uint32_t kInf16 = std::is_same<T, __nv_bfloat16>::value ? 0x7F80u : 0x7C00u;
+    const uint32_t x[4] = {w.x, w.y, w.z, w.w};
+    uint32_t mag[4], mx = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { mag[i] = x[i] & 0x7FFF7FFFu; mx = __vmaxu2(mx, mag[i]); }
+    if (max(mx & 0xFFFFu, mx >> 16) > kInf16) {
+        float v[8];
+        VecIO<T>::unpack(w, v);
+        float_fast_vec<8>(v, f);
+        return pack16<T>(v);
+    }
+    const uint32_t hi2 = r.sat * 0x10001u, k2 = (0x8000u - r.lo) * 0x10001u;
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t keep;  // 0xFFFF per half whose magnitude is >= lo (prmt with selector msb set replicates the sign bit of the byte)
+        asm("prmt.b32 %0, %1, %2, 0xBB99;" : "=r"(keep) : "r"(mag[i] + k2), "r"(0u));
+        o[i] = ((x[i] & 0x80008000u) | __vminu2(mag[i], hi2)) & keep;
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
 
 
 // ------------------------------------------------------------------------------------------------
