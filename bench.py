@@ -725,6 +725,17 @@ def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
                 with elide.enabled():
                     y1 = elide.materialise(q(ids))
                     t_el = timeit(lambda: elide.materialise(q(ids)))
+                # the same forward captured once in a CUDA graph (static shapes): what is left when the reference's python around
+                # the ~330 launches is taken out of the timed path
+                try:
+                    from dmx_compressor_b200 import graph
+
+                    fwd = graph.capture(q, ids, elide_casts=True)
+                    row["graph_equals_eager_bitwise"] = bool(torch.equal(fwd(ids), y1))
+                    row["ms_plugin_elided_cuda_graph"] = round(timeit(lambda: fwd(ids)), 2)
+                    del fwd
+                except Exception as e:  # pragma: no cover
+                    row["ms_plugin_elided_cuda_graph"] = "unavailable: " + repr(e)[:120]
             finally:
                 plugin.uninstall()
         row.update({"ms": [round(t_plain, 2), round(t_drop, 2), round(t_el, 2)], "tok/s_plugin_dropin": round(B * S / t_drop * 1e3),
@@ -732,6 +743,8 @@ def plugin_opt125m(dev, with_unpatched=False, dtypes=None):
                     "cast_overhead_elided": round((t_el - t_plain) / t_plain, 3), "elided_equals_dropin_bitwise": bool(torch.equal(y0, y1)),
                     "ms_unquantised_with_dmxq_softmax": round(t_plain_fs, 2),
                     "cast_overhead_elided_vs_dmxq_softmax_twin": round((t_el - t_plain_fs) / t_plain_fs, 3)})
+        if isinstance(row.get("ms_plugin_elided_cuda_graph"), float):
+            row["cast_overhead_elided_cuda_graph_vs_dmxq_softmax_twin"] = round((row["ms_plugin_elided_cuda_graph"] - t_plain_fs) / t_plain_fs, 3)
         if with_unpatched:
             row["dropin_equals_reference_bitwise"] = bool(torch.equal(y_ref, y0))
         res[str(dt).split(".")[-1]] = row
