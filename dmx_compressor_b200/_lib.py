@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdmxq.so")
 MAX_DIMS = 8
 MAX_STAGES = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # enums of include/dmxq.h
 F32, BF16, F16 = 0, 1, 2
@@ -58,6 +58,8 @@ def _load():
         "dmxq_launch_count": ([], I64),
         "dmxq_cast_chain": ([TP, TP, I, SP, I, TP, TP, VP, VP], I),
         "dmxq_cast_chain_multi": ([TP, TP, I, I, SP, I, VP, VP], I),
+        "dmxq_cast_chain_philox": ([TP, TP, I, SP, I, C.c_uint64, C.c_uint64, VP], I),
+        "dmxq_philox_fill": ([VP, I64, I, C.c_uint64, C.c_uint64, VP], I),
         "dmxq_bfp_qdq": ([TP, TP, I, I, I, I, I, VP, VP], I),
         "dmxq_sbfp_qdq": ([TP, TP] + [I] * 14 + [VP], I),
         "dmxq_float_qdq": ([TP, TP] + [I] * 7 + [VP, VP], I),

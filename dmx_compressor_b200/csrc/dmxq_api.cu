@@ -317,6 +317,13 @@ struct RowsPlan {
     RowsParams p;
 };
 
+// In-kernel random words (dmxq_cast_chain_philox): the call travels through chain_impl with this tag in place of a random
+// tensor, so every layout decision is the one an external tensor in logical element order would get; the rows kernels then
+// compute the words instead of loading them.  Layouts that need the cols / generic kernels return DMXQ_ERR_UNSUPPORTED (the
+// binding fills a tensor with dmxq_philox_fill -- the same stream -- and passes it explicitly).
+alignas(16) static const char kPhiloxTag[16] = {0};
+static thread_local unsigned long long g_ph_seed = 0, g_ph_stream = 0;
+
 int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const dmxq_stage *stages, int n_stages,
                const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, cudaStream_t st,
                const float *qscale = nullptr, const float *qzp = nullptr, const float *amax = nullptr, RowsPlan *plan = nullptr)
@@ -406,6 +413,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         RowsParams p;
         memset(&p, 0, sizeof(p));
         p.x = x->data; p.y = y->data; p.score = score_p; p.mask = mask_p; p.rnd = rand;
+        if (rand == kPhiloxTag) { p.rnd = nullptr; p.philox = 1; p.ph_seed = g_ph_seed; p.ph_stream = g_ph_stream; }
         p.K = c.k.n;
         p.kvec = (uint32_t)(p.K / V);
         int64_t tiles_per_row = (p.K + tile - 1) / tile;
@@ -478,6 +486,9 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     }
 
     if (qscale) return kNeedFallback;
+    if (rand == kPhiloxTag)
+        return fail(DMXQ_ERR_UNSUPPORTED, "in-kernel random words need the rows layout (blocked dim contiguous, 16-byte aligned, whole vectors); "
+                                          "pass a tensor filled by dmxq_philox_fill instead");
     if (amax)
         for (int s = 0; s < chain.n; ++s)
             if (chain.st[s].kind == ST_SBFP)
@@ -583,6 +594,24 @@ int dmxq_cast_chain(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, c
                     const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand, void *stream)
 {
     return chain_impl(x, y, block_dim, stages, n_stages, score, mask, rand, static_cast<cudaStream_t>(stream));
+}
+
+int dmxq_cast_chain_philox(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const dmxq_stage *stages, int n_stages,
+                           uint64_t seed, uint64_t stream_id, void *stream)
+{
+    g_ph_seed = seed;
+    g_ph_stream = stream_id;
+    return chain_impl(x, y, block_dim, stages, n_stages, nullptr, nullptr, kPhiloxTag, static_cast<cudaStream_t>(stream));
+}
+
+int dmxq_philox_fill(void *out, int64_t n, int as_float, uint64_t seed, uint64_t stream_id, void *stream)
+{
+    if (n < 0 || (n > 0 && !out)) return fail(DMXQ_ERR_BAD_ARG, "null argument");
+    if (n == 0) return DMXQ_OK;
+    if (!aligned(out, 16)) return fail(DMXQ_ERR_UNSUPPORTED, "philox_fill: 16-byte aligned output");
+    cudaError_t e = launch_philox_fill(out, n, as_float, seed, stream_id, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "philox_fill_kernel");
+    return DMXQ_OK;
 }
 
 int dmxq_cast_chain_multi(const dmxq_tensor *xs, const dmxq_tensor *ys, int n_tensors, int block_dim, const dmxq_stage *stages,

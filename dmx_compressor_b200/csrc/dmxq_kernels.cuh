@@ -74,6 +74,8 @@ struct RowsParams {
     const float *score;  // nullable, NM stage
     float *mask;         // nullable, NM stage
     const void *rnd;     // nullable, stochastic stage (int32 or fp32)
+    int philox;          // 1: no random tensor; word i = philox_word(logical element index i, ph_stream, ph_seed)
+    unsigned long long ph_seed, ph_stream;
     const float *qscale, *qzp;  // nullable: per-tensor FixedPoint affine parameters in device memory (K_FIXED)
     int64_t n_vec;       // total (padded) vectors = rows * vpr
     int64_t rows;
@@ -205,6 +207,7 @@ cudaError_t launch_histc(int dt, const void *x, int64_t n, float lo, float hi, i
                          float *out_max, cudaStream_t s);
 cudaError_t launch_add(int dt, const AddParams &p, cudaStream_t s);
 cudaError_t launch_softmax(int dt, const SoftmaxParams &p, cudaStream_t s);
+cudaError_t launch_philox_fill(void *out, int64_t n, int as_float, unsigned long long seed, unsigned long long stream_id, cudaStream_t s);
 cudaError_t launch_bfp_pack(int dt, const void *x, void *mant, uint8_t *exps, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_bfp_unpack(int dt, const void *mant, const uint8_t *exps, void *y, int64_t n, int B, int wl, cudaStream_t s);
 cudaError_t launch_sbfp_pack(int dt, const void *x, void *mant, uint8_t *scalers, unsigned int *n_inexact, int64_t n, int B, const SbfpFmt &f, int sc_man,

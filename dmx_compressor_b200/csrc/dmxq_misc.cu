@@ -1433,4 +1433,31 @@ cudaError_t launch_amax_multi(int dt, const MultiTable &t, float *out, cudaStrea
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// dmxq_philox_fill: the stream the kernels compute in registers, materialised (testing / layouts the rows kernels do not take)
+__global__ void __launch_bounds__(256) philox_fill_kernel(uint32_t *__restrict__ out, int64_t n, int as_float, unsigned long long seed,
+                                                          unsigned long long stream_id)
+{
+    const int64_t nq = (n + 3) >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        uint4 w = philox4x32_10((uint64_t)q, stream_id, seed);
+        if (as_float) { w.x = philox_unit_bits(w.x); w.y = philox_unit_bits(w.y); w.z = philox_unit_bits(w.z); w.w = philox_unit_bits(w.w); }
+        if (4 * q + 3 < n) {
+            *reinterpret_cast<uint4 *>(out + 4 * q) = w;
+        } else {
+            const uint32_t v[4] = {w.x, w.y, w.z, w.w};
+            for (int k = 0; 4 * q + k < n; ++k) out[4 * q + k] = v[k];
+        }
+    }
+}
+
+cudaError_t launch_philox_fill(void *out, int64_t n, int as_float, unsigned long long seed, unsigned long long stream_id, cudaStream_t s)
+{
+    const int64_t nq = (n + 3) >> 2;
+    const unsigned grid = (unsigned)std::min<int64_t>((nq + 255) / 256, 148 * 16);
+    philox_fill_kernel<<<grid, 256, 0, s>>>(static_cast<uint32_t *>(out), n, as_float, seed, stream_id);
+    count_launch();
+    return cudaGetLastError();
+}
+
 }  // namespace dmxq

@@ -57,6 +57,38 @@ __device__ __forceinline__ uint32_t round_bits_rt(uint32_t t, int sh, uint32_t m
 }
 
 // ---------------------------------------------------------------------------------------------
+// Counter-based random words for stochastic rounding without a random TENSOR.  The reference
+// draws `randint_like(a, INT_MAX)` / `rand_like(a)` into a full-size tensor per cast (Q/quant_cuda/quant.cu:40,118,160,244): 4 bytes
+// written and 4 read per element next to the 8 the cast itself moves.  Philox4x32-10 (Salmon et al., "Parallel random numbers: as
+// easy as 1, 2, 3", SC'11; the generator behind curand's and torch's CUDA streams) makes word i of a stream a pure function:
+//     word(i) = Philox4x32_10(counter = (i / 4 as 64 bits, stream id as 64 bits), key = seed)[i % 4],   i = logical element index
+// so the kernel computes the four words of four consecutive elements in registers.  dmxq_philox_fill materialises the very same
+// stream, which is how the fused path is pinned: cast(philox) == cast(external tensor = philox_fill) bit for bit, and the
+// external-tensor path is the one checked against the oracle and the reference's kernels.  (Not torch's randint_like stream: that one
+// depends on the launch geometry of ATen's distribution kernel; the explicit tensor input remains for seed-for-seed reproduction.)
+__device__ __forceinline__ uint4 philox4x32_10(uint64_t ctr, uint64_t stream, uint64_t seed)
+{
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ uint32_t philox_word(uint64_t idx, uint64_t stream, uint64_t seed)
+{
+    const uint4 q = philox4x32_10(idx >> 2, stream, seed);
+    const uint32_t k = (uint32_t)idx & 3u;
+    return k == 0 ? q.x : k == 1 ? q.y : k == 2 ? q.z : q.w;
+}
+// the word as the bit pattern of a uniform fp32 in [0, 1) with 24 random bits (what FixedPoint's stochastic mode consumes)
+__device__ __forceinline__ uint32_t philox_unit_bits(uint32_t w) { return f2u(__fmul_rn(__uint2float_rz(w >> 8), 0x1p-24f)); }
+
+// ---------------------------------------------------------------------------------------------
 // Block floating point.  Per block (uniform): E = exponent field of max|x| (in place, bits
 // 23..30), base = 6 * 2^e, maxnum = E | top (wl-2) mantissa bits.
 // Reference: block_kernel_*, Q/quant_cuda/block_kernel.cu:43-74 + clip_max_exponent,

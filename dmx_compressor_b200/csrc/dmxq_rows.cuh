@@ -292,9 +292,14 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
         }
         raw[u] = valid[u] ? ldg_stream(x + xoff) : make_uint4(0u, 0u, 0u, 0u);
         if (KIND == K_BFP_STOCH) {  // (FLAT only) one int32 random word per element, same offsets as the data
+            if (p.philox) {  // ... or computed: four consecutive elements share one Philox call (xoff is a multiple of V)
 #pragma unroll
-            for (int j = 0; j < V / 4; ++j)
-                rraw[u][j] = valid[u] ? ldg_stream(static_cast<const uint32_t *>(p.rnd) + xoff + 4 * j) : make_uint4(0u, 0u, 0u, 0u);
+                for (int j = 0; j < V / 4; ++j) rraw[u][j] = philox4x32_10((uint64_t)(xoff >> 2) + j, p.ph_stream, p.ph_seed);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V / 4; ++j)
+                    rraw[u][j] = valid[u] ? ldg_stream(static_cast<const uint32_t *>(p.rnd) + xoff + 4 * j) : make_uint4(0u, 0u, 0u, 0u);
+            }
         }
     }
 
@@ -546,7 +551,26 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
                 uint32_t r[V];
 #pragma unroll
                 for (int j = 0; j < V; ++j) r[j] = 0x3F000000u;  // 0.5f: deterministic FIXED
-                if (KIND == K_AUX && p.rnd != nullptr && valid[u]) {
+                if (KIND == K_AUX && p.philox && valid[u]) {
+                    const int mode = st.kind == ST_FLOAT ? st.ff.mode : st.kind == ST_FIXED ? st.xf.mode : st.kind == ST_BFP ? st.mode : 0;
+                    if (mode == R_STOCHASTIC) {  // the words the external tensor would hold at the same logical indices
+                        const uint64_t i0 = (uint64_t)aux_r[u];
+                        if ((FLAT || p.rks == 1) && (i0 & 3u) == 0u) {
+#pragma unroll
+                            for (int j = 0; j < V; j += 4) {
+                                const uint4 q = philox4x32_10((i0 >> 2) + (j >> 2), p.ph_stream, p.ph_seed);
+                                r[j] = q.x; r[j + 1] = q.y; r[j + 2] = q.z; r[j + 3] = q.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < V; ++j) r[j] = philox_word(i0 + (uint64_t)(FLAT ? (int64_t)j : j * p.rks), p.ph_stream, p.ph_seed);
+                        }
+                        if (st.kind == ST_FIXED) {
+#pragma unroll
+                            for (int j = 0; j < V; ++j) r[j] = philox_unit_bits(r[j]);
+                        }
+                    }
+                } else if (KIND == K_AUX && p.rnd != nullptr && valid[u]) {
                     const int mode = st.kind == ST_FLOAT ? st.ff.mode : st.kind == ST_FIXED ? st.xf.mode : st.kind == ST_BFP ? st.mode : 0;
                     if (mode == R_STOCHASTIC) {
                         const uint32_t *rp = static_cast<const uint32_t *>(p.rnd) + aux_r[u];

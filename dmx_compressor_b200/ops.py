@@ -92,10 +92,24 @@ def nm_stage(n_keep: int, m: int, nm_order: int = L.NM_STABLE) -> L.Stage:
     return make_stage(kind=L.ST_NM, block=m, n_keep=n_keep, nm_order=nm_order)
 
 
+def philox_fill(shape, seed: int, stream_id: int = 0, as_float: bool = False, device="cuda") -> torch.Tensor:
+    """the random stream the kernels compute in registers under ``philox=(seed, stream_id)``, as a tensor (dmxq_philox_fill):
+    int32 words, or -- ``as_float``, what FixedPoint's stochastic rounding consumes -- uniform fp32 values in [0, 1)"""
+    out = torch.empty(shape, dtype=torch.float32 if as_float else torch.int32, device=device)
+    with _guard(out.device):
+        rc = L.lib.dmxq_philox_fill(out.data_ptr(), out.numel(), int(as_float), seed & 0xFFFFFFFFFFFFFFFF, stream_id & 0xFFFFFFFFFFFFFFFF, L.stream_ptr(out.device))
+    L.check(rc, "dmxq_philox_fill")
+    return out
+
+
 def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, out: Optional[torch.Tensor] = None,
                out_dtype: Optional[torch.dtype] = None, score: Optional[torch.Tensor] = None,
-               mask: Optional[torch.Tensor] = None, rand: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """y = stages[-1](... stages[0](x)) in one pass over HBM (dmxq_cast_chain)."""
+               mask: Optional[torch.Tensor] = None, rand: Optional[torch.Tensor] = None, philox=None) -> torch.Tensor:
+    """y = stages[-1](... stages[0](x)) in one pass over HBM (dmxq_cast_chain).
+
+    Stochastic stages take their random words from ``rand`` (a tensor, as the reference draws one) or -- ``philox=(seed,
+    stream_id)`` -- compute them in the kernel (Philox4x32-10 over the logical element index, dmxq_cast_chain_philox): no
+    random tensor is written or read.  Both give the same result for ``rand = philox_fill(x.shape, seed, stream_id)``."""
     L.require_cuda(x)
     n = len(stages)
     if not 1 <= n <= L.MAX_STAGES:
@@ -103,6 +117,20 @@ def cast_chain(x: torch.Tensor, stages: Sequence[L.Stage], block_dim: int = -1, 
     y = out if out is not None else _out_like(x, out_dtype)
     arr = C.byref(stages[0]) if n == 1 else (L.Stage * n)(*stages)  # one stage: its own struct is the array
     vx, vy = L.view(x), L.view(y)
+    if philox is not None and rand is None and score is None and mask is None:
+        seed, sid = philox
+        with _guard(x.device):
+            rc = L.lib.dmxq_cast_chain_philox(C.byref(vx), C.byref(vy), block_dim, arr, n, seed & 0xFFFFFFFFFFFFFFFF, sid & 0xFFFFFFFFFFFFFFFF, L.stream_ptr(x.device))
+        if rc == -2:  # a layout the rows kernels do not take: the same stream as an explicit tensor
+            fixed = any(s.kind == L.ST_FIXED and s.rounding == L.ROUND["stochastic"] for s in stages)
+            rand = philox_fill(x.shape, seed, sid, as_float=fixed, device=x.device)
+        else:
+            L.check(rc, "dmxq_cast_chain_philox")
+            return y
+    elif philox is not None and rand is None:
+        seed, sid = philox
+        fixed = any(s.kind == L.ST_FIXED and s.rounding == L.ROUND["stochastic"] for s in stages)
+        rand = philox_fill(x.shape, seed, sid, as_float=fixed, device=x.device)
     vs = vm = None
     if score is not None:
         L.require_cuda(score, "score")
@@ -177,10 +205,32 @@ def cast_chain_multi(xs: Sequence[torch.Tensor], stages: Sequence[L.Stage], bloc
     return ys
 
 
+# Where stochastic rounding takes its random words from when the caller passes no tensor:
+#   "torch"  (default) draw a full-size tensor with torch's generator exactly as the reference's CUDA launchers do
+#            (randint_like / rand_like): the same torch seed reproduces the reference's stream;
+#   "philox" compute them in the cast kernel (dmxq_cast_chain_philox): no random tensor exists; seed = torch's initial seed
+#            unless given, one stream id per call (a counter), so results are reproducible per (seed, call order).
+_STOCH = {"source": "torch", "seed": None, "calls": 0}
+
+
+def stochastic_source(source: str = "torch", seed: Optional[int] = None) -> None:
+    if source not in ("torch", "philox"):
+        raise ValueError("source must be 'torch' or 'philox'")
+    _STOCH.update(source=source, seed=seed, calls=0)
+
+
+def _next_philox():
+    seed = _STOCH["seed"] if _STOCH["seed"] is not None else torch.initial_seed()
+    _STOCH["calls"] += 1
+    return seed, _STOCH["calls"]
+
+
 def bfp_qdq(x, block_dim=-1, block_size=64, precision=8, symmetric=True, rounding="nearest", rand=None, out=None,
             out_dtype=None):
     """BlockFloatingPoint.cast (reference S/numerical/format.py:304-372) via dmxq_bfp_qdq."""
     L.require_cuda(x)
+    if rounding == "stochastic" and rand is None and _STOCH["source"] == "philox":
+        return cast_chain(x, [bfp_stage(block_size, precision, symmetric, rounding)], block_dim, out=out, out_dtype=out_dtype, philox=_next_philox())
     if rounding == "stochastic" and rand is None:
         rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:40
     y = out if out is not None else _out_like(x, out_dtype)
@@ -212,6 +262,9 @@ def float_qdq(x, mantissa, exponent, bias, flush_subnormal=True, unsigned=False,
               rand=None, out=None, out_dtype=None):
     """FloatingPoint.cast (reference S/numerical/format.py:208-233) via dmxq_float_qdq."""
     L.require_cuda(x)
+    if rounding == "stochastic" and rand is None and _STOCH["source"] == "philox":
+        return cast_chain(x, [float_stage(mantissa, exponent, bias, flush_subnormal, unsigned, fp16_flush, rounding)], -1, out=out,
+                          out_dtype=out_dtype, philox=_next_philox())
     if rounding == "stochastic" and rand is None:
         rand = torch.randint_like(x, 2**31 - 1, dtype=torch.int32)  # Q/quant_cuda/quant.cu:160
     y = out if out is not None else _out_like(x, out_dtype)

@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define DMXQ_ABI_VERSION 2
+#define DMXQ_ABI_VERSION 3
 #define DMXQ_MAX_DIMS 8
 #define DMXQ_MAX_STAGES 4
 
@@ -165,6 +165,18 @@ int dmxq_cast_chain(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim,
                     const dmxq_stage *stages, int n_stages,
                     const dmxq_tensor *score, const dmxq_tensor *mask, const void *rand,
                     void *stream);
+
+/* ---- stochastic rounding without a random tensor.  The reference's launchers draw a full-size
+ * random tensor per cast (randint_like / rand_like, Q/quant_cuda/quant.cu:40,118,160,244): 4 bytes written + 4 read per element
+ * next to the 8 the cast moves.  dmxq_cast_chain_philox computes the words in registers instead:
+ *     word(i) = Philox4x32-10(counter = (i / 4, stream_id), key = seed)[i % 4],   i = logical element index of x
+ * (FixedPoint stages consume (word >> 8) * 2^-24, a uniform fp32 in [0, 1)).  dmxq_philox_fill writes exactly that stream into a
+ * tensor (as_float: the FixedPoint form), so cast_chain_philox(x, seed, stream_id) == cast_chain(x, rand = philox_fill(...)) bit
+ * for bit -- the property the tests pin, next to a numpy restatement of the generator.  Rows layouts only (blocked dim
+ * contiguous); DMXQ_ERR_UNSUPPORTED otherwise.  `rand` of dmxq_cast_chain stays the way to reproduce the reference seed for seed. */
+int dmxq_cast_chain_philox(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const dmxq_stage *stages, int n_stages,
+                           uint64_t seed, uint64_t stream_id, void *stream);
+int dmxq_philox_fill(void *out, int64_t n, int as_float, uint64_t seed, uint64_t stream_id, void *stream);
 
 /* ---- many tensors, one launch: the shards a rank owns in a sharded whole-model weight cast (SURVEY.md section 8e;
  * replaces the per-module python loop of DmxModel.fold_weights_and_biases, S/modeling/model.py:145-150, over

@@ -379,3 +379,30 @@ def cast(x, shorthand, block_dim=-1, tie=TIE_EVEN, rand=None, **affine):
     if m:  # MXINT(BlockFloatingPoint), S/numerical/format.py:605-627
         return bfp_cast(x, block_dim, int(m[2]), int(m[1]), True, "nearest")
     raise ValueError(f"unrecognized format shorthand: {sh}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Philox4x32-10 (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy as 1, 2, 3", SC'11), restated in numpy to pin the
+# stream dmxq_philox_fill / dmxq_cast_chain_philox produce: word i = Philox(counter = (i // 4, stream_id), key = seed)[i % 4].
+def philox_words(n, seed, stream_id=0):
+    import numpy as np
+
+    q = np.arange((n + 3) // 4, dtype=np.uint64)
+    c0 = (q & np.uint64(0xFFFFFFFF)).astype(np.uint64)
+    c1 = (q >> np.uint64(32)).astype(np.uint64)
+    c2 = np.full_like(c0, stream_id & 0xFFFFFFFF)
+    c3 = np.full_like(c0, (stream_id >> 32) & 0xFFFFFFFF)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2  # 32 x 32 -> 64 bit products (no overflow in uint64)
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & MASK, p1 >> np.uint64(32), p1 & MASK
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + 0x9E3779B9) & 0xFFFFFFFF, (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return np.stack([c0, c1, c2, c3], axis=1).reshape(-1)[:n].astype(np.uint32)
+
+
+def philox_unit_floats(n, seed, stream_id=0):
+    import numpy as np
+
+    return ((philox_words(n, seed, stream_id) >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)

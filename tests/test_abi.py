@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     lib = C.CDLL(os.path.join(ROOT, "dmx_compressor_b200", "lib", "libdmxq.so"))
     for name in sorted(declared):
         assert hasattr(lib, name), f"libdmxq.so does not export {name}"
-    assert lib.dmxq_abi_version() == 2
+    assert lib.dmxq_abi_version() == 3
     from dmx_compressor_b200 import _lib
 
     assert set(_lib.EXPORTS) == declared, "python binding and header disagree"
@@ -199,7 +199,7 @@ def test_binding_signatures_match_header_prototypes():
             return {"dmxq_tensor": C.POINTER(L.Tensor), "dmxq_stage": C.POINTER(L.Stage),
                     "char": C.c_char_p}.get(base, C.c_void_p)
         base = decl.rsplit(" ", 1)[0] if " " in decl else decl
-        return {"int": C.c_int, "int32_t": C.c_int, "int64_t": C.c_int64, "float": C.c_float,
+        return {"int": C.c_int, "int32_t": C.c_int, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "float": C.c_float,
                 "size_t": C.c_size_t}[base]
 
     protos = re.findall(r"([A-Za-z_][\w\s\*]*?)\b(dmxq_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)

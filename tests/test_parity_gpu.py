@@ -1178,6 +1178,77 @@ def test_packed16_low_bit_float(dt, sh):
         assert not ((yf.view(np.uint32) != bits(w)) & ~np.isnan(w)).any(), f"{sh} fp32"
 
 
+# ---- stochastic rounding with in-kernel random words (dmxq_cast_chain_philox) -----------------------------------------
+def test_philox_fill_equals_numpy_restatement():
+    for n, seed, sid in ((1, 0, 0), (4, 0, 0), (1003, 0x123456789ABCDEF, 5), (1 << 20, 2**63 + 11, 2**40 + 3)):
+        got = ops.philox_fill((n,), seed, sid).cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, O.philox_words(n, seed, sid)), (n, seed, sid)
+        gf = ops.philox_fill((n,), seed, sid, as_float=True).cpu().numpy()
+        assert np.array_equal(gf.view(np.uint32), O.philox_unit_floats(n, seed, sid).view(np.uint32))
+
+
+@pytest.mark.parametrize("dt", ["float32", "bfloat16"])
+@pytest.mark.parametrize("fmt", ["BFP[8|8]{64}(SS)", "BFP[4|8]{16}(SS)", "FP[1|4|3,7](_S)", "FP[1|5|10,15](FS)", "XP[8,0](CSS)", "XP[8,+4](CSS)"])
+def test_philox_in_kernel_equals_external_tensor(dt, fmt):
+    """cast(philox = (seed, stream)) == cast(rand = philox_fill(shape, seed, stream)) bit for bit, for every layout: flat rows (words
+    computed in registers, four elements per Philox call), strided rows, misaligned / column layouts (filled tensor behind the scenes).
+    The external-tensor path is the one pinned to the oracle and to the reference's kernels (test_oracle_stochastic_same_random_tensor)."""
+    tdt = getattr(torch, dt)
+    seed, sid = 0xC0FFEE12345, 17
+    st = [fmt_from(fmt).stage()]
+    fixed = fmt.startswith("XP")
+    g = torch.Generator().manual_seed(3)
+    base = (torch.randn(48, 6, 512, generator=g) * torch.pow(2.0, torch.randint(-6, 7, (48, 6, 1), generator=g).float())).to(tdt).to(DEV)
+    views = [("flat", base, -1), ("3-d rows, 2-d view", base[:, 0], -1), ("strided rows", base[:, :, 128:384], -1), ("blocks along dim 1", base, 1),
+             ("odd length", base.reshape(-1)[:4093], -1), ("misaligned", base.reshape(-1)[3:4099], -1)]
+    n0 = _lib_launches()
+    for name, x, bd in views:
+        r = ops.philox_fill(x.shape, seed, sid, as_float=fixed)
+        want = ops.cast_chain(x, st, bd, rand=r)
+        got = ops.cast_chain(x, st, bd, philox=(seed, sid))
+        assert torch.equal(got.view(torch.int32 if dt == "float32" else torch.int16), want.view(torch.int32 if dt == "float32" else torch.int16)), (fmt, dt, name)
+    # and it is random: another stream id moves results, the same one reproduces them
+    a = ops.cast_chain(base, st, -1, philox=(seed, sid))
+    b = ops.cast_chain(base, st, -1, philox=(seed, sid + 1))
+    c = ops.cast_chain(base, st, -1, philox=(seed, sid))
+    assert torch.equal(a, c)
+    if not (dt == "bfloat16" and fmt.startswith("FP[1|5|10")):  # (FLOAT16 keeps every bf16 value: nothing to round)
+        assert not torch.equal(a, b)
+
+
+def test_stochastic_source_switch():
+    """ops.stochastic_source("philox"): Format.cast with stochastic rounding draws no tensor; reproducible per (seed, call order)"""
+    x = torch.randn(64, 256, device=DEV)
+    f = fmt_from("BFP[8|8]{64}(SS)")
+    try:
+        ops.stochastic_source("philox", seed=42)
+        a1, a2 = f.cast(x, -1), f.cast(x, -1)
+        ops.stochastic_source("philox", seed=42)
+        b1, b2 = f.cast(x, -1), f.cast(x, -1)
+        assert torch.equal(a1, b1) and torch.equal(a2, b2) and not torch.equal(a1, a2)
+        want = ops.cast_chain(x, [f.stage()], -1, rand=ops.philox_fill(x.shape, 42, 1), out_dtype=torch.float32)
+        assert torch.equal(a1, want)
+    finally:
+        ops.stochastic_source("torch")
+
+
+def _lib_launches():
+    return L.lib.dmxq_launch_count()
+
+
+def test_philox_flat_path_launches_one_kernel_and_is_unbiased():
+    """the flat rows path computes the words in the cast kernel (ONE launch, no fill); stochastic rounding stays unbiased"""
+    x = torch.full((1 << 14, 64), 0.3, device=DEV)
+    x[:, 0] = 1.0  # block max 1.0: BFP[4|8] grid step 0.25 -> 0.3 rounds to 0.25 (p = 0.8) or 0.5 (p = 0.2)
+    st = [fmt_from("BFP[4|8]{64}(SS)").stage()]
+    n0 = _lib_launches()
+    y = ops.cast_chain(x, st, -1, philox=(99, 0))
+    assert _lib_launches() - n0 == 1
+    v = y[:, 1:].reshape(-1)
+    assert set(np.unique(v.cpu().numpy()).tolist()) == {0.25, 0.5}
+    assert abs(float(v.mean()) - 0.3) < 2e-3
+
+
 # ---- (f3) calibration histogram: dmxq_histc / HistogramObserver ---------------------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("bins,lo,hi", [(2048, -3, 4), (1000, -7, 10), (7, -1, 1), (2048, 0, 0), (12288, -40, 41), (1, -2, 2)])
