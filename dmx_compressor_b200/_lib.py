@@ -26,7 +26,7 @@ ROUND = {"nearest": 0, "stochastic": 1, "up": 2, "down": 3}
 TIE_AWAY, TIE_EVEN = 0, 1
 SCALE_DIV, SCALE_RECIP = 0, 1  # SBFP block scale: max / man_scaling (reference on CPU tensors) | max * fp32(1 / man_scaling) (on CUDA tensors)
 NM_STABLE, NM_TORCH_CUDA = 0, 1  # N:M tie order: stable argsort (reference on CPU tensors) | torch's CUDA bitonic order
-ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED, ST_MXFP = 0, 1, 2, 3, 4, 5, 6
+ST_NONE, ST_NM, ST_BFP, ST_SBFP, ST_FLOAT, ST_FIXED, ST_MXFP, ST_SCALE = 0, 1, 2, 3, 4, 5, 6, 7
 
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
 
@@ -41,7 +41,8 @@ class Stage(C.Structure):
         "kind", "block", "precision", "fraction", "man", "exp", "bias", "flush", "is_unsigned", "fp16_flush",
         "symmetric", "clamp", "rounding", "tie", "n_keep", "sc_man", "sc_exp", "sc_bias", "sc_flush", "sc_unsigned",
         "sc_fp16_flush", "sc_rounding")] + [("scale", C.c_float), ("zero_point", C.c_float),
-                                            ("scale_mode", C.c_int32), ("nm_order", C.c_int32)]
+                                            ("scale_mode", C.c_int32), ("nm_order", C.c_int32),
+                                            ("vec", C.c_void_p), ("vec_len", C.c_int32), ("vec_op", C.c_int32)]
 
 
 def _load():

@@ -171,12 +171,20 @@ int decode_stage(const dmxq_stage &s, StageDev &d)
         d.mx_largest = std::ldexp(1.0f, 1 << (s.exp - 1));  // FloatingPoint.largest_representable_power_of_two, format.py:235-237
         return DMXQ_OK;
     }
+    case DMXQ_STAGE_SCALE:
+        if (!s.vec || s.vec_len < 1) return fail(DMXQ_ERR_BAD_ARG, "scale stage needs a device vector");
+        if (s.vec_op != 0 && s.vec_op != 1) return fail(DMXQ_ERR_BAD_ARG, "scale stage: vec_op 0 (divide) or 1 (multiply)");
+        if ((reinterpret_cast<uintptr_t>(s.vec) & 15) != 0) return fail(DMXQ_ERR_UNSUPPORTED, "scale stage: 16-byte aligned vector");
+        d.vec = s.vec;
+        d.vec_op = s.vec_op;
+        d.block = s.vec_len;  // (checked against the extent of block_dim by the caller)
+        return DMXQ_OK;
     default:
         return fail(DMXQ_ERR_BAD_ARG, "unknown stage kind %d", s.kind);
     }
 }
 
-inline bool stage_blocked(const StageDev &d) { return d.kind == ST_NM || d.kind == ST_BFP || d.kind == ST_SBFP || d.kind == ST_MXFP; }
+inline bool stage_blocked(const StageDev &d) { return d.kind == ST_NM || d.kind == ST_BFP || d.kind == ST_SBFP || d.kind == ST_MXFP || d.kind == ST_SCALE; }
 inline int stage_mode(const StageDev &d) { return d.kind == ST_FLOAT ? d.ff.mode : d.kind == ST_FIXED ? d.xf.mode : d.kind == ST_BFP ? d.mode : 0; }
 
 struct Dim {
@@ -358,6 +366,11 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         kd = block_dim < 0 ? block_dim + x->ndim : block_dim;
         if (kd < 0 || kd >= x->ndim) return fail(DMXQ_ERR_BAD_ARG, "block_dim %d out of range for %d dims", block_dim, x->ndim);
         for (int s = 0; s < n_stages; ++s)
+            if (chain.st[s].kind == ST_SCALE) {
+                if (chain.st[s].block != x->shape[kd])
+                    return fail(DMXQ_ERR_BAD_ARG, "scale vector of %d entries along a dim of extent %lld", chain.st[s].block, (long long)x->shape[kd]);
+            }
+        for (int s = 0; s < n_stages; ++s)
             if (chain.st[s].kind == ST_NM && x->shape[kd] % chain.st[s].block != 0)
                 return fail(DMXQ_ERR_BAD_ARG, "score has size %lld at dimension %d, not a multiple of block size %d",
                             (long long)x->shape[kd], block_dim, chain.st[s].block);
@@ -486,6 +499,9 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
     }
 
     if (qscale) return kNeedFallback;
+    for (int s = 0; s < chain.n; ++s)
+        if (chain.st[s].kind == ST_SCALE)
+            return fail(DMXQ_ERR_UNSUPPORTED, "a scale stage needs the rows layout (channel dim contiguous, 16-byte aligned, whole vectors)");
     if (rand == kPhiloxTag)
         return fail(DMXQ_ERR_UNSUPPORTED, "in-kernel random words need the rows layout (blocked dim contiguous, 16-byte aligned, whole vectors); "
                                           "pass a tensor filled by dmxq_philox_fill instead");

@@ -37,6 +37,9 @@ struct StageDev {
     int sb_exp_bits;  // exponent bits of the scaler format (needed when the bias is derived on the device from an amax)
     // MXFP (element format in ff)
     float mx_largest;  // 2^(2^(exp_bits-1))
+    // SCALE: x / vec[k] or x * vec[k] along the blocked dim (SmoothQuant's scale application)
+    const float *vec;
+    int vec_op;
 };
 
 struct ChainDev {

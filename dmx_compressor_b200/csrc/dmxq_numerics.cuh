@@ -20,7 +20,7 @@ namespace dmxq {
 
 enum : int { R_NEAREST = 0, R_STOCHASTIC = 1, R_UP = 2, R_DOWN = 3 };
 enum : int { TIE_AWAY = 0, TIE_EVEN = 1 };
-enum : int { ST_NONE = 0, ST_NM = 1, ST_BFP = 2, ST_SBFP = 3, ST_FLOAT = 4, ST_FIXED = 5, ST_MXFP = 6 };
+enum : int { ST_NONE = 0, ST_NM = 1, ST_BFP = 2, ST_SBFP = 3, ST_FLOAT = 4, ST_FIXED = 5, ST_MXFP = 6, ST_SCALE = 7 };
 
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }

@@ -600,6 +600,24 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
                 case ST_FLOAT: float_stage<V>(v, st, r); break;
                 case ST_FIXED: fixed_stage<V>(v, st, r); break;
                 case ST_MXFP: mxfp_stage<V>(v, st, lanes); break;
+                case ST_SCALE:
+                    // SmoothQuant's scale application: x / scale[k] or x * scale[k] along the blocked dim, in fp32 (torch promotes
+                    // `tensor / fp32_vector` to fp32), one 16-byte load of the (L1-resident) vector per four elements
+                    if (valid[u]) {
+                        const int64_t g = g0 + (int64_t)u * kThreads;
+                        const uint32_t kv = p.n_vec <= 0x7FFFFFFFll ? (uint32_t)g - p.vpr_div.div((uint32_t)g) * p.vpr : (uint32_t)(g % p.vpr);
+                        const float *sp = st.vec + (size_t)kv * V;
+#pragma unroll
+                        for (int j = 0; j < V; j += 4) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(sp + j));
+                            if (st.vec_op) {
+                                v[j] = __fmul_rn(v[j], sc.x); v[j + 1] = __fmul_rn(v[j + 1], sc.y); v[j + 2] = __fmul_rn(v[j + 2], sc.z); v[j + 3] = __fmul_rn(v[j + 3], sc.w);
+                            } else {
+                                v[j] = __fdiv_rn(v[j], sc.x); v[j + 1] = __fdiv_rn(v[j + 1], sc.y); v[j + 2] = __fdiv_rn(v[j + 2], sc.z); v[j + 3] = __fdiv_rn(v[j + 3], sc.w);
+                            }
+                        }
+                    }
+                    break;
                 default: break;
                 }
                 if (st.requant) {

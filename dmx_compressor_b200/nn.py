@@ -125,8 +125,17 @@ class DmxModule:
         return self.weight_sparsifier.sparseness if self.weight_sparsifier is not None else None
 
     # ------------------------------------------------------------------ weight hypernet (core.py:178-213)
-    def _fusable_hypernet_stages(self):
-        """sparsify -> storage cast -> weight cast as dmxq stages, or None when some piece needs
+    def _sq_stage(self, t, ch_axis, multiply):
+        """SmoothQuant's scale as a chain pre-stage (ops.scale_stage) when its channel axis is t's last dim, else None"""
+        sq = self.smoothquant
+        sc = getattr(sq, "scale", None)
+        if not (isinstance(sc, torch.Tensor) and sc.is_cuda and sc.dtype == torch.float32 and t.dim() >= 1 and ch_axis in (-1, t.dim() - 1)
+                and sc.numel() == t.shape[-1] and sc.device == t.device):
+            return None
+        return ops.scale_stage(sc.reshape(-1).contiguous(), multiply=multiply)
+
+    def _fusable_hypernet_stages(self, scale=None):
+        """sparsify -> [SmoothQuant scale] -> storage cast -> weight cast as dmxq stages, or None when some piece needs
         the module-by-module path (score parameter, pre-transforms, observers, FixedPoint affine)."""
         stages = []
         sp = self.weight_sparsifier
@@ -138,6 +147,8 @@ class DmxModule:
             if not (sp.plastic and sp.score_func is abs_score):
                 return None
             stages.append(ops.nm_stage(sp.sparseness.K, sp.sparseness.block_size, sp.sparseness.nm_order))
+        if scale is not None:
+            stages.append(scale)
         for c in (self.weight_storage_cast, self.weight_cast):
             if c is not None and c._obs_on and not isinstance(c.format, Same):
                 return None  # calibrating: the observer must see the weight (even with fake-quant off)
@@ -151,6 +162,26 @@ class DmxModule:
             stages.append(st)
         return stages
 
+    def _fused_scaled_input(self, x):
+        """scale_input followed by the (single, plain) input cast as one cast chain -> fp32 like the reference's promoted quotient;
+        None when some piece needs the module-by-module path"""
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point() and len(self.input_casts) == 1):
+            return None
+        c = next(iter(self.input_casts.values()))
+        f = c.format
+        if c.pre_transform or c._obs_on or not c._fq_on or isinstance(f, Same) or not isinstance(f, Format) or hasattr(f, "tie"):
+            return None
+        if f.blocked and c.block_dim not in (-1, x.dim() - 1):
+            return None
+        sc = self._sq_stage(x, self.smoothquant.a_ch_axis, False)
+        if sc is None:
+            return None
+        try:
+            c.__dict__["physical_dtype"] = torch.float32
+            return ops.cast_chain(x, [sc, f.stage()], -1, out_dtype=torch.float32)
+        except RuntimeError:
+            return None
+
     @property
     def effective_weight(self):  # reference sparse.py:389-395
         return self.weight_sparsifier(self.weight) if self.weight_sparsifier is not None else self.weight
@@ -161,6 +192,17 @@ class DmxModule:
 
     def weight_hypernet(self, _w):
         if self._smoothing_weight():  # sparsify -> smoothquant scale -> storage cast -> weight cast (core.py:184-196)
+            if elide.active() and not torch.is_grad_enabled() and _w.is_cuda:
+                # ONE kernel: [prune ->] w * scale (rounded to w.dtype, scale_weight's `.to(wgt.dtype)`) -> storage cast -> weight cast
+                sc = self._sq_stage(_w, self.smoothquant.b_ch_axis, True)
+                sp = self.weight_sparsifier
+                dense = sp is None or isinstance(sp.sparseness, Dense)
+                stages = self._fusable_hypernet_stages(sc) if (sc is not None and dense) else None
+                if stages:
+                    try:
+                        return ops.cast_chain(_w, stages, -1)
+                    except RuntimeError:
+                        pass  # a layout the rows kernels do not take: module by module below
             if self.weight_sparsifier is not None:
                 _w = self.weight_sparsifier(_w)
             _w = self.smoothquant.scale_weight(_w)
@@ -238,12 +280,17 @@ class DmxModule:
     def forward(self, input, *args, **kwargs):
         _dtype = input.dtype
         sq = self.smoothquant
+        _input = None
         if sq is not None and (sq._on or sq._dyn or sq.calibrating):  # core.py:227-230
             input = elide.materialise(input)
             if sq._dyn or sq.calibrating:
                 sq(input, self.effective_weight)
-            input = sq.scale_input(input)
-        _input, args, kwargs = self.input_casts(input, *args, **kwargs)
+            if sq._on and elide.active() and not torch.is_grad_enabled() and not args and not kwargs:
+                _input = self._fused_scaled_input(input)  # input / scale and the input cast in ONE kernel
+            if _input is None:
+                input = sq.scale_input(input)
+        if _input is None:
+            _input, args, kwargs = self.input_casts(input, *args, **kwargs)
         _output = self._forward(_input, *args, **kwargs)
         output = self.output_casts(_output, output=True)
         if self.align_boundary_dtype:

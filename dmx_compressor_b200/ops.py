@@ -86,6 +86,18 @@ def mxfp_stage(block_size: int, mantissa: int, exponent: int) -> L.Stage:
     return make_stage(kind=L.ST_MXFP, block=block_size, man=mantissa, exp=exponent)
 
 
+def scale_stage(vec: torch.Tensor, multiply: bool = False) -> L.Stage:
+    """SmoothQuant's scale application as the first stage of a chain: x / vec[k] (or x * vec[k]) along block_dim, in fp32 --
+    `a / scale.view(..)`, `b * scale.view(..)` of S/numerical/smoothquant.py:253-283.  The chain's output is fp32 (torch promotes
+    `tensor / fp32_vector`): call cast_chain(..., out_dtype=torch.float32).  The stage keeps ``vec`` alive."""
+    L.require_cuda(vec, "vec")
+    if vec.dtype != torch.float32 or vec.dim() != 1 or not vec.is_contiguous():
+        raise RuntimeError("dmxq: the scale vector must be a contiguous 1-d fp32 CUDA tensor")
+    s = make_stage(kind=L.ST_SCALE, vec=vec.data_ptr(), vec_len=vec.numel(), vec_op=int(multiply))
+    s._keep = vec
+    return s
+
+
 def nm_stage(n_keep: int, m: int, nm_order: int = L.NM_STABLE) -> L.Stage:
     """N:M prune stage.  ``nm_order``: tie order inside a group -- NM_STABLE (torch.argsort(stable=True), what the reference
     gets on CPU tensors) or NM_TORCH_CUDA (what it gets on CUDA tensors; see include/dmxq.h)."""

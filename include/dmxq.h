@@ -123,6 +123,14 @@ typedef enum dmxq_stage_kind {
     DMXQ_STAGE_FLOAT = 4, /* low-bit float    : man, exp, bias, flush, is_unsigned, fp16_flush, rounding */
     DMXQ_STAGE_FIXED = 5, /* fixed point      : precision(wl), fraction(fl), clamp, symmetric,       */
                           /*                    rounding, tie, scale, zero_point (per-tensor affine) */
+    DMXQ_STAGE_SCALE = 7, /* per-channel scale: x / vec[k] (vec_op 0) or x * vec[k] (vec_op 1), k = index along      */
+                          /*                    block_dim, vec = fp32 device vector of vec_len = shape[block_dim]: the  */
+                          /*                    SmoothQuant scale application (S/numerical/smoothquant.py:253-283:      */
+                          /*                    `a / scale.view(..)`, `b * scale.view(..)`) as a pre-stage of the casts */
+                          /*                    that follow it.  The quotient / product is an fp32 value (torch         */
+                          /*                    promotes `tensor op fp32_vector`); with an fp32 output tensor it stays    */
+                          /*                    one (scale_input), with a 16-bit output it is rounded to that dtype      */
+                          /*                    before the next stage (scale_weight's `.to(wgt.dtype)`).  Rows layouts.  */
     DMXQ_STAGE_MXFP = 6   /* MX floating pt   : block, man, exp (element format E<exp>M<man>, bias    */
                           /*                    2^(exp-1)-1, subnormals kept, nearest); power-of-two  */
                           /*                    block scale 2^floor(log2 max) / 2^(2^(exp-1))         */
@@ -147,6 +155,9 @@ typedef struct dmxq_stage {
     float scale, zero_point; /* FIXED per-tensor affine (cast.py:293,296); scale = 1, zp = 0 for none */
     int32_t scale_mode; /* SBFP: dmxq_scale_mode */
     int32_t nm_order;   /* NM: dmxq_nm_order */
+    const float *vec;   /* SCALE: fp32 device vector (must stay alive until the launch has run) */
+    int32_t vec_len;    /* SCALE: its length = the extent of block_dim */
+    int32_t vec_op;     /* SCALE: 0 divide, 1 multiply */
 } dmxq_stage;
 
 int dmxq_abi_version(void);

@@ -30,7 +30,8 @@ def test_struct_layout_matches_header():
     from dmx_compressor_b200 import _lib as L
 
     assert C.sizeof(L.Tensor) == 8 + 4 + 4 + 8 * 8 * 2
-    assert C.sizeof(L.Stage) == 22 * 4 + 2 * 4 + 2 * 4
+    assert C.sizeof(L.Stage) == 22 * 4 + 2 * 4 + 2 * 4 + 8 + 2 * 4
+    assert L.Stage.vec.offset == 104 and L.Stage.vec_len.offset == 112
 
 
 def test_argument_validation_without_a_device():

@@ -322,6 +322,61 @@ def test_linear_with_smoothquant():
     assert torch.equal(lin(x), want)
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_smoothquant_scale_stage_equals_torch_ops(dt):
+    """DMXQ_STAGE_SCALE: `a / scale` (promoted to fp32) and `(b * scale).to(b.dtype)` of numerical/smoothquant.py:253-283 as the
+    first stage of a cast chain == the torch ops followed by the same casts, bit for bit"""
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format
+
+    g = torch.Generator(device=DEV).manual_seed(4)
+    x = (torch.randn(3, 40, 512, device=DEV, generator=g) * 4).to(dt)
+    sc = (torch.rand(512, device=DEV, generator=g) * 3 + 0.01)
+    sc[5] = 1.0; sc[6] = 2.0 ** -20; sc[7] = 3.0e4
+    for sh in ("BFP[8|8]{64}(SN)", "FP[1|5|10,15](FN)", "BFP[4|8]{128}(SN)", "SBFP<XP[4,0](CSN)><FP[0|4|4,7](FN)>{16}"):
+        st = Format.from_shorthand(sh).stage()
+        # input side: fp32 result
+        want = ops.cast_chain((x / sc), [st], -1)
+        got = ops.cast_chain(x, [ops.scale_stage(sc), st], -1, out_dtype=torch.float32)
+        assert got.dtype == torch.float32 and torch.equal(got.view(torch.int32), want.view(torch.int32)), (sh, "divide")
+        # weight side: product rounded to the tensor dtype, then the casts
+        w = x[0]
+        want = ops.cast_chain((w * sc).to(dt), [st], -1)
+        got = ops.cast_chain(w, [ops.scale_stage(sc, multiply=True), st], -1)
+        assert got.dtype == dt and torch.equal(got.view(torch.int32 if dt == torch.float32 else torch.int16), want.view(torch.int32 if dt == torch.float32 else torch.int16)), (sh, "multiply")
+    # strided rows are taken too; a channel axis that is not the contiguous dim is refused (callers keep the torch ops)
+    xs = x[:, :, 128:384]
+    st = Format.from_shorthand("BFP[8|8]{64}(SN)").stage()
+    assert torch.equal(ops.cast_chain(xs, [ops.scale_stage(sc[128:384].contiguous()), st], -1, out_dtype=torch.float32), ops.cast_chain(xs / sc[128:384], [st], -1))
+    with pytest.raises(RuntimeError, match="unsupported"):
+        ops.cast_chain(x.transpose(1, 2), [ops.scale_stage(sc[:40].contiguous()), st], -1, out_dtype=torch.float32)
+    with pytest.raises(RuntimeError):
+        ops.cast_chain(x, [ops.scale_stage(sc[:100].contiguous()), st], -1, out_dtype=torch.float32)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_linear_with_smoothquant_fused_under_elision(dt):
+    """under elision an enabled SmoothQuant costs no extra pass: input / s + input cast = one kernel, weight * s + storage + weight
+    cast = one kernel; logits bit-identical to the module-by-module forward"""
+    torch.manual_seed(3)
+    lin = dmxnn.Linear(256, 96).to(device=DEV, dtype=dt)
+    lin.configure(dict(input_formats=[fmt.BFP16_64], weight_format=fmt.BFP16_64, output_formats=[fmt.FLOAT16]))
+    x = (torch.randn(2, 33, 256, device=DEV) * torch.rand(256, device=DEV).mul(6).exp2()).to(dt)
+    sq = lin.smoothquant
+    with torch.no_grad():
+        sq.calibrating = True
+        lin(x)
+        sq.calibrating = False
+        sq.enable()
+        want = lin(x)
+        n0 = _lib.launch_count()
+        with elide.enabled():
+            got = elide.materialise(lin(x))
+        n1 = _lib.launch_count()
+    assert torch.equal(got, want)
+    assert n1 - n0 == 3  # input chain, weight chain, output cast
+
+
 class _FloatMLP(torch.nn.Module):
     def __init__(self):
         super().__init__()
