@@ -20,7 +20,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libdmxq.so")
 OBJDIR = os.path.join(HERE, "build")
-SOURCES = ["dmxq_api.cu", "dmxq_rows_a.cu", "dmxq_rows_b.cu", "dmxq_rows_c.cu", "dmxq_rows_d.cu", "dmxq_rows_e.cu", "dmxq_rows_f.cu", "dmxq_rows_g.cu", "dmxq_cols.cu", "dmxq_misc.cu", "dmxq_softmax.cu"]
+SOURCES = ["dmxq_api.cu", "dmxq_rows_a.cu", "dmxq_rows_b.cu", "dmxq_rows_c.cu", "dmxq_rows_d.cu", "dmxq_rows_e.cu", "dmxq_rows_f.cu", "dmxq_rows_g.cu", "dmxq_cols.cu", "dmxq_misc.cu", "dmxq_softmax.cu", "dmxq_tma.cu"]
 HEADERS = ["dmxq_numerics.cuh", "dmxq_kernels.cuh", "dmxq_stages.cuh", "dmxq_rows.cuh", os.path.join("..", "..", "include", "dmxq.h")]
 
 NVCC = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "bin", "nvcc")

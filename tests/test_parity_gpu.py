@@ -1178,6 +1178,30 @@ def test_packed16_low_bit_float(dt, sh):
         assert not ((yf.view(np.uint32) != bits(w)) & ~np.isnan(w)).any(), f"{sh} fp32"
 
 
+# ---- the TMA experiment (csrc/dmxq_tma.cu): not on the product path, but it ships in the library, so it is held to the same parity
+@pytest.mark.parametrize("dt", ["float32", "bfloat16", "float16"])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+def test_tma_tiled_cols_kernel_equals_production(dt, cfg):
+    import ctypes as C
+
+    fn = L.lib.dmxq_x_bfp_cols_tma
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    fn.restype = C.c_int
+    tdt = getattr(torch, dt)
+    for shape in ((5, 256, 64), (7, 200, 72), (3, 64, 8), (2, 130, 520)):
+        x = _rand(shape, 7, spread=5 if dt != "float16" else 3, dtype=tdt).to(DEV)
+        x[0, :, 1] = 0.0
+        x[1, :, 2] = x[1, :, 2] * (2.0**-100 if dt != "float16" else 2.0**-12)  # denormal-range column: literal path
+        x[1, 3, 4] = float("inf")
+        for wl in (8, 4):
+            want = ops.cast_chain(x, [fmt_from(f"BFP[{wl}|8]{{64}}(SN)").stage()], -2)
+            got = torch.empty_like(x)
+            assert fn(x.data_ptr(), got.data_ptr(), L.dtype_code(tdt), *shape, 64, wl, cfg, L.stream_ptr(x.device)) == 0
+            torch.cuda.synchronize()
+            it = torch.int32 if dt == "float32" else torch.int16
+            assert torch.equal(got.view(it), want.view(it)), (dt, cfg, shape, wl)
+
+
 # ---- stochastic rounding with in-kernel random words (dmxq_cast_chain_philox) -----------------------------------------
 def test_philox_fill_equals_numpy_restatement():
     for n, seed, sid in ((1, 0, 0), (4, 0, 0), (1003, 0x123456789ABCDEF, 5), (1 << 20, 2**63 + 11, 2**40 + 3)):
