@@ -42,7 +42,9 @@ def _flag(m, name: str) -> int:
     CUDA module that is an ``eq`` kernel plus a blocking 1-byte device-to-host copy, twice per ``CastTo.forward``, ~2000 times
     per OPT-125m forward, which leaves the whole forward host-bound.  The value is re-read only when the buffer object or its
     in-place version counter changes (``enable_fake_quant()``, ``load_state_dict``, ``.to(device)`` all do one or the other)."""
-    t = getattr(m, name)
+    t = m._buffers.get(name)  # (the switch buffers are registered buffers: skip nn.Module.__getattr__'s search order)
+    if t is None:
+        t = getattr(m, name)
     c = m.__dict__.get("_dmxq_" + name)
     v = t._version
     if c is not None and c[0] is t and c[1] == v:
@@ -214,7 +216,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
             def backward(ctx, g):
                 return g, None, None
 
-        def stage_of(f):
+        def _stage_of(f):
             if isinstance(f, fmt.ScaledBlockFloatingPoint):
                 return sbfp_stage_of(f)
             if isinstance(f, fmt.BlockFloatingPoint):
@@ -224,21 +226,52 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                                        repr(f) == "FP[1|5|10,15](FN)", f.rounding)
             return None
 
+        # (stage, repr) of a format object, memoised per object: a BASIC forward asks ~500 times for the stage struct and the
+        # shorthand of the same handful of format objects.  Valid while the object's defining fields are unchanged (they are
+        # re-read on every call: formats are plain python objects and nothing stops a user from editing one in place).
+        import operator
+
+        _fields = {fmt.FloatingPoint: operator.attrgetter("mantissa", "exponent", "bias", "flush_subnormal", "unsigned", "rounding"),
+                   fmt.BlockFloatingPoint: operator.attrgetter("block_size", "precision", "symmetric", "rounding")}
+        _fmt_memo = {}
+
+        def fmt_info(f):
+            g = _fields.get(type(f))
+            if g is None:
+                return None
+            state = g(f)
+            ent = _fmt_memo.get(id(f))
+            if ent is not None and ent[0] is f and ent[1] == state:
+                return ent
+            if len(_fmt_memo) > 1024:
+                _fmt_memo.clear()
+            ent = (f, state, _stage_of(f), repr(f))
+            _fmt_memo[id(f)] = ent
+            return ent
+
+        def stage_of(f):
+            ent = fmt_info(f)
+            return ent[2] if ent is not None else _stage_of(f)
+
+        def repr_of(f):
+            ent = fmt_info(f)
+            return ent[3] if ent is not None else repr(f)
+
         from . import elide as E
         from . import fused
 
         def ref_key(f, block_dim):
             """hashable identity of an idempotent cast of the reference's format classes (elide.format_key's rule)"""
             if isinstance(f, fmt.FloatingPoint) and f.rounding == "nearest":
-                return ("FP", repr(f))
+                return ("FP", repr_of(f))
             if isinstance(f, fmt.BlockFloatingPoint) and not isinstance(f, fmt.ScaledBlockFloatingPoint) and f.symmetric \
                     and f.rounding == "nearest" and f.block_size > 1:
-                return ("BFP", repr(f), block_dim)
+                return ("BFP", repr_of(f), block_dim)
             return None
 
         def fp_identity(f, dtype):
             return isinstance(f, fmt.FloatingPoint) and not f.unsigned and (
-                (dtype == torch.float32 and repr(f) == "FP[1|8|23,127](_N)") or (dtype == torch.float16 and repr(f) == "FP[1|5|10,15](_N)"))
+                (dtype == torch.float32 and repr_of(f) == "FP[1|8|23,127](_N)") or (dtype == torch.float16 and repr_of(f) == "FP[1|5|10,15](_N)"))
 
         def castto_elided(self, x, lazy_ok):
             """CastTo._forward_elided of the mirror (numerical/cast.py) on the reference's objects: value-identical fast path"""
