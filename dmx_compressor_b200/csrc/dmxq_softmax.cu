@@ -172,6 +172,12 @@ __global__ void __launch_bounds__(256, 2) softmax_cast_kernel(const __grid_const
         }
         float v[V];
         if (POST == POST_FLOAT_BFP) {
+            // every vector of this step holds nothing but zeros (the masked tail of a causal row): FLOAT then BFP of zeros are +0
+            constexpr uint32_t kMag = sizeof(T) == 4 ? 0x7FFFFFFFu : 0x7FFF7FFFu;
+            if (__all_sync(0xFFFFFFFFu, ((raw.x | raw.y | raw.z | raw.w) & kMag) == 0u)) {
+                if (ok) stg_stream(yr + (size_t)j * V, make_uint4(0u, 0u, 0u, 0u));
+                continue;
+            }
             float_bfp_apply<T, T, V>(raw, v, p.chain.st[0], p.chain.st[1], fb);
         } else {
             // chain_rows_kernel's runtime chain: the same stage functions, blocks reduced over neighbouring lanes
