@@ -323,9 +323,10 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
 
         def castto_forward(self, x):
             f = self.format
-            if elide and E.active() and not torch.is_grad_enabled() and isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point() \
+            m = x._raw if type(x) is E.Lazy else x  # (metadata of a deferred tensor: its raw tensor's -- no __torch_function__ trips)
+            if elide and E.active() and not torch.is_grad_enabled() and isinstance(m, torch.Tensor) and m.is_cuda and m.is_floating_point() \
                     and not self.pre_transform and _flag(self, "observer_enabled") != 1 and isinstance(f, fmt.Format):
-                self.physical_dtype = x.dtype
+                self.__dict__["physical_dtype"] = m.dtype
                 y = castto_elided(self, x, _out_depth[0] > 0 and E.defer_output_casts)
                 if y is not None:
                     return y
@@ -336,7 +337,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                      and getattr(f, "rounding", "nearest") != "stochastic")
             if isinstance(f, fmt.Same) and isinstance(x, torch.Tensor) and x.is_cuda and not self.pre_transform:
                 # the default format of every CastTo: the reference's own two steps (cast.py:281-296, 306) minus its device reads
-                self.physical_dtype = x.dtype
+                self.__dict__["physical_dtype"] = x.dtype
                 return cast.CastToFormat.apply(x, f, self.block_dim) if _flag(self, "fake_quant_enabled") == 1 else x
             if not plain or _flag(self, "observer_enabled") == 1 or _flag(self, "fake_quant_enabled") != 1:
                 return o_cfwd(self, x)
@@ -345,7 +346,7 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
             if isinstance(f, fmt.FloatingPoint) and ((x.dtype == torch.float32 and repr(f) == "FP[1|8|23,127](_N)")
                                                      or (x.dtype == torch.float16 and repr(f) == "FP[1|5|10,15](_N)")):
                 return o_cfwd(self, x)
-            self.physical_dtype = x.dtype
+            self.__dict__["physical_dtype"] = x.dtype
             return _Fused.apply(x, stage_of(f), self.block_dim)
 
         _patch(cast.CastTo, "forward", castto_forward)
@@ -429,19 +430,24 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                     sq = self.smoothquant
                     if sq is not None and (sq.calibrating or _flag(sq, "dynamic") == 1 or _flag(sq, "enabled") == 1):
                         return o_mod_fwd(self, E.materialise(input), *args, **kwargs)
-                    _dtype, _device = input.dtype, input.device
-                    if hasattr(self, "weight") and self.weight is not None:
-                        _device = self.weight.device
+                    meta = input._raw if type(input) is E.Lazy else input
+                    _dtype, _device = meta.dtype, meta.device
+                    w = self._parameters.get("weight") if "weight" in self._parameters else getattr(self, "weight", None)
+                    if w is not None:
+                        _device = w.device
                     _input, args, kwargs = self.input_casts(input, *args, **kwargs)
-                    if _input.device != _device or any(isinstance(a, torch.Tensor) and a.device != _device for a in args):
+                    mi = _input._raw if type(_input) is E.Lazy else _input
+                    if mi.device != _device or any(isinstance(a, torch.Tensor) and a.device != _device for a in args):
                         _input, args, kwargs = self.align_device(_input, args, kwargs, _device)
                     _output = self._forward(_input, *args, **kwargs)
                     output = self.output_casts(_output, output=True)
                     if self.align_boundary_dtype:
                         if isinstance(output, (tuple, list)):
                             output = type(output)(a if a.dtype == _dtype else a.to(_dtype) for a in output)
-                        elif output.dtype != _dtype:
-                            output = output.to(_dtype)
+                        else:
+                            mo = output._raw if type(output) is E.Lazy else output
+                            if mo.dtype != _dtype:
+                                output = output.to(_dtype)
                     return output
 
                 _patch(core.DmxModule, "forward", module_forward)
