@@ -83,6 +83,34 @@ def test_no_cpu_fallback():
             call()
 
 
+def test_round2_entry_points_validate_without_a_gpu():
+    """dmxq_softmax_cast / dmxq_cast_chain_philox / the SCALE stage reject what they do not take before any CUDA call, and have
+    no host stand-in"""
+    from dmx_compressor_b200 import _lib as L
+    from dmx_compressor_b200 import ops
+    from dmx_compressor_b200.numerical import Format
+
+    x = torch.zeros(4, 64)
+    assert not ops.softmax_supported(x)
+    for call in (lambda: ops.softmax_cast(x), lambda: ops.cast_chain(x, [Format.from_shorthand("BFP[8|8]{64}(SS)").stage()], -1, philox=(1, 2)),
+                 lambda: ops.scale_stage(torch.ones(64)), lambda: ops.philox_fill((4,), 1, device="cpu") and None):
+        with pytest.raises((RuntimeError, AssertionError)):
+            call()
+    vx, vy = L.view(x), L.view(torch.zeros(4, 64))
+    for n, msg in ((32, b"33..2048"), (4096, b"33..2048")):
+        t = torch.zeros(4, n)
+        v = L.view(t)
+        assert L.lib.dmxq_softmax_cast(C.byref(v), None, C.byref(v), None, None, None, None, 0, None) == -2 and msg in L.lib.dmxq_last_error()
+    st = Format.from_shorthand("BFP[8|8]{64}(SN)").stage()
+    assert L.lib.dmxq_softmax_cast(C.byref(vx), None, C.byref(vy), None, None, None, C.byref(st), 9, None) == -1
+    assert L.lib.dmxq_softmax_cast(C.byref(vx), None, C.byref(vy), C.byref(st), None, None, None, 0, None) == -1  # add stages without an addend
+    vt = L.view(torch.zeros(64, 4).t())
+    assert L.lib.dmxq_softmax_cast(C.byref(vt), None, C.byref(vt), None, None, None, None, 0, None) == -2  # softmax dim not contiguous
+    sc = ops.make_stage(kind=L.ST_SCALE, vec=None, vec_len=64, vec_op=0)
+    assert L.lib.dmxq_cast_chain(C.byref(vx), C.byref(vy), -1, C.byref(sc), 1, None, None, None, None) == -1 and b"device vector" in L.lib.dmxq_last_error()
+    assert L.lib.dmxq_philox_fill(None, 16, 0, 1, 2, None) == -1
+
+
 def test_packed_sbfp_argument_checks_without_a_gpu():
     """dmxq_sbfp_pack validates the format description before anything touches the device"""
     from dmx_compressor_b200 import _lib as L
