@@ -23,13 +23,18 @@ namespace dmxq {
 enum : int { POST_NONE = 0, POST_CHAIN = 1, POST_FLOAT_BFP = 2 };
 
 // the add in front of the softmax on one vector: ResAdd.forward with its casts, as add_cast_kernel computes it
-// (cast(a), cast(b) each rounded to T, fp32 add rounded to T, cast of the sum) -> the T-rounded result as a raw vector
-template <typename T, int V> __device__ __forceinline__ uint4 add_vec(const uint4 &ra, const uint4 &rb, const SoftmaxParams &p, const Range16 &qa,
-                                                                       const Range16 &qb, const Range16 &qo)
+// (cast(a), cast(b) each rounded to T, fp32 add rounded to T, cast of the sum) -> the T-rounded result as a raw vector.
+// Code size matters here (the row loop is fully unrolled around it: the kernel was instruction-fetch bound at 160 KB of SASS):
+// the common case -- every stage absent or the identity on this vector -- is inline, everything else ONE out-of-line copy.
+struct AddRanges {
+    Range16 a, b, o;
+};
+template <typename T, int V> static __device__ __noinline__ uint4 add_vec_general(uint4 ra, uint4 rb, const SoftmaxParams *pp, const AddRanges *rr)
 {
+    const SoftmaxParams &p = *pp;
     float va[V], vb[V];
     if constexpr (sizeof(T) == 2) {
-        // stages that keep T's significand (FLOAT16 on bf16 / fp16 tensors) stay on the packed words; others widen
+        const Range16 qa = rr->a, qb = rr->b, qo = rr->o;
         uint4 wa = ra, wb = rb;
         if (p.has_a && !inside16(wa, qa)) {
             if (qa.on) wa = flush_sat16_vec<T>(wa, p.fa, qa);
@@ -60,6 +65,60 @@ template <typename T, int V> __device__ __forceinline__ uint4 add_vec(const uint
         return make_uint4(f2u(va[0]), f2u(va[1]), f2u(va[2]), f2u(va[3]));
     }
 }
+template <typename T, int V> __device__ __forceinline__ uint4 add_vec(const uint4 &ra, const uint4 &rb, const SoftmaxParams &p, const Range16 &qa,
+                                                                       const Range16 &qb, const Range16 &qo)
+{
+    if constexpr (sizeof(T) == 2) {
+        if ((!p.has_a || inside16(ra, qa)) && (!p.has_b || inside16(rb, qb))) {
+            float va[V], vb[V];
+            VecIO<T>::unpack(ra, va);
+            VecIO<T>::unpack(rb, vb);
+#pragma unroll
+            for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);
+            const uint4 w = pack16<T>(va);
+            if (!p.has_o || inside16(w, qo)) return w;
+        }
+        const AddRanges rr{qa, qb, qo};
+        return add_vec_general<T, V>(ra, rb, &p, &rr);
+    } else {  // fp32: the stages are real work on every vector (rounding to the format's mantissa): inline
+        float va[V], vb[V];
+        VecIO<T>::unpack(ra, va);
+        VecIO<T>::unpack(rb, vb);
+        if (p.has_a) float_fast_vec<V>(va, p.fa);
+        if (p.has_b) float_fast_vec<V>(vb, p.fb);
+#pragma unroll
+        for (int j = 0; j < V; ++j) va[j] = __fadd_rn(va[j], vb[j]);
+        if (p.has_o) float_fast_vec<V>(va, p.fo);
+        return make_uint4(f2u(va[0]), f2u(va[1]), f2u(va[2]), f2u(va[3]));
+    }
+}
+
+// the FLOAT (nearest + flush) stage of the output chain on a 16-bit vector -> the stage's result rounded to T, packed: identity and
+// packed flush / saturate inline, anything else (NaN, formats that round T's significand, unsigned ones) out of line
+template <typename T> static __device__ __noinline__ uint4 post_float16_general(uint4 raw, const StageDev *sf)
+{
+    float v[8];
+    VecIO<T>::unpack(raw, v);
+    float_fast_vec<8>(v, sf->ff);
+    return pack16<T>(v);
+}
+// symmetric nearest BFP of a 16-bit vector whose block maximum is known: the two-add form inline, the literal form out of line
+template <typename T, int V> __device__ __forceinline__ void post_bfp16(float (&v)[V], uint32_t m, const StageDev &st)
+{
+    if (st.fast && st.fast16 && bfp_fast_ok(m)) {
+        const BfpFast b = bfp_fast_block(m, st.wl);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_fast16_elem(v[j], b);
+        if (b.clamp) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = bfp_clamp(v[j], b);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = bfp_elem_slow(v[j], m, st.wl, st.sh, st.mask, R_NEAREST, 0, 0u);
+    }
+}
+static __device__ __noinline__ float div_literal(float a, float b) { return b == 0.0f ? __int_as_float(0x7FC00000) : __fdiv_rn(a, b); }
 
 // FULL: the row length equals the padded length ITERS * 32 (no bounds checks anywhere)
 template <typename T, int ITERS, bool ADD, int POST, bool FULL>
@@ -126,11 +185,32 @@ __global__ void __launch_bounds__(256, 2) softmax_cast_kernel(const __grid_const
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
     float sum = 0.0f;
     uint32_t amin = 0xFFFFFFFFu;  // smallest non-zero exp pattern (minus one): decides whether the reciprocal form may divide
+    // Steps are taken in groups of G: when x - max < -110 for EVERY element of a group across the warp (the masked tail of a causal
+    // row), each expf is exactly +0 -- e^-110 is far below half the smallest denormal -- and adding +0 leaves the sum untouched, so
+    // the group's exponentials, additions and (below) divisions are skipped; one predicate AND per element and one vote per group.
+    constexpr int G = ITERS < 8 ? ITERS : 8;
+    bool zero_group[ITERS / G];
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        e[it] = expf(__fsub_rn(e[it], m));
-        sum = __fadd_rn(sum, e[it]);
-        amin = min(amin, f2u(e[it]) - 1u);
+    for (int g0 = 0; g0 < ITERS; g0 += G) {
+        bool low = true;
+#pragma unroll
+        for (int k = 0; k < G; ++k) {
+            e[g0 + k] = __fsub_rn(e[g0 + k], m);
+            low = low && e[g0 + k] < -110.0f;  // (false for NaN)
+        }
+        const bool z = __all_sync(0xFFFFFFFFu, low);
+        zero_group[g0 / G] = z;
+        if (z) {
+#pragma unroll
+            for (int k = 0; k < G; ++k) e[g0 + k] = 0.0f;
+        } else {
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                e[g0 + k] = expf(e[g0 + k]);
+                sum = __fadd_rn(sum, e[g0 + k]);
+                amin = min(amin, f2u(e[g0 + k]) - 1u);
+            }
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum = __fadd_rn(sum, __shfl_xor_sync(0xFFFFFFFFu, sum, off));
@@ -146,22 +226,27 @@ __global__ void __launch_bounds__(256, 2) softmax_cast_kernel(const __grid_const
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int idx = it * 32 + lane;
-            if (FULL || idx < n) s[idx] = Cvt<T>::from_f32(div_by_recip2(e[it], sum, rh, rl));
+            // (a skipped group holds zeros and the divisor is finite here: 0 / sum = +0)
+            const float r = zero_group[it / G] ? 0.0f : div_by_recip2(e[it], sum, rh, rl);
+            if (FULL || idx < n) s[idx] = Cvt<T>::from_f32(r);
         }
     } else {
 #pragma unroll  // (fully unrolled: a run-time index would put e[] into local memory for every path)
         for (int it = 0; it < ITERS; ++it) {
             const int idx = it * 32 + lane;
-            const float r = sum == 0.0f ? __int_as_float(0x7FC00000) : __fdiv_rn(e[it], sum);
-            if (FULL || idx < n) s[idx] = Cvt<T>::from_f32(r);
+            if (FULL || idx < n) s[idx] = Cvt<T>::from_f32(div_literal(e[it], sum));
         }
     }
     __syncwarp();
 
     // ---- 4. the output casts on vectors, streaming stores
     FloatBfpCtx fb{};
-    if (POST == POST_FLOAT_BFP) fb = float_bfp_ctx<T, T>(p.chain.st[0]);
-#pragma unroll 2
+    Range16 rg{};
+    if (POST == POST_FLOAT_BFP) {
+        fb = float_bfp_ctx<T, T>(p.chain.st[0]);
+        if constexpr (sizeof(T) == 2) rg = range16<T>(1, p.chain.st[0].ff);
+    }
+#pragma unroll 1
     for (int k = 0; k < NVL; ++k) {
         const int j = k * 32 + lane;
         const bool ok = (FULL && NV > 0) || j < nvec;
@@ -178,7 +263,25 @@ __global__ void __launch_bounds__(256, 2) softmax_cast_kernel(const __grid_const
                 if (ok) stg_stream(yr + (size_t)j * V, make_uint4(0u, 0u, 0u, 0u));
                 continue;
             }
-            float_bfp_apply<T, T, V>(raw, v, p.chain.st[0], p.chain.st[1], fb);
+            if constexpr (sizeof(T) == 2) {
+                // FLOAT stage on the packed words (identity / flush + saturate), its maximum straight from the result, then BFP
+                constexpr uint32_t kInf16 = std::is_same<T, __nv_bfloat16>::value ? 0x7F80u : 0x7C00u;
+                const uint32_t amax = raw16_absmax(raw);
+                uint4 w = raw;
+                uint32_t m16 = amax;
+                if (!rg.on || amax > kInf16) {
+                    w = post_float16_general<T>(raw, &p.chain.st[0]);
+                    m16 = raw16_absmax(w);
+                } else if (!(raw16_absmin(raw) >= rg.lo && amax <= rg.hi)) {
+                    w = flush_sat16_vec<T>(raw, p.chain.st[0].ff, rg);
+                    m16 = raw16_absmax(w);
+                }
+                const uint32_t m = lanes_max(widen16<T>(m16), p.chain.st[1].block / V);
+                VecIO<T>::unpack(w, v);
+                post_bfp16<T, V>(v, m, p.chain.st[1]);
+            } else {
+                float_bfp_apply<T, T, V>(raw, v, p.chain.st[0], p.chain.st[1], fb);
+            }
         } else {
             // chain_rows_kernel's runtime chain: the same stage functions, blocks reduced over neighbouring lanes
             VecIO<T>::unpack(raw, v);

@@ -704,6 +704,14 @@ __device__ __forceinline__ bool inside16(const uint4 &w, const Range16 &r) { ret
 // sign kept -- what float_elem_flush_nearest<true> followed by the rounding to T yields, element for element.  The flush mask
 // comes from bit 15 of (magnitude + 0x8000 - lo), replicated over its half by a sign-extending byte permute.  A NaN anywhere in
 // the vector (the one input class whose reference result depends on the payload) takes the per-element literal path.
+// (one out-of-line copy per kernel of the literal per-element path: it is reached by vectors that hold a NaN only)
+template <typename T> static __device__ __noinline__ uint4 float_vec16_literal(uint4 w, const FloatFmt *f)
+{
+    float v[8];
+    VecIO<T>::unpack(w, v);
+    float_fast_vec<8>(v, *f);
+    return pack16<T>(v);
+}
 template <typename T> __device__ __forceinline__ uint4 flush_sat16_vec(const uint4 &w, const FloatFmt &f, const Range16 &r)
 {
     constexpr uint32_t kInf16 = std::is_same<T, __nv_bfloat16>::value ? 0x7F80u : 0x7C00u;
@@ -711,12 +719,7 @@ template <typename T> __device__ __forceinline__ uint4 flush_sat16_vec(const uin
     uint32_t mag[4], mx = 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) { mag[i] = x[i] & 0x7FFF7FFFu; mx = __vmaxu2(mx, mag[i]); }
-    if (max(mx & 0xFFFFu, mx >> 16) > kInf16) {
-        float v[8];
-        VecIO<T>::unpack(w, v);
-        float_fast_vec<8>(v, f);
-        return pack16<T>(v);
-    }
+    if (max(mx & 0xFFFFu, mx >> 16) > kInf16) return float_vec16_literal<T>(w, &f);
     const uint32_t hi2 = r.sat * 0x10001u, k2 = (0x8000u - r.lo) * 0x10001u;
     uint32_t o[4];
 #pragma unroll
