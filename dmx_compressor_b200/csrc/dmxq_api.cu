@@ -458,8 +458,10 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         auto bfp_ns = [](const StageDev &d) { return d.kind == ST_BFP && d.mode == R_NEAREST && !d.asym; };
         auto float_fast = [](const StageDev &d) { return d.kind == ST_FLOAT && d.ff.fastpath; };
         int kind = 1;  // K_CHAIN
-        if (rand && !score_p && !mask_p && flat && chain.n == 1 && chain.st[0].kind == ST_BFP && chain.st[0].mode == R_STOCHASTIC && !chain.st[0].asym &&
-            aligned(rand, 16)) kind = 11;  // K_BFP_STOCH
+        const StageDev &s0 = chain.st[0];
+        const bool stoch1 = (s0.kind == ST_BFP && s0.mode == R_STOCHASTIC && !s0.asym) || (s0.kind == ST_FLOAT && s0.ff.mode == R_STOCHASTIC) ||
+                            (s0.kind == ST_FIXED && s0.xf.mode == R_STOCHASTIC && !s0.affine && !qscale);
+        if (rand && !score_p && !mask_p && flat && chain.n == 1 && stoch1 && aligned(rand, 16)) kind = 11;  // K_BFP_STOCH
         else if (score_p || mask_p || rand) kind = 0;  // K_AUX
         else if (chain.n == 1 && bfp_ns(chain.st[0])) kind = 2;  // K_BFP
         else if (chain.n == 1 && (float_fast(chain.st[0]) || (chain.st[0].kind == ST_FLOAT && chain.st[0].ff.nsub))) kind = 3;  // K_FLOAT

@@ -23,7 +23,8 @@
 //   K_FIXED      [FixedPoint nearest half-away, per-tensor affine (immediate or device qparams)]  INT8 / INT4
 //   K_MXFP       [MXFP]                                       OCP-MX style power-of-two block scale + low-bit float elements
 //   K_BFP_ASYM   [BFP nearest, asymmetric mantissa]            BFP16A / BFP12A (kept apart from K_BFP: it needs a copy of the inputs)
-//   K_BFP_STOCH  [BFP stochastic, external random tensor, FLAT]  the reference's default rounding; random words loaded with the data
+//   K_BFP_STOCH  [one stochastic stage: BFP / FLOAT / FixedPoint, FLAT]  the reference's default rounding; random words loaded with the
+//                data or computed in registers (Philox)
 //   K_NM24_BFP   [2:4 with score |x| -> BFP n.s.] on a bf16 / fp16 tensor: the whole-model weight cast of config #4, straight-line
 #pragma once
 #include "dmxq_stages.cuh"
@@ -312,16 +313,33 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
             uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
             bfp_ns_apply<V, SRC16>(v, m, st);
         } else if (KIND == K_BFP_STOCH) {
+            // ONE stochastic stage (the L1 default rounding, Q/quant_function.py:47,87,120) with its random words loaded next to the
+            // data or computed in registers: BFP, FLOAT, or FixedPoint without affine parameters (its words are fp32 values in [0, 1))
             const StageDev &st = p.chain.st[0];
-            const uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
-            const BfpBlock b = bfp_block(m, st.wl);
+            if (st.kind == ST_BFP) {
+                const uint32_t m = lanes_max(unpack_absmax<Tin>(raw[u], v), st.block / V);
+                const BfpBlock b = bfp_block(m, st.wl);
 #pragma unroll
-            for (int j = 0; j < V; j += 4) {
-                const uint4 q = rraw[u][j / 4];
-                v[j] = bfp_elem<R_STOCHASTIC>(v[j], b, st.sh, st.mask, q.x);
-                v[j + 1] = bfp_elem<R_STOCHASTIC>(v[j + 1], b, st.sh, st.mask, q.y);
-                v[j + 2] = bfp_elem<R_STOCHASTIC>(v[j + 2], b, st.sh, st.mask, q.z);
-                v[j + 3] = bfp_elem<R_STOCHASTIC>(v[j + 3], b, st.sh, st.mask, q.w);
+                for (int j = 0; j < V; j += 4) {
+                    const uint4 q = rraw[u][j / 4];
+                    v[j] = bfp_elem<R_STOCHASTIC>(v[j], b, st.sh, st.mask, q.x);
+                    v[j + 1] = bfp_elem<R_STOCHASTIC>(v[j + 1], b, st.sh, st.mask, q.y);
+                    v[j + 2] = bfp_elem<R_STOCHASTIC>(v[j + 2], b, st.sh, st.mask, q.z);
+                    v[j + 3] = bfp_elem<R_STOCHASTIC>(v[j + 3], b, st.sh, st.mask, q.w);
+                }
+            } else {
+                VecIO<Tin>::unpack(raw[u], v);
+                const bool fixed = st.kind == ST_FIXED;
+#pragma unroll
+                for (int j = 0; j < V; j += 4) {
+                    const uint4 q = rraw[u][j / 4];
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (fixed) v[j + k] = fixed_elem(v[j + k], st.xf, u2f(p.philox ? philox_unit_bits(w[k]) : w[k]));
+                        else v[j + k] = float_elem<R_STOCHASTIC>(v[j + k], st.ff, w[k]);
+                    }
+                }
             }
         } else if (KIND == K_BFP_ASYM) {
             // symmetric nearest result first, then make_mantissa_asymmetric (S/numerical/format.py:349-372): the edge
