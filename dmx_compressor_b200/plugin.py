@@ -380,15 +380,61 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                     return (repr(c.format), _flag(c, "fake_quant_enabled"), c.block_dim, repr(c.pre_transform) if c.pre_transform else None,
                             _pstate(getattr(c, "scale", None)), _pstate(getattr(c, "zero_point", None)), getattr(c, "group_size", None))
 
+                def _sq_stage(sq, t, ch_axis, multiply):
+                    """SmoothQuant's scale as a chain pre-stage (ops.scale_stage) when its channel axis is t's last dim, else None"""
+                    sc = getattr(sq, "scale", None)
+                    if not (isinstance(sc, torch.Tensor) and sc.is_cuda and sc.dtype == torch.float32 and t.dim() >= 1 and ch_axis in (-1, t.dim() - 1)
+                            and sc.numel() == t.shape[-1] and sc.device == t.device):
+                        return None
+                    return ops.scale_stage(sc.reshape(-1).contiguous(), multiply=multiply)
+
+                def _fused_scaled_input(self, sq, x):
+                    """scale_input (numerical/smoothquant.py:487-497) followed by the single plain input cast as one cast chain -> fp32"""
+                    if not (isinstance(x, torch.Tensor) and x.is_cuda and x.is_floating_point() and len(self.input_casts) == 1):
+                        return None
+                    c = next(iter(self.input_casts.values()))
+                    f = c.format
+                    if c.pre_transform or _flag(c, "observer_enabled") == 1 or _flag(c, "fake_quant_enabled") != 1 or isinstance(f, fmt.Same) \
+                            or getattr(f, "rounding", "nearest") == "stochastic":
+                        return None
+                    if isinstance(f, fmt.BlockFloatingPoint) and c.block_dim not in (-1, x.dim() - 1):
+                        return None
+                    st, sc = stage_of(f), _sq_stage(sq, x, sq.a_ch_axis, False)
+                    if st is None or sc is None:
+                        return None
+                    try:
+                        y = ops.cast_chain(x, [sc, st], -1, out_dtype=torch.float32)
+                    except RuntimeError:
+                        return None
+                    c.__dict__["physical_dtype"] = torch.float32
+                    return y
+
                 def hypernet(self):
                     """DmxModule.weight_hypernet applied to the weight (core.py:178-205): sparsify -> SmoothQuant scale -> storage cast ->
                     weight cast, with the SmoothQuant switches read through the host-side cache (scale_weight is the identity while
                     SmoothQuant is disabled, numerical/smoothquant.py:280-283)"""
                     w = self.weight
+                    sq = self.smoothquant
+                    smoothing = sq is not None and _flag(sq, "fused_to_weight") == 0 and _flag(sq, "enabled") == 1
+                    if smoothing and elide and E.active() and not torch.is_grad_enabled() and w.is_cuda:
+                        # ONE kernel: w * scale (rounded to w.dtype, scale_weight's `.to(wgt.dtype)`) -> storage cast -> weight cast
+                        sp = self.weight_sparsifier
+                        if sp is None or isinstance(sp.sparseness, sparse.Dense):
+                            stages = [_sq_stage(sq, w, sq.b_ch_axis, True)]
+                            for c in (self.weight_storage_cast, self.weight_cast):
+                                if c is None or isinstance(c.format, fmt.Same) or _flag(c, "fake_quant_enabled") != 1:
+                                    continue
+                                st = None if (c.pre_transform or _flag(c, "observer_enabled") == 1 or getattr(c.format, "rounding", "nearest") == "stochastic"
+                                              or (isinstance(c.format, fmt.BlockFloatingPoint) and c.block_dim not in (-1, w.dim() - 1))) else stage_of(c.format)
+                                stages.append(st)
+                            if all(st is not None for st in stages) and len(stages) <= L.MAX_STAGES:
+                                try:
+                                    return ops.cast_chain(w, stages, -1)
+                                except RuntimeError:
+                                    pass  # a layout the rows kernels do not take: the reference's own sequence below
                     if self.weight_sparsifier is not None:
                         w = self.weight_sparsifier(w)
-                    sq = self.smoothquant
-                    if sq is not None and _flag(sq, "fused_to_weight") == 0 and _flag(sq, "enabled") == 1:
+                    if smoothing:
                         w = sq.scale_weight(w)
                     if self.weight_storage_cast is not None:
                         w = self.weight_storage_cast(w)
@@ -428,14 +474,21 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
                             or not isinstance(input, torch.Tensor):
                         return o_mod_fwd(self, input, *args, **kwargs)
                     sq = self.smoothquant
+                    _input = None
                     if sq is not None and (sq.calibrating or _flag(sq, "dynamic") == 1 or _flag(sq, "enabled") == 1):
-                        return o_mod_fwd(self, E.materialise(input), *args, **kwargs)
+                        if elide and E.active() and not torch.is_grad_enabled() and not args and not kwargs and not sq.calibrating \
+                                and _flag(sq, "dynamic") != 1:
+                            input = E.materialise(input)
+                            _input = _fused_scaled_input(self, sq, input)  # input / scale and the input cast in ONE kernel (fp32, as torch promotes)
+                        if _input is None:
+                            return o_mod_fwd(self, E.materialise(input), *args, **kwargs)
                     meta = input._raw if type(input) is E.Lazy else input
                     _dtype, _device = meta.dtype, meta.device
                     w = self._parameters.get("weight") if "weight" in self._parameters else getattr(self, "weight", None)
                     if w is not None:
                         _device = w.device
-                    _input, args, kwargs = self.input_casts(input, *args, **kwargs)
+                    if _input is None:
+                        _input, args, kwargs = self.input_casts(input, *args, **kwargs)
                     mi = _input._raw if type(_input) is E.Lazy else _input
                     if mi.device != _device or any(isinstance(a, torch.Tensor) and a.device != _device for a in args):
                         _input, args, kwargs = self.align_device(_input, args, kwargs, _device)

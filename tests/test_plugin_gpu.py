@@ -445,6 +445,39 @@ def test_histogram_observer_on_gpu(ref, plugin):
         same_bits(u, v, what)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["float32", "bfloat16"])
+def test_reference_linear_with_smoothquant(ref, plugin, dtype):
+    """the reference's own Linear with an enabled ActivationWeightSmoothQuant (core.py:184-196, 227-230; smoothquant.py:253-283, 475-497):
+    unpatched == plugin drop-in == plugin with elision, where `input / scale` + input cast and `weight * scale` + weight cast are one
+    kernel each (DMXQ_STAGE_SCALE)"""
+    from dmx_compressor_b200 import elide
+
+    torch.manual_seed(4)
+    lin = ref.nn.Linear(256, 96).to(device=DEV, dtype=dtype)
+    lin.configure(_basic_config(ref, lin))
+    x = (torch.randn(2, 33, 256, device=DEV) * torch.rand(256, device=DEV).mul(6).exp2()).to(dtype)
+    sq = lin.smoothquant
+    assert sq is not None
+    with torch.no_grad():
+        sq.calibrating = True
+        lin(x)
+        sq.calibrating = False
+        sq.enable()
+        assert sq.scale.numel() == 256
+        a, b = both(plugin, lambda: lin(x))
+        same_bits(a, b, f"smoothquant drop-in {dtype}")
+        plugin.install("dmx.compressor", elide=True)
+        try:
+            n0 = launches()
+            with elide.enabled():
+                c = elide.materialise(lin(x))
+            n1 = launches()
+        finally:
+            plugin.uninstall()
+    same_bits(a, c, f"smoothquant elided {dtype}")
+    assert n1 - n0 <= 5, n1 - n0  # input chain, weight chain, bias cast, output cast (+ one the reference's forward adds); no separate scale passes
+
+
 def _ref_opt_stack(ref, cfg, dtype):
     """an OPT-shaped decoder assembled from the REFERENCE's own dmx.compressor.nn modules (the graph DmxModel.from_torch would
     produce for OPTForCausalLM), every module configured by the reference's config_rules.BASIC"""
