@@ -41,6 +41,28 @@ def test_softmax_equals_torch_bitwise(dt, n):
     assert torch.equal(_bits(torch.where(wn, torch.zeros_like(want), want)), _bits(torch.where(gn, torch.zeros_like(got), got)))
 
 
+@pytest.mark.parametrize("dt", list(DT))
+def test_softmax_nan_and_inf_rows_match_torch(dt):
+    """a NaN (or +inf) anywhere in a row makes the whole row NaN in torch's kernel (the sum is NaN); the maximum is taken with
+    fmaxf here instead of torch's comparison chain -- same rows, same NaN pattern after rounding to the dtype; the other rows stay
+    bit-identical.  Rows whose spread exceeds 110 exercise the skipped (exactly zero) exponentials and the literal division."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    x = torch.randn(64, 2048, device=DEV, generator=g) * 5
+    x[3, 17] = float("nan")
+    x[5, 2047] = float("nan")          # last element of its lane: torch's chain keeps the NaN as that lane's maximum
+    x[7, 0] = float("nan")             # first element: torch's chain drops it from the maximum
+    x[9, 100] = float("inf")
+    x[11, :] = float("-inf")
+    x[13, 64:] -= 400.0                # tails far below the maximum: exp underflows to exactly 0
+    x[15, 1:] -= 95.0                  # quotients in the denormal range: the literal division path
+    x = x.to(DT[dt])
+    want, got = torch.softmax(x, -1), ops.softmax_cast(x)
+    assert torch.equal(torch.isnan(want), torch.isnan(got))
+    assert torch.equal(_bits(want), _bits(got))  # NaN rows included: both produce the canonical NaN of the dtype
+    post = [F("FP[1|5|10,15](FN)"), F("BFP[8|8]{64}(SN)")]
+    assert torch.equal(_bits(ops.cast_chain(want, post, -1)), _bits(ops.softmax_cast(x, post)))
+
+
 @pytest.mark.parametrize("dt", ["float32", "bfloat16"])
 def test_softmax_equals_torch_at_scale(dt):
     """the OPT-125m attention shape: [96, 2048, 2048] probabilities"""
