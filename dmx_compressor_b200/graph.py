@@ -17,7 +17,9 @@ def _drop_weight_caches(model) -> None:
     for m in model.modules():
         if getattr(m, "_wcache", None) is not None:
             m._wcache = None
-        m.__dict__.pop("_dmxq_wcache", None)  # (the plugin's cache on the reference's own DmxModule objects)
+        m.__dict__.pop("_dmxq_wcache", None)  # (the plugin's caches on the reference's own DmxModule objects)
+        m.__dict__.pop("_dmxq_bcache", None)
+        m.__dict__.pop("_bcache", None)
 
 
 class Captured:

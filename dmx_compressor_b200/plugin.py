@@ -464,6 +464,25 @@ def install(package: str = "dmx.compressor", fuse_castto: bool = True, tie_order
 
                 _patch(core.DmxModule, "_weight", property(weight_cached))
 
+                def bias_cached(self):
+                    """DmxModule._bias (core.py:207-213); under elision cast once while the bias and its cast are unchanged"""
+                    c = self.bias_cast
+                    if c is None:
+                        return None
+                    b = self.bias
+                    if not (elide and E.active() and not torch.is_grad_enabled()) or b is None or _flag(c, "observer_enabled") == 1:
+                        return c(b)
+                    key = (b.data_ptr(), b._version, tuple(b.shape), _cstate(c))
+                    ent = self.__dict__.get("_dmxq_bcache")
+                    if ent is not None and ent[0] == key:
+                        return ent[1]
+                    out = E.materialise(c(b))
+                    self.__dict__["_dmxq_bcache"] = (key, out)
+                    return out
+
+                if elide:
+                    _patch(core.DmxModule, "_bias", property(bias_cached))
+
                 o_mod_fwd = core.DmxModule.forward
 
                 def module_forward(self, input, *args, **kwargs):
