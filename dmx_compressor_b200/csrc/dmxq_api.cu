@@ -464,7 +464,7 @@ int chain_impl(const dmxq_tensor *x, const dmxq_tensor *y, int block_dim, const 
         if (rand && !score_p && !mask_p && flat && chain.n == 1 && stoch1 && aligned(rand, 16)) kind = 11;  // K_BFP_STOCH
         else if (score_p || mask_p || rand) kind = 0;  // K_AUX
         else if (chain.n == 1 && bfp_ns(chain.st[0])) kind = 2;  // K_BFP
-        else if (chain.n == 1 && (float_fast(chain.st[0]) || (chain.st[0].kind == ST_FLOAT && chain.st[0].ff.nsub))) kind = 3;  // K_FLOAT
+        else if (chain.n == 1 && chain.st[0].kind == ST_FLOAT && chain.st[0].ff.mode == R_NEAREST) kind = 3;  // K_FLOAT
         else if (chain.n == 2 && float_fast(chain.st[0]) && bfp_ns(chain.st[1])) kind = 4;  // K_FLOAT_BFP
         else if (chain.n == 2 && chain.st[0].kind == ST_NM && bfp_ns(chain.st[1])) kind = 5;  // K_NM_BFP
         else if (chain.n == 1 && chain.st[0].kind == ST_SBFP && chain.st[0].sb.xp.mode == R_NEAREST && chain.st[0].sb.xp.tie == TIE_AWAY) kind = 6;  // K_SBFP

@@ -15,7 +15,8 @@
 //   K_AUX        runtime chain, score / mask / rand tensors honoured
 //   K_CHAIN      runtime chain, no auxiliary tensors
 //   K_BFP        [BFP nearest symmetric]                      BFP16 / BFP12 / MXINT casts
-//   K_FLOAT      [FLOAT nearest+flush+signed]                 FLOAT16 / BFLOAT16 boundary casts
+//   K_FLOAT      [FLOAT nearest: flush+signed fast form, subnormal-keeping form, or the general element function]  FLOAT16 / BFLOAT16
+//                boundary casts, FP8, bias casts
 //   K_FLOAT_BFP  [FLOAT nearest+flush+signed -> BFP n.s.]     output cast fused with next input cast
 //   K_NM_BFP     [N:M with score |x| -> BFP n.s.]             sparsify -> weight cast (hypernet)
 //   K_SBFP       [SBFP, XP nearest half-away]                 SBFP weight storage cast
@@ -373,6 +374,12 @@ __device__ __forceinline__ void chain_rows_body(const RowsParams &p, const Tin *
 #pragma unroll
                 for (int j = 0; j < V; ++j) v[j] = float_elem_slow(v[j], &st.ff, 0u);
             }
+        } else if (KIND == K_FLOAT && !p.chain.st[0].ff.fastpath) {
+            // every other nearest-rounding format (unsigned scalers, `BFP[24|8]{1}` = the BASIC bias format: 22 mantissa bits, nothing
+            // flushed): the same element function the runtime chain calls, without that kernel's ~6 us of fixed cost per launch
+            VecIO<Tin>::unpack(raw[u], v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) v[j] = float_elem_nearest(v[j], p.chain.st[0].ff);
         } else if (KIND == K_FLOAT) {
             if constexpr (SAME16) {
                 if (f16_same && raw16_absmin(raw[u]) >= f16_lo && raw16_absmax(raw[u]) <= f16_hi) {  // identity on this vector
