@@ -12,8 +12,8 @@ One "step" = those four casts over the batch.  Algorithmic bytes per cast = read
 cast touches 1-2 GiB, far above the 126 MB L2, so every step streams from HBM (no L2 flush
 needed; stated in config.l2).
 
-The LAST stdout line is the result (kept compact so a tail capture holds all of it); longer tables
-(the configs[1] size sweep, per-size OPT numbers) are printed BEFORE it as {"detail": ...} lines.
+The LAST stdout line is the result (kept compact -- ~5 KB -- so a tail capture holds all of it); longer tables
+(the configs[1] size sweep, the full OPT-125m blocks) are printed BEFORE it as {"detail": ...} lines.
 
 value      whole-job GB/s with inputs resident in HBM (CUDA events around the K steps, barrier +
            synchronize on both sides, max over ranks).
@@ -968,8 +968,28 @@ def run_ours(args):
         cpu_baseline = {"value": round(nb_tot / tot / 1e9, 4), "unit": "GB/s", "cores": cores, "kind": kind,
                         "sample": f"the step's 4 casts on n=2^24 elements per tensor, mean of {passes} passes (~10 s of CPU work); {how}"}
 
+    # the two OPT-125m blocks in full go out as a detail line; the result line keeps their numbers in compact form
+    def _opt_compact(o, dropin="cast_overhead_basic"):
+        if not isinstance(o, dict) or "error" in o or "unavailable" in o:
+            return o
+        out = {}
+        for dtn, short in (("bfloat16", "bf16"), ("float32", "fp32")):
+            r = o.get(dtn)
+            if isinstance(r, dict):
+                out[short] = {"ms": r.get("ms"), "overhead_dropin": r.get(dropin), "overhead_elided": r.get("cast_overhead_elided"),
+                              "overhead_elided_vs_dmxq_softmax_twin": r.get("cast_overhead_elided_vs_dmxq_softmax_twin"),
+                              "elided_equals_dropin_bitwise": r.get("elided_equals_dropin_bitwise")}
+                for k in ("ms_reference_unpatched", "ms_plugin_elided_cuda_graph", "dropin_equals_reference_bitwise"):
+                    if k in r:
+                        out[short][k] = r[k]
+        out["ms"] = "[unquantised torch twin, BASIC drop-in, BASIC + elision], batch 8 x seq 2048"
+        return out
+
+    if opt is not None or popt is not None:
+        details.append({"detail": "opt125m (full blocks)", "opt125m_basic_forward": opt, "opt125m_reference_modules_plus_plugin": popt})
     for d in details:
         print(json.dumps(d), flush=True)
+    opt, popt = _opt_compact(opt), _opt_compact(popt, "cast_overhead_dropin")
     line = {
         "metric": "BFP cast GB/s", "value": round(value, 1), "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
